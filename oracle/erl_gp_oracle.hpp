@@ -1,0 +1,879 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement (C++17 + OpenMP, no Eigen) of the erl_gaussian_process train/predict hot
+// path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may call into this; the product path (erl_gaussian_process_b200/csrc) never does.
+//
+// The reference binary cannot be built in this image (no Eigen, erl_common, erl_covariance,
+// erl_geometry), so this file restates the algorithm from the reference
+// sources, function by function, with the file:line each block follows.  Pinning status:
+//   * RBF kernel + K[i,i] = 1 + var[i] + LLT + alpha + mean: PINNED by the reference's own
+//     known-answer values (test/gtest/test_vanilla_gp.cpp:103,214,366-367), see
+//     tests/test_oracle_kat.py.
+//   * SPGP dense update/predict: PINNED to 5 digits (test_sparse_pseudo_input_gp.cpp:109).
+//   * Matern32 / OrnsteinUhlenbeck formulas, predictive variance, LidarFrame2D /
+//     RangeSensorFrame3D masks and frame coordinates: PARITY UNPINNED (the arithmetic lives in
+//     erl_covariance v0.2.0 / erl_geometry v0.2.0, whose sources are absent; no runnable
+//     reference test asserts a value).  Restated from the published definitions and from the
+//     call sites listed below.
+//
+// Layout conventions are the reference's: everything column-major, x is x_dim x n with one
+// point contiguous, K/L are the top-left n x n of an ld x ld buffer, L's strict upper
+// triangle is zero, Ktest is n x T with column j = k(X, x*_j).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace erl_gp_oracle {
+
+    enum KernelType : int { kOrnsteinUhlenbeck = 0, kMatern32 = 1, kRadialBiasFunction = 2 };
+
+    enum MappingType : int {  // include/erl_gaussian_process/mapping.hpp:11-20
+        kIdentity = 0,
+        kInverse = 1,
+        kInverseSqrt = 2,
+        kExp = 3,
+        kLog = 4,
+        kTanh = 5,
+        kSigmoid = 6,
+        kUnknown = 7
+    };
+
+    // ---------------------------------------------------------------------------------------
+    // erl_covariance v0.2.0 kernels.  Unit amplitude, r = ||x - x'||_2.
+    //   RadialBiasFunction : exp(-r^2 / (2 l^2))              [pinned by KAT]
+    //   Matern32           : (1 + sqrt(3) r / l) exp(-sqrt(3) r / l)   [unpinned]
+    //   OrnsteinUhlenbeck  : exp(-r / l)                      [unpinned]
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    inline T
+    KernelFromSquaredDistance(const int type, const T scale, const T r2) {
+        switch (type) {
+            case kRadialBiasFunction:
+                return std::exp(-r2 / (T(2) * scale * scale));
+            case kMatern32: {
+                const T a = std::sqrt(T(3)) / scale;
+                const T ar = a * std::sqrt(r2);
+                return (T(1) + ar) * std::exp(-ar);
+            }
+            case kOrnsteinUhlenbeck:
+            default:
+                return std::exp(-std::sqrt(r2) / scale);
+        }
+    }
+
+    template<typename T>
+    inline T
+    SquaredDistance(const T *a, const T *b, const long x_dim) {
+        T r2 = 0;
+        for (long d = 0; d < x_dim; ++d) {
+            const T diff = a[d] - b[d];
+            r2 += diff * diff;
+        }
+        return r2;
+    }
+
+    // Covariance::ComputeKtrain call site: src/vanilla_gp.cpp:486-487.  K is symmetric with
+    // K[i,i] = 1 + var[i]; the full square is stored (the reference keeps a dense MatrixX).
+    template<typename T>
+    void
+    ComputeKtrain(
+        const int type,
+        const T scale,
+        const long x_dim,
+        const T *x,
+        const long ld_x,
+        const T *var,
+        const long n,
+        T *k,
+        const long ld_k) {
+        for (long j = 0; j < n; ++j) {
+            k[j + j * ld_k] = T(1) + var[j];
+            for (long i = j + 1; i < n; ++i) {
+                const T r2 = SquaredDistance(x + i * ld_x, x + j * ld_x, x_dim);
+                const T v = KernelFromSquaredDistance(type, scale, r2);
+                k[i + j * ld_k] = v;
+                k[j + i * ld_k] = v;
+            }
+        }
+    }
+
+    // Covariance::ComputeKtest call sites: src/vanilla_gp.cpp:537,
+    // src/sparse_pseudo_input_gp.cpp:91-96, 340, 761-762.  No noise term.
+    template<typename T>
+    void
+    ComputeKtest(
+        const int type,
+        const T scale,
+        const long x_dim,
+        const T *x1,
+        const long ld_x1,
+        const long n1,
+        const T *x2,
+        const long ld_x2,
+        const long n2,
+        T *k,
+        const long ld_k) {
+        for (long j = 0; j < n2; ++j) {
+            for (long i = 0; i < n1; ++i) {
+                const T r2 = SquaredDistance(x1 + i * ld_x1, x2 + j * ld_x2, x_dim);
+                k[i + j * ld_k] = KernelFromSquaredDistance(type, scale, r2);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // Eigen `mat.llt().matrixL()` as used at src/vanilla_gp.cpp:499: lower Cholesky of the
+    // top-left n x n block, dense result with the strict upper triangle zeroed.  Eigen's
+    // unblocked kernel is the left-looking row-dot form restated here; on a non-positive pivot
+    // Eigen returns early with info()==NumericalIssue, which the reference never checks
+    // (SURVEY.md section 5): we return the 1-based failing column and leave NaN behind so a
+    // failure cannot be mistaken for a result.
+    // Blocked right-looking variant (panel nb) for large n so the CPU baseline is not
+    // artificially slow; same arithmetic up to summation order.
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    int
+    LltUnblockedInPlace(T *a, const long ld, const long n) {
+        for (long k = 0; k < n; ++k) {
+            T x = a[k + k * ld];
+            for (long p = 0; p < k; ++p) { x -= a[k + p * ld] * a[k + p * ld]; }
+            if (!(x > T(0))) {
+                for (long j = k; j < n; ++j) {
+                    for (long i = j; i < n; ++i) { a[i + j * ld] = std::numeric_limits<T>::quiet_NaN(); }
+                }
+                return static_cast<int>(k + 1);
+            }
+            x = std::sqrt(x);
+            a[k + k * ld] = x;
+            const T inv = T(1) / x;
+            for (long p = 0; p < k; ++p) {
+                const T akp = a[k + p * ld];
+                T *col_k = a + k * ld;
+                const T *col_p = a + p * ld;
+                for (long i = k + 1; i < n; ++i) { col_k[i] -= col_p[i] * akp; }
+            }
+            for (long i = k + 1; i < n; ++i) { a[i + k * ld] *= inv; }
+        }
+        return 0;
+    }
+
+    template<typename T>
+    int
+    LltInPlace(T *a, const long ld, const long n, const bool parallel = true) {
+        constexpr long nb = 64;
+        if (n <= 2 * nb) { return LltUnblockedInPlace(a, ld, n); }
+        for (long k = 0; k < n; k += nb) {
+            const long kb = std::min(nb, n - k);
+            // diagonal block
+            if (const int info = LltUnblockedInPlace(a + k + k * ld, ld, kb); info != 0) {
+                return static_cast<int>(k) + info;
+            }
+            const long m = n - k - kb;
+            if (m <= 0) { break; }
+            T *a21 = a + (k + kb) + k * ld;
+            const T *l11 = a + k + k * ld;
+            // A21 <- A21 * L11^{-T}   (row i of A21 solves L11 z = a_i)
+#pragma omp parallel for if (parallel) schedule(static)
+            for (long i = 0; i < m; ++i) {
+                for (long c = 0; c < kb; ++c) {
+                    T s = a21[i + c * ld];
+                    for (long p = 0; p < c; ++p) { s -= a21[i + p * ld] * l11[c + p * ld]; }
+                    a21[i + c * ld] = s / l11[c + c * ld];
+                }
+            }
+            // A22 <- A22 - A21 * A21^T  (lower part only)
+            T *a22 = a + (k + kb) + (k + kb) * ld;
+#pragma omp parallel for if (parallel) schedule(dynamic, 8)
+            for (long j = 0; j < m; ++j) {
+                T *col = a22 + j * ld;
+                for (long p = 0; p < kb; ++p) {
+                    const T ajp = a21[j + p * ld];
+                    const T *src = a21 + p * ld;
+                    for (long i = j; i < m; ++i) { col[i] -= src[i] * ajp; }
+                }
+            }
+        }
+        return 0;
+    }
+
+    // L <- chol_lower(K[0:n,0:n]); strict upper of L zeroed (matrixL() assignment, :499).
+    template<typename T>
+    int
+    Llt(const T *k, const long ld_k, const long n, T *l, const long ld_l, const bool parallel = true) {
+        for (long j = 0; j < n; ++j) {
+            for (long i = 0; i < j; ++i) { l[i + j * ld_l] = T(0); }
+            for (long i = j; i < n; ++i) { l[i + j * ld_l] = k[i + j * ld_k]; }
+        }
+        return LltInPlace(l, ld_l, n, parallel);
+    }
+
+    // triangularView<Lower>().solveInPlace(b): forward substitution, src/vanilla_gp.cpp:501,
+    // and the per-column solve of PrepareForVariance, :141-147.
+    template<typename T>
+    void
+    SolveLowerInPlace(const T *l, const long ld_l, const long n, T *b) {
+        for (long j = 0; j < n; ++j) {  // column-oriented (axpy) form, as Eigen's col-major trsv
+            const T bj = b[j] / l[j + j * ld_l];
+            b[j] = bj;
+            const T *col = l + j * ld_l;
+            for (long i = j + 1; i < n; ++i) { b[i] -= col[i] * bj; }
+        }
+    }
+
+    // L.transpose().triangularView<Upper>().solveInPlace(b): back substitution, :502.
+    template<typename T>
+    void
+    SolveLowerTransposeInPlace(const T *l, const long ld_l, const long n, T *b) {
+        for (long j = n - 1; j >= 0; --j) {
+            const T *col = l + j * ld_l;
+            T s = b[j];
+            for (long i = j + 1; i < n; ++i) { s -= col[i] * b[i]; }
+            b[j] = s / col[j];
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // Mapping<Dtype>::map / inv — src/mapping.cpp:112-164.
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    inline T
+    MappingMap(const int type, const T scale, const T x) {
+        switch (type) {
+            case kIdentity:
+                return x;
+            case kInverse:
+                return T(1) / x;
+            case kInverseSqrt:
+                return T(1) / std::sqrt(x);
+            case kExp:
+                return std::exp(-scale * x);
+            case kLog:
+                return std::log(scale * x);
+            case kTanh:
+                return std::tanh(scale * x);
+            case kSigmoid:
+                return T(1) / (T(1) + std::exp(-scale * x));
+            default:
+                return std::numeric_limits<T>::quiet_NaN();
+        }
+    }
+
+    template<typename T>
+    inline T
+    MappingInv(const int type, const T scale, const T y) {
+        switch (type) {
+            case kIdentity:
+                return y;
+            case kInverse:
+                return T(1) / y;
+            case kInverseSqrt:
+                return T(1) / (y * y);
+            case kExp:
+                return -std::log(y) / scale;
+            case kLog:
+                return std::exp(y) / scale;
+            case kTanh:
+                return std::atanh(y) / scale;
+            case kSigmoid:
+                if (y >= T(1)) { return std::numeric_limits<T>::infinity() / scale; }
+                if (y <= T(0)) { return -std::numeric_limits<T>::infinity() / scale; }
+                return std::log(y / (T(1) - y)) / scale;
+            default:
+                return std::numeric_limits<T>::quiet_NaN();
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // VanillaGaussianProcess — src/vanilla_gp.cpp.  State kept exactly as the reference keeps
+    // it: grow-only buffers (TrainSet::Reset :152-161, AllocateMemory :792-814), trained /
+    // trained_once / k_train_updated flags (:507-519).
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    struct VanillaGp {
+        int kernel_type = kRadialBiasFunction;
+        T scale = T(1);
+        long max_num_samples_setting = 256;  // Setting::max_num_samples, vanilla_gp.hpp:28
+
+        // TrainSet
+        long x_dim = 0, y_dim = 0, num_samples = 0;
+        long x_rows = 0, x_cols = 0;  // x is x_rows x x_cols, col-major
+        long y_rows = 0, y_cols = 0;
+        std::vector<T> x, y, var;
+
+        bool trained = false, trained_once = false, k_train_updated = false;
+        long k_rows = 0, k_cols = 0;  // m_k_train_rows_/cols_
+        long ld = 0;                  // rows of m_mat_k_train_ / m_mat_l_
+        long alpha_rows = 0, alpha_cols = 0;
+        std::vector<T> mat_k, mat_l, mat_alpha;
+        int llt_info = 0;
+
+        // Reset — :376-400.  Returns false where the reference would ERL_ASSERTM.
+        bool
+        Reset(const long max_n, const long xd, const long yd) {
+            if (max_n <= 0 || xd <= 0 || yd <= 0) { return false; }
+            if (!(max_num_samples_setting < 0 || max_n <= max_num_samples_setting)) { return false; }
+            x_dim = xd;
+            y_dim = yd;
+            if (x_rows < xd || x_cols < max_n) {
+                x_rows = xd;
+                x_cols = max_n;
+                x.assign(static_cast<std::size_t>(xd * max_n), T(0));
+            }
+            if (y_rows < max_n || y_cols < yd) {
+                y_rows = max_n;
+                y_cols = yd;
+                y.assign(static_cast<std::size_t>(max_n * yd), T(0));
+            }
+            if (static_cast<long>(var.size()) < max_n) { var.assign(static_cast<std::size_t>(max_n), T(0)); }
+            num_samples = 0;
+            if (ld < max_n) {
+                ld = max_n;
+                mat_k.assign(static_cast<std::size_t>(ld * ld), T(0));
+                mat_l.assign(static_cast<std::size_t>(ld * ld), T(0));
+            }
+            if (alpha_rows < max_n || alpha_cols < yd) {
+                alpha_rows = std::max(alpha_rows, max_n);
+                alpha_cols = std::max(alpha_cols, yd);
+                mat_alpha.assign(static_cast<std::size_t>(alpha_rows * alpha_cols), T(0));
+            }
+            trained = false;
+            k_train_updated = false;
+            k_rows = k_cols = 0;
+            return true;
+        }
+
+        // UpdateKtrain — :476-490
+        bool
+        UpdateKtrain() {
+            if (k_train_updated) { return true; }
+            if (num_samples <= 0) { return false; }
+            for (long c = 0; c < y_dim; ++c) {
+                for (long i = 0; i < num_samples; ++i) { mat_alpha[i + c * alpha_rows] = y[i + c * y_rows]; }
+            }
+            ComputeKtrain(kernel_type, scale, x_dim, x.data(), x_rows, var.data(), num_samples, mat_k.data(), ld);
+            k_rows = k_cols = num_samples;
+            k_train_updated = true;
+            return true;
+        }
+
+        // Solve — :492-505
+        void
+        Solve() {
+            llt_info = Llt(mat_k.data(), ld, k_rows, mat_l.data(), ld, /*parallel=*/k_rows > 512);
+            for (long c = 0; c < y_dim; ++c) {
+                T *a = mat_alpha.data() + c * alpha_rows;
+                SolveLowerInPlace(mat_l.data(), ld, k_cols, a);
+                SolveLowerTransposeInPlace(mat_l.data(), ld, k_cols, a);
+            }
+            trained_once = true;
+            trained = true;
+        }
+
+        // Train — :507-519 (including the `m_trained_ = m_trained_once_` quirk, App. C.5)
+        bool
+        Train() {
+            if (trained) { return false; }
+            trained = trained_once;
+            if (!UpdateKtrain()) { return false; }
+            Solve();
+            return true;
+        }
+
+        // ComputeKtest — :521-552.  k_test must hold k_cols x num_test.
+        bool
+        ComputeKtestInto(const T *x_test, const long ld_xt, const long num_test, T *k_test) const {
+            if (!trained || num_test == 0) { return false; }
+            ComputeKtest(kernel_type, scale, x_dim, x.data(), x_rows, num_samples, x_test, ld_xt, num_test, k_test, k_cols);
+            return true;
+        }
+
+        // Test + TestResult::GetMean + GetVariance — :554-559, :61-82, :106-150.
+        // `parallel` selects the per-column trsv under omp (:141-147); the serial mode is one
+        // TRSM over all columns (:149) which is the same arithmetic per column.
+        bool
+        Test(
+            const T *x_test,
+            const long ld_xt,
+            const long num_test,
+            T *mean /* num_test x y_dim or nullptr */,
+            T *variance /* num_test or nullptr */,
+            const bool parallel) const {
+            if (!trained || num_test == 0) { return false; }
+            const long n = k_cols;
+            std::vector<T> k_test(static_cast<std::size_t>(n * num_test));
+            ComputeKtestInto(x_test, ld_xt, num_test, k_test.data());
+            if (mean != nullptr) {
+                for (long c = 0; c < y_dim; ++c) {
+                    const T *alpha = mat_alpha.data() + c * alpha_rows;
+#pragma omp parallel for if (parallel) schedule(static)
+                    for (long i = 0; i < num_test; ++i) {
+                        const T *kc = k_test.data() + i * n;
+                        T f = 0;
+                        for (long p = 0; p < n; ++p) { f += kc[p] * alpha[p]; }
+                        mean[i + c * num_test] = f;
+                    }
+                }
+            }
+            if (variance != nullptr) {
+#pragma omp parallel for if (parallel) schedule(static)
+                for (long i = 0; i < num_test; ++i) {
+                    T *kc = k_test.data() + i * n;
+                    SolveLowerInPlace(mat_l.data(), ld, n, kc);
+                    T s = 0;
+                    for (long p = 0; p < n; ++p) { s += kc[p] * kc[p]; }
+                    variance[i] = T(1) - s;  // literal prior 1.0f, :121
+                }
+            }
+            return true;
+        }
+    };
+
+    // ---------------------------------------------------------------------------------------
+    // Partition tables.  LidarGaussianProcess2D::PartitionOnAngles — src/lidar_gp_2d.cpp:238-300
+    // (symmetric :255-276, asymmetric :279-299); the 3-D constructor applies the symmetric rule
+    // per axis — src/range_sensor_gp_3d.cpp:199-259.
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    struct Partition {
+        long index_left, index_right;
+        T coord_left, coord_right;
+    };
+
+    template<typename T>
+    std::vector<Partition<T>>
+    MakePartitions(
+        const T *coords,
+        const long coord_stride,
+        const long n,
+        const long group_size,
+        const long overlap_size,
+        const long margin,
+        const bool symmetric) {
+        std::vector<Partition<T>> parts;
+        auto c = [&](const long i) { return coords[i * coord_stride]; };
+        const long gs = group_size;
+        const long step = group_size - overlap_size;
+        const long num_groups = std::max(1l, n / step) + 1;
+        const long gs2 = (n - (num_groups - 2) * step) / 2;
+        const long half_overlap = overlap_size / 2;
+        parts.reserve(static_cast<std::size_t>(num_groups));
+        if (symmetric) {
+            parts.push_back({0, gs2 + half_overlap, c(margin), c(gs2)});
+            for (long i = 0; i < num_groups - 2; ++i) {
+                const long index_left = i * step + gs2 - half_overlap;
+                const long index_right = index_left + gs;
+                parts.push_back({index_left, index_right, c(index_left + half_overlap), c(index_right - half_overlap)});
+            }
+            parts.push_back({n - gs2 - half_overlap, n, c(n - 1 - gs2), c(n - 1 - margin)});
+            return parts;
+        }
+        for (long i = 0; i < num_groups - 2; ++i) {
+            const long index_left = i * step;
+            const long index_right = index_left + group_size;
+            parts.push_back({index_left, index_right, c(index_left), c(index_right - half_overlap)});
+        }
+        long index_left = (num_groups - 2) * step;
+        long index_right = index_left + (n - index_left + overlap_size) / 2;
+        parts.push_back({index_left, index_right, c(index_left), c(index_right - half_overlap)});
+        index_left = index_left + (n - index_left - overlap_size) / 2;
+        index_right = n;
+        parts.push_back({index_left, index_right, c(index_left), c(index_right - 1)});
+        return parts;
+    }
+
+    // SearchPartition — src/lidar_gp_2d.cpp:398-411 (closed interval, first match);
+    // src/range_sensor_gp_3d.cpp:366-393 (row half-open [l,r), col closed [l,r]).
+    template<typename T>
+    long
+    SearchPartition(const std::vector<Partition<T>> &parts, const T coord, const bool right_closed) {
+        if (!std::isfinite(coord)) { return -1; }
+        for (std::size_t i = 0; i < parts.size(); ++i) {
+            const bool in = right_closed ? (coord >= parts[i].coord_left && coord <= parts[i].coord_right)
+                                         : (coord >= parts[i].coord_left && coord < parts[i].coord_right);
+            if (in) { return static_cast<long>(i); }
+        }
+        return -1;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // LidarGaussianProcess2D — src/lidar_gp_2d.cpp.  The erl_geometry::LidarFrame2D outputs
+    // (angles in frame, hit mask, continuity mask, world->frame rotation) enter as plain
+    // arrays: that is the boundary of the hot path.
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    struct LidarGp2D {
+        // Setting (include/erl_gaussian_process/lidar_gp_2d.hpp:28-71)
+        bool symmetric_partitions = true;
+        long group_size = 26, overlap_size = 6, margin = 1;
+        T sensor_range_var = T(0.01), discontinuity_var = T(10), max_valid_range_var = T(0.1);
+        T occ_test_temperature = T(30);
+        bool discontinuity_detection = false;
+        int kernel_type = kOrnsteinUhlenbeck;
+        T kernel_scale = T(1);
+        int mapping_type = kInverseSqrt;
+        T mapping_scale = T(1);
+
+        std::vector<T> angles;  // LidarFrame2D::GetAnglesInFrame()
+        std::vector<Partition<T>> partitions;
+        std::vector<VanillaGp<T>> gps;
+        std::vector<T> mapped;
+        T rotation[4] = {1, 0, 0, 1};  // col-major 2x2, sensor -> world
+        bool trained = false;
+
+        // ctor + PartitionOnAngles — :169-183, :238-300
+        void
+        Init(const T *angles_in_frame, const long n) {
+            angles.assign(angles_in_frame, angles_in_frame + n);
+            partitions.clear();
+            gps.clear();
+            if (n <= overlap_size) { return; }
+            partitions = MakePartitions(angles.data(), 1, n, group_size, overlap_size, margin, symmetric_partitions);
+            gps.resize(partitions.size());
+            for (auto &gp: gps) {
+                gp.kernel_type = kernel_type;
+                gp.scale = kernel_scale;
+                gp.max_num_samples_setting = group_size;  // :249
+            }
+        }
+
+        // Train — :350-396.  ranges: valid ranges after LidarFrame2D::UpdateRanges;
+        // hit/continuity masks are the frame's.
+        bool
+        Train(const T *rot_colmajor, const T *ranges, const uint8_t *mask_hit, const uint8_t *mask_con, const bool frame_valid) {
+            trained = false;
+            std::memcpy(rotation, rot_colmajor, sizeof(rotation));
+            const long n = static_cast<long>(angles.size());
+            mapped.resize(static_cast<std::size_t>(n));
+            for (long i = 0; i < n; ++i) { mapped[i] = MappingMap(mapping_type, mapping_scale, ranges[i]); }
+            if (!frame_valid) { return false; }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (long p = 0; p < static_cast<long>(partitions.size()); ++p) {
+                const auto &part = partitions[p];
+                VanillaGp<T> &gp = gps[p];
+                gp.Reset(gp.max_num_samples_setting, 1, 1);
+                long cnt = 0;
+                for (long j = part.index_left; j < part.index_right; ++j) {
+                    if (!mask_hit[j]) { continue; }
+                    gp.x[cnt] = angles[j];
+                    gp.y[cnt] = mapped[j];
+                    gp.var[cnt] = (discontinuity_detection && !mask_con[j]) ? discontinuity_var : sensor_range_var;
+                    ++cnt;
+                }
+                gp.num_samples = cnt;
+                if (cnt > 0) { (void) gp.Train(); }
+            }
+            trained = true;
+            return true;
+        }
+
+        // Test — :413-426 with TestResult ctor :47-88 (serial loop), GetMean :102-126,
+        // GetVariance :128-167.  Outputs for invalid rays are left untouched.
+        bool
+        Test(
+            const T *query_angles,
+            const long num_test,
+            const bool angles_are_local,
+            const bool un_map,
+            T *mean,
+            T *variance,
+            uint8_t *valid) const {
+            if (!trained) { return false; }
+            std::vector<long> gp_index(static_cast<std::size_t>(num_test), -1);
+            std::vector<T> local(static_cast<std::size_t>(num_test));
+            for (long i = 0; i < num_test; ++i) {  // serial, as the reference's ctor
+                T a = query_angles[i];
+                if (!angles_are_local) {
+                    // LidarFrame2D::DirWorldToFrame = R^T * dir  [erl_geometry, inferred]
+                    const T dx = std::cos(a), dy = std::sin(a);
+                    const T lx = rotation[0] * dx + rotation[1] * dy;
+                    const T ly = rotation[2] * dx + rotation[3] * dy;
+                    a = std::atan2(ly, lx);
+                }
+                local[i] = a;
+                const long idx = SearchPartition(partitions, a, /*right_closed=*/true);
+                if (idx < 0 || !gps[idx].trained) { continue; }
+                gp_index[i] = idx;
+            }
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < num_test; ++i) {
+                if (gp_index[i] < 0) {
+                    valid[i] = 0;
+                    continue;
+                }
+                const VanillaGp<T> &gp = gps[gp_index[i]];
+                const long n = gp.k_cols;
+                std::vector<T> ktest(static_cast<std::size_t>(n));
+                gp.ComputeKtestInto(&local[i], 1, 1, ktest.data());
+                if (mean != nullptr) {
+                    T f = 0;
+                    for (long p = 0; p < n; ++p) { f += ktest[p] * gp.mat_alpha[p]; }
+                    if (un_map) { f = MappingInv(mapping_type, mapping_scale, f); }
+                    mean[i] = f;
+                }
+                if (variance != nullptr) {
+                    SolveLowerInPlace(gp.mat_l.data(), gp.ld, n, ktest.data());
+                    T s = 0;
+                    for (long p = 0; p < n; ++p) { s += ktest[p] * ktest[p]; }
+                    variance[i] = T(1) - s;
+                }
+                valid[i] = 1;
+            }
+            return true;
+        }
+
+        // ComputeOcc — :428-459
+        bool
+        ComputeOcc(const T px, const T py, T &dist_pos, T &range_pred, T &occ) const {
+            if (!trained) { return false; }
+            dist_pos = std::sqrt(px * px + py * py);
+            const T angle = std::atan2(py, px);
+            const long idx = SearchPartition(partitions, angle, true);
+            if (idx < 0 || !gps[idx].trained) { return false; }
+            T var;
+            gps[idx].Test(&angle, 1, 1, &range_pred, &var, false);
+            if (var > max_valid_range_var) { return false; }
+            const T a = dist_pos * occ_test_temperature;
+            occ = T(2) / (T(1) + std::exp(a * (range_pred - MappingMap(mapping_type, mapping_scale, dist_pos)))) - T(1);
+            range_pred = MappingInv(mapping_type, mapping_scale, range_pred);
+            return true;
+        }
+    };
+
+    // ---------------------------------------------------------------------------------------
+    // RangeSensorGaussianProcess3D — src/range_sensor_gp_3d.cpp.  frame_coords is the
+    // RangeSensorFrame3D::GetFrameCoords() matrix (rows x cols of 2-vectors), stored as
+    // coords[(r + c * rows) * 2 + {0,1}] (Eigen col-major matrix of Vector2).
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    struct RangeSensorGp3D {
+        long row_group_size = 24, row_overlap_size = 6, row_margin = 0;
+        long col_group_size = 8, col_overlap_size = 2, col_margin = 0;
+        long min_num_samples_per_group = 32;
+        T sensor_range_var = T(0.01), max_valid_range_var = T(0.1), occ_test_temperature = T(30);
+        int kernel_type = kOrnsteinUhlenbeck;
+        T kernel_scale = T(1);
+        int mapping_type = kInverseSqrt;
+        T mapping_scale = T(1);
+
+        long rows = 0, cols = 0;
+        std::vector<T> frame_coords;
+        std::vector<Partition<T>> row_partitions, col_partitions;
+        std::vector<VanillaGp<T>> gps;  // (row_part, col_part) col-major, :215,341
+        std::vector<T> mapped;
+        bool trained = false;
+
+        // ctor — :180-260
+        bool
+        Init(const T *coords, const long num_rows, const long num_cols) {
+            if (row_overlap_size % 2 != 0 || col_overlap_size % 2 != 0) { return false; }  // :190-197
+            rows = num_rows;
+            cols = num_cols;
+            frame_coords.assign(coords, coords + 2 * rows * cols);
+            // row coordinate: component 0 of frame_coords(r, 0); col: component 1 of frame_coords(0, c)
+            row_partitions = MakePartitions(frame_coords.data(), 2, rows, row_group_size, row_overlap_size, row_margin, true);
+            col_partitions = MakePartitions(frame_coords.data() + 1, 2 * rows, cols, col_group_size, col_overlap_size, col_margin, true);
+            gps.assign(row_partitions.size() * col_partitions.size(), VanillaGp<T>());
+            for (auto &gp: gps) {
+                gp.kernel_type = kernel_type;
+                gp.scale = kernel_scale;
+                gp.max_num_samples_setting = row_group_size * col_group_size;  // :213
+            }
+            return true;
+        }
+
+        // Train — :321-364.  ranges and mask_hit are rows x cols col-major.
+        bool
+        Train(const T *ranges, const uint8_t *mask_hit, const bool frame_valid) {
+            trained = false;
+            mapped.resize(static_cast<std::size_t>(rows * cols));
+            for (long i = 0; i < rows * cols; ++i) { mapped[i] = MappingMap(mapping_type, mapping_scale, ranges[i]); }
+            if (!frame_valid) { return false; }
+            const long nr = static_cast<long>(row_partitions.size());
+            const long nc = static_cast<long>(col_partitions.size());
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+            for (long j = 0; j < nc; ++j) {
+                for (long i = 0; i < nr; ++i) {
+                    const auto &rp = row_partitions[i];
+                    const auto &cp = col_partitions[j];
+                    VanillaGp<T> &gp = gps[i + j * nr];
+                    gp.Reset(gp.max_num_samples_setting, 2, 1);
+                    long cnt = 0;
+                    for (long c = cp.index_left; c < cp.index_right; ++c) {
+                        for (long r = rp.index_left; r < rp.index_right; ++r) {
+                            if (!mask_hit[r + c * rows]) { continue; }
+                            gp.x[2 * cnt] = frame_coords[2 * (r + c * rows)];
+                            gp.x[2 * cnt + 1] = frame_coords[2 * (r + c * rows) + 1];
+                            gp.y[cnt] = mapped[r + c * rows];
+                            gp.var[cnt] = sensor_range_var;
+                            ++cnt;
+                        }
+                    }
+                    gp.num_samples = cnt;
+                    if (cnt > min_num_samples_per_group) { (void) gp.Train(); }
+                }
+            }
+            trained = true;
+            return true;
+        }
+
+        long
+        SearchGp(const T row_coord, const T col_coord) const {
+            const long pr = SearchPartition(row_partitions, row_coord, /*right_closed=*/false);
+            if (pr < 0) { return -1; }
+            const long pc = SearchPartition(col_partitions, col_coord, /*right_closed=*/true);
+            if (pc < 0) { return -1; }
+            return pr + pc * static_cast<long>(row_partitions.size());
+        }
+
+        // Test on frame coordinates (the RangeSensorFrame3D::ComputeFrameCoords outputs);
+        // TestResult ctor :58-98, GetMean :121-139, GetVariance :147-178.
+        bool
+        TestFrameCoords(
+            const T *query_coords /* 2 x T */,
+            const uint8_t *coords_ok /* ComputeFrameCoords return, may be nullptr */,
+            const long num_test,
+            const bool un_map,
+            T *mean,
+            T *variance,
+            uint8_t *valid) const {
+            if (!trained) { return false; }
+            std::vector<long> gp_index(static_cast<std::size_t>(num_test), -1);
+            for (long i = 0; i < num_test; ++i) {
+                if (coords_ok != nullptr && !coords_ok[i]) { continue; }
+                const long idx = SearchGp(query_coords[2 * i], query_coords[2 * i + 1]);
+                if (idx < 0 || !gps[idx].trained) { continue; }
+                gp_index[i] = idx;
+            }
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < num_test; ++i) {
+                if (gp_index[i] < 0) {
+                    valid[i] = 0;
+                    continue;
+                }
+                const VanillaGp<T> &gp = gps[gp_index[i]];
+                const long n = gp.k_cols;
+                std::vector<T> ktest(static_cast<std::size_t>(n));
+                gp.ComputeKtestInto(query_coords + 2 * i, 2, 1, ktest.data());
+                if (mean != nullptr) {
+                    T f = 0;
+                    for (long p = 0; p < n; ++p) { f += ktest[p] * gp.mat_alpha[p]; }
+                    if (un_map) { f = MappingInv(mapping_type, mapping_scale, f); }
+                    mean[i] = f;
+                }
+                if (variance != nullptr) {
+                    SolveLowerInPlace(gp.mat_l.data(), gp.ld, n, ktest.data());
+                    T s = 0;
+                    for (long p = 0; p < n; ++p) { s += ktest[p] * ktest[p]; }
+                    variance[i] = T(1) - s;
+                }
+                valid[i] = 1;
+            }
+            return true;
+        }
+    };
+
+    // ---------------------------------------------------------------------------------------
+    // SparsePseudoInputGaussianProcess, dense mode only — src/sparse_pseudo_input_gp.cpp:
+    // ctor :313-356, UpdateDense :751-791, PrepareLqm :835-842, TestResult ctor :43-113,
+    // GetMean :133-163, GetVariance/PrepareForVariance :280-310.
+    // ---------------------------------------------------------------------------------------
+    template<typename T>
+    struct Spgp {
+        int kernel_type = kRadialBiasFunction;
+        T scale = T(1);
+        long x_dim = 0, m = 0;
+        std::vector<T> z;  // x_dim x m pseudo points
+        std::vector<T> k_m, l_km, q_m, l_qm, alpha;
+        bool l_qm_updated = false;
+
+        void
+        Init(const T *pseudo, const long xd, const long num_pseudo) {
+            x_dim = xd;
+            m = num_pseudo;
+            z.assign(pseudo, pseudo + xd * num_pseudo);
+            k_m.assign(static_cast<std::size_t>(m * m), T(0));
+            ComputeKtest(kernel_type, scale, x_dim, z.data(), x_dim, m, z.data(), x_dim, m, k_m.data(), m);  // :340
+            l_km.assign(static_cast<std::size_t>(m * m), T(0));
+            Llt(k_m.data(), m, m, l_km.data(), m);  // :341
+            q_m = k_m;                              // :349
+            alpha.assign(static_cast<std::size_t>(m), T(0));
+            l_qm_updated = false;
+        }
+
+        // UpdateDense — :751-791 (y_dim = 1)
+        bool
+        Update(const T *x, const T *y, const T *var, const long n) {
+            if (n <= 0) { return false; }
+            std::vector<T> k_mn(static_cast<std::size_t>(m * n));
+            ComputeKtest(kernel_type, scale, x_dim, z.data(), x_dim, m, x, x_dim, n, k_mn.data(), m);
+            std::vector<T> k_s = k_mn;
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < n; ++i) {
+                std::vector<T> beta(k_mn.begin() + i * m, k_mn.begin() + (i + 1) * m);
+                SolveLowerInPlace(l_km.data(), m, m, beta.data());
+                T s = 0;
+                for (long p = 0; p < m; ++p) { s += beta[p] * beta[p]; }
+                const T lambda = T(1) - s;
+                const T w = T(1) / (lambda + var[i]);
+                for (long p = 0; p < m; ++p) { k_s[p + i * m] *= w; }
+            }
+            // Q_M += Ks * K_MN^T ; alpha += Ks * y
+#pragma omp parallel for schedule(static)
+            for (long c = 0; c < m; ++c) {
+                T *qc = q_m.data() + c * m;
+                for (long i = 0; i < n; ++i) {
+                    const T b = k_mn[c + i * m];
+                    const T *ks = k_s.data() + i * m;
+                    for (long r = 0; r < m; ++r) { qc[r] += ks[r] * b; }
+                }
+            }
+            for (long i = 0; i < n; ++i) {
+                const T *ks = k_s.data() + i * m;
+                for (long r = 0; r < m; ++r) { alpha[r] += ks[r] * y[i]; }
+            }
+            l_qm_updated = false;
+            return true;
+        }
+
+        void
+        Test(const T *x_test, const long num_test, T *mean, T *variance) {
+            if (!l_qm_updated) {  // PrepareLqm :835-842
+                l_qm.assign(static_cast<std::size_t>(m * m), T(0));
+                Llt(q_m.data(), m, m, l_qm.data(), m);
+                l_qm_updated = true;
+            }
+            std::vector<T> a = alpha;  // :100-106
+            SolveLowerInPlace(l_qm.data(), m, m, a.data());
+            SolveLowerTransposeInPlace(l_qm.data(), m, m, a.data());
+            std::vector<T> k_t(static_cast<std::size_t>(m * num_test));
+            ComputeKtest(kernel_type, scale, x_dim, z.data(), x_dim, m, x_test, x_dim, num_test, k_t.data(), m);
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < num_test; ++i) {
+                const T *kc = k_t.data() + i * m;
+                if (mean != nullptr) {
+                    T f = 0;
+                    for (long p = 0; p < m; ++p) { f += kc[p] * a[p]; }
+                    mean[i] = f;
+                }
+                if (variance != nullptr) {
+                    std::vector<T> beta(kc, kc + m), gamma(kc, kc + m);
+                    SolveLowerInPlace(l_km.data(), m, m, beta.data());
+                    SolveLowerInPlace(l_qm.data(), m, m, gamma.data());
+                    T sb = 0, sg = 0;
+                    for (long p = 0; p < m; ++p) {
+                        sb += beta[p] * beta[p];
+                        sg += gamma[p] * gamma[p];
+                    }
+                    variance[i] = T(1) - sb + sg;  // :291
+                }
+            }
+        }
+    };
+
+}  // namespace erl_gp_oracle

@@ -1,0 +1,32 @@
+"""erl_gaussian_process_b200 — B200-native (sm_100a) train/predict hot path of
+ExistentialRobotics/erl_gaussian_process behind the C ABI of include/erl_gp_b200.h.
+
+Python here is only the thin host-side mirror used by tests and bench.py; the product is the
+CUDA library (csrc/) and the C++ drop-in headers (cpp/).
+"""
+from . import _capi
+from ._capi import ErlGpError, KERNELS, load
+from .host import (
+    BatchGp,
+    Context,
+    LidarGaussianProcess2D,
+    RangeSensorGaussianProcess3D,
+    SparsePseudoInputGaussianProcess,
+    VanillaGaussianProcess,
+    compute_ktest,
+    compute_ktrain,
+)
+
+__all__ = [
+    "BatchGp",
+    "Context",
+    "ErlGpError",
+    "KERNELS",
+    "LidarGaussianProcess2D",
+    "RangeSensorGaussianProcess3D",
+    "SparsePseudoInputGaussianProcess",
+    "VanillaGaussianProcess",
+    "compute_ktest",
+    "compute_ktrain",
+    "load",
+]

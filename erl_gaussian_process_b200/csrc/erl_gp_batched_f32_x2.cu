@@ -1,0 +1,6 @@
+// Instantiates the one-CTA-per-GP kernels for Dtype = float, x_dim = 2 (own translation unit: build time).
+#include "erl_gp_batched.cuh"
+
+namespace erl_gp {
+    template int LaunchBatchXdim<float, 2>(Context *, const BatchParams<float> &, int, int);
+}  // namespace erl_gp

@@ -1,0 +1,433 @@
+// C ABI: context, covariance and batched small-GP entry points (see include/erl_gp_b200.h).
+#include "erl_gp_internal.cuh"
+
+namespace erl_gp {
+
+    int
+    SetError(Context *ctx, const int status, const char *fmt, ...) {
+        if (ctx != nullptr) {
+            va_list args;
+            va_start(args, fmt);
+            vsnprintf(ctx->last_error, sizeof(ctx->last_error), fmt, args);
+            va_end(args);
+        }
+        return status;
+    }
+
+    template<typename T>
+    struct Batch {
+        Context *ctx = nullptr;
+        long num_gps = 0, max_n = 0, x_dim = 0;
+        int kernel = 0;
+        T scale = T(1);
+        DeviceBuffer<int> n_train, info;
+        DeviceBuffer<T> x, y, var, l, alpha;
+        // query-side staging for the host-pointer entry points
+        DeviceBuffer<long> q_offsets;
+        DeviceBuffer<T> q_x, mean, variance;
+        DeviceBuffer<uint8_t> valid;
+
+        BatchParams<T>
+        Params(const long min_num_samples, const int write_l) const {
+            BatchParams<T> p{};
+            p.cov = Covariance<T>::Make(kernel, scale);
+            p.num_gps = static_cast<int>(num_gps);
+            p.max_n = static_cast<int>(max_n);
+            p.min_train = static_cast<int>(min_num_samples < 0 ? 0 : min_num_samples);
+            p.write_l = write_l;
+            p.n_train = n_train.ptr;
+            p.x = x.ptr;
+            p.y = y.ptr;
+            p.var = var.ptr;
+            p.l = l.ptr;
+            p.alpha = alpha.ptr;
+            p.info = info.ptr;
+            p.mapping = ERL_GP_MAPPING_NONE;
+            p.mapping_scale = T(1);
+            return p;
+        }
+    };
+
+    template<typename T>
+    static int
+    BatchCreate(erl_gp_context *c, long num_gps, long max_n, long x_dim, int kernel, T scale, Batch<T> **out) {
+        Context *ctx = Ctx(c);
+        if (ctx == nullptr || out == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        *out = nullptr;
+        if (num_gps <= 0 || max_n <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: num_gps=%ld max_n=%ld", num_gps, max_n); }
+        if (x_dim < 1 || x_dim > 3) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "batch: x_dim=%ld (supported: 1, 2, 3)", x_dim); }
+        if (max_n > BatchMaxN<T>()) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "batch: max_n=%ld exceeds %ld", max_n, BatchMaxN<T>()); }
+        if (kernel < ERL_GP_KERNEL_OU || kernel > ERL_GP_KERNEL_RBF) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: unknown kernel %d", kernel); }
+        auto *b = new (std::nothrow) Batch<T>();
+        if (b == nullptr) { return ERL_GP_STATUS_ALLOC_FAILED; }
+        b->ctx = ctx;
+        b->num_gps = num_gps;
+        b->max_n = max_n;
+        b->x_dim = x_dim;
+        b->kernel = kernel;
+        b->scale = scale;
+        const size_t bn = static_cast<size_t>(num_gps) * max_n;
+        cudaError_t err = cudaSetDevice(ctx->device);
+        if (err == cudaSuccess) { err = b->n_train.Reserve(num_gps); }
+        if (err == cudaSuccess) { err = b->info.Reserve(num_gps); }
+        if (err == cudaSuccess) { err = b->x.Reserve(bn * x_dim); }
+        if (err == cudaSuccess) { err = b->y.Reserve(bn); }
+        if (err == cudaSuccess) { err = b->var.Reserve(bn); }
+        if (err == cudaSuccess) { err = b->alpha.Reserve(bn); }
+        if (err == cudaSuccess) { err = b->l.Reserve(bn * max_n); }
+        if (err == cudaSuccess) { err = cudaMemsetAsync(b->info.ptr, 0xff, sizeof(int) * num_gps, ctx->stream); }  // -1 = untrained
+        if (err != cudaSuccess) {
+            delete b;
+            return SetError(ctx, ERL_GP_STATUS_ALLOC_FAILED, "batch: %s", cudaGetErrorString(err));
+        }
+        *out = b;
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    BatchUpload(Batch<T> *b, const int *n_train, const T *x, const T *y, const T *var) {
+        if (b == nullptr || n_train == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = b->ctx;
+        const size_t bn = static_cast<size_t>(b->num_gps) * b->max_n;
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->n_train.ptr, n_train, sizeof(int) * b->num_gps, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->x.ptr, x, sizeof(T) * bn * b->x_dim, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->y.ptr, y, sizeof(T) * bn, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->var.ptr, var, sizeof(T) * bn, cudaMemcpyHostToDevice, ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    BatchTrainDev(Batch<T> *b, long min_num_samples, int write_l) {
+        if (b == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        const BatchParams<T> p = b->Params(min_num_samples, write_l);
+        return LaunchBatch<T>(b->ctx, p, static_cast<int>(b->x_dim), kBatchTrain, 1);
+    }
+
+    template<typename T>
+    static int
+    BatchPredictDev(Batch<T> *b, const long *q_offsets, const T *q_x, const int *q_out_index, long num_q, int mapping, T mapping_scale, T *mean, T *var, uint8_t *valid) {
+        if (b == nullptr || q_offsets == nullptr || q_x == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        if (num_q <= 0) { return ERL_GP_STATUS_OK; }
+        BatchParams<T> p = b->Params(0, 0);
+        p.q_offsets = q_offsets;
+        p.q_x = q_x;
+        p.q_out_index = q_out_index;
+        p.mean = mean;
+        p.variance = var;
+        p.valid = valid;
+        p.mapping = mapping;
+        p.mapping_scale = mapping_scale;
+        // CTAs sharing one GP's query list: aim at >= 4 CTAs per SM over the whole grid
+        const long tq = 64;
+        long tiles = CeilDiv(CeilDiv(num_q, b->num_gps), tq);
+        const long want = CeilDiv(4L * b->ctx->sm_count, b->num_gps);
+        if (tiles > want) { tiles = want; }
+        if (tiles < 1) { tiles = 1; }
+        if (tiles > 65535) { tiles = 65535; }
+        return LaunchBatch<T>(b->ctx, p, static_cast<int>(b->x_dim), kBatchPredict, static_cast<int>(tiles));
+    }
+
+    template<typename T>
+    static int
+    BatchTrainPredictDev(Batch<T> *b, long min_num_samples, int write_l, const long *q_offsets, const T *q_x, long num_q, T *mean, T *var, uint8_t *valid) {
+        if (b == nullptr || q_offsets == nullptr || (num_q > 0 && q_x == nullptr)) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        BatchParams<T> p = b->Params(min_num_samples, write_l);
+        p.q_offsets = q_offsets;
+        p.q_x = q_x;
+        p.mean = mean;
+        p.variance = var;
+        p.valid = valid;
+        return LaunchBatch<T>(b->ctx, p, static_cast<int>(b->x_dim), kBatchTrainPredict, 1);
+    }
+
+    template<typename T>
+    static int
+    BatchDownload(Batch<T> *b, T *l, T *alpha, int *info) {
+        if (b == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = b->ctx;
+        const size_t bn = static_cast<size_t>(b->num_gps) * b->max_n;
+        if (l != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(l, b->l.ptr, sizeof(T) * bn * b->max_n, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (alpha != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(alpha, b->alpha.ptr, sizeof(T) * bn, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (info != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(info, b->info.ptr, sizeof(int) * b->num_gps, cudaMemcpyDeviceToHost, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    BatchTrainPredictHost(
+        Batch<T> *b,
+        long min_num_samples,
+        const int *n_train,
+        const T *x,
+        const T *y,
+        const T *var,
+        const long *q_offsets,
+        const T *q_x,
+        long num_q,
+        T *l,
+        T *alpha,
+        int *info,
+        T *mean,
+        T *variance,
+        uint8_t *valid) {
+        if (b == nullptr || q_offsets == nullptr || num_q < 0) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = b->ctx;
+        int rc = BatchUpload(b, n_train, x, y, var);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        const size_t nq = static_cast<size_t>(num_q > 0 ? num_q : 1);
+        ERL_GP_CUDA_OK(ctx, b->q_offsets.Reserve(b->num_gps + 1));
+        ERL_GP_CUDA_OK(ctx, b->q_x.Reserve(nq * b->x_dim));
+        ERL_GP_CUDA_OK(ctx, b->mean.Reserve(nq));
+        ERL_GP_CUDA_OK(ctx, b->variance.Reserve(nq));
+        ERL_GP_CUDA_OK(ctx, b->valid.Reserve(nq));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->q_offsets.ptr, q_offsets, sizeof(long) * (b->num_gps + 1), cudaMemcpyHostToDevice, ctx->stream));
+        if (num_q > 0) {
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->q_x.ptr, q_x, sizeof(T) * num_q * b->x_dim, cudaMemcpyHostToDevice, ctx->stream));
+            ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(b->valid.ptr, 0, num_q, ctx->stream));
+            // outputs of untrained GPs must come back untouched: seed the device copies with the caller's values
+            if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->mean.ptr, mean, sizeof(T) * num_q, cudaMemcpyHostToDevice, ctx->stream)); }
+            if (variance != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->variance.ptr, variance, sizeof(T) * num_q, cudaMemcpyHostToDevice, ctx->stream)); }
+        }
+        rc = BatchTrainPredictDev(b, min_num_samples, l != nullptr ? 1 : 0, b->q_offsets.ptr, b->q_x.ptr, num_q, mean != nullptr ? b->mean.ptr : nullptr,
+                                  variance != nullptr ? b->variance.ptr : nullptr, b->valid.ptr);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        if (num_q > 0) {
+            if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean, b->mean.ptr, sizeof(T) * num_q, cudaMemcpyDeviceToHost, ctx->stream)); }
+            if (variance != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(variance, b->variance.ptr, sizeof(T) * num_q, cudaMemcpyDeviceToHost, ctx->stream)); }
+            if (valid != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(valid, b->valid.ptr, num_q, cudaMemcpyDeviceToHost, ctx->stream)); }
+        }
+        return BatchDownload(b, l, alpha, info);
+    }
+
+    template<typename T>
+    static int
+    BatchGetGp(Batch<T> *b, long g, int *info, long *n, T *l, long ld_l, T *alpha) {
+        if (b == nullptr || g < 0 || g >= b->num_gps) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = b->ctx;
+        int h_info = -1, h_n = 0;
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(&h_info, b->info.ptr + g, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(&h_n, b->n_train.ptr + g, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (info != nullptr) { *info = h_info; }
+        if (n != nullptr) { *n = h_n; }
+        if (h_info != 0 || h_n <= 0) { return ERL_GP_STATUS_OK; }
+        if (l != nullptr) {
+            if (ld_l < h_n) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "get_gp: ld_l=%ld < n=%d", ld_l, h_n); }
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l, sizeof(T) * ld_l, b->l.ptr + static_cast<size_t>(g) * b->max_n * b->max_n, sizeof(T) * b->max_n, sizeof(T) * h_n, h_n,
+                                                  cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (alpha != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(alpha, b->alpha.ptr + static_cast<size_t>(g) * b->max_n, sizeof(T) * h_n, cudaMemcpyDeviceToHost, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    // ---- covariance, host-pointer flavour: stage, launch, copy back ------------------------
+    template<typename T>
+    static int
+    GramHost(erl_gp_context *c, bool train, int kernel, T scale, long x_dim, const T *x1, long ld_x1, long n1, const T *x2, long ld_x2, long n2, const T *var, T *k, long ld_k) {
+        Context *ctx = Ctx(c);
+        if (ctx == nullptr || x1 == nullptr || x2 == nullptr || k == nullptr || (train && var == nullptr)) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        if (n1 <= 0 || n2 <= 0 || ld_k < n1) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "gram: bad shape"); }
+        DeviceBuffer<T> d_x1, d_x2, d_var, d_k;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        ERL_GP_CUDA_OK(ctx, d_x1.Reserve(static_cast<size_t>(n1) * ld_x1));
+        ERL_GP_CUDA_OK(ctx, d_k.Reserve(static_cast<size_t>(n1) * n2));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_x1.ptr, x1, sizeof(T) * n1 * ld_x1, cudaMemcpyHostToDevice, ctx->stream));
+        int rc;
+        if (train) {
+            ERL_GP_CUDA_OK(ctx, d_var.Reserve(n1));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_var.ptr, var, sizeof(T) * n1, cudaMemcpyHostToDevice, ctx->stream));
+            rc = LaunchKtrain<T>(ctx, kernel, scale, x_dim, d_x1.ptr, ld_x1, d_var.ptr, n1, d_k.ptr, n1);
+        } else {
+            ERL_GP_CUDA_OK(ctx, d_x2.Reserve(static_cast<size_t>(n2) * ld_x2));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_x2.ptr, x2, sizeof(T) * n2 * ld_x2, cudaMemcpyHostToDevice, ctx->stream));
+            rc = LaunchKtest<T>(ctx, kernel, scale, x_dim, d_x1.ptr, ld_x1, n1, d_x2.ptr, ld_x2, n2, d_k.ptr, n1);
+        }
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(k, sizeof(T) * ld_k, d_k.ptr, sizeof(T) * n1, sizeof(T) * n1, n2, cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+}  // namespace erl_gp
+
+using namespace erl_gp;
+
+struct erl_gp_batch_f32 : Batch<float> {};
+struct erl_gp_batch_f64 : Batch<double> {};
+
+extern "C" {
+
+int
+erl_gp_version(void) {
+    return ERL_GP_B200_VERSION;
+}
+
+const char *
+erl_gp_status_string(const int status) {
+    switch (status) {
+        case ERL_GP_STATUS_OK: return "ok";
+        case ERL_GP_STATUS_INVALID_ARGUMENT: return "invalid argument";
+        case ERL_GP_STATUS_CUDA_ERROR: return "CUDA error";
+        case ERL_GP_STATUS_NOT_TRAINED: return "not trained";
+        case ERL_GP_STATUS_UNSUPPORTED: return "unsupported shape or option";
+        case ERL_GP_STATUS_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case ERL_GP_STATUS_ALLOC_FAILED: return "allocation failed";
+        default: return "unknown status";
+    }
+}
+
+int
+erl_gp_device_count(int *count) {
+    if (count == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void) cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return n > 0 ? ERL_GP_STATUS_OK : ERL_GP_STATUS_NO_DEVICE;
+}
+
+int
+erl_gp_context_create(const int device, erl_gp_context **out) {
+    if (out == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        (void) cudaGetLastError();
+        return ERL_GP_STATUS_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    auto *ctx = new (std::nothrow) Context();
+    if (ctx == nullptr) { return ERL_GP_STATUS_ALLOC_FAILED; }
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return ERL_GP_STATUS_CUDA_ERROR;
+    }
+    ctx->own_stream = true;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    *out = ctx;
+    return ERL_GP_STATUS_OK;
+}
+
+int
+erl_gp_context_destroy(erl_gp_context *c) {
+    Context *ctx = Ctx(c);
+    if (ctx == nullptr) { return ERL_GP_STATUS_OK; }
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream != nullptr) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return ERL_GP_STATUS_OK;
+}
+
+int
+erl_gp_context_set_stream(erl_gp_context *c, void *cuda_stream) {
+    Context *ctx = Ctx(c);
+    if (ctx == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->own_stream && ctx->stream != nullptr) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->stream = nullptr;
+        ctx->own_stream = false;
+    }
+    if (cuda_stream == nullptr) {
+        ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    }
+    return ERL_GP_STATUS_OK;
+}
+
+int
+erl_gp_context_synchronize(erl_gp_context *c) {
+    Context *ctx = Ctx(c);
+    if (ctx == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ERL_GP_STATUS_OK;
+}
+
+const char *
+erl_gp_context_last_error(const erl_gp_context *ctx) {
+    return ctx == nullptr ? "null context" : ctx->last_error;
+}
+
+int
+erl_gp_context_kernel_launches(const erl_gp_context *ctx, long *count) {
+    if (ctx == nullptr || count == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    *count = ctx->launches;
+    return ERL_GP_STATUS_OK;
+}
+
+#define ERL_GP_DEFINE_TYPED(T, SFX)                                                                                                                                          \
+    int erl_gp_compute_ktrain_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, const T *x, long ld_x, const T *var, long n, T *k, long ld_k) {                    \
+        return GramHost<T>(ctx, true, kernel, scale, x_dim, x, ld_x, n, x, ld_x, n, var, k, ld_k);                                                                           \
+    }                                                                                                                                                                        \
+    int erl_gp_compute_ktest_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, const T *x1, long ld_x1, long n1, const T *x2, long ld_x2, long n2, T *k,           \
+                                   long ld_k) {                                                                                                                              \
+        return GramHost<T>(ctx, false, kernel, scale, x_dim, x1, ld_x1, n1, x2, ld_x2, n2, nullptr, k, ld_k);                                                                \
+    }                                                                                                                                                                        \
+    int erl_gp_compute_ktrain_dev_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, const T *x, long ld_x, const T *var, long n, T *k, long ld_k) {                \
+        if (ctx == nullptr || x == nullptr || var == nullptr || k == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                     \
+        return LaunchKtrain<T>(Ctx(ctx), kernel, scale, x_dim, x, ld_x, var, n, k, ld_k);                                                                                    \
+    }                                                                                                                                                                        \
+    int erl_gp_compute_ktest_dev_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, const T *x1, long ld_x1, long n1, const T *x2, long ld_x2, long n2, T *k,       \
+                                       long ld_k) {                                                                                                                          \
+        if (ctx == nullptr || x1 == nullptr || x2 == nullptr || k == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                     \
+        return LaunchKtest<T>(Ctx(ctx), kernel, scale, x_dim, x1, ld_x1, n1, x2, ld_x2, n2, k, ld_k);                                                                        \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_create_##SFX(erl_gp_context *ctx, long num_gps, long max_n, long x_dim, int kernel, T scale, erl_gp_batch_##SFX **batch) {                              \
+        return BatchCreate<T>(ctx, num_gps, max_n, x_dim, kernel, scale, reinterpret_cast<Batch<T> **>(batch));                                                              \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_destroy_##SFX(erl_gp_batch_##SFX *batch) {                                                                                                              \
+        if (batch != nullptr) {                                                                                                                                              \
+            cudaSetDevice(batch->ctx->device);                                                                                                                               \
+            cudaStreamSynchronize(batch->ctx->stream);                                                                                                                       \
+            delete static_cast<Batch<T> *>(batch);                                                                                                                           \
+        }                                                                                                                                                                    \
+        return ERL_GP_STATUS_OK;                                                                                                                                             \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_device_buffers_##SFX(erl_gp_batch_##SFX *batch, int **n_train, T **x, T **y, T **var, T **l, T **alpha, int **info) {                                   \
+        if (batch == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                                                                     \
+        if (n_train != nullptr) { *n_train = batch->n_train.ptr; }                                                                                                           \
+        if (x != nullptr) { *x = batch->x.ptr; }                                                                                                                             \
+        if (y != nullptr) { *y = batch->y.ptr; }                                                                                                                             \
+        if (var != nullptr) { *var = batch->var.ptr; }                                                                                                                       \
+        if (l != nullptr) { *l = batch->l.ptr; }                                                                                                                             \
+        if (alpha != nullptr) { *alpha = batch->alpha.ptr; }                                                                                                                 \
+        if (info != nullptr) { *info = batch->info.ptr; }                                                                                                                    \
+        return ERL_GP_STATUS_OK;                                                                                                                                             \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_upload_##SFX(erl_gp_batch_##SFX *batch, const int *n_train, const T *x, const T *y, const T *var) { return BatchUpload<T>(batch, n_train, x, y, var); } \
+    int erl_gp_batch_train_dev_##SFX(erl_gp_batch_##SFX *batch, long min_num_samples, int write_l) { return BatchTrainDev<T>(batch, min_num_samples, write_l); }             \
+    int erl_gp_batch_predict_dev_##SFX(erl_gp_batch_##SFX *batch, const long *q_offsets, const T *q_x, const int *q_out_index, long num_q, int mapping, T mapping_scale,     \
+                                       T *mean, T *var, uint8_t *valid) {                                                                                                    \
+        return BatchPredictDev<T>(batch, q_offsets, q_x, q_out_index, num_q, mapping, mapping_scale, mean, var, valid);                                                      \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_train_predict_dev_##SFX(erl_gp_batch_##SFX *batch, long min_num_samples, int write_l, const long *q_offsets, const T *q_x, long num_q, T *mean, T *var, \
+                                             uint8_t *valid) {                                                                                                               \
+        return BatchTrainPredictDev<T>(batch, min_num_samples, write_l, q_offsets, q_x, num_q, mean, var, valid);                                                            \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_train_predict_##SFX(erl_gp_batch_##SFX *batch, long min_num_samples, const int *n_train, const T *x, const T *y, const T *var, const long *q_offsets,   \
+                                         const T *q_x, long num_q, T *l, T *alpha, int *info, T *mean, T *variance, uint8_t *valid) {                                        \
+        return BatchTrainPredictHost<T>(batch, min_num_samples, n_train, x, y, var, q_offsets, q_x, num_q, l, alpha, info, mean, variance, valid);                           \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_download_##SFX(erl_gp_batch_##SFX *batch, T *l, T *alpha, int *info) { return BatchDownload<T>(batch, l, alpha, info); }                                \
+    int erl_gp_batch_get_gp_##SFX(erl_gp_batch_##SFX *batch, long gp_index, int *info, long *n, T *l, long ld_l, T *alpha) {                                                 \
+        return BatchGetGp<T>(batch, gp_index, info, n, l, ld_l, alpha);                                                                                                      \
+    }
+
+ERL_GP_DEFINE_TYPED(float, f32)
+ERL_GP_DEFINE_TYPED(double, f64)
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Internal declarations shared by the .cu translation units of liberl_gp_b200.so.
+#pragma once
+
+#include "erl_gp_common.cuh"
+
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct erl_gp_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    long launches = 0;
+    char last_error[512] = {0};
+};
+
+namespace erl_gp {
+
+    struct Context : erl_gp_context {};
+
+    inline Context *
+    Ctx(erl_gp_context *c) {
+        return static_cast<Context *>(c);
+    }
+
+    // Grow-only device buffer (mirrors the reference's grow-only Eigen buffers,
+    // src/vanilla_gp.cpp:152-161, 805-812): cudaMalloc is never on the steady-state path.
+    template<typename T>
+    struct DeviceBuffer {
+        T *ptr = nullptr;
+        size_t capacity = 0;  // elements
+
+        DeviceBuffer() = default;
+        DeviceBuffer(const DeviceBuffer &) = delete;
+        DeviceBuffer &
+        operator=(const DeviceBuffer &) = delete;
+
+        ~DeviceBuffer() { Free(); }
+
+        void
+        Free() {
+            if (ptr != nullptr) { cudaFree(ptr); }
+            ptr = nullptr;
+            capacity = 0;
+        }
+
+        cudaError_t
+        Reserve(size_t count) {
+            if (count <= capacity) { return cudaSuccess; }
+            Free();
+            const cudaError_t err = cudaMalloc(&ptr, count * sizeof(T));
+            if (err == cudaSuccess) { capacity = count; }
+            return err;
+        }
+    };
+
+    // Pinned host staging buffer, grow-only.
+    template<typename T>
+    struct PinnedBuffer {
+        T *ptr = nullptr;
+        size_t capacity = 0;
+
+        PinnedBuffer() = default;
+        PinnedBuffer(const PinnedBuffer &) = delete;
+        PinnedBuffer &
+        operator=(const PinnedBuffer &) = delete;
+
+        ~PinnedBuffer() {
+            if (ptr != nullptr) { cudaFreeHost(ptr); }
+        }
+
+        cudaError_t
+        Reserve(size_t count) {
+            if (count <= capacity) { return cudaSuccess; }
+            if (ptr != nullptr) { cudaFreeHost(ptr); }
+            ptr = nullptr;
+            capacity = 0;
+            const cudaError_t err = cudaMallocHost(&ptr, count * sizeof(T));
+            if (err == cudaSuccess) { capacity = count; }
+            return err;
+        }
+    };
+
+    // ---- launchers implemented in the kernel translation units (all async on ctx->stream) ----
+    template<typename T>
+    int
+    LaunchKtrain(Context *ctx, int kernel, T scale, long x_dim, const T *x, long ld_x, const T *var, long n, T *k, long ld_k);
+
+    template<typename T>
+    int
+    LaunchKtest(Context *ctx, int kernel, T scale, long x_dim, const T *x1, long ld_x1, long n1, const T *x2, long ld_x2, long n2, T *k, long ld_k);
+
+    template<typename T>
+    struct BatchParams {
+        Covariance<T> cov;
+        int num_gps;
+        int max_n;
+        int min_train;  // train iff n > min_train
+        int write_l;
+        const int *n_train;
+        const T *x;
+        const T *y;
+        const T *var;
+        T *l;
+        T *alpha;
+        int *info;
+        // prediction
+        const long *q_offsets;  // [num_gps + 1]
+        const T *q_x;           // [T][x_dim]
+        const int *q_out_index; // optional scatter index
+        T *mean;
+        T *variance;
+        uint8_t *valid;
+        int mapping;  // ERL_GP_MAPPING_NONE = no un-map
+        T mapping_scale;
+    };
+
+    enum BatchMode : int { kBatchTrain = 1, kBatchPredict = 2, kBatchTrainPredict = 3 };
+
+    // tiles_per_gp: how many CTAs share one GP's query list (predict-only mode), >= 1.
+    template<typename T>
+    int
+    LaunchBatch(Context *ctx, const BatchParams<T> &params, int x_dim, int mode, int tiles_per_gp);
+
+    // maximum capacity (max_n) the one-CTA-per-GP kernel supports for this Dtype
+    template<typename T>
+    long
+    BatchMaxN();
+
+}  // namespace erl_gp

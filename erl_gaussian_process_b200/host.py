@@ -1,0 +1,687 @@
+"""Host-side mirror of the reference's operator interface over the C ABI.
+
+Class and method names follow the reference (VanillaGaussianProcess.train/test,
+LidarGaussianProcess2D.train/test, RangeSensorGaussianProcess3D.train/test — see
+python/binding/bind_vanilla_gp.cpp:79-101, bind_lidar_gp_2d.cpp:77-95,
+bind_range_sensor_gp_3d.cpp:80-112) so the parity tests read like the reference's own tests.
+All numerics run in liberl_gp_b200.so; numpy arrays are only the host buffers the C ABI reads
+and writes.  Array conventions: points are rows here (``x[i]`` = sample i, C-contiguous
+``(n, x_dim)``), which is byte-identical to the reference's column-major ``x_dim x n``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, load
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32", C.c_float
+    if dtype == np.float64:
+        return "f64", C.c_double
+    raise TypeError(f"unsupported dtype {dtype} (the reference instantiates float and double)")
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor (device pointer for the *_dev entry points)
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def _kernel_id(kernel):
+    return _capi.KERNELS[kernel] if isinstance(kernel, str) else int(kernel)
+
+
+class Context:
+    """erl_gp_context: one per host thread and device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.handle = C.c_void_p()
+        check(self.lib.erl_gp_context_create(C.c_int(device), C.byref(self.handle)), "erl_gp_context_create")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.erl_gp_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(self.lib.erl_gp_context_set_stream(self.handle, C.c_void_p(cuda_stream or 0)), "set_stream", self.handle)
+
+    def synchronize(self):
+        check(self.lib.erl_gp_context_synchronize(self.handle), "synchronize", self.handle)
+
+    @property
+    def kernel_launches(self) -> int:
+        n = C.c_long(0)
+        check(self.lib.erl_gp_context_kernel_launches(self.handle, C.byref(n)), "kernel_launches")
+        return n.value
+
+    def fn(self, name, dtype):
+        return getattr(self.lib, f"{name}_{_sfx(dtype)[0]}")
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ------------------------------------------------------------------------------------------
+# Covariance::ComputeKtrain / ComputeKtest
+# ------------------------------------------------------------------------------------------
+def compute_ktrain(kernel, scale, x, var, ctx: Context | None = None):
+    """K (n, n) with K[i, i] = 1 + var[i].  x: (n, x_dim)."""
+    ctx = ctx or default_context()
+    x = np.ascontiguousarray(x)
+    n, d = x.shape
+    _, ct = _sfx(x.dtype)
+    var = np.ascontiguousarray(var, dtype=x.dtype)
+    k = np.empty((n, n), dtype=x.dtype)
+    check(ctx.fn("erl_gp_compute_ktrain", x.dtype)(ctx.handle, C.c_int(_kernel_id(kernel)), ct(scale), C.c_long(d), _p(x), C.c_long(d), _p(var), C.c_long(n), _p(k), C.c_long(n)),
+          "compute_ktrain", ctx.handle)
+    return k.T  # column-major n x n
+
+
+def compute_ktest(kernel, scale, x1, x2, ctx: Context | None = None):
+    """Ktest (n1, n2): [i, j] = k(x1_i, x2_j)."""
+    ctx = ctx or default_context()
+    x1 = np.ascontiguousarray(x1)
+    x2 = np.ascontiguousarray(x2, dtype=x1.dtype)
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    _, ct = _sfx(x1.dtype)
+    k = np.empty((n2, n1), dtype=x1.dtype)
+    check(ctx.fn("erl_gp_compute_ktest", x1.dtype)(ctx.handle, C.c_int(_kernel_id(kernel)), ct(scale), C.c_long(d), _p(x1), C.c_long(d), C.c_long(n1), _p(x2), C.c_long(d), C.c_long(n2),
+                                                   _p(k), C.c_long(n1)), "compute_ktest", ctx.handle)
+    return k.T
+
+
+# ------------------------------------------------------------------------------------------
+# VanillaGaussianProcess
+# ------------------------------------------------------------------------------------------
+class VanillaGaussianProcess:
+    """Mirror of erl::gaussian_process::VanillaGaussianProcess<Dtype> (include/.../vanilla_gp.hpp).
+
+    ``train(x, y, var)`` = Reset + fill TrainSet + Train (python/binding/bind_vanilla_gp.cpp:79-101);
+    ``test(x_test)`` returns a TestResult with ``get_mean(y_index)`` / ``get_variance()``.
+    """
+
+    class Setting:
+        def __init__(self, kernel_type="rbf", scale=1.0, max_num_samples=256):
+            self.kernel_type = kernel_type
+            self.scale = scale
+            self.max_num_samples = max_num_samples  # vanilla_gp.hpp:28
+
+    class TestResult:
+        def __init__(self, gp, x_test):
+            self._gp = gp
+            self._x_test = np.ascontiguousarray(x_test, dtype=gp.dtype)
+            self.num_test = self._x_test.shape[0]
+            self._mean = None
+            self._var = None
+
+        def _run(self, want_mean, want_var):
+            gp = self._gp
+            t, d = self._x_test.shape
+            mean = np.empty((gp.y_dim, t), dtype=gp.dtype) if want_mean else None
+            var = np.empty(t, dtype=gp.dtype) if want_var else None
+            check(gp.ctx.fn("erl_gp_vanilla_test", gp.dtype)(gp.handle, C.c_long(t), _p(self._x_test), C.c_long(d), _p(mean), _p(var)), "vanilla_test", gp.ctx.handle)
+            if want_mean:
+                self._mean = mean
+            if want_var:
+                self._var = var
+
+        def get_mean(self, y_index=0, parallel=True):
+            if self._mean is None:
+                self._run(True, False)
+            return self._mean[y_index].copy()
+
+        def get_variance(self, parallel=True):
+            if self._var is None:
+                self._run(False, True)
+            return self._var.copy()
+
+    def __init__(self, setting: "VanillaGaussianProcess.Setting", dtype=np.float64, ctx: Context | None = None):
+        self.setting = setting
+        self.dtype = np.dtype(dtype)
+        self.ctx = ctx or default_context()
+        self.handle = C.c_void_p()
+        check(self.ctx.fn("erl_gp_vanilla_create", dtype)(self.ctx.handle, C.byref(self.handle)), "vanilla_create", self.ctx.handle)
+        self.is_trained = False
+        self.n = 0
+        self.y_dim = 1
+        self.info = 0
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.fn("erl_gp_vanilla_destroy", self.dtype)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def train(self, x, y, var) -> bool:
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        n, d = x.shape
+        s = self.setting
+        if n <= 0:
+            return False  # UpdateKtrain: num_samples <= 0 -> false (src/vanilla_gp.cpp:481-484)
+        if not (s.max_num_samples < 0 or n <= s.max_num_samples):
+            raise ValueError(f"max_num_samples should be <= {s.max_num_samples}")  # ERL_ASSERTM, src/vanilla_gp.cpp:389-392
+        y = np.asarray(y, dtype=self.dtype)
+        if y.ndim == 1:
+            y = y[:, None]
+        yf = np.asfortranarray(y)
+        var = np.ascontiguousarray(var, dtype=self.dtype)
+        _, ct = _sfx(self.dtype)
+        info = C.c_int(0)
+        check(self.ctx.fn("erl_gp_vanilla_train", self.dtype)(self.handle, C.c_int(_kernel_id(s.kernel_type)), ct(s.scale), C.c_long(d), C.c_long(y.shape[1]), C.c_long(n), _p(x),
+                                                              C.c_long(d), _p(yf), C.c_long(n), _p(var), C.byref(info)), "vanilla_train", self.ctx.handle)
+        self.n, self.y_dim, self.info = n, y.shape[1], info.value
+        self.is_trained = True
+        return True
+
+    def get(self):
+        """(K, L, alpha) materialised on the host, as GetKtrain / GetCholeskyDecomposition / GetAlpha."""
+        n = self.n
+        k = np.empty((n, n), dtype=self.dtype)
+        l = np.empty((n, n), dtype=self.dtype)
+        a = np.empty((self.y_dim, n), dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_vanilla_get", self.dtype)(self.handle, _p(k), C.c_long(n), _p(l), C.c_long(n), _p(a), C.c_long(n)), "vanilla_get", self.ctx.handle)
+        return k.T, l.T, a.T
+
+    def test(self, x_test):
+        if not self.is_trained:
+            return None  # src/vanilla_gp.cpp:556-558
+        x_test = np.asarray(x_test)
+        if x_test.shape[0] == 0:
+            return None
+        return VanillaGaussianProcess.TestResult(self, x_test)
+
+
+# ------------------------------------------------------------------------------------------
+# Batched small GPs (BatchGaussianProcessUpdateTorch replacement / BASELINE config 4)
+# ------------------------------------------------------------------------------------------
+class BatchGp:
+    """A device-resident stream of ``num_gps`` independent small GPs with capacity ``max_n``."""
+
+    def __init__(self, num_gps, max_n, x_dim, kernel, scale, dtype=np.float32, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.dtype = np.dtype(dtype)
+        self.num_gps, self.max_n, self.x_dim = int(num_gps), int(max_n), int(x_dim)
+        _, self.ct = _sfx(dtype)
+        self.handle = C.c_void_p()
+        check(self.ctx.fn("erl_gp_batch_create", dtype)(self.ctx.handle, C.c_long(num_gps), C.c_long(max_n), C.c_long(x_dim), C.c_int(_kernel_id(kernel)), self.ct(scale),
+                                                       C.byref(self.handle)), "batch_create", self.ctx.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.fn("erl_gp_batch_destroy", self.dtype)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- host-buffer path (H2D + kernels + D2H inside; the e2e call) ----
+    def train_predict(self, n_train, x, y, var, q_offsets, q_x, min_num_samples=0, want_l=True, mean=None, variance=None):
+        b, mn, d = self.num_gps, self.max_n, self.x_dim
+        n_train = np.ascontiguousarray(n_train, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=self.dtype).reshape(b, mn, d)
+        y = np.ascontiguousarray(y, dtype=self.dtype).reshape(b, mn)
+        var = np.ascontiguousarray(var, dtype=self.dtype).reshape(b, mn)
+        q_offsets = np.ascontiguousarray(q_offsets, dtype=np.int64)
+        q_x = np.ascontiguousarray(q_x, dtype=self.dtype).reshape(-1, d)
+        t = q_x.shape[0]
+        l = np.zeros((b, mn, mn), dtype=self.dtype) if want_l else None
+        alpha = np.zeros((b, mn), dtype=self.dtype)
+        info = np.zeros(b, dtype=np.int32)
+        mean = np.full(t, np.nan, dtype=self.dtype) if mean is None else mean
+        variance = np.full(t, np.nan, dtype=self.dtype) if variance is None else variance
+        valid = np.zeros(t, dtype=np.uint8)
+        check(self.ctx.fn("erl_gp_batch_train_predict", self.dtype)(self.handle, C.c_long(min_num_samples), _p(n_train), _p(x), _p(y), _p(var), _p(q_offsets), _p(q_x), C.c_long(t),
+                                                                   _p(l), _p(alpha), _p(info), _p(mean), _p(variance), _p(valid)), "batch_train_predict", self.ctx.handle)
+        return dict(L=None if l is None else l.transpose(0, 2, 1), alpha=alpha, info=info, mean=mean, var=variance, valid=valid.astype(bool))
+
+    # ---- device-resident path ----
+    def upload(self, n_train, x, y, var):
+        b, mn, d = self.num_gps, self.max_n, self.x_dim
+        n_train = np.ascontiguousarray(n_train, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=self.dtype).reshape(b, mn, d)
+        y = np.ascontiguousarray(y, dtype=self.dtype).reshape(b, mn)
+        var = np.ascontiguousarray(var, dtype=self.dtype).reshape(b, mn)
+        check(self.ctx.fn("erl_gp_batch_upload", self.dtype)(self.handle, _p(n_train), _p(x), _p(y), _p(var)), "batch_upload", self.ctx.handle)
+        self.ctx.synchronize()
+
+    def device_buffers(self):
+        ptrs = [C.c_void_p() for _ in range(7)]
+        check(self.ctx.fn("erl_gp_batch_device_buffers", self.dtype)(self.handle, *[C.byref(p) for p in ptrs]), "batch_device_buffers", self.ctx.handle)
+        names = ["n_train", "x", "y", "var", "l", "alpha", "info"]
+        return {k: (p.value or 0) for k, p in zip(names, ptrs)}
+
+    def train_dev(self, min_num_samples=0, write_l=True):
+        check(self.ctx.fn("erl_gp_batch_train_dev", self.dtype)(self.handle, C.c_long(min_num_samples), C.c_int(int(write_l))), "batch_train_dev", self.ctx.handle)
+
+    def predict_dev(self, q_offsets, q_x, num_q, mean, var, valid=None, q_out_index=None, mapping=_capi.MAPPING_NONE, mapping_scale=1.0):
+        check(self.ctx.fn("erl_gp_batch_predict_dev", self.dtype)(self.handle, _p(q_offsets), _p(q_x), _p(q_out_index), C.c_long(num_q), C.c_int(mapping), self.ct(mapping_scale), _p(mean),
+                                                                 _p(var), _p(valid)), "batch_predict_dev", self.ctx.handle)
+
+    def train_predict_dev(self, q_offsets, q_x, num_q, mean, var, valid=None, min_num_samples=0, write_l=True):
+        check(self.ctx.fn("erl_gp_batch_train_predict_dev", self.dtype)(self.handle, C.c_long(min_num_samples), C.c_int(int(write_l)), _p(q_offsets), _p(q_x), C.c_long(num_q), _p(mean), _p(var),
+                                                                       _p(valid)), "batch_train_predict_dev", self.ctx.handle)
+
+    def download(self, want_l=True):
+        b, mn = self.num_gps, self.max_n
+        l = np.zeros((b, mn, mn), dtype=self.dtype) if want_l else None
+        alpha = np.zeros((b, mn), dtype=self.dtype)
+        info = np.zeros(b, dtype=np.int32)
+        check(self.ctx.fn("erl_gp_batch_download", self.dtype)(self.handle, _p(l), _p(alpha), _p(info)), "batch_download", self.ctx.handle)
+        return dict(L=None if l is None else l.transpose(0, 2, 1), alpha=alpha, info=info)
+
+
+# ------------------------------------------------------------------------------------------
+# Sensor frames: minimal stand-ins for erl_geometry::LidarFrame2D / LidarFrame3D outputs.
+# They only produce the arrays the hot path consumes (angles, hit / continuity masks, frame
+# coordinates); erl_geometry itself is out of scope.
+# ------------------------------------------------------------------------------------------
+class LidarFrame2D:
+    class Setting:
+        def __init__(self, angle_min=-np.pi, angle_max=np.pi, num_rays=360, valid_range_min=0.0, valid_range_max=np.inf, discontinuity_detection=False,
+                     discontinuity_factor=10.0, rolling_diff_discount=0.9):
+            self.angle_min, self.angle_max, self.num_rays = angle_min, angle_max, num_rays
+            self.valid_range_min, self.valid_range_max = valid_range_min, valid_range_max
+            self.discontinuity_detection = discontinuity_detection
+            self.discontinuity_factor = discontinuity_factor
+            self.rolling_diff_discount = rolling_diff_discount
+
+    def __init__(self, setting, dtype=np.float64):
+        self.setting = setting
+        self.dtype = np.dtype(dtype)
+        self.angles = np.linspace(setting.angle_min, setting.angle_max, setting.num_rays).astype(self.dtype)
+        self.rotation = np.eye(2, dtype=self.dtype)
+        self.translation = np.zeros(2, dtype=self.dtype)
+        self.ranges = None
+        self.mask_hit = None
+        self.mask_continuous = None
+
+    def update_ranges(self, rotation, translation, ranges):
+        s = self.setting
+        self.rotation = np.asarray(rotation, dtype=self.dtype)
+        self.translation = np.asarray(translation, dtype=self.dtype)
+        r = np.asarray(ranges, dtype=self.dtype)
+        self.ranges = r
+        self.mask_hit = np.isfinite(r) & (r >= s.valid_range_min) & (r <= s.valid_range_max)
+        con = np.ones(len(r), dtype=bool)
+        if s.discontinuity_detection:
+            # rolling mean of |range difference| between consecutive rays; a jump larger than
+            # discontinuity_factor x the rolling mean marks both rays as discontinuous
+            rolling = 0.0
+            for i in range(1, len(r)):
+                diff = abs(float(r[i]) - float(r[i - 1]))
+                if i > 1 and diff > s.discontinuity_factor * rolling and rolling > 0:
+                    con[i - 1] = con[i] = False
+                rolling = s.rolling_diff_discount * rolling + (1 - s.rolling_diff_discount) * diff if i > 1 else diff
+        self.mask_continuous = con
+
+    @property
+    def is_valid(self):
+        return self.mask_hit is not None and bool(self.mask_hit.any())
+
+
+class LidarGaussianProcess2D:
+    """Mirror of erl::gaussian_process::LidarGaussianProcess2D<Dtype> (include/.../lidar_gp_2d.hpp)."""
+
+    class Setting:
+        def __init__(self):
+            # defaults: include/erl_gaussian_process/lidar_gp_2d.hpp:28-62
+            self.partition_on_hit_rays = False
+            self.symmetric_partitions = True
+            self.group_size = 26
+            self.overlap_size = 6
+            self.margin = 1
+            self.init_variance = 1e6
+            self.sensor_range_var = 0.01
+            self.discontinuity_var = 10.0
+            self.max_valid_range_var = 0.1
+            self.occ_test_temperature = 30.0
+            self.sensor_frame = LidarFrame2D.Setting()
+            self.gp = VanillaGaussianProcess.Setting(kernel_type="ou", scale=1.0)
+            self.mapping_type = _capi.MAPPING_INVERSE_SQRT
+            self.mapping_scale = 1.0
+
+    class _CSetting(C.Structure):
+        _fields_ = [("symmetric_partitions", C.c_int), ("group_size", C.c_long), ("overlap_size", C.c_long), ("margin", C.c_long), ("sensor_range_var", C.c_double),
+                    ("discontinuity_var", C.c_double), ("discontinuity_detection", C.c_int), ("kernel", C.c_int), ("kernel_scale", C.c_double), ("mapping", C.c_int),
+                    ("mapping_scale", C.c_double)]
+
+    class TestResult:
+        def __init__(self, gp, angles, angles_are_local, un_map):
+            angles = np.ascontiguousarray(angles, dtype=gp.dtype)
+            t = len(angles)
+            self.num_test = t
+            # invalid rays are left unwritten by the reference (src/lidar_gp_2d.cpp:112,120): NaN marks them here
+            self._mean = np.full(t, np.nan, dtype=gp.dtype)
+            self._var = np.full(t, np.nan, dtype=gp.dtype)
+            valid = np.zeros(t, dtype=np.uint8)
+            check(gp.ctx.fn("erl_gp_lidar2d_test", gp.dtype)(gp.handle, _p(angles), C.c_long(t), C.c_int(int(angles_are_local)), C.c_int(int(un_map)), _p(self._mean), _p(self._var),
+                                                            _p(valid)), "lidar2d_test", gp.ctx.handle)
+            self._valid = valid.astype(bool)
+
+        def get_mean(self, parallel=True):
+            return self._mean.copy(), self._valid.copy()
+
+        def get_variance(self, parallel=True):
+            return self._var.copy(), self._valid.copy()
+
+    def __init__(self, setting: "LidarGaussianProcess2D.Setting", dtype=np.float64, ctx: Context | None = None):
+        if setting.partition_on_hit_rays:
+            raise NotImplementedError("partition_on_hit_rays (latent OOB in the reference, SURVEY.md App. C.8) is out of scope")
+        self.setting = setting
+        self.dtype = np.dtype(dtype)
+        self.ctx = ctx or default_context()
+        self.sensor_frame = LidarFrame2D(setting.sensor_frame, dtype)
+        cs = self._CSetting(int(setting.symmetric_partitions), setting.group_size, setting.overlap_size, setting.margin, setting.sensor_range_var, setting.discontinuity_var,
+                            int(setting.sensor_frame.discontinuity_detection), _kernel_id(setting.gp.kernel_type), setting.gp.scale, setting.mapping_type, setting.mapping_scale)
+        self.handle = C.c_void_p()
+        angles = self.sensor_frame.angles
+        check(self.ctx.fn("erl_gp_lidar2d_create", dtype)(self.ctx.handle, C.byref(cs), _p(angles), C.c_long(len(angles)), C.byref(self.handle)), "lidar2d_create", self.ctx.handle)
+        self.is_trained = False
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.fn("erl_gp_lidar2d_destroy", self.dtype)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def num_partitions(self):
+        n = C.c_long(0)
+        check(self.ctx.fn("erl_gp_lidar2d_num_partitions", self.dtype)(self.handle, C.byref(n)), "lidar2d_num_partitions")
+        return n.value
+
+    @property
+    def angle_partitions(self):
+        n = self.num_partitions
+        il, ir = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        cl, cr = np.zeros(n, dtype=self.dtype), np.zeros(n, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_lidar2d_partitions", self.dtype)(self.handle, _p(il), _p(ir), _p(cl), _p(cr)), "lidar2d_partitions")
+        return [(int(il[i]), int(ir[i]), cl[i], cr[i]) for i in range(n)]
+
+    def train(self, rotation, translation, ranges) -> bool:
+        self.is_trained = False
+        frame = self.sensor_frame
+        frame.update_ranges(rotation, translation, ranges)
+        if not frame.is_valid:
+            return False
+        rot = np.asfortranarray(frame.rotation)
+        r = np.ascontiguousarray(frame.ranges)
+        hit = np.ascontiguousarray(frame.mask_hit, dtype=np.uint8)
+        con = np.ascontiguousarray(frame.mask_continuous, dtype=np.uint8)
+        check(self.ctx.fn("erl_gp_lidar2d_train", self.dtype)(self.handle, _p(rot), _p(r), _p(hit), _p(con)), "lidar2d_train", self.ctx.handle)
+        self.is_trained = True
+        return True
+
+    def test(self, angles, angles_are_local, un_map=True):
+        if not self.is_trained:
+            return None
+        return LidarGaussianProcess2D.TestResult(self, angles, angles_are_local, un_map)
+
+    def get_gp(self, p):
+        gs = self.setting.group_size
+        info, n = C.c_int(0), C.c_long(0)
+        l = np.zeros((gs, gs), dtype=self.dtype)
+        a = np.zeros(gs, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_lidar2d_get_gp", self.dtype)(self.handle, C.c_long(p), C.byref(info), C.byref(n), _p(l), C.c_long(gs), _p(a)), "lidar2d_get_gp", self.ctx.handle)
+        nn = n.value
+        return info.value, nn, l.T[:nn, :nn].copy(), a[:nn].copy()
+
+    def compute_occ(self, pos_local):
+        """Batched ComputeOcc (src/lidar_gp_2d.cpp:428-459). pos_local: (T, 2). Returns ok, dist, range_pred, occ."""
+        pos = np.ascontiguousarray(pos_local, dtype=self.dtype)
+        t = pos.shape[0]
+        _, ct = _sfx(self.dtype)
+        dist = np.full(t, np.nan, dtype=self.dtype)
+        rp = np.full(t, np.nan, dtype=self.dtype)
+        occ = np.full(t, np.nan, dtype=self.dtype)
+        ok = np.zeros(t, dtype=np.uint8)
+        check(self.ctx.fn("erl_gp_lidar2d_compute_occ", self.dtype)(self.handle, _p(pos), C.c_long(t), ct(self.setting.max_valid_range_var), ct(self.setting.occ_test_temperature), _p(dist),
+                                                                   _p(rp), _p(occ), _p(ok)), "lidar2d_compute_occ", self.ctx.handle)
+        return ok.astype(bool), dist, rp, occ
+
+
+class LidarFrame3D:
+    """Azimuth x elevation ray grid: frame_coords[r, c] = (azimuth_r, elevation_c)
+    (test/gtest/test_range_sensor_gp_3d.cpp:39-44; rows follow azimuth, cols elevation)."""
+
+    class Setting:
+        def __init__(self, azimuth_min=-np.pi, azimuth_max=np.pi, num_azimuth_lines=360, elevation_min=-np.pi / 2, elevation_max=np.pi / 2, num_elevation_lines=181,
+                     valid_range_min=0.0, valid_range_max=np.inf):
+            self.azimuth_min, self.azimuth_max, self.num_azimuth_lines = azimuth_min, azimuth_max, num_azimuth_lines
+            self.elevation_min, self.elevation_max, self.num_elevation_lines = elevation_min, elevation_max, num_elevation_lines
+            self.valid_range_min, self.valid_range_max = valid_range_min, valid_range_max
+
+    def __init__(self, setting, dtype=np.float32):
+        self.setting = setting
+        self.dtype = np.dtype(dtype)
+        az = np.linspace(setting.azimuth_min, setting.azimuth_max, setting.num_azimuth_lines)
+        el = np.linspace(setting.elevation_min, setting.elevation_max, setting.num_elevation_lines)
+        self.frame_coords = np.stack(np.meshgrid(az, el, indexing="ij"), axis=-1).astype(self.dtype)  # (rows, cols, 2)
+        self.rotation = np.eye(3, dtype=self.dtype)
+        self.ranges = None
+        self.mask_hit = None
+
+    def update_ranges(self, rotation, translation, ranges):
+        s = self.setting
+        self.rotation = np.asarray(rotation, dtype=self.dtype)
+        r = np.asarray(ranges, dtype=self.dtype)
+        self.ranges = r
+        self.mask_hit = np.isfinite(r) & (r >= s.valid_range_min) & (r <= s.valid_range_max)
+
+    @property
+    def is_valid(self):
+        return self.mask_hit is not None and bool(self.mask_hit.any())
+
+    def dir_world_to_frame(self, dirs):
+        return np.asarray(dirs, dtype=self.dtype) @ self.rotation  # (R^T d) for row vectors
+
+    def compute_frame_coords(self, dirs_local):
+        d = np.asarray(dirs_local, dtype=self.dtype)
+        dist = np.linalg.norm(d, axis=1)
+        ok = dist > 0
+        safe = np.where(ok, dist, 1).astype(self.dtype)
+        az = np.arctan2(d[:, 1], d[:, 0])
+        el = np.arcsin(np.clip(d[:, 2] / safe, -1, 1))
+        return ok, dist.astype(self.dtype), np.stack([az, el], axis=1).astype(self.dtype)
+
+
+class RangeSensorGaussianProcess3D:
+    """Mirror of erl::gaussian_process::RangeSensorGaussianProcess3D<Dtype> (include/.../range_sensor_gp_3d.hpp)."""
+
+    class Setting:
+        def __init__(self):
+            # defaults: include/erl_gaussian_process/range_sensor_gp_3d.hpp:31-74
+            self.row_group_size, self.row_overlap_size, self.row_margin = 24, 6, 0
+            self.col_group_size, self.col_overlap_size, self.col_margin = 8, 2, 0
+            self.min_num_samples_per_group = 32
+            self.init_variance = 1e6
+            self.sensor_range_var = 0.01
+            self.max_valid_range_var = 0.1
+            self.occ_test_temperature = 30.0
+            self.sensor_frame = LidarFrame3D.Setting()
+            self.gp = VanillaGaussianProcess.Setting(kernel_type="ou", scale=1.0)
+            self.mapping_type = _capi.MAPPING_INVERSE_SQRT
+            self.mapping_scale = 1.0
+
+    class _CSetting(C.Structure):
+        _fields_ = [("row_group_size", C.c_long), ("row_overlap_size", C.c_long), ("row_margin", C.c_long), ("col_group_size", C.c_long), ("col_overlap_size", C.c_long),
+                    ("col_margin", C.c_long), ("min_num_samples_per_group", C.c_long), ("sensor_range_var", C.c_double), ("kernel", C.c_int), ("kernel_scale", C.c_double),
+                    ("mapping", C.c_int), ("mapping_scale", C.c_double)]
+
+    class TestResult:
+        def __init__(self, gp, directions, directions_are_local, un_map):
+            frame = gp.sensor_frame
+            d = np.asarray(directions, dtype=gp.dtype)
+            if not directions_are_local:
+                d = frame.dir_world_to_frame(d)
+            ok, _, coords = frame.compute_frame_coords(d)
+            self._init_from_coords(gp, coords, ok, un_map)
+
+        def _init_from_coords(self, gp, coords, ok, un_map):
+            coords = np.ascontiguousarray(coords, dtype=gp.dtype)
+            t = coords.shape[0]
+            self.num_test = t
+            self._mean = np.full(t, np.nan, dtype=gp.dtype)
+            self._var = np.full(t, np.nan, dtype=gp.dtype)
+            valid = np.zeros(t, dtype=np.uint8)
+            okb = None if ok is None else np.ascontiguousarray(ok, dtype=np.uint8)
+            check(gp.ctx.fn("erl_gp_range3d_test", gp.dtype)(gp.handle, _p(coords), _p(okb), C.c_long(t), C.c_int(int(un_map)), _p(self._mean), _p(self._var), _p(valid)), "range3d_test",
+                  gp.ctx.handle)
+            self._valid = valid.astype(bool)
+
+        def get_mean(self, parallel=True):
+            return self._mean.copy(), self._valid.copy()
+
+        def get_variance(self, parallel=True):
+            return self._var.copy(), self._valid.copy()
+
+    def __init__(self, setting: "RangeSensorGaussianProcess3D.Setting", dtype=np.float32, ctx: Context | None = None, sensor_frame=None):
+        if setting.row_overlap_size % 2 or setting.col_overlap_size % 2:
+            raise ValueError("row_overlap_size / col_overlap_size must be even")  # ERL_ASSERTM src/range_sensor_gp_3d.cpp:190-197
+        self.setting = setting
+        self.dtype = np.dtype(dtype)
+        self.ctx = ctx or default_context()
+        self.sensor_frame = sensor_frame or LidarFrame3D(setting.sensor_frame, dtype)
+        fc = self.sensor_frame.frame_coords
+        self.rows, self.cols = fc.shape[:2]
+        fcc = np.ascontiguousarray(fc.transpose(1, 0, 2))  # Eigen col-major matrix of Vector2
+        cs = self._CSetting(setting.row_group_size, setting.row_overlap_size, setting.row_margin, setting.col_group_size, setting.col_overlap_size, setting.col_margin,
+                            setting.min_num_samples_per_group, setting.sensor_range_var, _kernel_id(setting.gp.kernel_type), setting.gp.scale, setting.mapping_type, setting.mapping_scale)
+        self.handle = C.c_void_p()
+        check(self.ctx.fn("erl_gp_range3d_create", dtype)(self.ctx.handle, C.byref(cs), _p(fcc), C.c_long(self.rows), C.c_long(self.cols), C.byref(self.handle)), "range3d_create",
+              self.ctx.handle)
+        self.is_trained = False
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.fn("erl_gp_range3d_destroy", self.dtype)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def grid(self):
+        a, b = C.c_long(0), C.c_long(0)
+        check(self.ctx.fn("erl_gp_range3d_grid", self.dtype)(self.handle, C.byref(a), C.byref(b)), "range3d_grid")
+        return a.value, b.value
+
+    def partitions(self, axis):
+        n = self.grid[axis]
+        il, ir = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        cl, cr = np.zeros(n, dtype=self.dtype), np.zeros(n, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_range3d_partitions", self.dtype)(self.handle, C.c_int(axis), _p(il), _p(ir), _p(cl), _p(cr)), "range3d_partitions")
+        return [(int(il[i]), int(ir[i]), cl[i], cr[i]) for i in range(n)]
+
+    def train(self, rotation, translation, ranges) -> bool:
+        self.is_trained = False
+        frame = self.sensor_frame
+        frame.update_ranges(rotation, translation, ranges)
+        if not frame.is_valid:
+            return False
+        r = np.asfortranarray(frame.ranges)
+        m = np.asfortranarray(frame.mask_hit.astype(np.uint8))
+        check(self.ctx.fn("erl_gp_range3d_train", self.dtype)(self.handle, _p(r), _p(m)), "range3d_train", self.ctx.handle)
+        self.is_trained = True
+        return True
+
+    def test(self, directions, directions_are_local, un_map=True):
+        if not self.is_trained:
+            return None
+        return RangeSensorGaussianProcess3D.TestResult(self, directions, directions_are_local, un_map)
+
+    def test_frame_coords(self, coords, coords_ok=None, un_map=True):
+        if not self.is_trained:
+            return None
+        res = RangeSensorGaussianProcess3D.TestResult.__new__(RangeSensorGaussianProcess3D.TestResult)
+        res._init_from_coords(self, coords, coords_ok, un_map)
+        return res
+
+    def get_gp(self, row_part, col_part):
+        mn = self.setting.row_group_size * self.setting.col_group_size
+        info, n = C.c_int(0), C.c_long(0)
+        l = np.zeros((mn, mn), dtype=self.dtype)
+        a = np.zeros(mn, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_range3d_get_gp", self.dtype)(self.handle, C.c_long(row_part), C.c_long(col_part), C.byref(info), C.byref(n), _p(l), C.c_long(mn), _p(a)), "range3d_get_gp",
+              self.ctx.handle)
+        nn = n.value
+        return info.value, nn, l.T[:nn, :nn].copy(), a[:nn].copy()
+
+
+class SparsePseudoInputGaussianProcess:
+    """Mirror of erl::gaussian_process::SparsePseudoInputGaussianProcess<Dtype>, dense mode."""
+
+    def __init__(self, kernel, scale, pseudo_points, dtype=np.float64, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.dtype = np.dtype(dtype)
+        _, ct = _sfx(dtype)
+        z = np.ascontiguousarray(pseudo_points, dtype=self.dtype)
+        self.m, self.x_dim = z.shape
+        self.handle = C.c_void_p()
+        check(self.ctx.fn("erl_gp_spgp_create", dtype)(self.ctx.handle, C.c_int(_kernel_id(kernel)), ct(scale), C.c_long(self.x_dim), C.c_long(self.m), _p(z), C.byref(self.handle)),
+              "spgp_create", self.ctx.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.fn("erl_gp_spgp_destroy", self.dtype)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def update(self, x, y, var) -> bool:
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        n = x.shape[0]
+        if n == 0:
+            return False  # src/sparse_pseudo_input_gp.cpp:755
+        y = np.ascontiguousarray(y, dtype=self.dtype)
+        var = np.ascontiguousarray(var, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_spgp_update", self.dtype)(self.handle, C.c_long(n), _p(x), C.c_long(self.x_dim), _p(y), _p(var)), "spgp_update", self.ctx.handle)
+        return True
+
+    def test(self, x_test):
+        xt = np.ascontiguousarray(x_test, dtype=self.dtype)
+        t = xt.shape[0]
+        mean = np.empty(t, dtype=self.dtype)
+        var = np.empty(t, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_spgp_test", self.dtype)(self.handle, C.c_long(t), _p(xt), C.c_long(self.x_dim), _p(mean), _p(var)), "spgp_test", self.ctx.handle)
+        return mean, var
+
+    def get(self):
+        m = self.m
+        q = np.empty((m, m), dtype=self.dtype)
+        a = np.empty(m, dtype=self.dtype)
+        lk = np.empty((m, m), dtype=self.dtype)
+        lq = np.empty((m, m), dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_spgp_get", self.dtype)(self.handle, _p(q), _p(a), _p(lk), _p(lq)), "spgp_get", self.ctx.handle)
+        return q.T, a, lk.T, lq.T

@@ -1,0 +1,143 @@
+"""GPU parity: one-CTA-per-GP batched train / predict and the fused Gram kernels vs the oracle.
+Everything goes through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+
+from tests.util import TOL, err_mean, err_var, make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gp():
+    import erl_gaussian_process_b200 as m
+
+    return m
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel", ["ou", "matern32", "rbf"])
+@pytest.mark.parametrize("x_dim", [1, 2, 3])
+def test_gram_matches_oracle(gp, oracle, dtype, kernel, x_dim):
+    rng = np.random.default_rng(11)
+    n, t = 300, 517  # ragged vs the 128 x 32 tile
+    x = rng.uniform(-1, 1, (n, x_dim)).astype(dtype)
+    xt = rng.uniform(-1, 1, (t, x_dim)).astype(dtype)
+    var = rng.uniform(0.001, 0.1, n).astype(dtype)
+    scale = 0.3
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    k = gp.compute_ktrain(kernel, scale, x, var)
+    k_ref = oracle.gram_train(oracle.KERNELS[kernel], scale, x, var)
+    assert np.abs(k - k_ref).max() < tol
+    assert np.array_equal(np.diag(k), (dtype(1) + var).astype(dtype))  # K[i,i] = 1 + var[i] exactly
+    kt = gp.compute_ktest(kernel, scale, x, xt)
+    kt_ref = oracle.gram_test(oracle.KERNELS[kernel], scale, x, xt)
+    assert kt.shape == (n, t)
+    assert np.abs(kt - kt_ref).max() < tol
+
+
+def _check_batch(gp, oracle, dtype, kernel, scale, num_gps, max_n, x_dim, seed, min_num_samples=0, **kw):
+    rng = np.random.default_rng(seed)
+    n_train, x, y, var, q_offsets, q_x = make_batch(rng, num_gps, max_n, x_dim, dtype, **kw)
+    b = gp.BatchGp(num_gps, max_n, x_dim, kernel, scale, dtype)
+    out = b.train_predict(n_train, x, y, var, q_offsets, q_x, min_num_samples=min_num_samples)
+    kid = oracle.KERNELS[kernel]
+    nt_ref = np.where(n_train > min_num_samples, n_train, 0).astype(np.int32)  # the reference's `cnt > min` gate
+    ref = oracle.batched_train_predict(kid, scale, nt_ref, x, y, var, q_offsets, q_x)
+    ref64 = oracle.batched_train_predict(kid, scale, nt_ref, x.astype(np.float64), y.astype(np.float64), var.astype(np.float64), q_offsets, q_x.astype(np.float64))
+    tol = TOL[np.dtype(dtype)]
+    trained = nt_ref > 0
+    assert np.array_equal(out["info"] == 0, trained), "trained flags differ"
+    assert np.all(out["info"][~trained] == -1)
+    qmask = np.repeat(trained, np.diff(q_offsets))
+    assert np.array_equal(out["valid"], qmask)
+    assert np.isnan(out["mean"][~qmask]).all() and np.isnan(out["var"][~qmask]).all(), "outputs of untrained GPs must stay untouched"
+    if qmask.any():
+        for r, name in ((ref, "oracle"), (ref64, "oracle-f64")):
+            em = err_mean(out["mean"][qmask], r["mean"][qmask])
+            ev = err_var(out["var"][qmask], r["var"][qmask])
+            assert em < tol, f"mean vs {name}: {em:.3e}"
+            assert ev < tol, f"var vs {name}: {ev:.3e}"
+    # L / alpha materialisation
+    ltol = 2e-5 if dtype == np.float32 else 1e-11
+    for g in np.flatnonzero(trained)[:8]:
+        n = n_train[g]
+        lg, lr = out["L"][g][:n, :n], ref64["L"][g][:n, :n]
+        assert np.abs(np.triu(lg, 1)).max() == 0, "strict upper triangle of L must be zero"
+        assert np.abs(lg - lr).max() / np.abs(lr).max() < ltol
+        ag, ar = out["alpha"][g][:n], ref64["alpha"][g][:n]
+        assert np.abs(ag - ar).max() / np.abs(ar).max() < (5e-3 if dtype == np.float32 else 1e-8)
+    return out
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_batch_c4_shape(gp, oracle, dtype):
+    # BASELINE config 4 at reduced batch: n = 128, 3-D inputs, Matern32 l = 0.3, 128 test points per GP
+    _check_batch(gp, oracle, dtype, "matern32", 0.3, 96, 128, 3, seed=6, fixed_q=128)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("max_n,x_dim,kernel,scale", [(64, 1, "ou", 0.05), (43, 1, "ou", 0.05), (100, 2, "matern32", 0.2), (192, 2, "matern32", 0.3), (17, 3, "rbf", 0.5)])
+def test_batch_ragged(gp, oracle, dtype, max_n, x_dim, kernel, scale):
+    # ragged n (including 0 and tiny), ragged query counts (including 0 and > one tile)
+    _check_batch(gp, oracle, dtype, kernel, scale, 37, max_n, x_dim, seed=max_n, n_lo=0, n_hi=max_n, q_lo=0, q_hi=300)
+
+
+def test_batch_max_n_256_f32(gp, oracle):
+    _check_batch(gp, oracle, np.float32, "matern32", 0.3, 12, 256, 2, seed=3, n_lo=200, n_hi=256, q_lo=1, q_hi=200)
+
+
+def test_batch_min_num_samples_gate(gp, oracle):
+    # RangeSensorGaussianProcess3D trains iff cnt > min_num_samples_per_group (src/range_sensor_gp_3d.cpp:358)
+    out = _check_batch(gp, oracle, np.float32, "matern32", 0.3, 50, 96, 2, seed=9, min_num_samples=32, n_lo=20, n_hi=45, q_lo=1, q_hi=20)
+    assert (out["info"] == -1).any() and (out["info"] == 0).any()
+
+
+def test_batch_limits(gp):
+    with pytest.raises(gp.ErlGpError):
+        gp.BatchGp(4, 257, 2, "ou", 1.0, np.float32)
+    with pytest.raises(gp.ErlGpError):
+        gp.BatchGp(4, 193, 2, "ou", 1.0, np.float64)
+    with pytest.raises(gp.ErlGpError):
+        gp.BatchGp(4, 64, 4, "ou", 1.0, np.float32)
+
+
+def test_batch_not_spd_reports_info(gp):
+    rng = np.random.default_rng(0)
+    n_train, x, y, var, q_offsets, q_x = make_batch(rng, 4, 32, 2, np.float32, fixed_q=8)
+    var[1, :] = -5.0  # K[i,i] = 1 + var < 0: not positive definite
+    out = gp.BatchGp(4, 32, 2, "rbf", 0.5, np.float32).train_predict(n_train, x, y, var, q_offsets, q_x)
+    assert out["info"][1] > 0 and (out["info"][[0, 2, 3]] == 0).all()
+    assert not out["valid"][8:16].any() and out["valid"][:8].all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_batch_device_path_train_then_predict(gp, oracle, dtype):
+    """Device-resident buffers: train kernel, then the predict-only kernel with scatter index."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    num_gps, max_n, x_dim = 24, 64, 1
+    n_train, x, y, var, q_offsets, q_x = make_batch(rng, num_gps, max_n, x_dim, dtype, n_lo=30, n_hi=64, q_lo=100, q_hi=900)
+    t = q_x.shape[0]
+    b = gp.BatchGp(num_gps, max_n, x_dim, "ou", 0.05, dtype)
+    b.upload(n_train, x, y, var)
+    b.train_dev(write_l=True)
+    perm = rng.permutation(t).astype(np.int32)
+    dev = torch.device("cuda:0")
+    d_off = torch.from_numpy(q_offsets).to(dev)
+    d_qx = torch.from_numpy(q_x).to(dev)
+    d_perm = torch.from_numpy(perm).to(dev)
+    d_mean = torch.full((t,), float("nan"), dtype=d_qx.dtype, device=dev)
+    d_var = torch.full((t,), float("nan"), dtype=d_qx.dtype, device=dev)
+    d_valid = torch.zeros(t, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    b.predict_dev(d_off, d_qx, t, d_mean, d_var, d_valid, q_out_index=d_perm)
+    b.ctx.synchronize()
+    ref = oracle.batched_train_predict(oracle.OU, 0.05, n_train, x, y, var, q_offsets, q_x)
+    mean = d_mean.cpu().numpy()
+    varo = d_var.cpu().numpy()
+    assert d_valid.cpu().numpy().all()
+    tol = TOL[np.dtype(dtype)]
+    assert err_mean(mean[perm], ref["mean"]) < tol
+    assert err_var(varo[perm], ref["var"]) < tol

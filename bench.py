@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — GP train+predict test-points/sec on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c3|c1]
+
+Default workload = BASELINE.json configs[3] ("c4"): the batched small-GP stream, 50 000 independent
+GPs per GPU (n = 128, 3-D inputs, Matern32, 128 test points each, float32) — the configuration
+the metric's "at 1/2/4/8 B200" is quoted on.  A "step" is one pass of the hot path (fused
+Gram + Cholesky + alpha + predict, one kernel launch) over the whole batch.  GPUs shard the GP
+stream (weak scaling: 50k GPs per rank, no data-path collective; torch.distributed is used
+only for the barrier and the max-over-ranks of the device time).
+
+`value`  : test points / s with all inputs resident in HBM (CUDA events on the launch stream).
+`e2e`    : the same metric through the C-ABI host-buffer call erl_gp_batch_train_predict_f32
+           (pinned host buffers; H2D of the training sets and queries and D2H of mean /
+           variance / valid / info inside the timed region).
+`--impl reference`: the reference's CPU path (the OpenMP oracle restatement — the reference
+           itself cannot be built here) on all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 6
+WORKLOADS = {
+    # name: (description, num_gps per GPU, n, x_dim, queries per GP, kernel, scale, dtype)
+    "c4": dict(desc="batched small-GP stream: 50k independent GPs per GPU, n=128, x_dim=3, Matern32(0.3), 128 test points per GP, f32 (BASELINE.json configs[3])",
+               num_gps=50_000, n=128, x_dim=3, q_per_gp=128, kernel="matern32", scale=0.3, dtype="f32"),
+}
+
+
+def algorithmic_bytes_per_gp(n, d, t, s):
+    """n(d+2)s in, (n^2+n)s out (L, alpha), t*d*s queries in, t(2s+1) out."""
+    return n * (d + 2) * s + (n * n + n) * s + t * d * s + t * (2 * s + 1)
+
+
+def flops_per_gp(n, d, t):
+    """useful flops: Cholesky n^3/3 + alpha 2n^2 + predict t(n^2 + 2n); kernel evaluations not counted."""
+    return n ** 3 / 3 + 2 * n * n + t * (n * n + 2 * n)
+
+
+def synth_batch(w, rank):
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    b, n, d, t = w["num_gps"], w["n"], w["x_dim"], w["q_per_gp"]
+    dt = np.float32 if w["dtype"] == "f32" else np.float64
+    x = rng.random((b, n, d), dtype=np.float32).astype(dt)
+    wv = rng.uniform(1, 4, (b, 1, d)).astype(dt)
+    y = (0.5 * np.sin(wv * x * 3.0).sum(axis=2)).astype(dt)
+    var = np.full((b, n), 0.01, dtype=dt)
+    n_train = np.full(b, n, dtype=np.int32)
+    q_offsets = (np.arange(b + 1, dtype=np.int64) * t)
+    q_x = rng.random((b * t, d), dtype=np.float32).astype(dt)
+    return n_train, x, y, var, q_offsets, q_x
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def profile_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(w, sample_gps, threads=None):
+    """Time the CPU reference path (oracle port: OpenMP over GPs, each Reset/Train/Test) on a bounded sample."""
+    import oracle
+
+    if threads:
+        oracle.set_num_threads(threads)
+    cores = oracle.num_threads()
+    ww = dict(w, num_gps=sample_gps)
+    n_train, x, y, var, q_offsets, q_x = synth_batch(ww, 0)
+    kid = oracle.KERNELS[w["kernel"]]
+    oracle.batched_train_predict(kid, w["scale"], n_train[:64], x[:64], y[:64], var[:64], q_offsets[:65], q_x[: 64 * w["q_per_gp"]])  # warm
+    t0 = time.perf_counter()
+    oracle.batched_train_predict(kid, w["scale"], n_train, x, y, var, q_offsets, q_x)
+    dt = time.perf_counter() - t0
+    return {"value": sample_gps * w["q_per_gp"] / dt, "unit": "test-points/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_gps} of the workload's GPs (n={w['n']}, {w['q_per_gp']} test points each), {dt:.2f} s on {cores} OpenMP threads", "seconds": dt}
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(w, args.ref_sample)
+        if i >= args.warmup:
+            times.append(base["seconds"])
+    ms = 1e3 * sum(times) / len(times)
+    value = args.ref_sample * w["q_per_gp"] / (ms * 1e-3)
+    base["value"] = value
+    line = {"impl": "reference", "metric": "gp_train_predict_test_points_per_sec", "value": value, "unit": "test-points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["desc"], "sample": base["sample"], "note": "CPU reference path = OpenMP oracle port (the reference cannot be built in this image)"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": "test-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--num-gps", type=int, default=None, help="override GPs per GPU (smoke runs)")
+    ap.add_argument("--ref-sample", type=int, default=4000, help="GPs in the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    w = dict(WORKLOADS[args.workload])
+    if args.num_gps:
+        w["num_gps"] = args.num_gps
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import erl_gaussian_process_b200 as gp
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    b, n, d, t = w["num_gps"], w["n"], w["x_dim"], w["q_per_gp"]
+    np_dt = np.float32 if w["dtype"] == "f32" else np.float64
+    s = np.dtype(np_dt).itemsize
+    ctx = gp.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)  # our kernels run on torch's current stream: its events time them
+    batch = gp.BatchGp(b, n, d, w["kernel"], w["scale"], np_dt, ctx)
+
+    # pinned host buffers (the e2e path reads / writes these)
+    n_train, x, y, var, q_offsets, q_x = synth_batch(w, rank)
+
+    def pinned(a):
+        tns = torch.from_numpy(a).pin_memory()
+        return tns, tns.numpy()
+
+    keep = []
+    host = {}
+    for name, arr in (("n_train", n_train), ("x", x), ("y", y), ("var", var), ("q_offsets", q_offsets), ("q_x", q_x)):
+        tns, view = pinned(arr)
+        keep.append(tns)
+        host[name] = view
+    tq = b * t
+    h_mean_t, h_mean = pinned(np.zeros(tq, dtype=np_dt))
+    h_var_t, h_var = pinned(np.zeros(tq, dtype=np_dt))
+    h_valid_t, h_valid = pinned(np.zeros(tq, dtype=np.uint8))
+    h_info_t, h_info = pinned(np.zeros(b, dtype=np.int32))
+
+    # resident inputs for the kernel-only measurement
+    batch.upload(host["n_train"], host["x"], host["y"], host["var"])
+    d_off = torch.from_numpy(q_offsets).to(dev)
+    d_qx = torch.from_numpy(q_x).to(dev)
+    d_mean = torch.empty(tq, dtype=d_qx.dtype, device=dev)
+    d_var = torch.empty(tq, dtype=d_qx.dtype, device=dev)
+    d_valid = torch.empty(tq, dtype=torch.uint8, device=dev)
+
+    def step():
+        batch.train_predict_dev(d_off, d_qx, tq, d_mean, d_var, d_valid, min_num_samples=0, write_l=True)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop()
+    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / args.steps
+    value = world * tq / (ms_step * 1e-3)
+
+    # sanity: the timed kernel really produced finite predictions
+    assert bool(torch.isfinite(d_mean).all()) and bool(d_valid.all()), "kernel output invalid"
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+
+        from erl_gaussian_process_b200.host import _p
+
+        fn = ctx.fn("erl_gp_batch_train_predict", np_dt)
+
+        def e2e_step():
+            rc = fn(batch.handle, C.c_long(0), _p(host["n_train"]), _p(host["x"]), _p(host["y"]), _p(host["var"]), _p(host["q_offsets"]), _p(host["q_x"]), C.c_long(tq), None, None,
+                    _p(h_info), _p(h_mean), _p(h_var), _p(h_valid))
+            assert rc == 0, rc
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt_e2e = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_e2e = float(tt.item())
+        assert np.isfinite(h_mean).all() and h_valid.all() and (h_info == 0).all()
+        h2d = host["n_train"].nbytes + host["x"].nbytes + host["y"].nbytes + host["var"].nbytes + host["q_offsets"].nbytes + host["q_x"].nbytes + h_mean.nbytes + h_var.nbytes
+        d2h = h_mean.nbytes + h_var.nbytes + h_valid.nbytes + h_info.nbytes
+        e2e = {"value": world * tq / dt_e2e, "unit": "test-points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": dt_e2e * 1e3,
+               "api": "erl_gp_batch_train_predict_f32 (C ABI, pinned host buffers; L stays device-resident, materialised on demand by erl_gp_batch_download)"}
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        alg_bytes = algorithmic_bytes_per_gp(n, d, t, s) * b
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        peak = float(peaks["hbm_gbs"])
+        traffic = profile_traffic()
+        fl = flops_per_gp(n, d, t) * b
+        line = {
+            "metric": "gp_train_predict_test_points_per_sec", "value": value, "unit": "test-points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["desc"], "gps_per_gpu": b, "n_train": n, "x_dim": d, "test_points_per_gp": t, "kernel": w["kernel"], "scale": w["scale"], "seed": SEED,
+                       "sharding": f"{world} x {b} GPs, contiguous GP ranges per rank, no data-path collective",
+                       "l2": f"per-step inputs+outputs {alg_bytes / 1e9:.2f} GB >> 126 MB L2, no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind,
+                         "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                         "kernel": "BatchedGpKernel<float,3,8,train+predict> (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
+                         "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu; this kernel is FP32-pipe bound, see DESIGN.md"}},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base = cpu_baseline(w, args.ref_sample)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -191,7 +191,8 @@ namespace erl_gp {
             if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->mean.ptr, mean, sizeof(T) * num_q, cudaMemcpyHostToDevice, ctx->stream)); }
             if (variance != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->variance.ptr, variance, sizeof(T) * num_q, cudaMemcpyHostToDevice, ctx->stream)); }
         }
-        rc = BatchTrainPredictDev(b, min_num_samples, l != nullptr ? 1 : 0, b->q_offsets.ptr, b->q_x.ptr, num_q, mean != nullptr ? b->mean.ptr : nullptr,
+        // L is always materialised in HBM (downloaded only on demand)
+        rc = BatchTrainPredictDev(b, min_num_samples, 1, b->q_offsets.ptr, b->q_x.ptr, num_q, mean != nullptr ? b->mean.ptr : nullptr,
                                   variance != nullptr ? b->variance.ptr : nullptr, b->valid.ptr);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         if (num_q > 0) {
@@ -337,15 +338,9 @@ erl_gp_context_set_stream(erl_gp_context *c, void *cuda_stream) {
     if (ctx->own_stream && ctx->stream != nullptr) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
-        ctx->stream = nullptr;
-        ctx->own_stream = false;
     }
-    if (cuda_stream == nullptr) {
-        ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    } else {
-        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
-    }
+    ctx->own_stream = false;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL = the CUDA legacy default stream
     return ERL_GP_STATUS_OK;
 }
 

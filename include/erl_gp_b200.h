@@ -73,7 +73,8 @@ int erl_gp_device_count(int *count);
 /* One context per host thread and device (the reference objects are not thread-safe either). */
 int erl_gp_context_create(int device, erl_gp_context **ctx);
 int erl_gp_context_destroy(erl_gp_context *ctx);
-/* Borrow an external CUDA stream (cudaStream_t as void*, e.g. torch's current stream). NULL = own stream. */
+/* Borrow an external CUDA stream (cudaStream_t as void*, e.g. torch's current stream); the context's own
+ * stream is released.  NULL selects the CUDA legacy default stream. */
 int erl_gp_context_set_stream(erl_gp_context *ctx, void *cuda_stream);
 int erl_gp_context_synchronize(erl_gp_context *ctx);
 const char *erl_gp_context_last_error(const erl_gp_context *ctx);

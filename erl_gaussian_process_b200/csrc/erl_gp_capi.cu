@@ -15,41 +15,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    struct Batch {
-        Context *ctx = nullptr;
-        long num_gps = 0, max_n = 0, x_dim = 0;
-        int kernel = 0;
-        T scale = T(1);
-        DeviceBuffer<int> n_train, info;
-        DeviceBuffer<T> x, y, var, l, alpha;
-        // query-side staging for the host-pointer entry points
-        DeviceBuffer<long> q_offsets;
-        DeviceBuffer<T> q_x, mean, variance;
-        DeviceBuffer<uint8_t> valid;
-
-        BatchParams<T>
-        Params(const long min_num_samples, const int write_l) const {
-            BatchParams<T> p{};
-            p.cov = Covariance<T>::Make(kernel, scale);
-            p.num_gps = static_cast<int>(num_gps);
-            p.max_n = static_cast<int>(max_n);
-            p.min_train = static_cast<int>(min_num_samples < 0 ? 0 : min_num_samples);
-            p.write_l = write_l;
-            p.n_train = n_train.ptr;
-            p.x = x.ptr;
-            p.y = y.ptr;
-            p.var = var.ptr;
-            p.l = l.ptr;
-            p.alpha = alpha.ptr;
-            p.info = info.ptr;
-            p.mapping = ERL_GP_MAPPING_NONE;
-            p.mapping_scale = T(1);
-            return p;
-        }
-    };
-
-    template<typename T>
-    static int
+    int
     BatchCreate(erl_gp_context *c, long num_gps, long max_n, long x_dim, int kernel, T scale, Batch<T> **out) {
         Context *ctx = Ctx(c);
         if (ctx == nullptr || out == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
@@ -85,7 +51,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    static int
+    int
     BatchUpload(Batch<T> *b, const int *n_train, const T *x, const T *y, const T *var) {
         if (b == nullptr || n_train == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
@@ -98,7 +64,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    static int
+    int
     BatchTrainDev(Batch<T> *b, long min_num_samples, int write_l) {
         if (b == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         const BatchParams<T> p = b->Params(min_num_samples, write_l);
@@ -106,7 +72,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    static int
+    int
     BatchPredictDev(Batch<T> *b, const long *q_offsets, const T *q_x, const int *q_out_index, long num_q, int mapping, T mapping_scale, T *mean, T *var, uint8_t *valid) {
         if (b == nullptr || q_offsets == nullptr || q_x == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         if (num_q <= 0) { return ERL_GP_STATUS_OK; }
@@ -130,7 +96,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    static int
+    int
     BatchTrainPredictDev(Batch<T> *b, long min_num_samples, int write_l, const long *q_offsets, const T *q_x, long num_q, T *mean, T *var, uint8_t *valid) {
         if (b == nullptr || q_offsets == nullptr || (num_q > 0 && q_x == nullptr)) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         BatchParams<T> p = b->Params(min_num_samples, write_l);
@@ -143,7 +109,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    static int
+    int
     BatchDownload(Batch<T> *b, T *l, T *alpha, int *info) {
         if (b == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
@@ -204,7 +170,7 @@ namespace erl_gp {
     }
 
     template<typename T>
-    static int
+    int
     BatchGetGp(Batch<T> *b, long g, int *info, long *n, T *l, long ld_l, T *alpha) {
         if (b == nullptr || g < 0 || g >= b->num_gps) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
@@ -252,6 +218,19 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }
+
+    // explicit instantiations used by the other translation units
+#define ERL_GP_INSTANTIATE_BATCH(T)                                                                                                            \
+    template int BatchCreate<T>(erl_gp_context *, long, long, long, int, T, Batch<T> **);                                                      \
+    template int BatchUpload<T>(Batch<T> *, const int *, const T *, const T *, const T *);                                                     \
+    template int BatchTrainDev<T>(Batch<T> *, long, int);                                                                                      \
+    template int BatchPredictDev<T>(Batch<T> *, const long *, const T *, const int *, long, int, T, T *, T *, uint8_t *);                      \
+    template int BatchTrainPredictDev<T>(Batch<T> *, long, int, const long *, const T *, long, T *, T *, uint8_t *);                           \
+    template int BatchDownload<T>(Batch<T> *, T *, T *, int *);                                                                                \
+    template int BatchGetGp<T>(Batch<T> *, long, int *, long *, T *, long, T *);
+    ERL_GP_INSTANTIATE_BATCH(float)
+    ERL_GP_INSTANTIATE_BATCH(double)
+#undef ERL_GP_INSTANTIATE_BATCH
 
 }  // namespace erl_gp
 

@@ -131,4 +131,60 @@ namespace erl_gp {
     long
     BatchMaxN();
 
+    template<typename T>
+    struct Batch {
+        Context *ctx = nullptr;
+        long num_gps = 0, max_n = 0, x_dim = 0;
+        int kernel = 0;
+        T scale = T(1);
+        DeviceBuffer<int> n_train, info;
+        DeviceBuffer<T> x, y, var, l, alpha;
+        // query-side staging for the host-pointer entry points
+        DeviceBuffer<long> q_offsets;
+        DeviceBuffer<T> q_x, mean, variance;
+        DeviceBuffer<uint8_t> valid;
+
+        BatchParams<T>
+        Params(const long min_num_samples, const int write_l) const {
+            BatchParams<T> p{};
+            p.cov = Covariance<T>::Make(kernel, scale);
+            p.num_gps = static_cast<int>(num_gps);
+            p.max_n = static_cast<int>(max_n);
+            p.min_train = static_cast<int>(min_num_samples < 0 ? 0 : min_num_samples);
+            p.write_l = write_l;
+            p.n_train = n_train.ptr;
+            p.x = x.ptr;
+            p.y = y.ptr;
+            p.var = var.ptr;
+            p.l = l.ptr;
+            p.alpha = alpha.ptr;
+            p.info = info.ptr;
+            p.mapping = ERL_GP_MAPPING_NONE;
+            p.mapping_scale = T(1);
+            return p;
+        }
+    };
+
+    template<typename T>
+    int
+    BatchCreate(erl_gp_context *c, long num_gps, long max_n, long x_dim, int kernel, T scale, Batch<T> **out);
+    template<typename T>
+    int
+    BatchUpload(Batch<T> *b, const int *n_train, const T *x, const T *y, const T *var);
+    template<typename T>
+    int
+    BatchTrainDev(Batch<T> *b, long min_num_samples, int write_l);
+    template<typename T>
+    int
+    BatchPredictDev(Batch<T> *b, const long *q_offsets, const T *q_x, const int *q_out_index, long num_q, int mapping, T mapping_scale, T *mean, T *var, uint8_t *valid);
+    template<typename T>
+    int
+    BatchTrainPredictDev(Batch<T> *b, long min_num_samples, int write_l, const long *q_offsets, const T *q_x, long num_q, T *mean, T *var, uint8_t *valid);
+    template<typename T>
+    int
+    BatchDownload(Batch<T> *b, T *l, T *alpha, int *info);
+    template<typename T>
+    int
+    BatchGetGp(Batch<T> *b, long g, int *info, long *n, T *l, long ld_l, T *alpha);
+
 }  // namespace erl_gp

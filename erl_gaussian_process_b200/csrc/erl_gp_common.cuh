@@ -32,7 +32,7 @@ namespace erl_gp {
     //   Matern32          : (1 + sqrt(3) r / l) exp(-sqrt(3) r / l)
     //   RadialBiasFunction: exp(-r^2 / (2 l^2))
     // The functor is built once on the host (coefficients precomputed in the working precision,
-    // same expression order as the oracle) and passed by value to the kernels.
+    // same expression order as the CPU reference restatement) and passed by value to the kernels.
     template<typename T>
     struct Covariance {
         int type;

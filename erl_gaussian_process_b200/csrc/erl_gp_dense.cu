@@ -1,0 +1,497 @@
+// Dense (HBM-resident) linear algebra for large VanillaGaussianProcess and SPGP systems.
+//
+// Replaces Eigen's `llt()` and `triangularView::solve` as used at src/vanilla_gp.cpp:499-502,
+// :139-149 and src/sparse_pseudo_input_gp.cpp:341, 100-106, 304-309, 768-774, 840.
+//
+// Blocked right-looking Cholesky with a 128-wide panel:
+//   1. DiagFactorKernel: one CTA factors the 128x128 diagonal block entirely in shared memory (the same
+//      block-packed 16x16 machinery as the batched small-GP kernel) and also produces its INVERSE, so that
+//   2. the panel solve  L21 = A21 * L11^-T  and every later triangular solve (alpha, predictive variance)
+//      are plain GEMMs against the kept 128x128 inverses, and
+//   3. the trailing update A22 -= L21 L21^T is a lower-triangle-only GEMM (SYRK).
+// The GEMM is a register-tiled (8x8 per thread), double-buffered FMA kernel: on B200 the FP64 tensor
+// path (DMMA m8n8k4, 37.0 TFLOP/s measured) has the same peak as the FP64 FMA pipe (36.2 TFLOP/s
+// measured, tools/mma_rate.cu), and the FP32 path must stay true FP32 (3xTF32 mma.sync measures only
+// 92 TFLOP/s-equivalent vs 71 TFLOP/s FFMA, and plain TF32 breaks the 1e-4 parity).
+#include "erl_gp_dense.cuh"
+
+#include "erl_gp_batched.cuh"
+
+namespace erl_gp {
+
+    // =========================================================================================
+    // GEMM
+    // =========================================================================================
+    constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmThreads = 256, kGemmPad = 4;
+
+    // load a (ROWS x BK) operand tile into registers: ROWS = 128 "outer" index, BK = 16 reduction index
+    //   K_CONTIG = false: element (o, k) at src[o + k * ld]   (outer index contiguous)
+    //   K_CONTIG = true : element (o, k) at src[k + o * ld]   (reduction index contiguous)
+    template<typename T, bool K_CONTIG>
+    __device__ __forceinline__ void
+    GemmLoadTile(const T *__restrict__ src, const long ld, const long o0, const long o_lim, const long k0, const long k_lim, const int tid, T (&reg)[8]) {
+        if (!K_CONTIG) {
+            const int o = (tid & 31) * 4;
+            const int kk = tid >> 5;  // 0..7
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long k = k0 + kk + 8 * i;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long oo = o0 + o + j;
+                    reg[i * 4 + j] = (oo < o_lim && k < k_lim) ? src[oo + k * ld] : T(0);
+                }
+            }
+        } else {
+            const int kk = tid & 15;
+            const int o = tid >> 4;  // 0..15
+            const long k = k0 + kk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long oo = o0 + o + 16 * i;
+                reg[i] = (oo < o_lim && k < k_lim) ? src[k + oo * ld] : T(0);
+            }
+        }
+    }
+
+    template<typename T, bool K_CONTIG>
+    __device__ __forceinline__ void
+    GemmStoreTile(T *__restrict__ dst /* [BK][128 + pad] */, const int tid, const T (&reg)[8]) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        if (!K_CONTIG) {
+            const int o = (tid & 31) * 4;
+            const int kk = tid >> 5;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                T t4[4] = {reg[i * 4], reg[i * 4 + 1], reg[i * 4 + 2], reg[i * 4 + 3]};
+                Store4(dst + (kk + 8 * i) * kLd + o, t4);
+            }
+        } else {
+            const int kk = tid & 15;
+            const int o = tid >> 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dst[kk * kLd + o + 16 * i] = reg[i]; }
+        }
+    }
+
+    template<typename T, bool A_KC, bool B_KC>
+    __global__ void __launch_bounds__(kGemmThreads, sizeof(T) == 4 ? 2 : 1)
+    GemmKernel(
+        const long m,
+        const long n,
+        const long k,
+        const T alpha,
+        const T *__restrict__ a,
+        const long lda,
+        const T *__restrict__ b,
+        const long ldb,
+        const T beta,
+        T *__restrict__ c,
+        const long ldc,
+        const int lower_only) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        T *as = reinterpret_cast<T *>(smem_raw);       // [2][BK][kLd]
+        T *bs = as + 2 * kGemmBK * kLd;                // [2][BK][kLd]
+        const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
+        const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
+        if (lower_only && col0 > row0 + kGemmBM - 1) { return; }  // tile strictly above the diagonal
+        const int tid = threadIdx.x;
+        const int tx = tid & 15, ty = tid >> 4;
+
+        T acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[i][j] = T(0); }
+        }
+        T ra[8], rb[8];
+        GemmLoadTile<T, A_KC>(a, lda, row0, m, 0, k, tid, ra);
+        GemmLoadTile<T, B_KC>(b, ldb, col0, n, 0, k, tid, rb);
+        GemmStoreTile<T, A_KC>(as, tid, ra);
+        GemmStoreTile<T, B_KC>(bs, tid, rb);
+        __syncthreads();
+        const long num_kt = (k + kGemmBK - 1) / kGemmBK;
+        for (long kt = 0; kt < num_kt; ++kt) {
+            const int cur = static_cast<int>(kt & 1);
+            if (kt + 1 < num_kt) {
+                GemmLoadTile<T, A_KC>(a, lda, row0, m, (kt + 1) * kGemmBK, k, tid, ra);
+                GemmLoadTile<T, B_KC>(b, ldb, col0, n, (kt + 1) * kGemmBK, k, tid, rb);
+            }
+            const T *at = as + cur * kGemmBK * kLd;
+            const T *bt = bs + cur * kGemmBK * kLd;
+#pragma unroll
+            for (int kk = 0; kk < kGemmBK; ++kk) {
+                T av[8], bv[8];
+                T t4[4];
+                Load4(at + kk * kLd + tx * 4, t4);
+                av[0] = t4[0], av[1] = t4[1], av[2] = t4[2], av[3] = t4[3];
+                Load4(at + kk * kLd + 64 + tx * 4, t4);
+                av[4] = t4[0], av[5] = t4[1], av[6] = t4[2], av[7] = t4[3];
+                Load4(bt + kk * kLd + ty * 4, t4);
+                bv[0] = t4[0], bv[1] = t4[1], bv[2] = t4[2], bv[3] = t4[3];
+                Load4(bt + kk * kLd + 64 + ty * 4, t4);
+                bv[4] = t4[0], bv[5] = t4[1], bv[6] = t4[2], bv[7] = t4[3];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc[i][j] += av[i] * bv[j]; }
+                }
+            }
+            if (kt + 1 < num_kt) {
+                GemmStoreTile<T, A_KC>(as + (cur ^ 1) * kGemmBK * kLd, tid, ra);
+                GemmStoreTile<T, B_KC>(bs + (cur ^ 1) * kGemmBK * kLd, tid, rb);
+            }
+            __syncthreads();
+        }
+        // epilogue
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long col = col0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
+            if (col >= n) { continue; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long row = row0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+                if (row >= m || (lower_only && row < col)) { continue; }
+                T *dst = c + row + col * ldc;
+                const T prev = beta == T(0) ? T(0) : beta * (*dst);
+                *dst = alpha * acc[i][j] + prev;
+            }
+        }
+    }
+
+    template<typename T>
+    int
+    Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, bool lower_only) {
+        if (m <= 0 || n <= 0) { return ERL_GP_STATUS_OK; }
+        const dim3 grid(static_cast<unsigned>(CeilDiv(m, kGemmBM)), static_cast<unsigned>(CeilDiv(n, kGemmBN)));
+        const size_t smem = sizeof(T) * 4 * kGemmBK * (kGemmBM + kGemmPad);
+        // op(A)(m,k): N -> a[m + k lda] (outer contiguous), T -> a[k + m lda] (k contiguous)
+        // op(B)(k,n): N -> b[k + n ldb] (k contiguous),     T -> b[n + k ldb] (outer contiguous)
+#define ERL_GP_GEMM_LAUNCH(AKC, BKC)                                                                                          \
+    {                                                                                                                         \
+        auto kern = GemmKernel<T, AKC, BKC>;                                                                                  \
+        ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+        kern<<<grid, kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only ? 1 : 0);    \
+    }
+        if (op_a == kOpN && op_b == kOpT) {
+            ERL_GP_GEMM_LAUNCH(false, false)
+        } else if (op_a == kOpN && op_b == kOpN) {
+            ERL_GP_GEMM_LAUNCH(false, true)
+        } else if (op_a == kOpT && op_b == kOpN) {
+            ERL_GP_GEMM_LAUNCH(true, true)
+        } else {
+            ERL_GP_GEMM_LAUNCH(true, false)
+        }
+#undef ERL_GP_GEMM_LAUNCH
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        return ERL_GP_STATUS_OK;
+    }
+
+    // =========================================================================================
+    // 128 x 128 diagonal block: Cholesky + inverse in one CTA
+    // =========================================================================================
+    constexpr int kDiagBlocks = kPanel / kNB;  // 8
+
+    // V = L^-1 (identity right-hand side), register-resident right-looking blocked substitution.
+    // Thread (tr, tc) owns rows tr + 16 m and columns col0 + QPT * tc + j.
+    template<typename T>
+    __device__ void
+    InverseColumns(const T *lp, const T *dinv, T *r_buf, T *s_buf, const int nblk, const int col0, T *__restrict__ out /* 128 x 128 col-major */) {
+        using Smem = BatchSmem<T, 1, kDiagBlocks>;
+        constexpr int kQpt = Smem::kQpt;
+        constexpr int kTq = Smem::kTq;
+        constexpr int kLd = DinvLd<T>::value;
+        const int tid = threadIdx.x;
+        const int tr = tid & 15;
+        const int tc = tid >> 4;
+        const int qbase = tc * kQpt;
+        T v[kDiagBlocks][kQpt];
+#pragma unroll
+        for (int m = 0; m < kDiagBlocks; ++m) {
+#pragma unroll
+            for (int j = 0; j < kQpt; ++j) { v[m][j] = (tr + kNB * m == col0 + qbase + j) ? T(1) : T(0); }
+        }
+        for (int kb = 0; kb < nblk; ++kb) {
+            T rk[kQpt];
+#pragma unroll
+            for (int m = 0; m < kDiagBlocks; ++m) {
+                if (m == kb) {
+#pragma unroll
+                    for (int j = 0; j < kQpt; ++j) { rk[j] = v[m][j]; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kQpt; j += 4) {
+                T t4[4] = {rk[j], rk[j + 1], rk[j + 2], rk[j + 3]};
+                Store4(r_buf + tr * kTq + qbase + j, t4);
+            }
+            __syncthreads();
+            T res[kQpt];
+#pragma unroll
+            for (int j = 0; j < kQpt; ++j) { res[j] = T(0); }
+            const T *dk = dinv + kb * kNB * kLd + tr * kLd;
+#pragma unroll
+            for (int p4 = 0; p4 < kNB; p4 += 4) {
+                T d4[4];
+                Load4(dk + p4, d4);
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+#pragma unroll
+                    for (int j = 0; j < kQpt; j += 4) {
+                        T r4[4];
+                        Load4(r_buf + (p4 + pp) * kTq + qbase + j, r4);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) { res[j + jj] += d4[pp] * r4[jj]; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kQpt; j += 4) {
+                T t4[4] = {res[j], res[j + 1], res[j + 2], res[j + 3]};
+                Store4(s_buf + tr * kTq + qbase + j, t4);
+            }
+#pragma unroll
+            for (int j = 0; j < kQpt; ++j) { out[(kb * kNB + tr) + static_cast<long>(col0 + qbase + j) * kPanel] = res[j]; }
+            __syncthreads();
+            if (kb + 1 < nblk) {
+#pragma unroll
+                for (int p2 = 0; p2 < kNB; p2 += 2) {
+                    T s2[2][kQpt];
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) {
+#pragma unroll
+                        for (int j = 0; j < kQpt; j += 4) {
+                            T t4[4];
+                            Load4(s_buf + (p2 + pp) * kTq + qbase + j, t4);
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) { s2[pp][j + jj] = t4[jj]; }
+                        }
+                    }
+#pragma unroll
+                    for (int m = 1; m < kDiagBlocks; ++m) {
+                        if (m > kb && m < nblk) {
+                            const T *lrow = lp + LowerBlock(m, kb) + tr + kNB * p2;
+                            const T l0 = lrow[0];
+                            const T l1 = lrow[kNB];
+#pragma unroll
+                            for (int j = 0; j < kQpt; ++j) {
+                                v[m][j] -= l0 * s2[0][j];
+                                v[m][j] -= l1 * s2[1][j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // a: nk x nk block (lower triangle read, ld).  On exit a holds L11 (strict upper of the block zeroed),
+    // linv the 128 x 128 inverse (identity padded).  info: set to col_offset + failing column if not SPD.
+    template<typename T>
+    __global__ void __launch_bounds__(kBatchThreads, 1)
+    DiagFactorKernel(T *__restrict__ a, const long ld, const int nk, T *__restrict__ linv, int *__restrict__ info, const int col_offset) {
+        using Smem = BatchSmem<T, 1, kDiagBlocks>;
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        T *smem = reinterpret_cast<T *>(smem_raw);
+        T *lp = smem + Smem::kLp;
+        T *dinv = smem + Smem::kDinv;
+        T *r_buf = smem + Smem::kR;
+        T *s_buf = smem + Smem::kS;
+        int *s_fail = reinterpret_cast<int *>(smem + Smem::kEnd);
+        constexpr int kLd = DinvLd<T>::value;
+        const int tid = threadIdx.x;
+        const int warp = tid >> 5;
+        const int lane = tid & 31;
+        const int nblk = (nk + kNB - 1) / kNB;
+        const int npad = nblk * kNB;
+        if (tid == 0) { *s_fail = 0; }
+        for (int c = warp; c < npad; c += kBatchThreads / 32) {
+            for (int r = (c & ~15) + lane; r < npad; r += 32) {
+                T val;
+                if (r < nk && c < nk) {
+                    val = r >= c ? a[r + static_cast<long>(c) * ld] : T(0);
+                } else {
+                    val = r == c ? T(1) : T(0);
+                }
+                lp[LowerBlock(r >> 4, c >> 4) + (r & 15) + kNB * (c & 15)] = val;
+            }
+        }
+        __syncthreads();
+        CholeskySmem(lp, dinv, nblk, s_fail);
+        __syncthreads();
+        if (*s_fail != 0) {
+            if (tid == 0 && *info == 0) { *info = col_offset + *s_fail; }
+        }
+        // the last diagonal block's inverse is not produced inside CholeskySmem's loop when it breaks early: it is
+        // (DiagInverse runs before the break), so dinv is complete here.
+        for (int c = warp; c < nk; c += kBatchThreads / 32) {
+            for (int r = (c & ~15) + lane; r < nk; r += 32) { a[r + static_cast<long>(c) * ld] = r >= c ? lp[LowerBlock(r >> 4, c >> 4) + (r & 15) + kNB * (c & 15)] : T(0); }
+        }
+        // zero + identity-pad the inverse, then fill the columns of the active blocks
+        for (int e = tid; e < kPanel * kPanel; e += kBatchThreads) { linv[e] = (e % kPanel == e / kPanel && e / kPanel >= npad) ? T(1) : T(0); }
+        __syncthreads();
+        constexpr int kTq = Smem::kTq;
+        for (int col0 = 0; col0 < npad; col0 += kTq) { InverseColumns<T>(lp, dinv, r_buf, s_buf, nblk, col0, linv); }
+        (void) kLd;
+    }
+
+    template<typename T>
+    __global__ void
+    CopyLowerKernel(const long n, const T *__restrict__ k, const long ld_k, T *__restrict__ l, const long ld_l) {
+        const long r = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        const long c = blockIdx.y;
+        if (r < n) { l[r + c * ld_l] = r >= c ? k[r + c * ld_k] : T(0); }
+    }
+
+    template<typename T>
+    int
+    CopyLower(Context *ctx, long n, const T *k, long ld_k, T *l, long ld_l) {
+        const dim3 grid(static_cast<unsigned>(CeilDiv(n, 256)), static_cast<unsigned>(n));
+        CopyLowerKernel<T><<<grid, 256, 0, ctx->stream>>>(n, k, ld_k, l, ld_l);
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    int
+    Potrf(Context *ctx, long n, T *l, long ld, T *linv, T *panel, int *info) {
+        using Smem = BatchSmem<T, 1, kDiagBlocks>;
+        auto diag = DiagFactorKernel<T>;
+        ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(diag, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Smem::kBytes)));
+        ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
+        for (long k0 = 0, kb = 0; k0 < n; k0 += kPanel, ++kb) {
+            const long nk = n - k0 < kPanel ? n - k0 : kPanel;
+            T *l11 = l + k0 + k0 * ld;
+            T *linv_k = linv + kb * kPanel * kPanel;
+            diag<<<1, kBatchThreads, Smem::kBytes, ctx->stream>>>(l11, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
+            ctx->launches += 1;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            const long m = n - k0 - nk;
+            if (m <= 0) { break; }
+            T *l21 = l + (k0 + nk) + k0 * ld;
+            // panel solve: P = A21 * L11^-T  (GEMM N,T against the kept inverse), then L21 <- P
+            int rc = Gemm<T>(ctx, kOpN, kOpT, m, nk, nk, T(1), l21, ld, linv_k, kPanel, T(0), panel, m, false);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l21, sizeof(T) * ld, panel, sizeof(T) * m, sizeof(T) * m, nk, cudaMemcpyDeviceToDevice, ctx->stream));
+            // trailing update: A22 -= P P^T (lower tiles only)
+            rc = Gemm<T>(ctx, kOpN, kOpT, m, m, nk, T(-1), panel, m, panel, m, T(1), l + (k0 + nk) + (k0 + nk) * ld, ld, true);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+        }
+        return ERL_GP_STATUS_OK;
+    }
+
+    // acc[j] += sum_i s[i + j * lds]^2 for i < rows
+    template<typename T>
+    __global__ void
+    ColSumSqKernel(const long rows, const long t, const T *__restrict__ s, const long lds, T *__restrict__ acc) {
+        const long j = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int lane = threadIdx.x & 31;
+        if (j >= t) { return; }
+        T sum = 0;
+        for (long i = lane; i < rows; i += 32) {
+            const T v = s[i + j * lds];
+            sum += v * v;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, off); }
+        if (lane == 0) { acc[j] += sum; }
+    }
+
+    template<typename T>
+    int
+    TrsmLower(Context *ctx, long n, long t, const T *l, long ld, const T *linv, T *w, long ldw, T *s_buf, T *sumsq, bool keep) {
+        for (long k0 = 0, kb = 0; k0 < n; k0 += kPanel, ++kb) {
+            const long nk = n - k0 < kPanel ? n - k0 : kPanel;
+            // S = L_kk^-1 * W_k
+            int rc = Gemm<T>(ctx, kOpN, kOpN, nk, t, nk, T(1), linv + kb * kPanel * kPanel, kPanel, w + k0, ldw, T(0), s_buf, kPanel, false);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            if (sumsq != nullptr) {
+                ColSumSqKernel<T><<<static_cast<unsigned>(CeilDiv(t, 8)), 256, 0, ctx->stream>>>(nk, t, s_buf, kPanel, sumsq);
+                ctx->launches += 1;
+                ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            }
+            if (keep) { ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(w + k0, sizeof(T) * ldw, s_buf, sizeof(T) * kPanel, sizeof(T) * nk, t, cudaMemcpyDeviceToDevice, ctx->stream)); }
+            const long m = n - k0 - nk;
+            if (m <= 0) { break; }
+            // W_below -= L(below, k) * S
+            rc = Gemm<T>(ctx, kOpN, kOpN, m, t, nk, T(-1), l + (k0 + nk) + k0 * ld, ld, s_buf, kPanel, T(1), w + k0 + nk, ldw, false);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+        }
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    int
+    TrsmLowerTrans(Context *ctx, long n, long t, const T *l, long ld, const T *linv, T *z, long ldz, T *s_buf) {
+        const long num_panels = CeilDiv(n, kPanel);
+        for (long kb = num_panels - 1; kb >= 0; --kb) {
+            const long k0 = kb * kPanel;
+            const long nk = n - k0 < kPanel ? n - k0 : kPanel;
+            // S = L_kk^-T * Z_k
+            int rc = Gemm<T>(ctx, kOpT, kOpN, nk, t, nk, T(1), linv + kb * kPanel * kPanel, kPanel, z + k0, ldz, T(0), s_buf, kPanel, false);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(z + k0, sizeof(T) * ldz, s_buf, sizeof(T) * kPanel, sizeof(T) * nk, t, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (k0 <= 0) { break; }
+            // Z_above -= L(k, above)^T * S
+            rc = Gemm<T>(ctx, kOpT, kOpN, k0, t, nk, T(-1), l + k0, ld, s_buf, kPanel, T(1), z, ldz, false);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+        }
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    __global__ void
+    GemvTKernel(const long n, const long t, const T *__restrict__ w, const long ldw, const T *__restrict__ alpha, const long ld_a, const long y_dim, T *__restrict__ out, const long ld_out) {
+        const long j = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int lane = threadIdx.x & 31;
+        if (j >= t) { return; }
+        for (long c = 0; c < y_dim; ++c) {
+            T sum = 0;
+            for (long i = lane; i < n; i += 32) { sum += w[i + j * ldw] * alpha[i + c * ld_a]; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, off); }
+            if (lane == 0) { out[j + c * ld_out] = sum; }
+        }
+    }
+
+    template<typename T>
+    int
+    GemvT(Context *ctx, long n, long t, const T *w, long ldw, const T *alpha, long ld_a, long y_dim, T *out, long ld_out) {
+        GemvTKernel<T><<<static_cast<unsigned>(CeilDiv(t, 8)), 256, 0, ctx->stream>>>(n, t, w, ldw, alpha, ld_a, y_dim, out, ld_out);
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    __global__ void
+    VarianceFinalizeKernel(const long t, const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ var) {
+        const long j = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (j < t) { var[j] = b != nullptr ? T(1) - a[j] + b[j] : T(1) - a[j]; }  // literal prior 1.0f: src/vanilla_gp.cpp:121, src/sparse_pseudo_input_gp.cpp:291
+    }
+
+    template<typename T>
+    int
+    VarianceFinalize(Context *ctx, long t, const T *a, const T *b, T *var) {
+        VarianceFinalizeKernel<T><<<static_cast<unsigned>(CeilDiv(t, 256)), 256, 0, ctx->stream>>>(t, a, b, var);
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        return ERL_GP_STATUS_OK;
+    }
+
+#define ERL_GP_INSTANTIATE_DENSE(T)                                                                                            \
+    template int Gemm<T>(Context *, int, int, long, long, long, T, const T *, long, const T *, long, T, T *, long, bool);      \
+    template int Potrf<T>(Context *, long, T *, long, T *, T *, int *);                                                        \
+    template int TrsmLower<T>(Context *, long, long, const T *, long, const T *, T *, long, T *, T *, bool);                   \
+    template int TrsmLowerTrans<T>(Context *, long, long, const T *, long, const T *, T *, long, T *);                         \
+    template int CopyLower<T>(Context *, long, const T *, long, T *, long);                                                    \
+    template int GemvT<T>(Context *, long, long, const T *, long, const T *, long, long, T *, long);                           \
+    template int VarianceFinalize<T>(Context *, long, const T *, const T *, T *);
+    ERL_GP_INSTANTIATE_DENSE(float)
+    ERL_GP_INSTANTIATE_DENSE(double)
+#undef ERL_GP_INSTANTIATE_DENSE
+
+}  // namespace erl_gp

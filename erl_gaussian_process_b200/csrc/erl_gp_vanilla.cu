@@ -1,0 +1,419 @@
+// VanillaGaussianProcess (any n, device resident) and dense SparsePseudoInputGaussianProcess on top of
+// the dense building blocks (erl_gp_dense.cuh) and the fused Gram kernels.
+//
+//   VanillaGaussianProcess::UpdateKtrain / Solve      src/vanilla_gp.cpp:476-505
+//   VanillaGaussianProcess::ComputeKtest / Test       src/vanilla_gp.cpp:521-559
+//   TestResult::GetMean / GetVariance                 src/vanilla_gp.cpp:61-150
+//   SparsePseudoInputGaussianProcess ctor / UpdateDense / PrepareLqm / TestResult
+//                                                     src/sparse_pseudo_input_gp.cpp:313-356, 751-791, 835-842, 43-113, 133-163, 280-310
+// Test points are processed in tiles: the n x T Ktest of the reference is never materialised beyond one
+// n x tile workspace (config 5: 16384 x 1e6 doubles would be 122 GiB).
+#include "erl_gp_dense.cuh"
+
+#include <algorithm>
+
+namespace erl_gp {
+
+    // test-point tile: workspace n x tile stays near 256 MiB
+    static long
+    TestTile(const long n, const size_t elem) {
+        long tile = static_cast<long>((size_t(1) << 28) / (static_cast<size_t>(n) * elem));
+        tile = (tile / 128) * 128;
+        if (tile < 256) { tile = 256; }
+        if (tile > 8192) { tile = 8192; }
+        return tile;
+    }
+
+    template<typename T>
+    struct Vanilla {
+        Context *ctx = nullptr;
+        long n = 0, x_dim = 0, y_dim = 0;
+        int kernel = 0;
+        T scale = T(1);
+        bool trained = false;
+        DeviceBuffer<T> x, var, k, l, alpha, linv, panel;
+        DeviceBuffer<int> info;
+        // test workspaces
+        DeviceBuffer<T> xt, w, s_buf, sumsq, mean, variance;
+    };
+
+    template<typename T>
+    static int
+    VanillaTrainDev(Vanilla<T> *gp, int kernel, T scale, long x_dim, long y_dim, long n, const T *x, long ld_x, const T *y, long ld_y, const T *var, cudaMemcpyKind kind) {
+        if (gp == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        gp->trained = false;
+        if (n <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: num_samples = %ld, it should be > 0", n); }  // src/vanilla_gp.cpp:481-484
+        if (x_dim < 1 || x_dim > 3) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "vanilla: x_dim=%ld (supported: 1, 2, 3)", x_dim); }
+        if (y_dim < 1 || ld_x < x_dim || ld_y < n) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: bad y_dim / leading dimensions"); }
+        if (kernel < ERL_GP_KERNEL_OU || kernel > ERL_GP_KERNEL_RBF) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: unknown kernel %d", kernel); }
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        gp->n = n, gp->x_dim = x_dim, gp->y_dim = y_dim, gp->kernel = kernel, gp->scale = scale;
+        const long num_panels = CeilDiv(n, kPanel);
+        ERL_GP_CUDA_OK(ctx, gp->x.Reserve(static_cast<size_t>(n) * x_dim));
+        ERL_GP_CUDA_OK(ctx, gp->var.Reserve(n));
+        ERL_GP_CUDA_OK(ctx, gp->alpha.Reserve(static_cast<size_t>(n) * y_dim));
+        ERL_GP_CUDA_OK(ctx, gp->k.Reserve(static_cast<size_t>(n) * n));
+        ERL_GP_CUDA_OK(ctx, gp->l.Reserve(static_cast<size_t>(n) * n));
+        ERL_GP_CUDA_OK(ctx, gp->linv.Reserve(static_cast<size_t>(num_panels) * kPanel * kPanel));
+        ERL_GP_CUDA_OK(ctx, gp->panel.Reserve(static_cast<size_t>(n) * kPanel));
+        ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * (y_dim > 8192 ? y_dim : 8192)));
+        ERL_GP_CUDA_OK(ctx, gp->info.Reserve(1));
+        // stage the training set (x packed to ld = x_dim); alpha <- y (src/vanilla_gp.cpp:485)
+        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->x.ptr, sizeof(T) * x_dim, x, sizeof(T) * ld_x, sizeof(T) * x_dim, n, kind, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->alpha.ptr, sizeof(T) * n, y, sizeof(T) * ld_y, sizeof(T) * n, y_dim, kind, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->var.ptr, var, sizeof(T) * n, kind, ctx->stream));
+        int rc = LaunchKtrain<T>(ctx, kernel, scale, x_dim, gp->x.ptr, x_dim, gp->var.ptr, n, gp->k.ptr, n);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        rc = CopyLower<T>(ctx, n, gp->k.ptr, n, gp->l.ptr, n);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        rc = Potrf<T>(ctx, n, gp->l.ptr, n, gp->linv.ptr, gp->panel.ptr, gp->info.ptr);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        // alpha = L^-T L^-1 y (src/vanilla_gp.cpp:501-502)
+        rc = TrsmLower<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n, gp->s_buf.ptr, nullptr, true);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        rc = TrsmLowerTrans<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n, gp->s_buf.ptr);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        gp->trained = true;
+        return ERL_GP_STATUS_OK;
+    }
+
+    // mean: num_test x y_dim (ld = num_test) or null; var: num_test or null.  kind selects host / device pointers.
+    template<typename T>
+    static int
+    VanillaTest(Vanilla<T> *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
+        if (gp == nullptr || x_test == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        if (!gp->trained) { return SetError(ctx, ERL_GP_STATUS_NOT_TRAINED, "vanilla: Test() before Train()"); }  // src/vanilla_gp.cpp:556-558
+        if (num_test <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: num_test = %ld, it should be > 0", num_test); }  // :529-532
+        if (ld_xt < gp->x_dim) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: ld_xt < x_dim"); }
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        const long n = gp->n, d = gp->x_dim;
+        const long tile = std::min(TestTile(n, sizeof(T)), ((num_test + 127) / 128) * 128);
+        ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(tile) * d));
+        ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(n) * tile));
+        ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * tile));
+        ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(tile));
+        ERL_GP_CUDA_OK(ctx, gp->mean.Reserve(static_cast<size_t>(tile) * gp->y_dim));
+        ERL_GP_CUDA_OK(ctx, gp->variance.Reserve(tile));
+        for (long t0 = 0; t0 < num_test; t0 += tile) {
+            const long tt = std::min(tile, num_test - t0);
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test + t0 * ld_xt, sizeof(T) * ld_xt, sizeof(T) * d, tt, in_kind, ctx->stream));
+            int rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->x.ptr, d, n, gp->xt.ptr, d, tt, gp->w.ptr, n);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            if (mean != nullptr) {
+                rc = GemvT<T>(ctx, n, tt, gp->w.ptr, n, gp->alpha.ptr, n, gp->y_dim, gp->mean.ptr, tt);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(mean + t0, sizeof(T) * num_test, gp->mean.ptr, sizeof(T) * tt, sizeof(T) * tt, gp->y_dim, out_kind, ctx->stream));
+            }
+            if (var != nullptr) {
+                ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq.ptr, 0, sizeof(T) * tt, ctx->stream));
+                rc = TrsmLower<T>(ctx, n, tt, gp->l.ptr, n, gp->linv.ptr, gp->w.ptr, n, gp->s_buf.ptr, gp->sumsq.ptr, false);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                rc = VarianceFinalize<T>(ctx, tt, gp->sumsq.ptr, nullptr, gp->variance.ptr);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var + t0, gp->variance.ptr, sizeof(T) * tt, out_kind, ctx->stream));
+            }
+        }
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    VanillaGet(Vanilla<T> *gp, T *k, long ld_k, T *l, long ld_l, T *alpha, long ld_a) {
+        if (gp == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        if (!gp->trained) { return SetError(ctx, ERL_GP_STATUS_NOT_TRAINED, "vanilla: not trained"); }
+        const long n = gp->n;
+        if (k != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(k, sizeof(T) * ld_k, gp->k.ptr, sizeof(T) * n, sizeof(T) * n, n, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (l != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l, sizeof(T) * ld_l, gp->l.ptr, sizeof(T) * n, sizeof(T) * n, n, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (alpha != nullptr) {
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(alpha, sizeof(T) * ld_a, gp->alpha.ptr, sizeof(T) * n, sizeof(T) * n, gp->y_dim, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    ReadInfo(Context *ctx, const int *d_info, int *info) {
+        int h = 0;
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(&h, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (info != nullptr) { *info = h; }
+        return ERL_GP_STATUS_OK;
+    }
+
+    // =========================================================================================
+    // SPGP (dense)
+    // =========================================================================================
+    template<typename T>
+    __global__ void
+    SpgpScaleKernel(const long m, const long n, const T *__restrict__ k_mn, const T *__restrict__ sumsq, const T *__restrict__ var, T *__restrict__ k_s) {
+        // Ks[:, i] = K_MN[:, i] / (lambda_i + var_i), lambda_i = 1 - ||beta_i||^2 — src/sparse_pseudo_input_gp.cpp:768-774
+        const long r = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        const long i = blockIdx.y;
+        if (r < m) {
+            const T lambda = T(1) - sumsq[i];
+            k_s[r + i * m] = k_mn[r + i * m] * (T(1) / (lambda + var[i]));
+        }
+    }
+
+    template<typename T>
+    struct Spgp {
+        Context *ctx = nullptr;
+        long m = 0, x_dim = 0;
+        int kernel = 0;
+        T scale = T(1);
+        bool l_qm_updated = false;
+        DeviceBuffer<T> z, k_m, l_km, linv_km, q_m, l_qm, linv_qm, alpha, alpha_solved, panel;
+        DeviceBuffer<int> info;
+        DeviceBuffer<T> x, y, var, k_mn, k_s, w, s_buf, sumsq, sumsq2, xt, mean, variance;
+    };
+
+    template<typename T>
+    static int
+    SpgpCreate(erl_gp_context *c, int kernel, T scale, long x_dim, long m, const T *pseudo, Spgp<T> **out) {
+        Context *ctx = Ctx(c);
+        if (ctx == nullptr || pseudo == nullptr || out == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        *out = nullptr;
+        if (m <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "spgp: pseudo_points must have at least one column"); }  // :319
+        if (x_dim < 1 || x_dim > 3) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "spgp: x_dim=%ld (supported: 1, 2, 3)", x_dim); }
+        if (kernel < ERL_GP_KERNEL_OU || kernel > ERL_GP_KERNEL_RBF) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "spgp: unknown kernel %d", kernel); }
+        auto *gp = new (std::nothrow) Spgp<T>();
+        if (gp == nullptr) { return ERL_GP_STATUS_ALLOC_FAILED; }
+        gp->ctx = ctx, gp->m = m, gp->x_dim = x_dim, gp->kernel = kernel, gp->scale = scale;
+        const size_t mm = static_cast<size_t>(m) * m;
+        const size_t lin = static_cast<size_t>(CeilDiv(m, kPanel)) * kPanel * kPanel;
+        cudaError_t err = cudaSetDevice(ctx->device);
+        if (err == cudaSuccess) { err = gp->z.Reserve(static_cast<size_t>(m) * x_dim); }
+        if (err == cudaSuccess) { err = gp->k_m.Reserve(mm); }
+        if (err == cudaSuccess) { err = gp->l_km.Reserve(mm); }
+        if (err == cudaSuccess) { err = gp->q_m.Reserve(mm); }
+        if (err == cudaSuccess) { err = gp->l_qm.Reserve(mm); }
+        if (err == cudaSuccess) { err = gp->linv_km.Reserve(lin); }
+        if (err == cudaSuccess) { err = gp->linv_qm.Reserve(lin); }
+        if (err == cudaSuccess) { err = gp->alpha.Reserve(m); }
+        if (err == cudaSuccess) { err = gp->alpha_solved.Reserve(m); }
+        if (err == cudaSuccess) { err = gp->panel.Reserve(static_cast<size_t>(m) * kPanel); }
+        if (err == cudaSuccess) { err = gp->info.Reserve(2); }
+        if (err != cudaSuccess) {
+            delete gp;
+            return SetError(ctx, ERL_GP_STATUS_ALLOC_FAILED, "spgp: %s", cudaGetErrorString(err));
+        }
+        int rc = ERL_GP_STATUS_OK;
+        auto fail = [&](int code) {
+            delete gp;
+            return code;
+        };
+        if (cudaMemcpyAsync(gp->z.ptr, pseudo, sizeof(T) * m * x_dim, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { return fail(ERL_GP_STATUS_CUDA_ERROR); }
+        // K_M = ComputeKtest(Z, Z): no noise on the diagonal (:340); L_KM = chol(K_M) (:341); Q_M = K_M (:349); alpha = 0
+        rc = LaunchKtest<T>(ctx, kernel, scale, x_dim, gp->z.ptr, x_dim, m, gp->z.ptr, x_dim, m, gp->k_m.ptr, m);
+        if (rc != ERL_GP_STATUS_OK) { return fail(rc); }
+        rc = CopyLower<T>(ctx, m, gp->k_m.ptr, m, gp->l_km.ptr, m);
+        if (rc != ERL_GP_STATUS_OK) { return fail(rc); }
+        rc = Potrf<T>(ctx, m, gp->l_km.ptr, m, gp->linv_km.ptr, gp->panel.ptr, gp->info.ptr);
+        if (rc != ERL_GP_STATUS_OK) { return fail(rc); }
+        if (cudaMemcpyAsync(gp->q_m.ptr, gp->k_m.ptr, sizeof(T) * mm, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemsetAsync(gp->alpha.ptr, 0, sizeof(T) * m, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            return fail(SetError(ctx, ERL_GP_STATUS_CUDA_ERROR, "spgp: %s", cudaGetErrorString(cudaGetLastError())));
+        }
+        *out = gp;
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    SpgpUpdate(Spgp<T> *gp, long n, const T *x, long ld_x, const T *y, const T *var) {
+        if (gp == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        if (n <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "spgp: no training samples"); }  // :755
+        const long m = gp->m, d = gp->x_dim;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        ERL_GP_CUDA_OK(ctx, gp->x.Reserve(static_cast<size_t>(n) * d));
+        ERL_GP_CUDA_OK(ctx, gp->y.Reserve(n));
+        ERL_GP_CUDA_OK(ctx, gp->var.Reserve(n));
+        ERL_GP_CUDA_OK(ctx, gp->k_mn.Reserve(static_cast<size_t>(m) * n));
+        ERL_GP_CUDA_OK(ctx, gp->k_s.Reserve(static_cast<size_t>(m) * n));
+        ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(m) * n));
+        ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * n));
+        ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(n));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->x.ptr, sizeof(T) * d, x, sizeof(T) * ld_x, sizeof(T) * d, n, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->y.ptr, y, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->var.ptr, var, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+        // K_MN (:759-762), kept; the triangular solve runs on a copy
+        int rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->z.ptr, d, m, gp->x.ptr, d, n, gp->k_mn.ptr, m);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->w.ptr, gp->k_mn.ptr, sizeof(T) * m * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq.ptr, 0, sizeof(T) * n, ctx->stream));
+        rc = TrsmLower<T>(ctx, m, n, gp->l_km.ptr, m, gp->linv_km.ptr, gp->w.ptr, m, gp->s_buf.ptr, gp->sumsq.ptr, false);  // ||L_KM^-1 k_n||^2
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        const dim3 grid(static_cast<unsigned>(CeilDiv(m, 256)), static_cast<unsigned>(n));
+        SpgpScaleKernel<T><<<grid, 256, 0, ctx->stream>>>(m, n, gp->k_mn.ptr, gp->sumsq.ptr, gp->var.ptr, gp->k_s.ptr);
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        // Q_M += Ks K_MN^T (:778) ; alpha += Ks y (:780)
+        rc = Gemm<T>(ctx, kOpN, kOpT, m, m, n, T(1), gp->k_s.ptr, m, gp->k_mn.ptr, m, T(1), gp->q_m.ptr, m, false);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        rc = Gemm<T>(ctx, kOpN, kOpN, m, 1, n, T(1), gp->k_s.ptr, m, gp->y.ptr, n, T(1), gp->alpha.ptr, m, false);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        gp->l_qm_updated = false;
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    SpgpPrepareLqm(Spgp<T> *gp) {  // :835-842 + TestResult ctor :100-106
+        if (gp->l_qm_updated) { return ERL_GP_STATUS_OK; }
+        Context *ctx = gp->ctx;
+        const long m = gp->m;
+        int rc = CopyLower<T>(ctx, m, gp->q_m.ptr, m, gp->l_qm.ptr, m);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        rc = Potrf<T>(ctx, m, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->panel.ptr, gp->info.ptr + 1);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * 8192));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->alpha_solved.ptr, gp->alpha.ptr, sizeof(T) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = TrsmLower<T>(ctx, m, 1, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->alpha_solved.ptr, m, gp->s_buf.ptr, nullptr, true);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        rc = TrsmLowerTrans<T>(ctx, m, 1, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->alpha_solved.ptr, m, gp->s_buf.ptr);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        gp->l_qm_updated = true;
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    SpgpTest(Spgp<T> *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {
+        if (gp == nullptr || x_test == nullptr || num_test <= 0) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        int rc = SpgpPrepareLqm(gp);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        const long m = gp->m, d = gp->x_dim;
+        const long tile = std::min(TestTile(m, sizeof(T)), ((num_test + 127) / 128) * 128);
+        ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(tile) * d));
+        ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(m) * tile));
+        ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * tile));
+        ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(tile));
+        ERL_GP_CUDA_OK(ctx, gp->sumsq2.Reserve(tile));
+        ERL_GP_CUDA_OK(ctx, gp->mean.Reserve(tile));
+        ERL_GP_CUDA_OK(ctx, gp->variance.Reserve(tile));
+        for (long t0 = 0; t0 < num_test; t0 += tile) {
+            const long tt = std::min(tile, num_test - t0);
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test + t0 * ld_xt, sizeof(T) * ld_xt, sizeof(T) * d, tt, cudaMemcpyHostToDevice, ctx->stream));
+            rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->z.ptr, d, m, gp->xt.ptr, d, tt, gp->w.ptr, m);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            if (mean != nullptr) {  // mean = Kt^T Q_M^-1 alpha (:150-162)
+                rc = GemvT<T>(ctx, m, tt, gp->w.ptr, m, gp->alpha_solved.ptr, m, 1, gp->mean.ptr, tt);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean + t0, gp->mean.ptr, sizeof(T) * tt, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (var != nullptr) {  // var = 1 - ||L_KM^-1 kt||^2 + ||L_QM^-1 kt||^2 (:288-292, :304-309)
+                ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq.ptr, 0, sizeof(T) * tt, ctx->stream));
+                ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq2.ptr, 0, sizeof(T) * tt, ctx->stream));
+                rc = TrsmLower<T>(ctx, m, tt, gp->l_km.ptr, m, gp->linv_km.ptr, gp->w.ptr, m, gp->s_buf.ptr, gp->sumsq.ptr, false);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->z.ptr, d, m, gp->xt.ptr, d, tt, gp->w.ptr, m);  // the solve consumed Kt: regenerate
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                rc = TrsmLower<T>(ctx, m, tt, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->w.ptr, m, gp->s_buf.ptr, gp->sumsq2.ptr, false);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                rc = VarianceFinalize<T>(ctx, tt, gp->sumsq.ptr, gp->sumsq2.ptr, gp->variance.ptr);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var + t0, gp->variance.ptr, sizeof(T) * tt, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        }
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    SpgpGet(Spgp<T> *gp, T *q_m, T *alpha, T *l_km, T *l_qm) {
+        if (gp == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        const size_t mm = static_cast<size_t>(gp->m) * gp->m;
+        if (l_qm != nullptr) {
+            const int rc = SpgpPrepareLqm(gp);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(l_qm, gp->l_qm.ptr, sizeof(T) * mm, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (q_m != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(q_m, gp->q_m.ptr, sizeof(T) * mm, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (alpha != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(alpha, gp->alpha.ptr, sizeof(T) * gp->m, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (l_km != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(l_km, gp->l_km.ptr, sizeof(T) * mm, cudaMemcpyDeviceToHost, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+}  // namespace erl_gp
+
+using namespace erl_gp;
+
+struct erl_gp_vanilla_f32 : Vanilla<float> {};
+struct erl_gp_vanilla_f64 : Vanilla<double> {};
+struct erl_gp_spgp_f32 : Spgp<float> {};
+struct erl_gp_spgp_f64 : Spgp<double> {};
+
+extern "C" {
+
+#define ERL_GP_DEFINE_DENSE(T, SFX)                                                                                                                                          \
+    int erl_gp_vanilla_create_##SFX(erl_gp_context *ctx, erl_gp_vanilla_##SFX **gp) {                                                                                        \
+        if (ctx == nullptr || gp == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                                                      \
+        auto *v = new (std::nothrow) Vanilla<T>();                                                                                                                           \
+        if (v == nullptr) { return ERL_GP_STATUS_ALLOC_FAILED; }                                                                                                             \
+        v->ctx = Ctx(ctx);                                                                                                                                                   \
+        *gp = static_cast<erl_gp_vanilla_##SFX *>(v);                                                                                                                        \
+        return ERL_GP_STATUS_OK;                                                                                                                                             \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_destroy_##SFX(erl_gp_vanilla_##SFX *gp) {                                                                                                             \
+        if (gp != nullptr) {                                                                                                                                                 \
+            cudaSetDevice(gp->ctx->device);                                                                                                                                  \
+            cudaStreamSynchronize(gp->ctx->stream);                                                                                                                          \
+            delete static_cast<Vanilla<T> *>(gp);                                                                                                                            \
+        }                                                                                                                                                                    \
+        return ERL_GP_STATUS_OK;                                                                                                                                             \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_train_##SFX(erl_gp_vanilla_##SFX *gp, int kernel, T scale, long x_dim, long y_dim, long n, const T *x, long ld_x, const T *y, long ld_y,              \
+                                   const T *var, int *info) {                                                                                                                \
+        const int rc = VanillaTrainDev<T>(gp, kernel, scale, x_dim, y_dim, n, x, ld_x, y, ld_y, var, cudaMemcpyHostToDevice);                                                \
+        if (rc != ERL_GP_STATUS_OK) { return rc; }                                                                                                                           \
+        return ReadInfo<T>(gp->ctx, gp->info.ptr, info);                                                                                                                     \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_train_dev_##SFX(erl_gp_vanilla_##SFX *gp, int kernel, T scale, long x_dim, long y_dim, long n, const T *x, long ld_x, const T *y, long ld_y,          \
+                                       const T *var) {                                                                                                                       \
+        return VanillaTrainDev<T>(gp, kernel, scale, x_dim, y_dim, n, x, ld_x, y, ld_y, var, cudaMemcpyDeviceToDevice);                                                      \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_info_##SFX(erl_gp_vanilla_##SFX *gp, int *info) {                                                                                                     \
+        if (gp == nullptr || info == nullptr || gp->info.ptr == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                          \
+        return ReadInfo<T>(gp->ctx, gp->info.ptr, info);                                                                                                                     \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_get_##SFX(erl_gp_vanilla_##SFX *gp, T *k, long ld_k, T *l, long ld_l, T *alpha, long ld_a) { return VanillaGet<T>(gp, k, ld_k, l, ld_l, alpha, ld_a); } \
+    int erl_gp_vanilla_test_##SFX(erl_gp_vanilla_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                                                   \
+        const int rc = VanillaTest<T>(gp, num_test, x_test, ld_xt, mean, var, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost);                                               \
+        if (rc != ERL_GP_STATUS_OK) { return rc; }                                                                                                                           \
+        return erl_gp_context_synchronize(gp->ctx);                                                                                                                          \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_test_dev_##SFX(erl_gp_vanilla_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                                               \
+        return VanillaTest<T>(gp, num_test, x_test, ld_xt, mean, var, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);                                                   \
+    }                                                                                                                                                                        \
+    int erl_gp_spgp_create_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, long num_pseudo, const T *pseudo_points, erl_gp_spgp_##SFX **gp) {                    \
+        return SpgpCreate<T>(ctx, kernel, scale, x_dim, num_pseudo, pseudo_points, reinterpret_cast<Spgp<T> **>(gp));                                                        \
+    }                                                                                                                                                                        \
+    int erl_gp_spgp_destroy_##SFX(erl_gp_spgp_##SFX *gp) {                                                                                                                   \
+        if (gp != nullptr) {                                                                                                                                                 \
+            cudaSetDevice(gp->ctx->device);                                                                                                                                  \
+            cudaStreamSynchronize(gp->ctx->stream);                                                                                                                          \
+            delete static_cast<Spgp<T> *>(gp);                                                                                                                               \
+        }                                                                                                                                                                    \
+        return ERL_GP_STATUS_OK;                                                                                                                                             \
+    }                                                                                                                                                                        \
+    int erl_gp_spgp_update_##SFX(erl_gp_spgp_##SFX *gp, long n, const T *x, long ld_x, const T *y, const T *var) { return SpgpUpdate<T>(gp, n, x, ld_x, y, var); }           \
+    int erl_gp_spgp_test_##SFX(erl_gp_spgp_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                                                         \
+        return SpgpTest<T>(gp, num_test, x_test, ld_xt, mean, var);                                                                                                          \
+    }                                                                                                                                                                        \
+    int erl_gp_spgp_get_##SFX(erl_gp_spgp_##SFX *gp, T *q_m, T *alpha, T *l_km, T *l_qm) { return SpgpGet<T>(gp, q_m, alpha, l_km, l_qm); }
+
+ERL_GP_DEFINE_DENSE(float, f32)
+ERL_GP_DEFINE_DENSE(double, f64)
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""GPU parity: dense VanillaGaussianProcess (blocked Cholesky + GEMM-based solves) and SPGP vs the oracle
+and the reference's known-answer values."""
+import numpy as np
+import pytest
+
+from tests.util import TOL, err_mean, err_var
+
+pytestmark = pytest.mark.gpu
+
+KAT_SISO = 0.00024246430481069056  # test/gtest/test_vanilla_gp.cpp:103
+KAT_MIMO = (0.0005035569336460478, 0.0011257545588707807)  # :366-367
+KAT_SPGP = 0.00013951539277877418  # test/gtest/test_sparse_pseudo_input_gp.cpp:109
+
+
+@pytest.fixture(scope="module")
+def gp():
+    import erl_gaussian_process_b200 as m
+
+    return m
+
+
+def _vanilla_pair(gp, oracle, dtype, kernel, scale, x, y, var):
+    s = gp.VanillaGaussianProcess.Setting(kernel, scale, max_num_samples=len(x))
+    g = gp.VanillaGaussianProcess(s, dtype)
+    assert g.train(x, y, var)
+    assert g.info == 0
+    o = oracle.VanillaGp(oracle.KERNELS[kernel], scale, dtype, max_num_samples=len(x))
+    assert o.train(x, y, var) == 0
+    return g, o
+
+
+def test_vanilla_kat_siso(gp, oracle):
+    n, t = 100, 200
+    x = np.linspace(0, 2 * np.pi, n)[:, None]
+    xt = np.linspace(0, 2 * np.pi, t)[:, None]
+    g, o = _vanilla_pair(gp, oracle, np.float64, "rbf", 0.5, x, np.sin(x[:, 0]), np.full(n, 1e-3))
+    res = g.test(xt)
+    mean = res.get_mean(0)
+    mae = np.abs(mean - np.sin(xt[:, 0])).mean()
+    assert mae == pytest.approx(KAT_SISO, rel=1e-8)
+    assert mae < 3.0e-4
+    m_ref, v_ref = o.test(xt)
+    assert err_mean(mean, m_ref) < 1e-10 and err_var(res.get_variance(), v_ref) < 1e-10
+
+
+def test_vanilla_kat_mimo(gp, oracle):
+    g1 = np.linspace(-1, 1, 50)
+    tr = np.array([[a, b] for a in g1 for b in g1])
+    g2 = np.linspace(-1, 1, 100)
+    te = np.array([[a, b] for a in g2 for b in g2])
+    f1 = lambda p: 2 * np.sin(10 * p[:, 0]) * np.cos(10 * p[:, 1])
+    f2 = lambda p: 3 * (np.sin(10 * p[:, 0]) + np.cos(10 * p[:, 1]))
+    s = gp.VanillaGaussianProcess.Setting("rbf", 0.1, max_num_samples=len(tr))
+    g = gp.VanillaGaussianProcess(s, np.float64)
+    assert g.train(tr, np.stack([f1(tr), f2(tr)], axis=1), np.full(len(tr), 1e-3))
+    res = g.test(te)
+    mae1 = np.abs(res.get_mean(0) - f1(te)).mean()
+    mae2 = np.abs(res.get_mean(1) - f2(te)).mean()
+    # cond(K) ~ 1e7 here: agreement with the reference's printed value to ~1e-6 relative
+    assert mae1 == pytest.approx(KAT_MIMO[0], rel=1e-5)
+    assert mae2 == pytest.approx(KAT_MIMO[1], rel=1e-5)
+    assert mae1 < 5.1e-4 and mae2 < 1.2e-3
+
+
+def test_vanilla_c1(gp, oracle):
+    """BASELINE config 1: VanillaGp<double>, Matern32 l = 0.25, N = 1024, T = 8192, 2-D."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, (1024, 2))
+    y = 2 * np.sin(10 * x[:, 0]) * np.cos(10 * x[:, 1])
+    var = np.full(1024, 1e-3)
+    xt = np.random.default_rng(2).uniform(-1, 1, (8192, 2))
+    g, o = _vanilla_pair(gp, oracle, np.float64, "matern32", 0.25, x, y, var)
+    res = g.test(xt)
+    m_ref, v_ref = o.test(xt)
+    em, ev = err_mean(res.get_mean(0), m_ref), err_var(res.get_variance(), v_ref)
+    assert em < 1e-10, em
+    assert ev < 1e-10, ev
+    k, l, a = g.get()
+    k_ref, l_ref, a_ref = o.get()
+    assert np.abs(k - k_ref).max() < 1e-13
+    assert np.abs(np.triu(l, 1)).max() == 0
+    assert np.abs(l - l_ref).max() / np.abs(l_ref).max() < 1e-11
+    assert np.abs(a - a_ref).max() / np.abs(a_ref).max() < 1e-8
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,t,d,kernel,scale,ydim", [(5, 3, 1, "ou", 0.5, 1), (129, 300, 3, "matern32", 0.5, 1), (700, 1000, 2, "matern32", 0.3, 2), (384, 130, 2, "ou", 0.2, 1)])
+def test_vanilla_shapes(gp, oracle, dtype, n, t, d, kernel, scale, ydim):
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, (n, d)).astype(dtype)
+    y = np.stack([np.sin(3 * x).sum(axis=1) * (c + 1) for c in range(ydim)], axis=1).astype(dtype)
+    var = rng.uniform(0.005, 0.02, n).astype(dtype)
+    xt = rng.uniform(-1, 1, (t, d)).astype(dtype)
+    g, o = _vanilla_pair(gp, oracle, dtype, kernel, scale, x, y if ydim > 1 else y[:, 0], var)
+    res = g.test(xt)
+    m_ref, v_ref = o.test(xt)
+    tol = TOL[np.dtype(dtype)]
+    for c in range(ydim):
+        ref_c = m_ref[:, c] if ydim > 1 else m_ref
+        assert err_mean(res.get_mean(c), ref_c) < tol
+    assert err_var(res.get_variance(), v_ref) < tol
+
+
+def test_vanilla_misuse(gp):
+    s = gp.VanillaGaussianProcess.Setting("rbf", 0.5, max_num_samples=10)
+    g = gp.VanillaGaussianProcess(s, np.float64)
+    assert g.test(np.zeros((3, 1))) is None  # not trained -> nullptr (src/vanilla_gp.cpp:556-558)
+    with pytest.raises(ValueError):
+        g.train(np.zeros((11, 1)), np.zeros(11), np.ones(11))  # > max_num_samples asserts (:389-392)
+    assert not g.train(np.zeros((0, 1)), np.zeros(0), np.zeros(0))
+    x = np.linspace(0, 1, 8)[:, None]
+    assert g.train(x, np.sin(x[:, 0]), np.full(8, -3.0))  # not SPD: the reference does not check either
+    assert g.info > 0
+
+
+def test_spgp_kat_and_oracle(gp, oracle):
+    m, n, t = 20, 1000, 200
+    z = np.linspace(0, 2 * np.pi, m)[:, None]
+    x = np.linspace(0, 2 * np.pi, n)[:, None]
+    y = np.sin(x[:, 0])
+    xt = np.linspace(0, 2 * np.pi, t)[:, None]
+    var = np.full(n, 1e-3)
+    g = gp.SparsePseudoInputGaussianProcess("rbf", 0.6, z, np.float64)
+    assert g.update(x, y, var)
+    mean, variance = g.test(xt)
+    mae = np.abs(mean - np.sin(xt[:, 0])).mean()
+    assert mae == pytest.approx(KAT_SPGP, rel=2e-4)  # cond(K_M) ~ 1e6: 5 digits
+    assert mae < 4.02e-4
+    o = oracle.Spgp(oracle.RBF, 0.6, z, np.float64)
+    o.update(x, y, var)
+    m_ref, v_ref = o.test(xt)
+    assert err_mean(mean, m_ref) < 1e-6 and err_var(variance, v_ref) < 1e-6  # limited by cond(K_M)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_spgp_2d_incremental(gp, oracle, dtype):
+    """Occupancy-map shaped use: Matern32 2-D pseudo-point grid, several incremental updates (config/spgp_occupancy_map_2d.yaml)."""
+    rng = np.random.default_rng(4)
+    gx = np.linspace(-3, 3, 18)
+    z = np.array([[a, b] for a in gx for b in gx])  # M = 324 (not a multiple of 128)
+    g = gp.SparsePseudoInputGaussianProcess("matern32", 0.6, z, dtype)
+    o = oracle.Spgp(oracle.MATERN32, 0.6, z, dtype)
+    for it in range(3):
+        x = rng.uniform(-3, 3, (500 + 37 * it, 2))
+        y = np.tanh(x[:, 0] * x[:, 1])
+        var = np.full(len(x), 1e-2)
+        assert g.update(x, y, var) and o.update(x, y, var)
+    xt = rng.uniform(-3, 3, (1000, 2))
+    mean, variance = g.test(xt)
+    m_ref, v_ref = o.test(xt)
+    tol = 2e-3 if dtype == np.float32 else 1e-9
+    assert err_mean(mean, m_ref) < tol
+    assert err_var(variance, v_ref) < tol
+    q, a, lk, lq = g.get()
+    q_ref, a_ref, lk_ref, lq_ref = o.get()
+    rel = 1e-4 if dtype == np.float32 else 1e-11
+    assert np.abs(q - q_ref).max() / np.abs(q_ref).max() < rel
+    assert np.abs(a - a_ref).max() / np.abs(a_ref).max() < rel
+    assert np.abs(lk - lk_ref).max() / np.abs(lk_ref).max() < (1e-3 if dtype == np.float32 else 1e-10)

@@ -1,0 +1,206 @@
+// RangeSensorGaussianProcess3D<Dtype> — drop-in host class over the C ABI
+// (include/erl_gaussian_process/range_sensor_gp_3d.hpp, src/range_sensor_gp_3d.cpp).
+#pragma once
+
+#include "mapping.hpp"
+#include "sensor_frames.hpp"
+#include "vanilla_gp.hpp"
+
+#include <tuple>
+
+namespace erl::gaussian_process {
+
+    template<typename Dtype>
+    class RangeSensorGaussianProcess3D {
+    public:
+        using Gp = VanillaGaussianProcess<Dtype>;
+        using MappingDtype = Mapping<Dtype>;
+        using RangeSensorFrame = geometry::LidarFrame3D<Dtype>;
+        using Matrix3 = Eigen::Matrix3<Dtype>;
+        using Matrix3X = Eigen::Matrix3X<Dtype>;
+        using Vector3 = Eigen::Vector3<Dtype>;
+        using MatrixX = Eigen::MatrixX<Dtype>;
+        using VectorX = Eigen::VectorX<Dtype>;
+        using Api = b200::Api<Dtype>;
+
+        struct Setting {  // defaults: include/erl_gaussian_process/range_sensor_gp_3d.hpp:31-74
+            long row_group_size = 24;
+            long row_overlap_size = 6;
+            long row_margin = 0;
+            long col_group_size = 8;
+            long col_overlap_size = 2;
+            long col_margin = 0;
+            long min_num_samples_per_group = 32;
+            Dtype init_variance = 1e6f;
+            Dtype sensor_range_var = 0.01f;
+            Dtype max_valid_range_var = 0.1f;
+            Dtype occ_test_temperature = 30.0f;
+            std::string sensor_frame_type = "erl::geometry::LidarFrame3D";
+            std::shared_ptr<typename RangeSensorFrame::Setting> sensor_frame = std::make_shared<typename RangeSensorFrame::Setting>();
+            std::shared_ptr<typename Gp::Setting> gp = std::make_shared<typename Gp::Setting>();
+            std::shared_ptr<typename MappingDtype::Setting> mapping = []() {
+                auto s = std::make_shared<typename MappingDtype::Setting>();
+                s->type = MappingType::kInverseSqrt;
+                s->scale = 1.0;
+                return s;
+            }();
+        };
+
+        class TestResult {
+        protected:
+            VectorX m_mean_, m_var_;
+            Eigen::VectorXb m_valid_;
+
+        public:
+            TestResult(const RangeSensorGaussianProcess3D *gp, const Eigen::Ref<const Matrix3X> &directions, const bool directions_are_local, const bool un_map) {
+                const long n = directions.cols();
+                MatrixX coords(2, n);
+                Eigen::VectorXb coords_ok(n);
+                const RangeSensorFrame *frame = gp->m_sensor_frame_.get();
+                for (long i = 0; i < n; ++i) {  // DirWorldToFrame + ComputeFrameCoords, src/range_sensor_gp_3d.cpp:81-85
+                    Dtype dir[3] = {directions(0, i), directions(1, i), directions(2, i)};
+                    if (!directions_are_local) {
+                        Dtype local[3];
+                        frame->DirWorldToFrame(dir, local);
+                        dir[0] = local[0], dir[1] = local[1], dir[2] = local[2];
+                    }
+                    Dtype dist;
+                    coords_ok[i] = frame->ComputeFrameCoords(dir, dist, &coords(0, i));
+                }
+                m_mean_.resize(n);
+                m_var_.resize(n);
+                m_valid_.resize(n);
+                gp->m_ctx_->Check(Api::range3d_test(gp->m_handle_, coords.data(), coords_ok.data(), n, un_map, m_mean_.data(), m_var_.data(), m_valid_.data()), "erl_gp_range3d_test");
+            }
+
+            [[nodiscard]] long
+            GetNumTest() const {
+                return m_mean_.size();
+            }
+
+            [[nodiscard]] Eigen::VectorXb
+            GetMean(Eigen::Ref<VectorX> vec_f_out, const bool parallel) const {
+                (void) parallel;
+                for (long i = 0; i < m_mean_.size(); ++i) {
+                    if (m_valid_[i]) { vec_f_out[i] = m_mean_[i]; }
+                }
+                return m_valid_;
+            }
+
+            [[nodiscard]] Eigen::VectorXb
+            GetVariance(Eigen::Ref<VectorX> vec_var_out, const bool parallel) const {
+                (void) parallel;
+                for (long i = 0; i < m_var_.size(); ++i) {
+                    if (m_valid_[i]) { vec_var_out[i] = m_var_[i]; }
+                }
+                return m_valid_;
+            }
+        };
+
+    protected:
+        std::shared_ptr<Setting> m_setting_ = nullptr;
+        std::shared_ptr<b200::DeviceContext> m_ctx_ = nullptr;
+        typename Api::Range3d *m_handle_ = nullptr;
+        bool m_trained_ = false;
+        std::vector<std::tuple<long, long, Dtype, Dtype>> m_row_partitions_, m_col_partitions_;
+        std::shared_ptr<RangeSensorFrame> m_sensor_frame_ = nullptr;
+        std::shared_ptr<MappingDtype> m_mapping_ = nullptr;
+
+    public:
+        explicit RangeSensorGaussianProcess3D(std::shared_ptr<Setting> setting, std::shared_ptr<b200::DeviceContext> ctx = nullptr)
+            : m_setting_(std::move(setting)),
+              m_ctx_(ctx ? std::move(ctx) : b200::DeviceContext::Default()),
+              m_sensor_frame_(std::make_shared<RangeSensorFrame>(m_setting_->sensor_frame)),
+              m_mapping_(MappingDtype::Create(m_setting_->mapping)) {
+            b200::AssertM(m_setting_->row_overlap_size % 2 == 0, "row_overlap_size must be even.");  // src/range_sensor_gp_3d.cpp:190-193
+            b200::AssertM(m_setting_->col_overlap_size % 2 == 0, "col_overlap_size must be even.");  // :194-197
+            m_setting_->gp->max_num_samples = m_setting_->row_group_size * m_setting_->col_group_size;  // :213
+            m_setting_->gp->kernel->x_dim = 2;                                                        // :214
+            erl_gp_range3d_setting s{};
+            s.row_group_size = m_setting_->row_group_size, s.row_overlap_size = m_setting_->row_overlap_size, s.row_margin = m_setting_->row_margin;
+            s.col_group_size = m_setting_->col_group_size, s.col_overlap_size = m_setting_->col_overlap_size, s.col_margin = m_setting_->col_margin;
+            s.min_num_samples_per_group = m_setting_->min_num_samples_per_group;
+            s.sensor_range_var = m_setting_->sensor_range_var;
+            s.kernel = covariance::KernelFromTypeName(m_setting_->gp->kernel_type);
+            s.kernel_scale = m_setting_->gp->kernel->scale;
+            s.mapping = static_cast<int>(m_setting_->mapping->type);
+            s.mapping_scale = m_setting_->mapping->scale;
+            m_ctx_->Check(Api::range3d_create(m_ctx_->Get(), &s, m_sensor_frame_->GetFrameCoordsData(), m_sensor_frame_->Rows(), m_sensor_frame_->Cols(), &m_handle_), "erl_gp_range3d_create");
+            long nr = 0, nc = 0;
+            m_ctx_->Check(Api::range3d_grid(m_handle_, &nr, &nc), "erl_gp_range3d_grid");
+            for (int axis = 0; axis < 2; ++axis) {
+                const long num = axis == 0 ? nr : nc;
+                std::vector<long> il(num), ir(num);
+                std::vector<Dtype> cl(num), cr(num);
+                m_ctx_->Check(Api::range3d_partitions(m_handle_, axis, il.data(), ir.data(), cl.data(), cr.data()), "erl_gp_range3d_partitions");
+                auto &dst = axis == 0 ? m_row_partitions_ : m_col_partitions_;
+                for (long i = 0; i < num; ++i) { dst.emplace_back(il[i], ir[i], cl[i], cr[i]); }
+            }
+        }
+
+        RangeSensorGaussianProcess3D(const RangeSensorGaussianProcess3D &) = delete;
+        RangeSensorGaussianProcess3D &
+        operator=(const RangeSensorGaussianProcess3D &) = delete;
+
+        ~RangeSensorGaussianProcess3D() { Api::range3d_destroy(m_handle_); }
+
+        [[nodiscard]] bool
+        IsTrained() const {
+            return m_trained_;
+        }
+
+        [[nodiscard]] std::shared_ptr<const Setting>
+        GetSetting() const {
+            return m_setting_;
+        }
+
+        [[nodiscard]] const std::vector<std::tuple<long, long, Dtype, Dtype>> &
+        GetRowPartitions() const {
+            return m_row_partitions_;
+        }
+
+        [[nodiscard]] const std::vector<std::tuple<long, long, Dtype, Dtype>> &
+        GetColPartitions() const {
+            return m_col_partitions_;
+        }
+
+        [[nodiscard]] std::shared_ptr<const RangeSensorFrame>
+        GetSensorFrame() const {
+            return m_sensor_frame_;
+        }
+
+        void
+        Reset() {
+            m_trained_ = false;
+        }
+
+        [[nodiscard]] bool
+        GetGp(const long row_part, const long col_part, long &n, MatrixX &mat_l, VectorX &alpha) const {
+            const long max_n = m_setting_->row_group_size * m_setting_->col_group_size;
+            int info = -1;
+            mat_l.resize(max_n, max_n);
+            alpha.resize(max_n);
+            m_ctx_->Check(Api::range3d_get_gp(m_handle_, row_part, col_part, &info, &n, mat_l.data(), max_n, alpha.data()), "erl_gp_range3d_get_gp");
+            return info == 0;
+        }
+
+        [[nodiscard]] bool
+        Train(const Matrix3 &rotation, const Vector3 &translation, MatrixX ranges) {  // src/range_sensor_gp_3d.cpp:321-364
+            Reset();
+            m_sensor_frame_->UpdateRanges(rotation, translation, std::move(ranges));
+            if (!m_sensor_frame_->IsValid()) { return false; }
+            m_ctx_->Check(Api::range3d_train(m_handle_, m_sensor_frame_->GetRanges().data(), m_sensor_frame_->GetHitMask().data()), "erl_gp_range3d_train");
+            m_trained_ = true;
+            return true;
+        }
+
+        [[nodiscard]] std::shared_ptr<TestResult>
+        Test(const Eigen::Ref<const Matrix3X> &directions, const bool directions_are_local, const bool un_map) const {
+            if (!m_trained_) { return nullptr; }
+            return std::make_shared<TestResult>(this, directions, directions_are_local, un_map);
+        }
+    };
+
+    using RangeSensorGaussianProcess3Dd = RangeSensorGaussianProcess3D<double>;
+    using RangeSensorGaussianProcess3Df = RangeSensorGaussianProcess3D<float>;
+}  // namespace erl::gaussian_process

@@ -511,8 +511,9 @@ namespace erl_gp_oracle {
         // Setting (include/erl_gaussian_process/lidar_gp_2d.hpp:28-71)
         bool symmetric_partitions = true;
         long group_size = 26, overlap_size = 6, margin = 1;
-        T sensor_range_var = T(0.01), discontinuity_var = T(10), max_valid_range_var = T(0.1);
-        T occ_test_temperature = T(30);
+        // float literals, as the reference's defaults (lidar_gp_2d.hpp:42-53): 0.01f widened to double is not 0.01
+        T sensor_range_var = 0.01f, discontinuity_var = 10.0f, max_valid_range_var = 0.1f;
+        T occ_test_temperature = 30.0f;
         bool discontinuity_detection = false;
         int kernel_type = kOrnsteinUhlenbeck;
         T kernel_scale = T(1);
@@ -655,7 +656,7 @@ namespace erl_gp_oracle {
         long row_group_size = 24, row_overlap_size = 6, row_margin = 0;
         long col_group_size = 8, col_overlap_size = 2, col_margin = 0;
         long min_num_samples_per_group = 32;
-        T sensor_range_var = T(0.01), max_valid_range_var = T(0.1), occ_test_temperature = T(30);
+        T sensor_range_var = 0.01f, max_valid_range_var = 0.1f, occ_test_temperature = 30.0f;  // range_sensor_gp_3d.hpp:45-52
         int kernel_type = kOrnsteinUhlenbeck;
         T kernel_scale = T(1);
         int mapping_type = kInverseSqrt;

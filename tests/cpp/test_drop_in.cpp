@@ -1,0 +1,268 @@
+// C++ parity driver for the drop-in host classes (erl_gaussian_process_b200/cpp): written the way the
+// reference's gtests drive the API (test/gtest/test_vanilla_gp.cpp:13-45, test_lidar_gp_2d.cpp:130-175) and
+// checked against the CPU oracle.  TEST INFRASTRUCTURE: this is the only C++ translation unit that includes the
+// oracle.  Needs a CUDA device; run by tests/test_gpu_cpp_dropin.py.
+#include "erl_gaussian_process_b200/lidar_gp_2d.hpp"
+#include "erl_gaussian_process_b200/range_sensor_gp_3d.hpp"
+#include "erl_gaussian_process_b200/vanilla_gp.hpp"
+
+#include "../../oracle/erl_gp_oracle.hpp"
+
+#include <cstdio>
+#include <random>
+
+using namespace erl::gaussian_process;
+
+static int g_failures = 0;
+
+#define CHECK(cond, ...)                                      \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            ++g_failures;                                     \
+            std::printf("FAIL %s:%d %s ", __FILE__, __LINE__, #cond); \
+            std::printf(__VA_ARGS__);                         \
+            std::printf("\n");                                \
+        }                                                     \
+    } while (0)
+
+template<typename Dtype>
+static void
+TestVanillaSiso(const char *name, const double tol) {
+    // test/gtest/test_vanilla_gp.cpp:13-45: RBF 1-D, l = 0.5, n = 100, y = sin(x), 200 test points
+    constexpr long n = 100, n_test = 200;
+    auto setting = std::make_shared<typename VanillaGaussianProcess<Dtype>::Setting>();
+    setting->kernel->scale = 0.5;
+    setting->kernel->x_dim = 1;
+    setting->kernel_type = "erl::covariance::RadialBiasFunction1d";
+    setting->max_num_samples = n;
+    VanillaGaussianProcess<Dtype> gp(setting);
+    CHECK(gp.Test(Eigen::MatrixX<Dtype>(1, 3)) == nullptr, "Test before Train must return nullptr");
+    gp.Reset(n, 1, 1);
+    auto &train_set = gp.GetTrainSet();
+    erl_gp_oracle::VanillaGp<Dtype> ref;
+    ref.kernel_type = erl_gp_oracle::kRadialBiasFunction;
+    ref.scale = 0.5;
+    ref.max_num_samples_setting = n;
+    ref.Reset(n, 1, 1);
+    for (long i = 0; i < n; ++i) {
+        const Dtype x = Dtype(2 * M_PI * i / (n - 1));
+        train_set.x(0, i) = x;
+        train_set.y(i, 0) = std::sin(x);
+        train_set.var[i] = Dtype(0.001);
+        ref.x[i] = x, ref.y[i] = std::sin(x), ref.var[i] = Dtype(0.001);
+    }
+    train_set.num_samples = n;
+    ref.num_samples = n;
+    CHECK(gp.Train(), "Train");
+    CHECK(!gp.Train(), "second Train without Reset must return false (src/vanilla_gp.cpp:511-514)");
+    CHECK(ref.Train(), "oracle Train");
+    Eigen::MatrixX<Dtype> x_test(1, n_test);
+    for (long i = 0; i < n_test; ++i) { x_test(0, i) = Dtype(2 * M_PI * i / (n_test - 1)); }
+    auto result = gp.Test(x_test);
+    CHECK(result != nullptr, "Test");
+    Eigen::VectorX<Dtype> mean(n_test), var(n_test);
+    result->GetMean(0, mean, true);
+    result->GetVariance(var, true);
+    std::vector<Dtype> m_ref(n_test), v_ref(n_test);
+    ref.Test(x_test.data(), 1, n_test, m_ref.data(), v_ref.data(), true);
+    double em = 0, ev = 0, mae = 0;
+    for (long i = 0; i < n_test; ++i) {
+        em = std::max(em, std::abs(double(mean[i]) - double(m_ref[i])));
+        ev = std::max(ev, std::abs(double(var[i]) - double(v_ref[i])));
+        mae += std::abs(double(mean[i]) - std::sin(double(x_test(0, i)))) / n_test;
+    }
+    CHECK(em < tol && ev < tol, "mean err %.3e var err %.3e", em, ev);
+    if (sizeof(Dtype) == 8) { CHECK(std::abs(mae - 0.00024246430481069056) < 1e-11, "KAT test_vanilla_gp.cpp:103 mae=%.17g", mae); }
+    CHECK(mae < 3.0e-4, "reference threshold");
+    // host materialisation of L / alpha
+    const auto &mat_l = gp.GetCholeskyDecomposition();
+    double el = 0;
+    for (long c = 0; c < n; ++c) {
+        for (long r = 0; r < n; ++r) { el = std::max(el, std::abs(double(mat_l(r, c)) - double(ref.mat_l[r + c * ref.ld]))); }
+    }
+    CHECK(el < tol * 10, "L err %.3e", el);
+    CHECK(gp.GetLltInfo() == 0, "llt info");
+    std::printf("%s %s: mean err %.2e, var err %.2e, mae %.6e\n", g_failures ? "----" : "PASS", name, em, ev, mae);
+}
+
+template<typename Dtype>
+static void
+TestLidar(const char *name, const double tol) {
+    // synthetic 1080-beam scan, group 64 / overlap 18 (BASELINE config 2), OU l = 0.05
+    using Lidar = LidarGaussianProcess2D<Dtype>;
+    constexpr long n = 1080, n_test = 20000;
+    auto setting = std::make_shared<typename Lidar::Setting>();
+    setting->group_size = 64;
+    setting->overlap_size = 18;
+    setting->margin = 1;
+    setting->sensor_frame->angle_min = Dtype(-3 * M_PI / 4);
+    setting->sensor_frame->angle_max = Dtype(3 * M_PI / 4);
+    setting->sensor_frame->num_rays = n;
+    setting->sensor_frame->valid_range_min = Dtype(0.1);
+    setting->sensor_frame->valid_range_max = Dtype(30);
+    setting->gp->kernel_type = "erl::covariance::OrnsteinUhlenbeck1d";
+    setting->gp->kernel->scale = Dtype(0.05);
+    Lidar gp(setting);
+    CHECK(gp.GetAnglePartitions().size() == 24, "24 partitions expected, got %zu", gp.GetAnglePartitions().size());
+    Eigen::VectorX<Dtype> dummy(1);
+    dummy[0] = 0;
+    CHECK(gp.Test(dummy, true, true) == nullptr, "Test before Train must return nullptr");
+
+    std::mt19937 rng(3);
+    std::uniform_real_distribution<double> uni(0, 1);
+    Eigen::VectorX<Dtype> ranges(n);
+    const auto &angles = gp.GetSensorFrame()->GetAnglesInFrame();
+    for (long i = 0; i < n; ++i) {
+        ranges[i] = Dtype(5 + 2 * std::sin(3 * double(angles[i])));
+        if (uni(rng) < 0.02) { ranges[i] = Dtype(1000); }
+    }
+    Eigen::MatrixX<Dtype> rot(2, 2);
+    rot.setZero();
+    rot(0, 0) = rot(1, 1) = 1;
+    Eigen::VectorX<Dtype> trans(2);
+    trans.setZero();
+    CHECK(gp.Train(rot, trans, ranges), "Train");
+    const auto frame = gp.GetSensorFrame();
+
+    erl_gp_oracle::LidarGp2D<Dtype> ref;
+    ref.group_size = 64, ref.overlap_size = 18, ref.margin = 1;
+    ref.kernel_type = erl_gp_oracle::kOrnsteinUhlenbeck, ref.kernel_scale = Dtype(0.05);
+    ref.sensor_range_var = setting->sensor_range_var, ref.max_valid_range_var = setting->max_valid_range_var, ref.occ_test_temperature = setting->occ_test_temperature;
+    ref.Init(angles.data(), n);
+    ref.Train(rot.data(), frame->GetRanges().data(), frame->GetHitMask().data(), frame->GetContinuityMask().data(), true);
+
+    Eigen::VectorX<Dtype> q(n_test), mean(n_test), var(n_test);
+    for (long i = 0; i < n_test; ++i) {
+        q[i] = Dtype(-3 * M_PI / 4 - 0.05 + uni(rng) * (1.5 * M_PI + 0.1));
+        mean[i] = var[i] = Dtype(-777);
+    }
+    auto result = gp.Test(q, true, true);
+    CHECK(result != nullptr, "Test");
+    const auto ok_mean = result->GetMean(mean, true);
+    const auto ok_var = result->GetVariance(var, true);
+    std::vector<Dtype> m_ref(n_test, Dtype(-777)), v_ref(n_test, Dtype(-777));
+    std::vector<uint8_t> ok_ref(n_test);
+    ref.Test(q.data(), n_test, true, true, m_ref.data(), v_ref.data(), ok_ref.data());
+    double em = 0, ev = 0, scale = 0;
+    long invalid = 0;
+    for (long i = 0; i < n_test; ++i) {
+        CHECK(bool(ok_mean[i]) == bool(ok_ref[i]) && bool(ok_var[i]) == bool(ok_ref[i]), "valid mask differs at %ld", i);
+        if (!ok_ref[i]) {
+            ++invalid;
+            CHECK(mean[i] == Dtype(-777) && var[i] == Dtype(-777), "invalid ray %ld must stay unwritten", i);
+            continue;
+        }
+        scale = std::max(scale, std::abs(double(m_ref[i])));
+        em = std::max(em, std::abs(double(mean[i]) - double(m_ref[i])));
+        ev = std::max(ev, std::abs(double(var[i]) - double(v_ref[i])));
+    }
+    CHECK(invalid > 0, "expected some rays outside the field of view");
+    CHECK(em / scale < tol && ev < tol, "mean err %.3e var err %.3e", em / scale, ev);
+    // single-position ComputeOcc against the oracle
+    long occ_checked = 0;
+    for (int i = 0; i < 50; ++i) {
+        const double a = -2.0 + 4.0 * uni(rng), d = 1.0 + 6.0 * uni(rng);
+        Eigen::VectorX<Dtype> pos(2);
+        pos[0] = Dtype(d * std::cos(a)), pos[1] = Dtype(d * std::sin(a));
+        Dtype dist = 0, range_pred = 0, occ = 0, dist_r = 0, range_r = 0, occ_r = 0;
+        const bool ok = gp.ComputeOcc(pos, dist, range_pred, occ);
+        const bool ok_r = ref.ComputeOcc(pos[0], pos[1], dist_r, range_r, occ_r);
+        CHECK(ok == ok_r, "ComputeOcc validity differs");
+        if (ok && ok_r) {
+            ++occ_checked;
+            CHECK(std::abs(double(range_pred) - double(range_r)) < 1e3 * tol * std::max(1.0, std::abs(double(range_r))), "range_pred %g vs %g", double(range_pred), double(range_r));
+            CHECK(std::abs(double(occ) - double(occ_r)) < (sizeof(Dtype) == 4 ? 5e-3 : 1e-7), "occ %g vs %g", double(occ), double(occ_r));
+        }
+    }
+    CHECK(occ_checked > 10, "too few valid ComputeOcc samples");
+    std::printf("%s %s: mean err %.2e, var err %.2e, %ld invalid rays\n", g_failures ? "----" : "PASS", name, em / scale, ev, invalid);
+}
+
+template<typename Dtype>
+static void
+TestRangeSensor(const char *name, const double tol) {
+    using Rs = RangeSensorGaussianProcess3D<Dtype>;
+    constexpr long rows = 72, cols = 40;
+    auto setting = std::make_shared<typename Rs::Setting>();
+    setting->sensor_frame->azimuth_min = Dtype(-0.5), setting->sensor_frame->azimuth_max = Dtype(0.5), setting->sensor_frame->num_azimuth_lines = rows;
+    setting->sensor_frame->elevation_min = Dtype(-0.3), setting->sensor_frame->elevation_max = Dtype(0.3), setting->sensor_frame->num_elevation_lines = cols;
+    setting->sensor_frame->valid_range_min = Dtype(0.1), setting->sensor_frame->valid_range_max = Dtype(30);
+    setting->gp->kernel_type = "erl::covariance::Matern32<float, 2>";
+    setting->gp->kernel->scale = Dtype(0.05);
+    Rs gp(setting);
+    std::mt19937 rng(5);
+    std::uniform_real_distribution<double> uni(0, 1);
+    Eigen::MatrixX<Dtype> ranges(rows, cols);
+    for (long c = 0; c < cols; ++c) {
+        for (long r = 0; r < rows; ++r) { ranges(r, c) = uni(rng) < 0.05 ? Dtype(1e3) : Dtype(4 + 0.8 * std::sin(r / 9.0) * std::cos(c / 13.0)); }
+    }
+    Eigen::MatrixX<Dtype> rot(3, 3);
+    rot.setZero();
+    rot(0, 0) = rot(1, 1) = rot(2, 2) = 1;
+    Eigen::VectorX<Dtype> trans(3);
+    trans.setZero();
+    CHECK(gp.Train(rot, trans, ranges), "Train");
+    const auto frame = gp.GetSensorFrame();
+    erl_gp_oracle::RangeSensorGp3D<Dtype> ref;
+    ref.kernel_type = erl_gp_oracle::kMatern32, ref.kernel_scale = Dtype(0.05);
+    ref.sensor_range_var = setting->sensor_range_var;
+    CHECK(ref.Init(frame->GetFrameCoordsData(), rows, cols), "oracle Init");
+    CHECK(gp.GetRowPartitions().size() == ref.row_partitions.size() && gp.GetColPartitions().size() == ref.col_partitions.size(), "partition grid");
+    ref.Train(frame->GetRanges().data(), frame->GetHitMask().data(), true);
+    constexpr long n_test = 5000;
+    Eigen::MatrixX<Dtype> dirs(3, n_test), coords(2, n_test);
+    for (long i = 0; i < n_test; ++i) {
+        const double az = -0.55 + 1.1 * uni(rng), el = -0.33 + 0.66 * uni(rng);
+        dirs(0, i) = Dtype(std::cos(el) * std::cos(az)), dirs(1, i) = Dtype(std::cos(el) * std::sin(az)), dirs(2, i) = Dtype(std::sin(el));
+        Dtype dist;
+        (void) frame->ComputeFrameCoords(&dirs(0, i), dist, &coords(0, i));
+    }
+    auto result = gp.Test(dirs, true, true);
+    CHECK(result != nullptr, "Test");
+    Eigen::VectorX<Dtype> mean(n_test), var(n_test);
+    const auto ok = result->GetMean(mean, true);
+    (void) result->GetVariance(var, true);
+    std::vector<Dtype> m_ref(n_test), v_ref(n_test);
+    std::vector<uint8_t> ok_ref(n_test);
+    ref.TestFrameCoords(coords.data(), nullptr, n_test, true, m_ref.data(), v_ref.data(), ok_ref.data());
+    double em = 0, ev = 0, scale = 0;
+    long valid = 0;
+    for (long i = 0; i < n_test; ++i) {
+        CHECK(bool(ok[i]) == bool(ok_ref[i]), "valid mask differs at %ld", i);
+        if (!ok_ref[i]) { continue; }
+        ++valid;
+        scale = std::max(scale, std::abs(double(m_ref[i])));
+        em = std::max(em, std::abs(double(mean[i]) - double(m_ref[i])));
+        ev = std::max(ev, std::abs(double(var[i]) - double(v_ref[i])));
+    }
+    CHECK(valid > 1000, "too few valid rays: %ld", valid);
+    CHECK(em / scale < tol && ev < tol, "mean err %.3e var err %.3e", em / scale, ev);
+    std::printf("%s %s: mean err %.2e, var err %.2e, %ld valid rays\n", g_failures ? "----" : "PASS", name, em / scale, ev, valid);
+}
+
+int
+main() {
+    try {
+        TestVanillaSiso<double>("VanillaGaussianProcess<double> SISO", 1e-10);
+        TestVanillaSiso<float>("VanillaGaussianProcess<float> SISO", 1e-4);
+        TestLidar<double>("LidarGaussianProcess2D<double>", 1e-10);
+        TestLidar<float>("LidarGaussianProcess2D<float>", 1e-4);
+        TestRangeSensor<float>("RangeSensorGaussianProcess3D<float>", 1e-4);
+        TestRangeSensor<double>("RangeSensorGaussianProcess3D<double>", 1e-10);
+        // misuse: hard assertion as ERL_ASSERTM (src/vanilla_gp.cpp:389-392)
+        bool threw = false;
+        try {
+            auto s = std::make_shared<VanillaGaussianProcess<double>::Setting>();
+            s->kernel_type = "erl::covariance::Matern32<double, 2>";
+            s->max_num_samples = 8;
+            VanillaGaussianProcess<double> gp(s);
+            gp.Reset(9, 2, 1);
+        } catch (const std::logic_error &) { threw = true; }
+        CHECK(threw, "Reset beyond max_num_samples must assert");
+    } catch (const std::exception &e) {
+        std::printf("FAIL exception: %s\n", e.what());
+        return 2;
+    }
+    std::printf(g_failures == 0 ? "ALL PASS\n" : "%d FAILURES\n", g_failures);
+    return g_failures == 0 ? 0 : 1;
+}

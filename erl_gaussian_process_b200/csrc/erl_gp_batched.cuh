@@ -27,6 +27,9 @@
 #pragma once
 
 #include "erl_gp_internal.cuh"
+#include "erl_gp_rowgp.cuh"
+
+#include <cstdlib>
 
 namespace erl_gp {
 
@@ -640,6 +643,12 @@ namespace erl_gp {
     int
     LaunchBatchXdim(Context *ctx, const BatchParams<T> &params, const int mode, const int tiles_per_gp) {
         const int max_n = params.max_n;
+        if constexpr (sizeof(T) == 4) {
+            // FP32, n <= 128: the register-resident "row GP" kernel (erl_gp_rowgp.cuh); ERL_GP_BATCH_LEGACY=1 keeps the
+            // generic shared-memory kernel below (A/B measurements and tests of the generic path)
+            static const bool legacy = std::getenv("ERL_GP_BATCH_LEGACY") != nullptr;
+            if (max_n <= 128 && !legacy) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
+        }
         if (max_n <= 64) { return LaunchBatchMode<T, XDIM, 4>(ctx, params, mode, tiles_per_gp); }
         if (max_n <= 128) { return LaunchBatchMode<T, XDIM, 8>(ctx, params, mode, tiles_per_gp); }
         if (max_n <= 192) { return LaunchBatchMode<T, XDIM, 12>(ctx, params, mode, tiles_per_gp); }

@@ -1,0 +1,618 @@
+// FP32 fast path of the one-CTA-per-GP batched train / predict kernel for n <= 128 ("row GP" kernel).
+//
+// Same contract as BatchedGpKernel (erl_gp_batched.cuh) and the same reference code replaced:
+//   VanillaGaussianProcess::UpdateKtrain + Solve        src/vanilla_gp.cpp:476-505
+//   VanillaGaussianProcess::ComputeKtest                src/vanilla_gp.cpp:521-552
+//   TestResult::GetMean / GetVariance                   src/vanilla_gp.cpp:61-150
+// driven per partition by src/lidar_gp_2d.cpp:366-392 / src/range_sensor_gp_3d.cpp:334-360.
+//
+// Design, from the measurements in tools/fma_lds_rate.cu (B200): a plain FFMA with two fresh register
+// operands sustains only ~37 TFLOP/s, FFMA2 (fma.rn.f32x2, scalar-broadcast operand form) ~55 TFLOP/s when every
+// LDS.128 feeds >= 8 FMAs; a warp-uniform LDS.128 costs 2 shared-memory cycles per SM.  Hence:
+//   * 128 threads per GP, ~42 KB of shared memory, 3 CTAs per SM: the serial parts of one GP (pivot-block
+//     factorisation, alpha back-substitution) overlap with the FMA-bound parts of the other two;
+//   * the Gram matrix is never stored: every 16-column panel of K is generated in registers right
+//     before it is eliminated (fused distance + covariance + noise diagonal);
+//   * left-looking blocked Cholesky, 16-column panels.  A thread PAIR accumulates the update of two
+//     rows (each thread 8 of the 16 panel columns, FFMA2 against warp-uniform broadcasts of the 16
+//     pivot rows), the pair then swaps halves so that each thread owns one row; the 16 x 16 pivot block
+//     is factorised by one warp with shuffles (rows of the same warp follow along), the other rows
+//     are eliminated in-thread against the published pivot block.  z = L^-1 y rides along as a 17th
+//     column, alpha = L^-T z is a blocked back-substitution with thread = column;
+//   * L lives in shared memory column-major, packed by 16-column blocks (column block b keeps rows
+//     >= 16 b) with a 4-float pad per column, so that "one row per lane", "one column per lane" and
+//     warp-uniform float4 accesses are all bank-conflict free;
+//   * predict: a thread pair owns 2 queries; each thread keeps 64 of the 128 rows of both V = L^-1 k*
+//     columns in registers (rows 8m + 4h .. +3), Ktest entries are generated in registers, the
+//     right-looking substitution is fully unrolled (column index static => register-resident V, no
+//     barrier at all), v_j is exchanged inside the pair with one shuffle per query and column, every
+//     LDS.128 of L feeds 4 FFMA2.  mean = k*^T alpha and ||v||^2 are accumulated on the way.
+// HBM traffic per GP is the algorithmic minimum (x, y, var in; L, alpha out; queries in; mean/var out).
+#pragma once
+
+#include "erl_gp_internal.cuh"
+
+#include <type_traits>
+
+namespace erl_gp {
+    namespace rowgp {
+
+        // compile-time loop: the body sees its index as a constant, so register-resident arrays stay in registers
+        // however long the unrolled body gets (#pragma unroll gives up on the 128-column substitution)
+        template<int I, int N, typename F>
+        __device__ __forceinline__ void
+        StaticFor(F &&f) {
+            if constexpr (I < N) {
+                f(std::integral_constant<int, I>{});
+                StaticFor<I + 1, N>(f);
+            }
+        }
+
+        constexpr int kThreads = 128;
+        constexpr unsigned kFull = 0xffffffffu;
+
+        template<int NBLK>
+        struct Layout {
+            static constexpr int kNp = 16 * NBLK;
+
+            __host__ __device__ static constexpr int
+            Stride(const int cb) {  // floats between consecutive columns of column block cb (== 4 mod 16)
+                return kNp - 16 * cb + 4;
+            }
+
+            __host__ __device__ static constexpr int
+            Base(const int cb) {  // first float of column block cb: sum_{b < cb} 16 * Stride(b)
+                return 16 * cb * (kNp + 4) - 128 * cb * (cb - 1);
+            }
+
+            static constexpr int kL = 0;
+            static constexpr int kLFloats = 16 * NBLK * (kNp + 4) - 128 * NBLK * (NBLK - 1);
+            static constexpr int kPts = kL + kLFloats;  // float4[kNp]: (x, y, z, alpha)
+            static constexpr int kRs = kPts + 4 * kNp;  // 1 / L_jj
+            static constexpr int kAl = kRs + kNp;       // y -> z -> alpha
+            static constexpr int kVar = kAl + kNp;      // noise variances
+            static constexpr int kMisc = kVar + kNp;    // int fail flag
+            static constexpr int kEnd = kMisc + 4;
+            static constexpr size_t kBytes = static_cast<size_t>(kEnd) * sizeof(float);
+        };
+
+        __device__ __forceinline__ float2
+        Fma2(const float2 a, const float s, const float2 c) {  // c + a * s, both halves (FFMA2 with broadcast operand)
+            return __ffma2_rn(a, make_float2(s, s), c);
+        }
+
+        __device__ __forceinline__ float
+        RsqrtRefined(const float d) {  // MUFU.RSQ + one Newton step
+            const float r = rsqrtf(d);
+            return r * fmaf(-0.5f * d * r, r, 1.5f);
+        }
+
+        template<int XDIM>
+        __device__ __forceinline__ float
+        Dist2(const float4 a, const float (&b)[XDIM]) {
+            float r2 = 0;
+            const float av[3] = {a.x, a.y, a.z};
+#pragma unroll
+            for (int d = 0; d < XDIM; ++d) {
+                const float diff = av[d] - b[d];
+                r2 = fmaf(diff, diff, r2);
+            }
+            return r2;
+        }
+
+        // --------------------------------------------------------------------------------------
+        // train: blocked left-looking Cholesky with the Gram panel generated on the fly
+        // --------------------------------------------------------------------------------------
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ int
+        Factorize(const Covariance<float> cov, float *__restrict__ smem, const int n, const int nblk) {
+            using Lay = Layout<NBLK>;
+            float *lp = smem + Lay::kL;
+            const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
+            float *rs = smem + Lay::kRs;
+            float *al = smem + Lay::kAl;
+            const float *sv = smem + Lay::kVar;
+            const int tid = threadIdx.x;
+            const int warp = tid >> 5;
+            const int lane = tid & 31;
+            const int h = tid & 1;
+            const int npr = nblk * 16;
+            int fail = 0;
+
+            for (int kb = 0; kb < nblk; ++kb) {
+                const int c0 = 16 * kb;
+                const int nact = npr - c0;
+                const int half = nact >> 1;  // multiple of 8
+                const bool warp_active = warp * 16 < half;
+                if (warp_active) {
+                    int q = tid >> 1;
+                    const bool active = q < half;
+                    if (!active) { q = half - 1; }  // duplicate the last pair: same code path, no stores
+                    const int r_a = c0 + q;
+                    const int r_b = r_a + half;
+                    const int rme = h ? r_b : r_a;
+
+                    // (a) this pair's update of rows r_a, r_b: thread h takes panel columns [8h, 8h + 8)
+                    float2 s_a[4], s_b[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { s_a[k] = s_b[k] = make_float2(0.f, 0.f); }
+                    float zsum = 0.f;
+                    for (int jb = 0; jb < kb; ++jb) {
+                        const int stride = Lay::Stride(jb);
+                        const float *blk = lp + Lay::Base(jb) - 16 * jb;
+                        const float *colp = blk + c0 + 8 * h;
+                        const float *own_a = blk + r_a;
+                        const float *own_b = blk + r_b;
+                        const float4 *z4 = reinterpret_cast<const float4 *>(al + 16 * jb);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 zq = z4[j4];
+                            const float zv[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * j4 + jj;
+                                const float4 p0 = *reinterpret_cast<const float4 *>(colp + j * stride);
+                                const float4 p1 = *reinterpret_cast<const float4 *>(colp + j * stride + 4);
+                                const float la = own_a[j * stride];
+                                const float lb = own_b[j * stride];
+                                s_a[0] = Fma2(make_float2(p0.x, p0.y), la, s_a[0]);
+                                s_a[1] = Fma2(make_float2(p0.z, p0.w), la, s_a[1]);
+                                s_a[2] = Fma2(make_float2(p1.x, p1.y), la, s_a[2]);
+                                s_a[3] = Fma2(make_float2(p1.z, p1.w), la, s_a[3]);
+                                s_b[0] = Fma2(make_float2(p0.x, p0.y), lb, s_b[0]);
+                                s_b[1] = Fma2(make_float2(p0.z, p0.w), lb, s_b[1]);
+                                s_b[2] = Fma2(make_float2(p1.x, p1.y), lb, s_b[2]);
+                                s_b[3] = Fma2(make_float2(p1.z, p1.w), lb, s_b[3]);
+                                zsum = fmaf(h ? lb : la, zv[jj], zsum);
+                            }
+                        }
+                    }
+                    // swap halves inside the pair: I keep row rme, the partner the other row
+                    float acc[16];
+                    {
+                        float mine[8], recv[8];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 keep = h ? s_b[k] : s_a[k];
+                            const float2 send = h ? s_a[k] : s_b[k];
+                            mine[2 * k] = keep.x;
+                            mine[2 * k + 1] = keep.y;
+                            recv[2 * k] = __shfl_xor_sync(kFull, send.x, 1);
+                            recv[2 * k + 1] = __shfl_xor_sync(kFull, send.y, 1);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            acc[k] = h ? recv[k] : mine[k];      // columns 0..7 were computed by h = 0
+                            acc[8 + k] = h ? mine[k] : recv[k];  // columns 8..15 by h = 1
+                        }
+                    }
+                    // (b) Gram panel entries of my row, fused: acc = K(rme, c0 + c) - sum
+                    {
+                        const float4 pme = pts[rme];
+                        float xme[XDIM];
+                        xme[0] = pme.x;
+                        if (XDIM > 1) { xme[XDIM > 1 ? 1 : 0] = pme.y; }
+                        if (XDIM > 2) { xme[XDIM > 2 ? 2 : 0] = pme.z; }
+                        const float diag = 1.0f + sv[rme];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int col = c0 + c;
+                            float kv = cov(Dist2<XDIM>(pts[col], xme));
+                            if (rme >= n || col >= n) { kv = 0.f; }
+                            if (rme == col) { kv = rme < n ? diag : 1.0f; }
+                            acc[c] = kv - acc[c];
+                        }
+                    }
+                    float zacc = al[rme] - zsum;  // al[rme] still holds y (rme >= c0)
+                    float l[16];
+
+                    if (warp == 0) {
+                        // (c) pivot block: rows c0 + c live in lanes src(c); every lane's row follows along
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int src = c < half ? 2 * c : 2 * (c - half) + 1;
+                            const float d = __shfl_sync(kFull, acc[c], src);
+                            const float zc = __shfl_sync(kFull, zacc, src);
+                            float t[16];
+#pragma unroll
+                            for (int cc = c + 1; cc < 16; ++cc) {
+                                const int src2 = cc < half ? 2 * cc : 2 * (cc - half) + 1;
+                                t[cc] = __shfl_sync(kFull, acc[c], src2);
+                            }
+                            if (!(d > 0.f) && fail == 0) { fail = c0 + c + 1; }
+                            const float invd = __frcp_rn(d);
+                            const float rsv = RsqrtRefined(d);
+                            const float sc = acc[c] * invd;
+#pragma unroll
+                            for (int cc = c + 1; cc < 16; ++cc) { acc[cc] = fmaf(-sc, t[cc], acc[cc]); }
+                            zacc = fmaf(-sc, zc, zacc);
+                            l[c] = acc[c] * rsv;
+                            if (lane == 0) {
+                                rs[c0 + c] = rsv;
+                                al[c0 + c] = zc * rsv;
+                            }
+                        }
+                    }
+                    if (warp == 0 && active) {
+                        float *dst = lp + Lay::Base(kb) + (rme - c0);
+                        const int stride = Lay::Stride(kb);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { dst[c * stride] = (c > rme - c0) ? 0.f : l[c]; }
+                    }
+                    __syncthreads();  // #1: pivot block, rs, z of this panel are published
+                    if (half > 16) {
+                        if (warp != 0) {
+                            // (d) in-thread elimination of my row against the pivot block
+                            const float *dblk = lp + Lay::Base(kb);
+                            const int stride = Lay::Stride(kb);
+                            float rsb[16], zb[16];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float4 r4 = *reinterpret_cast<const float4 *>(rs + c0 + 4 * k);
+                                const float4 z4 = *reinterpret_cast<const float4 *>(al + c0 + 4 * k);
+                                rsb[4 * k] = r4.x, rsb[4 * k + 1] = r4.y, rsb[4 * k + 2] = r4.z, rsb[4 * k + 3] = r4.w;
+                                zb[4 * k] = z4.x, zb[4 * k + 1] = z4.y, zb[4 * k + 2] = z4.z, zb[4 * k + 3] = z4.w;
+                            }
+#pragma unroll
+                            for (int pcol = 0; pcol < 16; ++pcol) {
+                                const float lv = acc[pcol] * rsb[pcol];
+                                l[pcol] = lv;
+                                zacc = fmaf(-lv, zb[pcol], zacc);
+#pragma unroll
+                                for (int k4 = (pcol + 1) / 4; k4 < 4; ++k4) {
+                                    const float4 dv = *reinterpret_cast<const float4 *>(dblk + pcol * stride + 4 * k4);
+                                    // rows <= pcol of the pivot column are zero (or the dead diagonal): harmless
+                                    acc[4 * k4] = fmaf(-lv, dv.x, acc[4 * k4]);
+                                    acc[4 * k4 + 1] = fmaf(-lv, dv.y, acc[4 * k4 + 1]);
+                                    acc[4 * k4 + 2] = fmaf(-lv, dv.z, acc[4 * k4 + 2]);
+                                    acc[4 * k4 + 3] = fmaf(-lv, dv.w, acc[4 * k4 + 3]);
+                                }
+                            }
+                            if (active) {
+                                float *dst = lp + Lay::Base(kb) + (rme - c0);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) { dst[c * stride] = l[c]; }
+                            }
+                        }
+                        __syncthreads();  // #2: the whole panel is published
+                    }
+                    (void) zacc;
+                } else {
+                    __syncthreads();  // #1
+                    if (half > 16) { __syncthreads(); }  // #2
+                }
+            }
+            return fail;
+        }
+
+        // alpha = L^-T z (al holds z on entry, alpha on exit); thread = column, blocked from the bottom
+        template<int NBLK>
+        __device__ __forceinline__ void
+        BackSolve(float *__restrict__ smem, const int nblk) {
+            using Lay = Layout<NBLK>;
+            const float *lp = smem + Lay::kL;
+            const float *rs = smem + Lay::kRs;
+            float *al = smem + Lay::kAl;
+            const int tid = threadIdx.x;
+            const int warp = tid >> 5;
+            const int lane = tid & 31;
+            float s = 0.f;
+            for (int kb = nblk - 1; kb >= 0; --kb) {
+                const int c0 = 16 * kb;
+                if (warp == (c0 >> 5)) {
+                    const int lb = c0 & 31;
+                    const bool mine = lane >= lb && lane < lb + 16;
+                    const int jj = mine ? lane - lb : 0;
+                    const float *colp = lp + Lay::Base(kb) + jj * Lay::Stride(kb);  // rows c0.. of column c0 + jj
+                    float lblk[16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 v = *reinterpret_cast<const float4 *>(colp + 4 * k);
+                        lblk[4 * k] = v.x, lblk[4 * k + 1] = v.y, lblk[4 * k + 2] = v.z, lblk[4 * k + 3] = v.w;
+                    }
+                    const float zj = al[c0 + jj];
+                    const float rsj = rs[c0 + jj];
+                    float amine = 0.f;
+#pragma unroll
+                    for (int c = 15; c >= 0; --c) {
+                        const float a = (zj - s) * rsj;
+                        const float ac = __shfl_sync(kFull, a, lb + c);
+                        if (jj == c) { amine = a; }
+                        if (mine && jj < c) { s = fmaf(lblk[c], ac, s); }  // L(c0 + c, c0 + jj) * alpha_c
+                    }
+                    if (mine) { al[c0 + jj] = amine; }
+                }
+                __syncthreads();
+                if (tid < c0) {
+                    const int cb = tid >> 4;
+                    const float *colp = lp + Lay::Base(cb) + (tid & 15) * Lay::Stride(cb) + (c0 - 16 * cb);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 lv = *reinterpret_cast<const float4 *>(colp + 4 * k);
+                        const float4 av = *reinterpret_cast<const float4 *>(al + c0 + 4 * k);
+                        s = fmaf(lv.x, av.x, s);
+                        s = fmaf(lv.y, av.y, s);
+                        s = fmaf(lv.z, av.z, s);
+                        s = fmaf(lv.w, av.w, s);
+                    }
+                }
+            }
+        }
+
+        // --------------------------------------------------------------------------------------
+        // predict one tile of up to 128 queries: thread pair = 2 queries, V in registers
+        // --------------------------------------------------------------------------------------
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ void
+        PredictTile(const BatchParams<float> &p, const float *__restrict__ smem, const int n, const long q_begin, const int nq) {
+            using Lay = Layout<NBLK>;
+            constexpr int kNp8 = 2 * NBLK;
+            const float *lp = smem + Lay::kL;
+            const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
+            const float4 *rs4 = reinterpret_cast<const float4 *>(smem + Lay::kRs);
+            const int tid = threadIdx.x;
+            const int lane = tid & 31;
+            const int h = tid & 1;
+            const int pair = tid >> 1;
+
+            float xq0[XDIM], xq1[XDIM];
+#pragma unroll
+            for (int d = 0; d < XDIM; ++d) {
+                xq0[d] = 2 * pair < nq ? p.q_x[(q_begin + 2 * pair) * XDIM + d] : 0.f;
+                xq1[d] = 2 * pair + 1 < nq ? p.q_x[(q_begin + 2 * pair + 1) * XDIM + d] : 0.f;
+            }
+
+            // Ktest entries of rows 8m + 4h + r for both queries, mean accumulated on the way
+            float2 va[2 * kNp8], vb[2 * kNp8];
+            float mean0 = 0.f, mean1 = 0.f;
+            const int nh = n - 4 * h;
+            const float4 *pth = pts + 4 * h;
+#pragma unroll
+            for (int m = 0; m < kNp8; ++m) {
+                float k0[4], k1[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float4 pt = pth[8 * m + r];
+                    float a = p.cov(Dist2<XDIM>(pt, xq0));
+                    float b = p.cov(Dist2<XDIM>(pt, xq1));
+                    if (!(8 * m + r < nh)) { a = b = 0.f; }
+                    mean0 = fmaf(a, pt.w, mean0);
+                    mean1 = fmaf(b, pt.w, mean1);
+                    k0[r] = a;
+                    k1[r] = b;
+                }
+                va[2 * m] = make_float2(k0[0], k0[1]);
+                va[2 * m + 1] = make_float2(k0[2], k0[3]);
+                vb[2 * m] = make_float2(k1[0], k1[1]);
+                vb[2 * m + 1] = make_float2(k1[2], k1[3]);
+            }
+
+            float ss0 = 0.f, ss1 = 0.f;
+            const float *lph = lp + 4 * h;
+            StaticFor<0, 4 * NBLK>([&](auto j4c) {
+                constexpr int j4 = decltype(j4c)::value;
+                const float4 rq = rs4[j4];
+                const float rsv[4] = {rq.x, rq.y, rq.z, rq.w};
+                StaticFor<0, 4>([&](auto jrc) {
+                    constexpr int jr = decltype(jrc)::value;
+                    constexpr int j = 4 * j4 + jr;
+                    constexpr int mj = j >> 3;
+                    constexpr int hj = (j >> 2) & 1;
+                    constexpr int slot = 2 * mj + (jr >> 1);
+                    constexpr int cb = j >> 4;
+                    const float c0 = ((jr & 1) ? va[slot].y : va[slot].x) * rsv[jr];
+                    const float c1 = ((jr & 1) ? vb[slot].y : vb[slot].x) * rsv[jr];
+                    const int src = (lane & ~1) | hj;
+                    const float vj0 = __shfl_sync(kFull, c0, src);
+                    const float vj1 = __shfl_sync(kFull, c1, src);
+                    ss0 = fmaf(vj0, vj0, ss0);
+                    ss1 = fmaf(vj1, vj1, ss1);
+                    const float *col = lph + (Lay::Base(cb) + (j & 15) * Lay::Stride(cb) - 16 * cb);
+                    StaticFor<mj, kNp8>([&](auto mc) {
+                        constexpr int m = decltype(mc)::value;
+                        const float4 lv = *reinterpret_cast<const float4 *>(col + 8 * m);
+                        va[2 * m] = Fma2(make_float2(lv.x, lv.y), -vj0, va[2 * m]);
+                        va[2 * m + 1] = Fma2(make_float2(lv.z, lv.w), -vj0, va[2 * m + 1]);
+                        vb[2 * m] = Fma2(make_float2(lv.x, lv.y), -vj1, vb[2 * m]);
+                        vb[2 * m + 1] = Fma2(make_float2(lv.z, lv.w), -vj1, vb[2 * m + 1]);
+                    });
+                });
+            });
+            mean0 += __shfl_xor_sync(kFull, mean0, 1);
+            mean1 += __shfl_xor_sync(kFull, mean1, 1);
+
+            const int myq = 2 * pair + h;
+            if (myq < nq) {
+                const long src = q_begin + myq;
+                const long dst = p.q_out_index != nullptr ? p.q_out_index[src] : src;
+                if (p.mean != nullptr) {
+                    float f = h ? mean1 : mean0;
+                    if (p.mapping != ERL_GP_MAPPING_NONE) { f = MappingInv<float>(p.mapping, p.mapping_scale, f); }
+                    p.mean[dst] = f;
+                }
+                if (p.variance != nullptr) { p.variance[dst] = 1.0f - (h ? ss1 : ss0); }  // literal prior 1.0f, src/vanilla_gp.cpp:121
+                if (p.valid != nullptr) { p.valid[dst] = 1; }
+            }
+        }
+
+        template<int XDIM, int NBLK, int MODE>
+        __global__ void __launch_bounds__(kThreads, 3)
+        RowGpKernel(const BatchParams<float> p) {
+            using Lay = Layout<NBLK>;
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            float *smem = reinterpret_cast<float *>(smem_raw);
+            float *lp = smem + Lay::kL;
+            float4 *pts = reinterpret_cast<float4 *>(smem + Lay::kPts);
+            float *rs = smem + Lay::kRs;
+            float *al = smem + Lay::kAl;
+            float *sv = smem + Lay::kVar;
+
+            const int g = blockIdx.x;
+            const int tid = threadIdx.x;
+            const int warp = tid >> 5;
+            const int lane = tid & 31;
+            const int n = p.n_train[g];
+            const long q0 = (MODE & kBatchPredict) ? p.q_offsets[g] : 0;
+            const long q1 = (MODE & kBatchPredict) ? p.q_offsets[g + 1] : 0;
+
+            if constexpr ((MODE & kBatchTrain) != 0) {
+                if (n <= p.min_train || n <= 0) {  // the reference's `cnt > min_num_samples_per_group` / `cnt > 0` gate
+                    if (tid == 0) { p.info[g] = -1; }
+                    if ((MODE & kBatchPredict) && p.valid != nullptr) {
+                        for (long q = q0 + tid; q < q1; q += kThreads) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
+                    }
+                    return;
+                }
+            } else {
+                if (p.info[g] != 0 || q1 <= q0) { return; }  // untrained / failed GP: outputs stay untouched
+            }
+            const int nblk = (n + 15) >> 4;
+            const int npr = nblk * 16;
+
+            // ---- stage the training inputs; identity-fill what the factorisation will not touch ----
+            const float *gx = p.x + static_cast<long>(g) * p.max_n * XDIM;
+            for (int e = tid; e < Lay::kNp; e += kThreads) {
+                float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < n) {
+                    pt.x = gx[e * XDIM];
+                    if (XDIM > 1) { pt.y = gx[e * XDIM + (XDIM > 1 ? 1 : 0)]; }
+                    if (XDIM > 2) { pt.z = gx[e * XDIM + (XDIM > 2 ? 2 : 0)]; }
+                    if (!(MODE & kBatchTrain)) { pt.w = p.alpha[static_cast<long>(g) * p.max_n + e]; }
+                }
+                pts[e] = pt;
+                rs[e] = 1.0f;
+            }
+            if (nblk < NBLK || !(MODE & kBatchTrain)) {
+                for (int e = tid; e < Lay::kLFloats; e += kThreads) { lp[e] = 0.f; }
+            }
+
+            if constexpr ((MODE & kBatchTrain) != 0) {
+                const float *gy = p.y + static_cast<long>(g) * p.max_n;
+                const float *gv = p.var + static_cast<long>(g) * p.max_n;
+                for (int e = tid; e < Lay::kNp; e += kThreads) {
+                    al[e] = e < n ? gy[e] : 0.f;
+                    sv[e] = e < n ? gv[e] : 0.f;
+                }
+                __syncthreads();
+                if (nblk < NBLK) {
+                    for (int e = npr + tid; e < Lay::kNp; e += kThreads) { lp[Lay::Base(e >> 4) + (e & 15) * Lay::Stride(e >> 4) + (e & 15)] = 1.0f; }
+                }
+                const int fail = Factorize<XDIM, NBLK>(p.cov, smem, n, nblk);
+                int *s_fail = reinterpret_cast<int *>(smem + Lay::kMisc);
+                if (tid == 0) { *s_fail = fail; }  // warp 0 tracked every pivot
+                __syncthreads();
+                const int failed = *s_fail;
+                if (failed != 0) {
+                    if (tid == 0) { p.info[g] = failed; }
+                    if ((MODE & kBatchPredict) && p.valid != nullptr) {
+                        for (long q = q0 + tid; q < q1; q += kThreads) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
+                    }
+                    return;
+                }
+                // ---- L write-back (coalesced, one column per warp and step), issued before the back-substitution ----
+                if (p.write_l) {
+                    float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
+                    if ((p.max_n & 3) == 0) {
+                        const int r4 = 4 * lane;
+                        for (int c = warp; c < n; c += kThreads / 32) {
+                            const int cb = c >> 4;
+                            if (r4 < n) {
+                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (r4 >= 16 * cb) { v = *reinterpret_cast<const float4 *>(lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) + (r4 - 16 * cb)); }
+                                float *dst = gl + r4 + static_cast<long>(c) * p.max_n;
+                                if (r4 + 3 < n) {
+                                    *reinterpret_cast<float4 *>(dst) = v;
+                                } else {
+                                    dst[0] = v.x;
+                                    if (r4 + 1 < n) { dst[1] = v.y; }
+                                    if (r4 + 2 < n) { dst[2] = v.z; }
+                                }
+                            }
+                        }
+                    } else {
+                        for (int c = warp; c < n; c += kThreads / 32) {
+                            const int cb = c >> 4;
+                            for (int r = lane; r < n; r += 32) {
+                                gl[r + static_cast<long>(c) * p.max_n] = r >= 16 * cb ? lp[Lay::Base(cb) + (c & 15) * Lay::Stride(cb) + (r - 16 * cb)] : 0.f;
+                            }
+                        }
+                    }
+                }
+                BackSolve<NBLK>(smem, nblk);
+                __syncthreads();
+                float *ga = p.alpha + static_cast<long>(g) * p.max_n;
+                for (int e = tid; e < n; e += kThreads) {
+                    const float a = al[e];
+                    ga[e] = a;
+                    smem[Lay::kPts + 4 * e + 3] = a;
+                }
+                if (tid == 0) { p.info[g] = 0; }
+            } else {
+                // ---- predict-only: reload L, rebuild 1 / L_jj ----
+                __syncthreads();
+                const float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
+                for (int c = warp; c < Lay::kNp; c += kThreads / 32) {
+                    const int cb = c >> 4;
+                    float *colp = lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) - 16 * cb;
+                    for (int r = 16 * cb + lane; r < Lay::kNp; r += 32) {
+                        float val;
+                        if (r < n && c < n) {
+                            val = r >= c ? gl[r + static_cast<long>(c) * p.max_n] : 0.f;
+                        } else {
+                            val = r == c ? 1.0f : 0.f;
+                        }
+                        colp[r] = val;
+                        if (r == c) { rs[c] = 1.0f / val; }
+                    }
+                }
+            }
+
+            if constexpr ((MODE & kBatchPredict) != 0) {
+                __syncthreads();
+                for (long qb = q0 + static_cast<long>(blockIdx.y) * kThreads; qb < q1; qb += static_cast<long>(gridDim.y) * kThreads) {
+                    const int nq = static_cast<int>(q1 - qb < kThreads ? q1 - qb : kThreads);
+                    PredictTile<XDIM, NBLK>(p, smem, n, qb, nq);
+                }
+            }
+        }
+
+        template<int XDIM, int NBLK, int MODE>
+        static int
+        LaunchInstance(Context *ctx, const BatchParams<float> &params, const int tiles_per_gp) {
+            using Lay = Layout<NBLK>;
+            auto kernel = RowGpKernel<XDIM, NBLK, MODE>;
+            if (static_cast<int>(Lay::kBytes) > ctx->max_smem_optin) {
+                return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "row-GP kernel needs %zu B of shared memory, device allows %d", Lay::kBytes, ctx->max_smem_optin);
+            }
+            ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Lay::kBytes)));
+            const dim3 grid(static_cast<unsigned>(params.num_gps), static_cast<unsigned>(tiles_per_gp < 1 ? 1 : tiles_per_gp));
+            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(params);
+            ctx->launches += 1;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            return ERL_GP_STATUS_OK;
+        }
+
+        template<int XDIM, int NBLK>
+        static int
+        LaunchMode(Context *ctx, const BatchParams<float> &params, const int mode, const int tiles_per_gp) {
+            switch (mode) {
+                case kBatchTrain: return LaunchInstance<XDIM, NBLK, kBatchTrain>(ctx, params, 1);
+                case kBatchPredict: return LaunchInstance<XDIM, NBLK, kBatchPredict>(ctx, params, tiles_per_gp);
+                case kBatchTrainPredict: return LaunchInstance<XDIM, NBLK, kBatchTrainPredict>(ctx, params, 1);
+                default: return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: bad mode %d", mode);
+            }
+        }
+
+        // max_n <= 128 only
+        template<int XDIM>
+        int
+        Launch(Context *ctx, const BatchParams<float> &params, const int mode, const int tiles_per_gp) {
+            const int max_n = params.max_n;
+            if (max_n <= 32) { return LaunchMode<XDIM, 2>(ctx, params, mode, tiles_per_gp); }
+            if (max_n <= 64) { return LaunchMode<XDIM, 4>(ctx, params, mode, tiles_per_gp); }
+            if (max_n <= 96) { return LaunchMode<XDIM, 6>(ctx, params, mode, tiles_per_gp); }
+            return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp);
+        }
+
+    }  // namespace rowgp
+}  // namespace erl_gp

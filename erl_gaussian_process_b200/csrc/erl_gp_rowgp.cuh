@@ -100,12 +100,33 @@ namespace erl_gp {
             return r2;
         }
 
+        // Branch-free form of the three erl_covariance kernels: with s = sqrt(r2),
+        //   k = (1 + a s) exp(-(b s + c r2))      OU: a = 0, b = 1/l     Matern32: a = b = sqrt(3)/l     RBF: c = 1/(2 l^2)
+        // One code path instead of three keeps the unrolled Gram / Ktest generators small (instruction cache).
+        struct CovCoef {
+            float a, b, c;
+
+            __device__ __forceinline__ explicit CovCoef(const Covariance<float> &cov) {
+                a = cov.type == ERL_GP_KERNEL_MATERN32 ? cov.c0 : 0.f;
+                b = cov.type == ERL_GP_KERNEL_MATERN32 ? cov.c0 : (cov.type == ERL_GP_KERNEL_OU ? 1.0f / cov.c0 : 0.f);
+                c = cov.type == ERL_GP_KERNEL_RBF ? 1.0f / cov.c0 : 0.f;
+            }
+
+            __device__ __forceinline__ float
+            operator()(const float r2) const {
+                float sq;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(r2));
+                const float e = expf(-fmaf(b, sq, c * r2));
+                return fmaf(a * sq, e, e);
+            }
+        };
+
         // --------------------------------------------------------------------------------------
         // train: blocked left-looking Cholesky with the Gram panel generated on the fly
         // --------------------------------------------------------------------------------------
         template<int XDIM, int NBLK>
         __device__ __forceinline__ int
-        Factorize(const Covariance<float> cov, float *__restrict__ smem, const int n, const int nblk) {
+        Factorize(const CovCoef cov, float *__restrict__ smem, const int n, const int nblk) {
             using Lay = Layout<NBLK>;
             float *lp = smem + Lay::kL;
             const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
@@ -340,103 +361,195 @@ namespace erl_gp {
         }
 
         // --------------------------------------------------------------------------------------
-        // predict one tile of up to 128 queries: thread pair = 2 queries, V in registers
+        // predict one tile of up to 64 queries: a thread QUAD owns 2 queries, thread h of the quad keeps rows
+        // 16 m + 4 h + {0..3} of both V = L^-1 k* columns in registers (64 registers for n = 128, which leaves room
+        // under the 128-register / 4-CTAs-per-SM budget to have all L entries of a column in flight at once).
+        // Register slot s holds block row m = nblk - 1 - s: slots count from the BOTTOM of the matrix, so the rows
+        // still to be updated are always the static prefix [0, live) of the slots and the loop over the 16-column
+        // blocks is a runtime loop with compact code (the fully unrolled form was 110 KB of SASS and starved the
+        // instruction cache: ncu stall_no_instruction).
         // --------------------------------------------------------------------------------------
+        constexpr int kTileQ = kThreads / 2;  // queries per tile
+
+        struct Slot {
+            float2 a[2];  // query 0: rows (0,1), (2,3)
+            float2 b[2];  // query 1
+        };
+
+        __device__ __forceinline__ void
+        SlotUpdate(Slot &v, const float4 lv, const float nv0, const float nv1) {
+            v.a[0] = Fma2(make_float2(lv.x, lv.y), nv0, v.a[0]);
+            v.a[1] = Fma2(make_float2(lv.z, lv.w), nv0, v.a[1]);
+            v.b[0] = Fma2(make_float2(lv.x, lv.y), nv1, v.b[0]);
+            v.b[1] = Fma2(make_float2(lv.z, lv.w), nv1, v.b[1]);
+        }
+
+        __device__ __forceinline__ float4
+        Lds4(const float *__restrict__ ptr) {
+            return *reinterpret_cast<const float4 *>(ptr);
+        }
+
+        // ld.shared.v4.f32 [addr + OFF]: one base register per column and immediate offsets.  (Left to itself the
+        // compiler re-derived every address of the column from the block index: ~8 integer instructions per LDS.)
+        template<int OFF>
+        __device__ __forceinline__ float4
+        LdsOff(const uint32_t addr) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+            return v;
+        }
+
+        template<int S, int N, int S0>
+        __device__ __forceinline__ void
+        LoadLive(float4 (&l)[N], const uint32_t low_addr, const int live) {  // l[S] = L entries of slot S0 + S (if live)
+            if constexpr (S < N) {
+                if (S0 + S < live) { l[S] = LdsOff<-64 * (S0 + S + 1)>(low_addr); }
+                LoadLive<S + 1, N, S0>(l, low_addr, live);
+            }
+        }
+
+        // uniform binary-tree fetch of slot s (s is warp-uniform): log2(KG) branches + 8 moves
+        template<int LO, int HI, int KG>
+        __device__ __forceinline__ void
+        SlotFetch(const Slot (&v)[KG], const int s, Slot &out) {
+            if constexpr (HI - LO == 1) {
+                out = v[LO];
+            } else {
+                constexpr int kMid = (LO + HI) / 2;
+                if (s < kMid) {
+                    SlotFetch<LO, kMid, KG>(v, s, out);
+                } else {
+                    SlotFetch<kMid, HI, KG>(v, s, out);
+                }
+            }
+        }
+
+        // rows below the current block: slots [S, live) with their L entries in l[S - L0 ...], nested early exit
+        template<int S, int END, int L0, int NL, int KG>
+        __device__ __forceinline__ void
+        LiveChain(Slot (&v)[KG], const float4 (&l)[NL], const int live, const float nv0, const float nv1) {
+            if constexpr (S < END) {
+                if (S < live) {
+                    SlotUpdate(v[S], l[S - L0], nv0, nv1);
+                    LiveChain<S + 1, END, L0, NL, KG>(v, l, live, nv0, nv1);
+                }
+            }
+        }
+
         template<int XDIM, int NBLK>
         __device__ __forceinline__ void
-        PredictTile(const BatchParams<float> &p, const float *__restrict__ smem, const int n, const long q_begin, const int nq) {
+        PredictTile(const BatchParams<float> &p, const CovCoef cov, const float *__restrict__ smem, const int n, const int nblk, const long q_begin, const int nq) {
             using Lay = Layout<NBLK>;
-            constexpr int kNp8 = 2 * NBLK;
             const float *lp = smem + Lay::kL;
             const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
-            const float4 *rs4 = reinterpret_cast<const float4 *>(smem + Lay::kRs);
+            const float *rs = smem + Lay::kRs;
             const int tid = threadIdx.x;
             const int lane = tid & 31;
-            const int h = tid & 1;
-            const int pair = tid >> 1;
+            const int h = tid & 3;
+            const int quad = tid >> 2;
+            const int npr = 16 * nblk;
 
             float xq0[XDIM], xq1[XDIM];
 #pragma unroll
             for (int d = 0; d < XDIM; ++d) {
-                xq0[d] = 2 * pair < nq ? p.q_x[(q_begin + 2 * pair) * XDIM + d] : 0.f;
-                xq1[d] = 2 * pair + 1 < nq ? p.q_x[(q_begin + 2 * pair + 1) * XDIM + d] : 0.f;
+                xq0[d] = 2 * quad < nq ? p.q_x[(q_begin + 2 * quad) * XDIM + d] : 0.f;
+                xq1[d] = 2 * quad + 1 < nq ? p.q_x[(q_begin + 2 * quad + 1) * XDIM + d] : 0.f;
             }
 
-            // Ktest entries of rows 8m + 4h + r for both queries, mean accumulated on the way
-            float2 va[2 * kNp8], vb[2 * kNp8];
+            // Ktest entries of my rows for both queries (never stored anywhere but registers); mean on the way
+            Slot v[NBLK];
             float mean0 = 0.f, mean1 = 0.f;
-            const int nh = n - 4 * h;
-            const float4 *pth = pts + 4 * h;
 #pragma unroll
-            for (int m = 0; m < kNp8; ++m) {
-                float k0[4], k1[4];
+            for (int s = 0; s < NBLK; ++s) {
+                if (s < nblk) {
+                    const int row0 = npr - 16 * (s + 1) + 4 * h;
+                    float k0[4], k1[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float4 pt = pth[8 * m + r];
-                    float a = p.cov(Dist2<XDIM>(pt, xq0));
-                    float b = p.cov(Dist2<XDIM>(pt, xq1));
-                    if (!(8 * m + r < nh)) { a = b = 0.f; }
-                    mean0 = fmaf(a, pt.w, mean0);
-                    mean1 = fmaf(b, pt.w, mean1);
-                    k0[r] = a;
-                    k1[r] = b;
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 pt = pts[row0 + r];
+                        float a = cov(Dist2<XDIM>(pt, xq0));
+                        float b = cov(Dist2<XDIM>(pt, xq1));
+                        if (row0 + r >= n) { a = b = 0.f; }
+                        mean0 = fmaf(a, pt.w, mean0);
+                        mean1 = fmaf(b, pt.w, mean1);
+                        k0[r] = a;
+                        k1[r] = b;
+                    }
+                    v[s].a[0] = make_float2(k0[0], k0[1]);
+                    v[s].a[1] = make_float2(k0[2], k0[3]);
+                    v[s].b[0] = make_float2(k1[0], k1[1]);
+                    v[s].b[1] = make_float2(k1[2], k1[3]);
                 }
-                va[2 * m] = make_float2(k0[0], k0[1]);
-                va[2 * m + 1] = make_float2(k0[2], k0[3]);
-                vb[2 * m] = make_float2(k1[0], k1[1]);
-                vb[2 * m + 1] = make_float2(k1[2], k1[3]);
             }
 
             float ss0 = 0.f, ss1 = 0.f;
-            const float *lph = lp + 4 * h;
-            StaticFor<0, 4 * NBLK>([&](auto j4c) {
-                constexpr int j4 = decltype(j4c)::value;
-                const float4 rq = rs4[j4];
-                const float rsv[4] = {rq.x, rq.y, rq.z, rq.w};
-                StaticFor<0, 4>([&](auto jrc) {
-                    constexpr int jr = decltype(jrc)::value;
-                    constexpr int j = 4 * j4 + jr;
-                    constexpr int mj = j >> 3;
-                    constexpr int hj = (j >> 2) & 1;
-                    constexpr int slot = 2 * mj + (jr >> 1);
-                    constexpr int cb = j >> 4;
-                    const float c0 = ((jr & 1) ? va[slot].y : va[slot].x) * rsv[jr];
-                    const float c1 = ((jr & 1) ? vb[slot].y : vb[slot].x) * rsv[jr];
-                    const int src = (lane & ~1) | hj;
+            for (int jb = 0; jb < nblk; ++jb) {
+                const int live = nblk - 1 - jb;  // == slot of the current block; the slots below it are still to be updated
+                Slot cur;
+                SlotFetch<0, NBLK, NBLK>(v, live, cur);
+                const uint32_t stride_b = 4u * static_cast<uint32_t>(Lay::Stride(jb));
+                // column 16 jb of L, my row offset: 32-bit shared address of element (row 16 jb + 4 h, column 16 jb)
+                const uint32_t col_a = static_cast<uint32_t>(__cvta_generic_to_shared(lp + Lay::Base(jb) + 4 * h));
+                const uint32_t low_off = 4u * static_cast<uint32_t>(npr - 16 * jb);  // slot s rows at + low_off - 64 (s + 1)
+                const float *rsp = rs + 16 * jb;
+#pragma unroll 4
+                for (int jr = 0; jr < 16; ++jr) {
+                    const int hj = jr >> 2;
+                    const int r = jr & 3;
+                    // L entries of this column: my current rows and the first (up to) four live slots are requested before
+                    // the pivot exchange, the rest while the first ones are consumed (two batches keep the live
+                    // registers under the 128-register budget; one base register + immediate offsets per column)
+                    constexpr int kLive = NBLK - 1;               // most live slots
+                    constexpr int kA = kLive < 4 ? kLive : 4;     // first batch
+                    constexpr int kB = kLive - kA;                // second batch
+                    const uint32_t cur_a = col_a + static_cast<uint32_t>(jr) * stride_b;
+                    const uint32_t low_a = cur_a + low_off;
+                    const float4 lcur = LdsOff<0>(cur_a);
+                    float4 la[kA > 0 ? kA : 1];
+                    LoadLive<0, kA, 0>(la, low_a, live);
+                    const float rsv = rsp[jr];
+                    const float c0 = (r == 0 ? cur.a[0].x : r == 1 ? cur.a[0].y : r == 2 ? cur.a[1].x : cur.a[1].y) * rsv;
+                    const float c1 = (r == 0 ? cur.b[0].x : r == 1 ? cur.b[0].y : r == 2 ? cur.b[1].x : cur.b[1].y) * rsv;
+                    const int src = (lane & ~3) | hj;
                     const float vj0 = __shfl_sync(kFull, c0, src);
                     const float vj1 = __shfl_sync(kFull, c1, src);
                     ss0 = fmaf(vj0, vj0, ss0);
                     ss1 = fmaf(vj1, vj1, ss1);
-                    const float *col = lph + (Lay::Base(cb) + (j & 15) * Lay::Stride(cb) - 16 * cb);
-                    StaticFor<mj, kNp8>([&](auto mc) {
-                        constexpr int m = decltype(mc)::value;
-                        const float4 lv = *reinterpret_cast<const float4 *>(col + 8 * m);
-                        va[2 * m] = Fma2(make_float2(lv.x, lv.y), -vj0, va[2 * m]);
-                        va[2 * m + 1] = Fma2(make_float2(lv.z, lv.w), -vj0, va[2 * m + 1]);
-                        vb[2 * m] = Fma2(make_float2(lv.x, lv.y), -vj1, vb[2 * m]);
-                        vb[2 * m + 1] = Fma2(make_float2(lv.z, lv.w), -vj1, vb[2 * m + 1]);
-                    });
-                });
-            });
+                    // rows of the current block (entries on / above the diagonal are stored as zeros or hit dead rows)
+                    SlotUpdate(cur, lcur, -vj0, -vj1);
+                    if constexpr (kB > 0) {
+                        float4 lb[kB];
+                        LoadLive<0, kB, kA>(lb, low_a, live);
+                        LiveChain<0, kA, 0, kA, NBLK>(v, la, live, -vj0, -vj1);
+                        LiveChain<kA, kLive, kA, kB, NBLK>(v, lb, live, -vj0, -vj1);
+                    } else if constexpr (kA > 0) {
+                        LiveChain<0, kA, 0, kA, NBLK>(v, la, live, -vj0, -vj1);
+                    }
+                }
+            }
             mean0 += __shfl_xor_sync(kFull, mean0, 1);
             mean1 += __shfl_xor_sync(kFull, mean1, 1);
+            mean0 += __shfl_xor_sync(kFull, mean0, 2);
+            mean1 += __shfl_xor_sync(kFull, mean1, 2);
 
-            const int myq = 2 * pair + h;
-            if (myq < nq) {
-                const long src = q_begin + myq;
-                const long dst = p.q_out_index != nullptr ? p.q_out_index[src] : src;
-                if (p.mean != nullptr) {
-                    float f = h ? mean1 : mean0;
-                    if (p.mapping != ERL_GP_MAPPING_NONE) { f = MappingInv<float>(p.mapping, p.mapping_scale, f); }
-                    p.mean[dst] = f;
+            if (h < 2) {
+                const int myq = 2 * quad + h;
+                if (myq < nq) {
+                    const long src = q_begin + myq;
+                    const long dst = p.q_out_index != nullptr ? p.q_out_index[src] : src;
+                    if (p.mean != nullptr) {
+                        float f = h ? mean1 : mean0;
+                        if (p.mapping != ERL_GP_MAPPING_NONE) { f = MappingInv<float>(p.mapping, p.mapping_scale, f); }
+                        p.mean[dst] = f;
+                    }
+                    if (p.variance != nullptr) { p.variance[dst] = 1.0f - (h ? ss1 : ss0); }  // literal prior 1.0f, src/vanilla_gp.cpp:121
+                    if (p.valid != nullptr) { p.valid[dst] = 1; }
                 }
-                if (p.variance != nullptr) { p.variance[dst] = 1.0f - (h ? ss1 : ss0); }  // literal prior 1.0f, src/vanilla_gp.cpp:121
-                if (p.valid != nullptr) { p.valid[dst] = 1; }
             }
         }
 
         template<int XDIM, int NBLK, int MODE>
-        __global__ void __launch_bounds__(kThreads, 3)
+        __global__ void __launch_bounds__(kThreads, 4)
         RowGpKernel(const BatchParams<float> p) {
             using Lay = Layout<NBLK>;
             extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -468,8 +581,9 @@ namespace erl_gp {
             }
             const int nblk = (n + 15) >> 4;
             const int npr = nblk * 16;
+            const CovCoef cov(p.cov);
 
-            // ---- stage the training inputs; identity-fill what the factorisation will not touch ----
+            // ---- stage the training inputs (everything below works on the first 16 * nblk rows / columns only) ----
             const float *gx = p.x + static_cast<long>(g) * p.max_n * XDIM;
             for (int e = tid; e < Lay::kNp; e += kThreads) {
                 float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -482,9 +596,6 @@ namespace erl_gp {
                 pts[e] = pt;
                 rs[e] = 1.0f;
             }
-            if (nblk < NBLK || !(MODE & kBatchTrain)) {
-                for (int e = tid; e < Lay::kLFloats; e += kThreads) { lp[e] = 0.f; }
-            }
 
             if constexpr ((MODE & kBatchTrain) != 0) {
                 const float *gy = p.y + static_cast<long>(g) * p.max_n;
@@ -494,10 +605,7 @@ namespace erl_gp {
                     sv[e] = e < n ? gv[e] : 0.f;
                 }
                 __syncthreads();
-                if (nblk < NBLK) {
-                    for (int e = npr + tid; e < Lay::kNp; e += kThreads) { lp[Lay::Base(e >> 4) + (e & 15) * Lay::Stride(e >> 4) + (e & 15)] = 1.0f; }
-                }
-                const int fail = Factorize<XDIM, NBLK>(p.cov, smem, n, nblk);
+                const int fail = Factorize<XDIM, NBLK>(cov, smem, n, nblk);
                 int *s_fail = reinterpret_cast<int *>(smem + Lay::kMisc);
                 if (tid == 0) { *s_fail = fail; }  // warp 0 tracked every pivot
                 __syncthreads();
@@ -548,30 +656,42 @@ namespace erl_gp {
                 }
                 if (tid == 0) { p.info[g] = 0; }
             } else {
-                // ---- predict-only: reload L, rebuild 1 / L_jj ----
+                // ---- predict-only: reload L (float4 along the rows when the layout allows), rebuild 1 / L_jj ----
                 __syncthreads();
                 const float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
-                for (int c = warp; c < Lay::kNp; c += kThreads / 32) {
+                const bool vec_ok = (p.max_n & 3) == 0;
+                for (int c = warp; c < npr; c += kThreads / 32) {
                     const int cb = c >> 4;
                     float *colp = lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) - 16 * cb;
-                    for (int r = 16 * cb + lane; r < Lay::kNp; r += 32) {
-                        float val;
-                        if (r < n && c < n) {
-                            val = r >= c ? gl[r + static_cast<long>(c) * p.max_n] : 0.f;
+                    const float *gcol = gl + static_cast<long>(c) * p.max_n;
+                    for (int r4 = 16 * cb + 4 * lane; r4 < npr; r4 += 128) {
+                        float val[4];
+                        if (vec_ok && c < n && r4 + 3 < n) {
+                            const float4 t = *reinterpret_cast<const float4 *>(gcol + r4);
+                            val[0] = t.x, val[1] = t.y, val[2] = t.z, val[3] = t.w;
                         } else {
-                            val = r == c ? 1.0f : 0.f;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { val[k] = (c < n && r4 + k < n) ? gcol[r4 + k] : 0.f; }
                         }
-                        colp[r] = val;
-                        if (r == c) { rs[c] = 1.0f / val; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r = r4 + k;
+                            if (r < c) { val[k] = 0.f; }
+                            if (r == c) {
+                                if (c >= n) { val[k] = 1.0f; }
+                                rs[c] = 1.0f / val[k];
+                            }
+                        }
+                        *reinterpret_cast<float4 *>(colp + r4) = make_float4(val[0], val[1], val[2], val[3]);
                     }
                 }
             }
 
             if constexpr ((MODE & kBatchPredict) != 0) {
                 __syncthreads();
-                for (long qb = q0 + static_cast<long>(blockIdx.y) * kThreads; qb < q1; qb += static_cast<long>(gridDim.y) * kThreads) {
-                    const int nq = static_cast<int>(q1 - qb < kThreads ? q1 - qb : kThreads);
-                    PredictTile<XDIM, NBLK>(p, smem, n, qb, nq);
+                for (long qb = q0 + static_cast<long>(blockIdx.y) * kTileQ; qb < q1; qb += static_cast<long>(gridDim.y) * kTileQ) {
+                    const int nq = static_cast<int>(q1 - qb < kTileQ ? q1 - qb : kTileQ);
+                    PredictTile<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
                 }
             }
         }

@@ -106,17 +106,21 @@ namespace erl_gp {
         struct CovCoef {
             float a, b, c;
 
+            // b and c are pre-multiplied by -log2(e): exp(-t) = ex2(-t log2 e) is one FFMA-fed MUFU.EX2 (max relative
+            // error 2^-22 + |t| 2^-23, far inside the 1e-4 parity budget; expf() costs ~8 more instructions per entry
+            // and the Gram / Ktest entries were 17 % of all instructions of the kernel)
             __device__ __forceinline__ explicit CovCoef(const Covariance<float> &cov) {
+                constexpr float kLog2e = 1.4426950408889634f;
                 a = cov.type == ERL_GP_KERNEL_MATERN32 ? cov.c0 : 0.f;
-                b = cov.type == ERL_GP_KERNEL_MATERN32 ? cov.c0 : (cov.type == ERL_GP_KERNEL_OU ? 1.0f / cov.c0 : 0.f);
-                c = cov.type == ERL_GP_KERNEL_RBF ? 1.0f / cov.c0 : 0.f;
+                b = -kLog2e * (cov.type == ERL_GP_KERNEL_MATERN32 ? cov.c0 : (cov.type == ERL_GP_KERNEL_OU ? 1.0f / cov.c0 : 0.f));
+                c = -kLog2e * (cov.type == ERL_GP_KERNEL_RBF ? 1.0f / cov.c0 : 0.f);
             }
 
             __device__ __forceinline__ float
             operator()(const float r2) const {
-                float sq;
-                asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(r2));
-                const float e = expf(-fmaf(b, sq, c * r2));
+                float sq, e;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(r2));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(b, sq, c * r2)));
                 return fmaf(a * sq, e, e);
             }
         };
@@ -361,27 +365,32 @@ namespace erl_gp {
         }
 
         // --------------------------------------------------------------------------------------
-        // predict one tile of up to 64 queries: a thread QUAD owns 2 queries, thread h of the quad keeps rows
-        // 16 m + 4 h + {0..3} of both V = L^-1 k* columns in registers (64 registers for n = 128, which leaves room
-        // under the 128-register / 4-CTAs-per-SM budget to have all L entries of a column in flight at once).
-        // Register slot s holds block row m = nblk - 1 - s: slots count from the BOTTOM of the matrix, so the rows
-        // still to be updated are always the static prefix [0, live) of the slots and the loop over the 16-column
-        // blocks is a runtime loop with compact code (the fully unrolled form was 110 KB of SASS and starved the
-        // instruction cache: ncu stall_no_instruction).
+        // predict one tile of up to 64 queries.  A thread OCTET owns 4 queries; thread h of the octet keeps rows
+        // 32 M + 4 h + {0..3} (M = 0 .. n/32 - 1, "superblocks") of the four V = L^-1 k* columns in registers: 64
+        // registers at n = 128, so the kernel fits the 128-register / 4-CTAs-per-SM budget, and every LDS.128 of L (4
+        // rows of one column, 4 shared-memory wavefronts per warp) feeds 16 FMAs per thread = 128 FMAs per wavefront
+        // and cycle, which is what the FFMA2 pipe can absorb (with 2 queries per thread the loop was shared-memory
+        // bound at half that: ncu l1tex wavefronts 75 % of the cycles).
+        // The substitution is right-looking: column j finalises v_j = r_j / L_jj in its owner thread, one shuffle
+        // per query hands it to the octet, every thread then updates its rows below j.  The loop over the
+        // 16-column blocks is a runtime loop; the code of a block is specialised on its superblock index so that all
+        // register indices are static (a fully unrolled substitution was 110 KB of SASS and starved the instruction
+        // cache).  Rows on / above the diagonal of the current superblock are updated with stored zeros or, once
+        // they are final, with whatever the packed column holds there (dead registers).
         // --------------------------------------------------------------------------------------
         constexpr int kTileQ = kThreads / 2;  // queries per tile
 
-        struct Slot {
-            float2 a[2];  // query 0: rows (0,1), (2,3)
-            float2 b[2];  // query 1
+        struct Slot {          // 4 rows x 4 queries
+            float2 q[4][2];    // q[query][0] = rows (0,1), q[query][1] = rows (2,3)
         };
 
         __device__ __forceinline__ void
-        SlotUpdate(Slot &v, const float4 lv, const float nv0, const float nv1) {
-            v.a[0] = Fma2(make_float2(lv.x, lv.y), nv0, v.a[0]);
-            v.a[1] = Fma2(make_float2(lv.z, lv.w), nv0, v.a[1]);
-            v.b[0] = Fma2(make_float2(lv.x, lv.y), nv1, v.b[0]);
-            v.b[1] = Fma2(make_float2(lv.z, lv.w), nv1, v.b[1]);
+        SlotUpdate(Slot &v, const float4 lv, const float (&nv)[4]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v.q[k][0] = Fma2(make_float2(lv.x, lv.y), nv[k], v.q[k][0]);
+                v.q[k][1] = Fma2(make_float2(lv.z, lv.w), nv[k], v.q[k][1]);
+            }
         }
 
         __device__ __forceinline__ float4
@@ -399,39 +408,58 @@ namespace erl_gp {
             return v;
         }
 
-        template<int S, int N, int S0>
+        template<int S, int CNT, int N>
         __device__ __forceinline__ void
-        LoadLive(float4 (&l)[N], const uint32_t low_addr, const int live) {  // l[S] = L entries of slot S0 + S (if live)
-            if constexpr (S < N) {
-                if (S0 + S < live) { l[S] = LdsOff<-64 * (S0 + S + 1)>(low_addr); }
-                LoadLive<S + 1, N, S0>(l, low_addr, live);
+        LoadBelow(float4 (&l)[N], const uint32_t addr) {  // l[S] = my rows of superblock (current + 1 + S): + 128 B per superblock
+            if constexpr (S < CNT) {
+                l[S] = LdsOff<128 * (S + 1)>(addr);
+                LoadBelow<S + 1, CNT, N>(l, addr);
             }
         }
 
-        // uniform binary-tree fetch of slot s (s is warp-uniform): log2(KG) branches + 8 moves
-        template<int LO, int HI, int KG>
+        // One 16-column block (PART = 0 / 1: first / second half of superblock M) of the substitution.
+        //   cur_a: shared address of element (row 32 M + 4 h, column j0) of L, j0 = first column of the block
+        template<int M, int NSB>
         __device__ __forceinline__ void
-        SlotFetch(const Slot (&v)[KG], const int s, Slot &out) {
-            if constexpr (HI - LO == 1) {
-                out = v[LO];
-            } else {
-                constexpr int kMid = (LO + HI) / 2;
-                if (s < kMid) {
-                    SlotFetch<LO, kMid, KG>(v, s, out);
-                } else {
-                    SlotFetch<kMid, HI, KG>(v, s, out);
+        SolveBlock(Slot (&v)[NSB], float (&ss)[4], uint32_t cur_a, const uint32_t stride_b, const float *__restrict__ rsp, const int lane, const int part) {
+            constexpr int kBelow = NSB - 1 - M;
+            for (int hq = 0; hq < 4; ++hq) {
+                const int src = (lane & ~7) | (4 * part + hq);  // owner of columns 4 hq .. 4 hq + 3 of this block
+                const float4 rs4 = *reinterpret_cast<const float4 *>(rsp + 4 * hq);
+                const float rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float4 lcur = LdsOff<0>(cur_a);
+                    float4 lb[kBelow > 0 ? kBelow : 1];
+                    LoadBelow<0, kBelow, (kBelow > 0 ? kBelow : 1)>(lb, cur_a);
+                    float nv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 pr = v[M].q[k][r >> 1];
+                        const float c = ((r & 1) ? pr.y : pr.x) * rsv[r];
+                        const float vj = __shfl_sync(kFull, c, src);
+                        ss[k] = fmaf(vj, vj, ss[k]);
+                        nv[k] = -vj;
+                    }
+                    SlotUpdate(v[M], lcur, nv);
+#pragma unroll
+                    for (int s = 0; s < kBelow; ++s) { SlotUpdate(v[M + 1 + s], lb[s], nv); }
+                    cur_a += stride_b;
                 }
             }
         }
 
-        // rows below the current block: slots [S, live) with their L entries in l[S - L0 ...], nested early exit
-        template<int S, int END, int L0, int NL, int KG>
+        template<int LO, int HI, int NSB>
         __device__ __forceinline__ void
-        LiveChain(Slot (&v)[KG], const float4 (&l)[NL], const int live, const float nv0, const float nv1) {
-            if constexpr (S < END) {
-                if (S < live) {
-                    SlotUpdate(v[S], l[S - L0], nv0, nv1);
-                    LiveChain<S + 1, END, L0, NL, KG>(v, l, live, nv0, nv1);
+        SolveBlockDispatch(const int m, Slot (&v)[NSB], float (&ss)[4], const uint32_t cur_a, const uint32_t stride_b, const float *__restrict__ rsp, const int lane, const int part) {
+            if constexpr (HI - LO == 1) {
+                SolveBlock<LO, NSB>(v, ss, cur_a, stride_b, rsp, lane, part);
+            } else {
+                constexpr int kMid = (LO + HI) / 2;
+                if (m < kMid) {
+                    SolveBlockDispatch<LO, kMid, NSB>(m, v, ss, cur_a, stride_b, rsp, lane, part);
+                } else {
+                    SolveBlockDispatch<kMid, HI, NSB>(m, v, ss, cur_a, stride_b, rsp, lane, part);
                 }
             }
         }
@@ -440,109 +468,77 @@ namespace erl_gp {
         __device__ __forceinline__ void
         PredictTile(const BatchParams<float> &p, const CovCoef cov, const float *__restrict__ smem, const int n, const int nblk, const long q_begin, const int nq) {
             using Lay = Layout<NBLK>;
+            static_assert(NBLK % 2 == 0, "superblocks are 32 rows");
+            constexpr int kNsb = NBLK / 2;
             const float *lp = smem + Lay::kL;
             const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
             const float *rs = smem + Lay::kRs;
             const int tid = threadIdx.x;
             const int lane = tid & 31;
-            const int h = tid & 3;
-            const int quad = tid >> 2;
-            const int npr = 16 * nblk;
+            const int h = tid & 7;
+            const int octet = tid >> 3;
 
-            float xq0[XDIM], xq1[XDIM];
+            float xq[4][XDIM];
 #pragma unroll
-            for (int d = 0; d < XDIM; ++d) {
-                xq0[d] = 2 * quad < nq ? p.q_x[(q_begin + 2 * quad) * XDIM + d] : 0.f;
-                xq1[d] = 2 * quad + 1 < nq ? p.q_x[(q_begin + 2 * quad + 1) * XDIM + d] : 0.f;
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int d = 0; d < XDIM; ++d) { xq[k][d] = 4 * octet + k < nq ? p.q_x[(q_begin + 4 * octet + k) * XDIM + d] : 0.f; }
             }
 
-            // Ktest entries of my rows for both queries (never stored anywhere but registers); mean on the way
-            Slot v[NBLK];
-            float mean0 = 0.f, mean1 = 0.f;
+            // Ktest entries of my rows for the four queries (never stored anywhere but registers); mean on the way
+            Slot v[kNsb];
+            float mean[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int s = 0; s < NBLK; ++s) {
-                if (s < nblk) {
-                    const int row0 = npr - 16 * (s + 1) + 4 * h;
-                    float k0[4], k1[4];
+            for (int m = 0; m < kNsb; ++m) {
+                const int row0 = 32 * m + 4 * h;
+                float kv[4][4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float4 pt = pts[row0 + r];
-                        float a = cov(Dist2<XDIM>(pt, xq0));
-                        float b = cov(Dist2<XDIM>(pt, xq1));
-                        if (row0 + r >= n) { a = b = 0.f; }
-                        mean0 = fmaf(a, pt.w, mean0);
-                        mean1 = fmaf(b, pt.w, mean1);
-                        k0[r] = a;
-                        k1[r] = b;
+                for (int r = 0; r < 4; ++r) {
+                    const float4 pt = pts[row0 + r];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float a = cov(Dist2<XDIM>(pt, xq[k]));
+                        if (row0 + r >= n) { a = 0.f; }
+                        mean[k] = fmaf(a, pt.w, mean[k]);
+                        kv[k][r] = a;
                     }
-                    v[s].a[0] = make_float2(k0[0], k0[1]);
-                    v[s].a[1] = make_float2(k0[2], k0[3]);
-                    v[s].b[0] = make_float2(k1[0], k1[1]);
-                    v[s].b[1] = make_float2(k1[2], k1[3]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[m].q[k][0] = make_float2(kv[k][0], kv[k][1]);
+                    v[m].q[k][1] = make_float2(kv[k][2], kv[k][3]);
                 }
             }
 
-            float ss0 = 0.f, ss1 = 0.f;
+            float ss[4] = {0.f, 0.f, 0.f, 0.f};
             for (int jb = 0; jb < nblk; ++jb) {
-                const int live = nblk - 1 - jb;  // == slot of the current block; the slots below it are still to be updated
-                Slot cur;
-                SlotFetch<0, NBLK, NBLK>(v, live, cur);
+                const int m = jb >> 1;
+                const int part = jb & 1;
                 const uint32_t stride_b = 4u * static_cast<uint32_t>(Lay::Stride(jb));
-                // column 16 jb of L, my row offset: 32-bit shared address of element (row 16 jb + 4 h, column 16 jb)
-                const uint32_t col_a = static_cast<uint32_t>(__cvta_generic_to_shared(lp + Lay::Base(jb) + 4 * h));
-                const uint32_t low_off = 4u * static_cast<uint32_t>(npr - 16 * jb);  // slot s rows at + low_off - 64 (s + 1)
-                const float *rsp = rs + 16 * jb;
-#pragma unroll 4
-                for (int jr = 0; jr < 16; ++jr) {
-                    const int hj = jr >> 2;
-                    const int r = jr & 3;
-                    // L entries of this column: my current rows and the first (up to) four live slots are requested before
-                    // the pivot exchange, the rest while the first ones are consumed (two batches keep the live
-                    // registers under the 128-register budget; one base register + immediate offsets per column)
-                    constexpr int kLive = NBLK - 1;               // most live slots
-                    constexpr int kA = kLive < 4 ? kLive : 4;     // first batch
-                    constexpr int kB = kLive - kA;                // second batch
-                    const uint32_t cur_a = col_a + static_cast<uint32_t>(jr) * stride_b;
-                    const uint32_t low_a = cur_a + low_off;
-                    const float4 lcur = LdsOff<0>(cur_a);
-                    float4 la[kA > 0 ? kA : 1];
-                    LoadLive<0, kA, 0>(la, low_a, live);
-                    const float rsv = rsp[jr];
-                    const float c0 = (r == 0 ? cur.a[0].x : r == 1 ? cur.a[0].y : r == 2 ? cur.a[1].x : cur.a[1].y) * rsv;
-                    const float c1 = (r == 0 ? cur.b[0].x : r == 1 ? cur.b[0].y : r == 2 ? cur.b[1].x : cur.b[1].y) * rsv;
-                    const int src = (lane & ~3) | hj;
-                    const float vj0 = __shfl_sync(kFull, c0, src);
-                    const float vj1 = __shfl_sync(kFull, c1, src);
-                    ss0 = fmaf(vj0, vj0, ss0);
-                    ss1 = fmaf(vj1, vj1, ss1);
-                    // rows of the current block (entries on / above the diagonal are stored as zeros or hit dead rows)
-                    SlotUpdate(cur, lcur, -vj0, -vj1);
-                    if constexpr (kB > 0) {
-                        float4 lb[kB];
-                        LoadLive<0, kB, kA>(lb, low_a, live);
-                        LiveChain<0, kA, 0, kA, NBLK>(v, la, live, -vj0, -vj1);
-                        LiveChain<kA, kLive, kA, kB, NBLK>(v, lb, live, -vj0, -vj1);
-                    } else if constexpr (kA > 0) {
-                        LiveChain<0, kA, 0, kA, NBLK>(v, la, live, -vj0, -vj1);
-                    }
-                }
+                // element (row 32 m + 4 h, column 16 jb) of L: column block jb starts at row 16 jb
+                const uint32_t cur_a = static_cast<uint32_t>(__cvta_generic_to_shared(lp + Lay::Base(jb) + (32 * m + 4 * h - 16 * jb)));
+                SolveBlockDispatch<0, kNsb, kNsb>(m, v, ss, cur_a, stride_b, rs + 16 * jb, lane, part);
             }
-            mean0 += __shfl_xor_sync(kFull, mean0, 1);
-            mean1 += __shfl_xor_sync(kFull, mean1, 1);
-            mean0 += __shfl_xor_sync(kFull, mean0, 2);
-            mean1 += __shfl_xor_sync(kFull, mean1, 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mean[k] += __shfl_xor_sync(kFull, mean[k], 1);
+                mean[k] += __shfl_xor_sync(kFull, mean[k], 2);
+                mean[k] += __shfl_xor_sync(kFull, mean[k], 4);
+            }
 
-            if (h < 2) {
-                const int myq = 2 * quad + h;
+            if (h < 4) {
+                const int myq = 4 * octet + h;
                 if (myq < nq) {
                     const long src = q_begin + myq;
                     const long dst = p.q_out_index != nullptr ? p.q_out_index[src] : src;
+                    const float mk = h == 0 ? mean[0] : h == 1 ? mean[1] : h == 2 ? mean[2] : mean[3];
+                    const float sk = h == 0 ? ss[0] : h == 1 ? ss[1] : h == 2 ? ss[2] : ss[3];
                     if (p.mean != nullptr) {
-                        float f = h ? mean1 : mean0;
+                        float f = mk;
                         if (p.mapping != ERL_GP_MAPPING_NONE) { f = MappingInv<float>(p.mapping, p.mapping_scale, f); }
                         p.mean[dst] = f;
                     }
-                    if (p.variance != nullptr) { p.variance[dst] = 1.0f - (h ? ss1 : ss0); }  // literal prior 1.0f, src/vanilla_gp.cpp:121
+                    if (p.variance != nullptr) { p.variance[dst] = 1.0f - sk; }  // literal prior 1.0f, src/vanilla_gp.cpp:121
                     if (p.valid != nullptr) { p.valid[dst] = 1; }
                 }
             }

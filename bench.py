@@ -88,6 +88,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs ~1 s to start: block until it delivers so that short timed regions are still sampled."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+        self.lines.clear()  # keep only samples taken under load
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -134,8 +141,9 @@ def profile_traffic():
     return None
 
 
-def cpu_baseline(w, sample_gps, threads=None):
-    """Time the CPU reference path (oracle port: OpenMP over GPs, each Reset/Train/Test) on a bounded sample."""
+def cpu_baseline(w, sample_gps, threads=None, min_seconds=10.0):
+    """Time the CPU reference path (oracle port: OpenMP over GPs, each Reset/Train/Test) on a bounded sample:
+    `sample_gps` GPs of the workload, repeated until at least `min_seconds` of CPU work have been timed."""
     import oracle
 
     if threads:
@@ -145,11 +153,17 @@ def cpu_baseline(w, sample_gps, threads=None):
     n_train, x, y, var, q_offsets, q_x = synth_batch(ww, 0)
     kid = oracle.KERNELS[w["kernel"]]
     oracle.batched_train_predict(kid, w["scale"], n_train[:64], x[:64], y[:64], var[:64], q_offsets[:65], q_x[: 64 * w["q_per_gp"]])  # warm
+    reps = 0
     t0 = time.perf_counter()
-    oracle.batched_train_predict(kid, w["scale"], n_train, x, y, var, q_offsets, q_x)
-    dt = time.perf_counter() - t0
-    return {"value": sample_gps * w["q_per_gp"] / dt, "unit": "test-points/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_gps} of the workload's GPs (n={w['n']}, {w['q_per_gp']} test points each), {dt:.2f} s on {cores} OpenMP threads", "seconds": dt}
+    while True:
+        oracle.batched_train_predict(kid, w["scale"], n_train, x, y, var, q_offsets, q_x)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return {"value": reps * sample_gps * w["q_per_gp"] / dt, "unit": "test-points/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x {sample_gps} of the workload's GPs (n={w['n']}, {w['q_per_gp']} test points each), {dt:.2f} s on {cores} OpenMP threads", "seconds": dt,
+            "points": reps * sample_gps * w["q_per_gp"]}
 
 
 def run_reference(args, w, rank, world):
@@ -158,12 +172,13 @@ def run_reference(args, w, rank, world):
     times = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(w, args.ref_sample)
+        base = cpu_baseline(w, args.ref_sample, min_seconds=args.ref_seconds)
         if i >= args.warmup:
-            times.append(base["seconds"])
-    ms = 1e3 * sum(times) / len(times)
-    value = args.ref_sample * w["q_per_gp"] / (ms * 1e-3)
+            times.append(base["seconds"] * 1e3 / base["points"])  # ms per test point
+    ms_per_point = sum(times) / len(times)
+    value = 1e3 / ms_per_point
     base["value"] = value
+    ms = base["seconds"] * 1e3
     line = {"impl": "reference", "metric": "gp_train_predict_test_points_per_sec", "value": value, "unit": "test-points/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
             "config": {"workload": w["desc"], "sample": base["sample"], "note": "CPU reference path = OpenMP oracle port (the reference cannot be built in this image)"},
@@ -181,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--num-gps", type=int, default=None, help="override GPs per GPU (smoke runs)")
     ap.add_argument("--ref-sample", type=int, default=4000, help="GPs in the CPU reference sample")
+    ap.add_argument("--ref-seconds", type=float, default=2.0, help="--impl reference: CPU seconds per step (the sample is repeated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--phase", default="fused", choices=["fused", "train", "predict", "split"],
@@ -267,6 +283,10 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first_sample()
+    for _ in range(2):  # the GPU is busy again when the sampled region starts
+        step()
+    barrier()
     launches0 = ctx.kernel_launches
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -278,6 +298,13 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.kernel_launches - launches0
+    if len(sampler.lines) < 3:
+        # the K timed steps were shorter than a few sampler periods: keep the same load running (untimed) until
+        # nvidia-smi has reported the clocks it runs at
+        t_s = time.perf_counter()
+        while len(sampler.lines) < 3 and time.perf_counter() - t_s < 3.0:
+            step()
+            torch.cuda.synchronize()
     clocks = sampler.stop()
     tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -336,8 +363,8 @@ def main():
                        "l2": f"per-step inputs+outputs {alg_bytes / 1e9:.2f} GB >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                         "kernel": "BatchedGpKernel<float,3,8,train+predict> (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu; this kernel is FP32-pipe bound, see DESIGN.md"}},
+                         "kernel": "rowgp::RowGpKernel<x_dim=3, NBLK=8, train+predict> (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
+                         "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu (FFMA2 with fresh operands sustains ~55, tools/fma_lds_rate.cu); this kernel is FP32-pipe / issue bound, see DESIGN.md"}},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -656,29 +656,39 @@ namespace erl_gp {
                 __syncthreads();
                 const float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                 const bool vec_ok = (p.max_n & 3) == 0;
-                for (int c = warp; c < npr; c += kThreads / 32) {
-                    const int cb = c >> 4;
-                    float *colp = lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) - 16 * cb;
-                    const float *gcol = gl + static_cast<long>(c) * p.max_n;
-                    for (int r4 = 16 * cb + 4 * lane; r4 < npr; r4 += 128) {
-                        float val[4];
+                constexpr int kBatch = 8;  // columns in flight per warp: the loads of a batch are all issued before the first store
+                for (int c0 = warp * kBatch; c0 < npr; c0 += (kThreads / 32) * kBatch) {
+                    float val[kBatch][4];
+#pragma unroll
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int c = c0 + u;
+                        const int r4 = 16 * (c >> 4) + 4 * lane;
+                        const float *gcol = gl + static_cast<long>(c) * p.max_n;
                         if (vec_ok && c < n && r4 + 3 < n) {
                             const float4 t = *reinterpret_cast<const float4 *>(gcol + r4);
-                            val[0] = t.x, val[1] = t.y, val[2] = t.z, val[3] = t.w;
+                            val[u][0] = t.x, val[u][1] = t.y, val[u][2] = t.z, val[u][3] = t.w;
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) { val[k] = (c < n && r4 + k < n) ? gcol[r4 + k] : 0.f; }
+                            for (int k = 0; k < 4; ++k) { val[u][k] = (c < n && r4 + k < n) ? gcol[r4 + k] : 0.f; }
                         }
+                    }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int r = r4 + k;
-                            if (r < c) { val[k] = 0.f; }
-                            if (r == c) {
-                                if (c >= n) { val[k] = 1.0f; }
-                                rs[c] = 1.0f / val[k];
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int c = c0 + u;
+                        const int cb = c >> 4;
+                        const int r4 = 16 * cb + 4 * lane;
+                        if (c < npr && r4 < npr) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int r = r4 + k;
+                                if (r < c) { val[u][k] = 0.f; }
+                                if (r == c) {
+                                    if (c >= n) { val[u][k] = 1.0f; }
+                                    rs[c] = 1.0f / val[u][k];
+                                }
                             }
+                            *reinterpret_cast<float4 *>(lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) + (r4 - 16 * cb)) = make_float4(val[u][0], val[u][1], val[u][2], val[u][3]);
                         }
-                        *reinterpret_cast<float4 *>(colp + r4) = make_float4(val[0], val[1], val[2], val[3]);
                     }
                 }
             }

@@ -47,6 +47,20 @@ namespace erl_gp {
     int
     GemvT(Context *ctx, long n, long t, const T *w, long ldw, const T *alpha, long ld_a, long y_dim, T *out, long ld_out);
 
+    // Fused predict of the dense VanillaGaussianProcess (erl_gp_predict_dense.cu): Ktest generated on the fly.
+    //   PredictMean:     out[j + c * ld_out] = sum_i k(x_i, x*_j) alpha[i + c * ld_a]   (ERL_GP_STATUS_UNSUPPORTED when y_dim > 4)
+    //   PredictVariance: sumsq[j] = || L^-1 k(X, x*_j) ||^2, left-looking, one CTA per 128 test points; v_slabs needs
+    //                    PredictVarianceSlabElems() elements
+    template<typename T>
+    size_t
+    PredictVarianceSlabElems(const Context *ctx, long n, long t);
+    template<typename T>
+    int
+    PredictVariance(Context *ctx, int kernel, T scale, long x_dim, long n, long t, const T *x_train, const T *x_test, const T *l, long ldl, const T *linv, T *v_slabs, T *sumsq);
+    template<typename T>
+    int
+    PredictMean(Context *ctx, int kernel, T scale, long x_dim, long n, long t, const T *x_train, const T *x_test, const T *alpha, long ld_a, long y_dim, T *out, long ld_out);
+
     // var[j] = 1 - a[j] (+ b[j] when b != nullptr)
     template<typename T>
     int

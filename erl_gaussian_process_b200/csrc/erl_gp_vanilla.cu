@@ -89,6 +89,35 @@ namespace erl_gp {
         if (ld_xt < gp->x_dim) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: ld_xt < x_dim"); }
         ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         const long n = gp->n, d = gp->x_dim;
+        // ---- fused path (erl_gp_predict_dense.cu): Ktest is generated where it is consumed, test points in chunks of <= 2^20 ----
+        if (gp->y_dim <= 4 || mean == nullptr) {
+            const long chunk = std::min<long>(num_test, 1L << 20);
+            ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(chunk) * d));
+            if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, gp->mean.Reserve(static_cast<size_t>(chunk) * gp->y_dim)); }
+            if (var != nullptr) {
+                ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(chunk));
+                ERL_GP_CUDA_OK(ctx, gp->variance.Reserve(chunk));
+                ERL_GP_CUDA_OK(ctx, gp->w.Reserve(PredictVarianceSlabElems<T>(ctx, n, chunk)));
+            }
+            for (long t0 = 0; t0 < num_test; t0 += chunk) {
+                const long tt = std::min(chunk, num_test - t0);
+                ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test + t0 * ld_xt, sizeof(T) * ld_xt, sizeof(T) * d, tt, in_kind, ctx->stream));
+                if (mean != nullptr) {
+                    const int rc = PredictMean<T>(ctx, gp->kernel, gp->scale, d, n, tt, gp->x.ptr, gp->xt.ptr, gp->alpha.ptr, n, gp->y_dim, gp->mean.ptr, tt);
+                    if (rc != ERL_GP_STATUS_OK) { return rc; }
+                    ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(mean + t0, sizeof(T) * num_test, gp->mean.ptr, sizeof(T) * tt, sizeof(T) * tt, gp->y_dim, out_kind, ctx->stream));
+                }
+                if (var != nullptr) {
+                    int rc = PredictVariance<T>(ctx, gp->kernel, gp->scale, d, n, tt, gp->x.ptr, gp->xt.ptr, gp->l.ptr, n, gp->linv.ptr, gp->w.ptr, gp->sumsq.ptr);
+                    if (rc != ERL_GP_STATUS_OK) { return rc; }
+                    rc = VarianceFinalize<T>(ctx, tt, gp->sumsq.ptr, nullptr, gp->variance.ptr);
+                    if (rc != ERL_GP_STATUS_OK) { return rc; }
+                    ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var + t0, gp->variance.ptr, sizeof(T) * tt, out_kind, ctx->stream));
+                }
+            }
+            return ERL_GP_STATUS_OK;
+        }
+        // ---- materialised-tile path (y_dim > 4): Ktest tile, GEMV mean, right-looking solve ----
         const long tile = std::min(TestTile(n, sizeof(T)), ((num_test + 127) / 128) * 128);
         ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(tile) * d));
         ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(n) * tile));

@@ -14,6 +14,9 @@
 // measured, tools/mma_rate.cu), and the FP32 path must stay true FP32 (3xTF32 mma.sync measures only
 // 92 TFLOP/s-equivalent vs 71 TFLOP/s FFMA, and plain TF32 breaks the 1e-4 parity).
 #include "erl_gp_dense.cuh"
+#include "erl_gp_dense_mma.cuh"
+
+#include <cstdlib>
 
 #include "erl_gp_batched.cuh"
 
@@ -160,6 +163,84 @@ namespace erl_gp {
         }
     }
 
+    // FP64 on the tensor path (DMMA m8n8k4): same tiling / staging as GemmKernel, the 8 x 8 DFMA register tile is replaced
+    // by the warp-level fragments of erl_gp_dense_mma.cuh (the DFMA loop is register-file bound at ~52 % of the FP64 peak)
+    template<bool A_KC, bool B_KC>
+    __global__ void __launch_bounds__(kGemmThreads, 1)
+    GemmKernelDmma(const long m, const long n, const long k, const double alpha, const double *__restrict__ a, const long lda, const double *__restrict__ b, const long ldb, const double beta,
+                   double *__restrict__ c, const long ldc, const int lower_only) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        static_assert(kLd == kMmaLd && kGemmBK == kMmaBk, "slab layout shared with erl_gp_dense_mma.cuh");
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        double *as = reinterpret_cast<double *>(smem_raw);
+        double *bs = as + 2 * kGemmBK * kLd;
+        const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
+        const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
+        if (lower_only && col0 > row0 + kGemmBM - 1) { return; }
+        const int tid = threadIdx.x;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wm = warp & 1, wn = warp >> 1;
+        const int g = lane >> 2, kq = lane & 3;
+        double acc[8][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = acc[mi][ni][1] = 0.0; }
+        }
+        double ra[8], rb[8];
+        GemmLoadTile<double, A_KC>(a, lda, row0, m, 0, k, tid, ra);
+        GemmLoadTile<double, B_KC>(b, ldb, col0, n, 0, k, tid, rb);
+        GemmStoreTile<double, A_KC>(as, tid, ra);
+        GemmStoreTile<double, B_KC>(bs, tid, rb);
+        __syncthreads();
+        const long num_kt = (k + kGemmBK - 1) / kGemmBK;
+        for (long kt = 0; kt < num_kt; ++kt) {
+            const int cur = static_cast<int>(kt & 1);
+            if (kt + 1 < num_kt) {
+                GemmLoadTile<double, A_KC>(a, lda, row0, m, (kt + 1) * kGemmBK, k, tid, ra);
+                GemmLoadTile<double, B_KC>(b, ldb, col0, n, (kt + 1) * kGemmBK, k, tid, rb);
+            }
+            SlabMma(acc, as + cur * kGemmBK * kLd, bs + cur * kGemmBK * kLd, wm, wn, lane);
+            if (kt + 1 < num_kt) {
+                GemmStoreTile<double, A_KC>(as + (cur ^ 1) * kGemmBK * kLd, tid, ra);
+                GemmStoreTile<double, B_KC>(bs + (cur ^ 1) * kGemmBK * kLd, tid, rb);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long col = col0 + 32 * wn + 8 * ni + 2 * kq + e;
+                if (col >= n) { continue; }
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) {
+                    const long row = row0 + 64 * wm + 8 * mi + g;
+                    if (row >= m || (lower_only && row < col)) { continue; }
+                    double *dst = c + row + col * ldc;
+                    const double prev = beta == 0.0 ? 0.0 : beta * (*dst);
+                    *dst = alpha * acc[mi][ni][e] + prev;
+                }
+            }
+        }
+    }
+
+    template<typename T, bool A_KC, bool B_KC>
+    struct GemmSelect {
+        static auto
+        Get() {
+            return GemmKernel<T, A_KC, B_KC>;
+        }
+    };
+    template<bool A_KC, bool B_KC>
+    struct GemmSelect<double, A_KC, B_KC> {
+        static auto
+        Get() {
+            static const bool fma = std::getenv("ERL_GP_DENSE_FMA") != nullptr;  // A/B measurements of the DFMA loop
+            return fma ? GemmKernel<double, A_KC, B_KC> : GemmKernelDmma<A_KC, B_KC>;
+        }
+    };
+
     template<typename T>
     int
     Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, bool lower_only) {
@@ -170,7 +251,7 @@ namespace erl_gp {
         // op(B)(k,n): N -> b[k + n ldb] (k contiguous),     T -> b[n + k ldb] (outer contiguous)
 #define ERL_GP_GEMM_LAUNCH(AKC, BKC)                                                                                          \
     {                                                                                                                         \
-        auto kern = GemmKernel<T, AKC, BKC>;                                                                                  \
+        auto kern = GemmSelect<T, AKC, BKC>::Get();                                                                               \
         ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
         kern<<<grid, kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only ? 1 : 0);    \
     }
@@ -442,6 +523,116 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // =========================================================================================
+    // alpha = L^-T L^-1 y for a few right-hand sides (y_dim <= 4): blocked substitution with vector kernels.
+    // (Running these solves through 128-wide GEMM tiles cost 35 % of Train() at n = 4096: 4 launches per panel, each
+    // computing 127 useless columns.)  Memory-bound: L is read once per direction.
+    // =========================================================================================
+    constexpr int kTrsvYmax = 4;
+
+    // y_k <- M * y_k with M = Linv_k (forward) or Linv_k^T (backward); one CTA, thread = row
+    template<typename T>
+    __global__ void __launch_bounds__(kPanel)
+    TrsvDiagKernel(const T *__restrict__ linv_k, const int nk, T *__restrict__ y, const long ldy, const int y_dim, const int trans) {
+        __shared__ T ys[kPanel * kTrsvYmax];
+        const int i = threadIdx.x;
+        for (int c = 0; c < y_dim; ++c) { ys[i + c * kPanel] = i < nk ? y[i + c * ldy] : T(0); }
+        __syncthreads();
+        T sum[kTrsvYmax];
+#pragma unroll
+        for (int c = 0; c < kTrsvYmax; ++c) { sum[c] = T(0); }
+        for (int j = 0; j < nk; ++j) {
+            const T mij = trans ? linv_k[j + i * kPanel] : linv_k[i + j * kPanel];
+#pragma unroll
+            for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += mij * ys[j + c * kPanel]; }
+        }
+        if (i < nk) {
+            for (int c = 0; c < y_dim; ++c) { y[i + c * ldy] = sum[c]; }
+        }
+    }
+
+    // forward: y[r] -= sum_c L[r, k0 + c] z[c] for the rows r below the panel; thread = row (coalesced along r)
+    template<typename T>
+    __global__ void __launch_bounds__(128)
+    TrsvUpdateBelowKernel(const T *__restrict__ l, const long ld, const long n, const long k0, const int nk, T *__restrict__ y, const long ldy, const int y_dim) {
+        __shared__ T zs[kPanel * kTrsvYmax];
+        for (int e = threadIdx.x; e < kPanel * kTrsvYmax; e += blockDim.x) {
+            const int j = e % kPanel, c = e / kPanel;
+            zs[e] = (j < nk && c < y_dim) ? y[k0 + j + c * ldy] : T(0);
+        }
+        __syncthreads();
+        const long r = k0 + nk + static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (r >= n) { return; }
+        T sum[kTrsvYmax];
+#pragma unroll
+        for (int c = 0; c < kTrsvYmax; ++c) { sum[c] = T(0); }
+        const T *lr = l + r + k0 * ld;
+#pragma unroll 8
+        for (int j = 0; j < nk; ++j) {
+            const T lv = lr[static_cast<long>(j) * ld];
+#pragma unroll
+            for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += lv * zs[j + c * kPanel]; }
+        }
+        for (int c = 0; c < y_dim; ++c) { y[r + c * ldy] -= sum[c]; }
+    }
+
+    // backward: y[j] -= sum_c L[k0 + c, j] z[c] for the columns j left of the panel; warp = column (coalesced along c)
+    template<typename T>
+    __global__ void __launch_bounds__(256)
+    TrsvUpdateAboveKernel(const T *__restrict__ l, const long ld, const long k0, const int nk, T *__restrict__ y, const long ldy, const int y_dim) {
+        __shared__ T zs[kPanel * kTrsvYmax];
+        for (int e = threadIdx.x; e < kPanel * kTrsvYmax; e += blockDim.x) {
+            const int j = e % kPanel, c = e / kPanel;
+            zs[e] = (j < nk && c < y_dim) ? y[k0 + j + c * ldy] : T(0);
+        }
+        __syncthreads();
+        const long j = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int lane = threadIdx.x & 31;
+        if (j >= k0) { return; }
+        T sum[kTrsvYmax];
+#pragma unroll
+        for (int c = 0; c < kTrsvYmax; ++c) { sum[c] = T(0); }
+        const T *lc = l + k0 + j * ld;
+        for (int i = lane; i < nk; i += 32) {
+            const T lv = lc[i];
+#pragma unroll
+            for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += lv * zs[i + c * kPanel]; }
+        }
+#pragma unroll
+        for (int c = 0; c < kTrsvYmax; ++c) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) { sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], off); }
+        }
+        if (lane == 0) {
+            for (int c = 0; c < y_dim; ++c) { y[j + c * ldy] -= sum[c]; }
+        }
+    }
+
+    template<typename T>
+    int
+    TrsvSolve(Context *ctx, long n, long y_dim, const T *l, long ld, const T *linv, T *y, long ldy) {
+        if (y_dim < 1 || y_dim > kTrsvYmax) { return ERL_GP_STATUS_UNSUPPORTED; }
+        const long num_panels = CeilDiv(n, kPanel);
+        const int yd = static_cast<int>(y_dim);
+        for (long kb = 0; kb < num_panels; ++kb) {  // z = L^-1 y
+            const long k0 = kb * kPanel;
+            const int nk = static_cast<int>(n - k0 < kPanel ? n - k0 : kPanel);
+            TrsvDiagKernel<T><<<1, kPanel, 0, ctx->stream>>>(linv + kb * kPanel * kPanel, nk, y + k0, ldy, yd, 0);
+            const long m = n - k0 - nk;
+            if (m > 0) { TrsvUpdateBelowKernel<T><<<static_cast<unsigned>(CeilDiv(m, 128)), 128, 0, ctx->stream>>>(l, ld, n, k0, nk, y, ldy, yd); }
+            ctx->launches += m > 0 ? 2 : 1;
+        }
+        for (long kb = num_panels - 1; kb >= 0; --kb) {  // alpha = L^-T z
+            const long k0 = kb * kPanel;
+            const int nk = static_cast<int>(n - k0 < kPanel ? n - k0 : kPanel);
+            TrsvDiagKernel<T><<<1, kPanel, 0, ctx->stream>>>(linv + kb * kPanel * kPanel, nk, y + k0, ldy, yd, 1);
+            if (k0 > 0) { TrsvUpdateAboveKernel<T><<<static_cast<unsigned>(CeilDiv(k0, 8)), 256, 0, ctx->stream>>>(l, ld, k0, nk, y, ldy, yd); }
+            ctx->launches += k0 > 0 ? 2 : 1;
+        }
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        return ERL_GP_STATUS_OK;
+    }
+
     template<typename T>
     __global__ void
     GemvTKernel(const long n, const long t, const T *__restrict__ w, const long ldw, const T *__restrict__ alpha, const long ld_a, const long y_dim, T *__restrict__ out, const long ld_out) {
@@ -489,6 +680,7 @@ namespace erl_gp {
     template int TrsmLowerTrans<T>(Context *, long, long, const T *, long, const T *, T *, long, T *);                         \
     template int CopyLower<T>(Context *, long, const T *, long, T *, long);                                                    \
     template int GemvT<T>(Context *, long, long, const T *, long, const T *, long, long, T *, long);                           \
+    template int TrsvSolve<T>(Context *, long, long, const T *, long, const T *, T *, long);                                    \
     template int VarianceFinalize<T>(Context *, long, const T *, const T *, T *);
     ERL_GP_INSTANTIATE_DENSE(float)
     ERL_GP_INSTANTIATE_DENSE(double)

@@ -37,6 +37,11 @@ namespace erl_gp {
     int
     TrsmLowerTrans(Context *ctx, long n, long t, const T *l, long ld, const T *linv, T *z, long ldz, T *s_buf);
 
+    // Y (n x y_dim, ldy) <- L^-T L^-1 Y with vector kernels; ERL_GP_STATUS_UNSUPPORTED when y_dim > 4 (use the TRSMs)
+    template<typename T>
+    int
+    TrsvSolve(Context *ctx, long n, long y_dim, const T *l, long ld, const T *linv, T *y, long ldy);
+
     // L = tril(K), strict upper zero (the reference's `mat_l = ktrain.llt().matrixL()` dense assignment)
     template<typename T>
     int

@@ -18,6 +18,7 @@
 // during the 128-row diagonal solves.  All CTAs walk L in step, so a panel row of L is fetched from HBM once
 // and served to the other CTAs from L2.  Bound: FP64 / FP32 FMA pipe; useful flops = T (n^2 + n).
 #include "erl_gp_dense.cuh"
+#include "erl_gp_dense_mma.cuh"
 
 #include <cstdlib>
 
@@ -29,6 +30,7 @@ namespace erl_gp {
         constexpr int kBk = 16;       // reduction slab
         constexpr int kPad = 4;
         constexpr int kLd = kTile + kPad;
+        static_assert(kLd == kMmaLd && kBk == kMmaBk, "slab layout shared with erl_gp_dense_mma.cuh");
         constexpr int kThreads = 256;
 
         template<typename T>
@@ -296,33 +298,6 @@ namespace erl_gp {
         // registers.  Warp w owns rows 64 (w & 1) .. +63 and columns 32 (w >> 1) .. +31 of the tile:
         //   acc[mi][ni][e] = C[64 wm + 8 mi + lane / 4][32 wn + 8 ni + 2 (lane % 4) + e]
         // ---------------------------------------------------------------------------------------------
-        __device__ __forceinline__ void
-        Dmma884(double (&c)[2], const double a, const double b) {
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-        }
-
-        // acc += A(slab)^T-layout at[kk][row] * bt[kk][col] over one 16-deep slab
-        __device__ __forceinline__ void
-        SlabMma(double (&acc)[8][4][2], const double *__restrict__ at, const double *__restrict__ bt, const int wm, const int wn, const int lane) {
-            const int kq = lane & 3;
-            const int g = lane >> 2;
-#pragma unroll
-            for (int k4 = 0; k4 < kBk / 4; ++k4) {
-                const double *ap = at + (4 * k4 + kq) * kLd + 64 * wm + g;
-                const double *bp = bt + (4 * k4 + kq) * kLd + 32 * wn + g;
-                double a[8], b[4];
-#pragma unroll
-                for (int mi = 0; mi < 8; ++mi) { a[mi] = ap[8 * mi]; }
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) { b[ni] = bp[8 * ni]; }
-#pragma unroll
-                for (int mi = 0; mi < 8; ++mi) {
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) { Dmma884(acc[mi][ni], a[mi], b[ni]); }
-                }
-            }
-        }
-
         template<int XDIM>
         __global__ void __launch_bounds__(kThreads, 1)
         PredictVarianceKernelDmma(

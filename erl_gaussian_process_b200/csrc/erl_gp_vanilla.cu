@@ -70,9 +70,12 @@ namespace erl_gp {
         rc = Potrf<T>(ctx, n, gp->l.ptr, n, gp->linv.ptr, gp->panel.ptr, gp->info.ptr);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         // alpha = L^-T L^-1 y (src/vanilla_gp.cpp:501-502)
-        rc = TrsmLower<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n, gp->s_buf.ptr, nullptr, true);
-        if (rc != ERL_GP_STATUS_OK) { return rc; }
-        rc = TrsmLowerTrans<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n, gp->s_buf.ptr);
+        rc = TrsvSolve<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n);
+        if (rc == ERL_GP_STATUS_UNSUPPORTED) {  // many outputs: GEMM-based triangular solves
+            rc = TrsmLower<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n, gp->s_buf.ptr, nullptr, true);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            rc = TrsmLowerTrans<T>(ctx, n, y_dim, gp->l.ptr, n, gp->linv.ptr, gp->alpha.ptr, n, gp->s_buf.ptr);
+        }
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         gp->trained = true;
         return ERL_GP_STATUS_OK;

@@ -305,6 +305,12 @@ erl_gp_context_destroy(erl_gp_context *c) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    if (ctx->side_stream != nullptr) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->ev_panel != nullptr) { cudaEventDestroy(ctx->ev_panel); }
+    if (ctx->ev_diag != nullptr) { cudaEventDestroy(ctx->ev_diag); }
     delete ctx;
     return ERL_GP_STATUS_OK;
 }

@@ -99,6 +99,7 @@ namespace erl_gp {
         const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
         const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
         if (lower_only && col0 > row0 + kGemmBM - 1) { return; }  // tile strictly above the diagonal
+        if (lower_only == 2 && blockIdx.x == 0 && blockIdx.y == 0) { return; }  // diagonal tile (0, 0) is updated by the look-ahead stream
         const int tid = threadIdx.x;
         const int tx = tid & 15, ty = tid >> 4;
 
@@ -177,6 +178,7 @@ namespace erl_gp {
         const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
         const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
         if (lower_only && col0 > row0 + kGemmBM - 1) { return; }
+        if (lower_only == 2 && blockIdx.x == 0 && blockIdx.y == 0) { return; }  // diagonal tile (0, 0) is updated by the look-ahead stream
         const int tid = threadIdx.x;
         const int lane = tid & 31, warp = tid >> 5;
         const int wm = warp & 1, wn = warp >> 1;
@@ -243,7 +245,7 @@ namespace erl_gp {
 
     template<typename T>
     int
-    Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, bool lower_only) {
+    Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, int lower_only) {
         if (m <= 0 || n <= 0) { return ERL_GP_STATUS_OK; }
         const dim3 grid(static_cast<unsigned>(CeilDiv(m, kGemmBM)), static_cast<unsigned>(CeilDiv(n, kGemmBN)));
         const size_t smem = sizeof(T) * 4 * kGemmBK * (kGemmBM + kGemmPad);
@@ -253,7 +255,7 @@ namespace erl_gp {
     {                                                                                                                         \
         auto kern = GemmSelect<T, AKC, BKC>::Get();                                                                               \
         ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-        kern<<<grid, kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only ? 1 : 0);    \
+        kern<<<grid, kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only);    \
     }
         if (op_a == kOpN && op_b == kOpT) {
             ERL_GP_GEMM_LAUNCH(false, false)
@@ -443,24 +445,86 @@ namespace erl_gp {
         auto diag = DiagFactorKernel<T>;
         ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(diag, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Smem::kBytes)));
         ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
-        for (long k0 = 0, kb = 0; k0 < n; k0 += kPanel, ++kb) {
-            const long nk = n - k0 < kPanel ? n - k0 : kPanel;
-            T *l11 = l + k0 + k0 * ld;
-            T *linv_k = linv + kb * kPanel * kPanel;
-            diag<<<1, kBatchThreads, Smem::kBytes, ctx->stream>>>(l11, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
-            ctx->launches += 1;
-            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
-            const long m = n - k0 - nk;
-            if (m <= 0) { break; }
-            T *l21 = l + (k0 + nk) + k0 * ld;
-            // panel solve: P = A21 * L11^-T  (GEMM N,T against the kept inverse), then L21 <- P
-            int rc = Gemm<T>(ctx, kOpN, kOpT, m, nk, nk, T(1), l21, ld, linv_k, kPanel, T(0), panel, m, false);
-            if (rc != ERL_GP_STATUS_OK) { return rc; }
-            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l21, sizeof(T) * ld, panel, sizeof(T) * m, sizeof(T) * m, nk, cudaMemcpyDeviceToDevice, ctx->stream));
-            // trailing update: A22 -= P P^T (lower tiles only)
-            rc = Gemm<T>(ctx, kOpN, kOpT, m, m, nk, T(-1), panel, m, panel, m, T(1), l + (k0 + nk) + (k0 + nk) * ld, ld, true);
-            if (rc != ERL_GP_STATUS_OK) { return rc; }
+        // Two-level blocking: inside an outer block of kOuter columns the 128-column panels are factored right-looking,
+        // but their rank-128 updates are applied to the rest of the OUTER BLOCK only; everything to the right of it gets
+        // one rank-kOuter update per outer block (4x less read-modify-write traffic on the trailing matrix and 4x longer
+        // reduction loops than a rank-128 SYRK per panel, which ran at 19 of 37 TFLOP/s).
+        // Look-ahead: the 128 x 128 diagonal block of the NEXT panel is updated and factored (a one-CTA kernel, ~140 us)
+        // on a side stream while the main stream runs the bulk of the current update (which skips that tile).
+        constexpr long kOuter = 4 * kPanel;
+        if (ctx->side_stream == nullptr) {
+            // highest priority: its one-CTA kernels must get the first SM slot that frees up while the bulk update still has
+            // thousands of CTAs queued (with equal priorities they only start when the bulk kernel has drained)
+            int prio_lo = 0, prio_hi = 0;
+            ERL_GP_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
+            ERL_GP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming));
+            ERL_GP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_diag, cudaEventDisableTiming));
         }
+        cudaStream_t main_stream = ctx->stream;
+        cudaStream_t side = ctx->side_stream;
+        bool diag_pending = false;  // the diagonal block of the panel about to be processed was factored on the side stream
+        for (long j0 = 0; j0 < n; j0 += kOuter) {
+            const long j1 = j0 + kOuter < n ? j0 + kOuter : n;  // end of the outer block
+            for (long k0 = j0; k0 < j1; k0 += kPanel) {
+                const long kb = k0 / kPanel;
+                const long nk = n - k0 < kPanel ? n - k0 : kPanel;
+                T *l11 = l + k0 + k0 * ld;
+                T *linv_k = linv + kb * kPanel * kPanel;
+                if (diag_pending) {
+                    ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_diag, 0));
+                    diag_pending = false;
+                } else {
+                    diag<<<1, kBatchThreads, Smem::kBytes, main_stream>>>(l11, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
+                    ctx->launches += 1;
+                    ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+                }
+                const long m = n - k0 - nk;
+                if (m <= 0) { break; }
+                const long k1 = k0 + nk;
+                T *l21 = l + k1 + k0 * ld;
+                // panel solve: P = A21 * L11^-T  (GEMM N,T against the kept inverse), then L21 <- P
+                int rc = Gemm<T>(ctx, kOpN, kOpT, m, nk, nk, T(1), l21, ld, linv_k, kPanel, T(0), panel, m, 0);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l21, sizeof(T) * ld, panel, sizeof(T) * m, sizeof(T) * m, nk, cudaMemcpyDeviceToDevice, main_stream));
+                const long rest = j1 - k1;  // columns of the outer block still to the right of this panel
+                // the update that touches the next diagonal block: the rank-128 one inside the outer block, or the
+                // rank-kOuter one when this was the last panel of the block
+                const bool inner = rest > 0;
+                const T *upd_a = inner ? panel : l + j1 + j0 * ld;
+                const long upd_lda = inner ? m : ld;
+                const long upd_k = inner ? nk : j1 - j0;
+                const long upd_m = inner ? m : n - j1;
+                const long upd_n = inner ? rest : n - j1;
+                T *upd_c = inner ? l + k1 + k1 * ld : l + j1 + j1 * ld;
+                // look-ahead pays only while the bulk update is long enough to hide (tile update + factorisation) of one CTA
+                const bool lookahead = upd_m >= 6 * 1024;
+                if (upd_m > 0 && !lookahead) {
+                    rc = Gemm<T>(ctx, kOpN, kOpT, upd_m, upd_n, upd_k, T(-1), upd_a, upd_lda, upd_a, upd_lda, T(1), upd_c, ld, 1);
+                    if (rc != ERL_GP_STATUS_OK) { return rc; }
+                }
+                if (upd_m > 0 && lookahead) {
+                    const long next_nk = upd_m < kPanel ? upd_m : kPanel;
+                    // side stream: tile (0, 0) of the update, then the next diagonal factorisation
+                    ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_panel, main_stream));
+                    ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(side, ctx->ev_panel, 0));
+                    ctx->stream = side;
+                    rc = Gemm<T>(ctx, kOpN, kOpT, next_nk, next_nk, upd_k, T(-1), upd_a, upd_lda, upd_a, upd_lda, T(1), upd_c, ld, 1);
+                    ctx->stream = main_stream;
+                    if (rc != ERL_GP_STATUS_OK) { return rc; }
+                    const long next_k0 = inner ? k1 : j1;
+                    diag<<<1, kBatchThreads, Smem::kBytes, side>>>(upd_c, ld, static_cast<int>(next_nk), linv + (next_k0 / kPanel) * kPanel * kPanel, info, static_cast<int>(next_k0));
+                    ctx->launches += 1;
+                    ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+                    ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_diag, side));
+                    diag_pending = true;
+                    // main stream: the rest of the update (lower tiles only, diagonal tile (0, 0) skipped)
+                    rc = Gemm<T>(ctx, kOpN, kOpT, upd_m, upd_n, upd_k, T(-1), upd_a, upd_lda, upd_a, upd_lda, T(1), upd_c, ld, 2);
+                    if (rc != ERL_GP_STATUS_OK) { return rc; }
+                }
+            }
+        }
+        if (diag_pending) { ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_diag, 0)); }
         return ERL_GP_STATUS_OK;
     }
 
@@ -530,50 +594,81 @@ namespace erl_gp {
     // =========================================================================================
     constexpr int kTrsvYmax = 4;
 
-    // y_k <- M * y_k with M = Linv_k (forward) or Linv_k^T (backward); one CTA, thread = row
+    // y_k <- M * y_k with M = Linv_k (forward) or Linv_k^T (backward); one CTA of 1024 threads: thread (i, jq) sums 16
+    // columns of row i (all loads independent), the 8 partial sums are combined through shared memory
     template<typename T>
-    __global__ void __launch_bounds__(kPanel)
+    __global__ void __launch_bounds__(1024)
     TrsvDiagKernel(const T *__restrict__ linv_k, const int nk, T *__restrict__ y, const long ldy, const int y_dim, const int trans) {
         __shared__ T ys[kPanel * kTrsvYmax];
-        const int i = threadIdx.x;
-        for (int c = 0; c < y_dim; ++c) { ys[i + c * kPanel] = i < nk ? y[i + c * ldy] : T(0); }
+        __shared__ T part[8][kPanel * kTrsvYmax];
+        const int i = threadIdx.x & (kPanel - 1);
+        const int jq = threadIdx.x >> 7;  // 0..7
+        if (threadIdx.x < kPanel) {
+            for (int c = 0; c < kTrsvYmax; ++c) { ys[i + c * kPanel] = (i < nk && c < y_dim) ? y[i + c * ldy] : T(0); }
+        }
         __syncthreads();
         T sum[kTrsvYmax];
 #pragma unroll
         for (int c = 0; c < kTrsvYmax; ++c) { sum[c] = T(0); }
-        for (int j = 0; j < nk; ++j) {
-            const T mij = trans ? linv_k[j + i * kPanel] : linv_k[i + j * kPanel];
+        T mv[16];
 #pragma unroll
-            for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += mij * ys[j + c * kPanel]; }
+        for (int u = 0; u < 16; ++u) {
+            const int j = 16 * jq + u;
+            mv[u] = trans ? linv_k[j + i * kPanel] : linv_k[i + j * kPanel];  // identity-padded beyond nk
         }
-        if (i < nk) {
-            for (int c = 0; c < y_dim; ++c) { y[i + c * ldy] = sum[c]; }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += mv[u] * ys[16 * jq + u + c * kPanel]; }
+        }
+#pragma unroll
+        for (int c = 0; c < kTrsvYmax; ++c) { part[jq][i + c * kPanel] = sum[c]; }
+        __syncthreads();
+        if (threadIdx.x < kPanel && i < nk) {
+            for (int c = 0; c < y_dim; ++c) {
+                T tot = T(0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { tot += part[q][i + c * kPanel]; }
+                y[i + c * ldy] = tot;
+            }
         }
     }
 
-    // forward: y[r] -= sum_c L[r, k0 + c] z[c] for the rows r below the panel; thread = row (coalesced along r)
+    // forward: y[r] -= sum_c L[r, k0 + c] z[c] for the rows r below the panel.  CTA = 64 rows x 4 column quarters
+    // (coalesced along r, 32 independent loads per thread), partial sums combined through shared memory
     template<typename T>
-    __global__ void __launch_bounds__(128)
+    __global__ void __launch_bounds__(256)
     TrsvUpdateBelowKernel(const T *__restrict__ l, const long ld, const long n, const long k0, const int nk, T *__restrict__ y, const long ldy, const int y_dim) {
         __shared__ T zs[kPanel * kTrsvYmax];
+        __shared__ T part[4][64 * kTrsvYmax];
         for (int e = threadIdx.x; e < kPanel * kTrsvYmax; e += blockDim.x) {
             const int j = e % kPanel, c = e / kPanel;
             zs[e] = (j < nk && c < y_dim) ? y[k0 + j + c * ldy] : T(0);
         }
         __syncthreads();
-        const long r = k0 + nk + static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-        if (r >= n) { return; }
+        const int rl = threadIdx.x & 63;
+        const int cq = threadIdx.x >> 6;
+        const long r = k0 + nk + static_cast<long>(blockIdx.x) * 64 + rl;
         T sum[kTrsvYmax];
 #pragma unroll
         for (int c = 0; c < kTrsvYmax; ++c) { sum[c] = T(0); }
-        const T *lr = l + r + k0 * ld;
-#pragma unroll 8
-        for (int j = 0; j < nk; ++j) {
-            const T lv = lr[static_cast<long>(j) * ld];
+        if (r < n) {
+            const T *lr = l + r + (k0 + 32 * cq) * ld;
+            T lv[32];
 #pragma unroll
-            for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += lv * zs[j + c * kPanel]; }
+            for (int u = 0; u < 32; ++u) { lv[u] = 32 * cq + u < nk ? lr[static_cast<long>(u) * ld] : T(0); }
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+#pragma unroll
+                for (int c = 0; c < kTrsvYmax; ++c) { sum[c] += lv[u] * zs[32 * cq + u + c * kPanel]; }
+            }
         }
-        for (int c = 0; c < y_dim; ++c) { y[r + c * ldy] -= sum[c]; }
+#pragma unroll
+        for (int c = 0; c < kTrsvYmax; ++c) { part[cq][rl + c * 64] = sum[c]; }
+        __syncthreads();
+        if (cq == 0 && r < n) {
+            for (int c = 0; c < y_dim; ++c) { y[r + c * ldy] -= part[0][rl + c * 64] + part[1][rl + c * 64] + part[2][rl + c * 64] + part[3][rl + c * 64]; }
+        }
     }
 
     // backward: y[j] -= sum_c L[k0 + c, j] z[c] for the columns j left of the panel; warp = column (coalesced along c)
@@ -617,15 +712,15 @@ namespace erl_gp {
         for (long kb = 0; kb < num_panels; ++kb) {  // z = L^-1 y
             const long k0 = kb * kPanel;
             const int nk = static_cast<int>(n - k0 < kPanel ? n - k0 : kPanel);
-            TrsvDiagKernel<T><<<1, kPanel, 0, ctx->stream>>>(linv + kb * kPanel * kPanel, nk, y + k0, ldy, yd, 0);
+            TrsvDiagKernel<T><<<1, 1024, 0, ctx->stream>>>(linv + kb * kPanel * kPanel, nk, y + k0, ldy, yd, 0);
             const long m = n - k0 - nk;
-            if (m > 0) { TrsvUpdateBelowKernel<T><<<static_cast<unsigned>(CeilDiv(m, 128)), 128, 0, ctx->stream>>>(l, ld, n, k0, nk, y, ldy, yd); }
+            if (m > 0) { TrsvUpdateBelowKernel<T><<<static_cast<unsigned>(CeilDiv(m, 64)), 256, 0, ctx->stream>>>(l, ld, n, k0, nk, y, ldy, yd); }
             ctx->launches += m > 0 ? 2 : 1;
         }
         for (long kb = num_panels - 1; kb >= 0; --kb) {  // alpha = L^-T z
             const long k0 = kb * kPanel;
             const int nk = static_cast<int>(n - k0 < kPanel ? n - k0 : kPanel);
-            TrsvDiagKernel<T><<<1, kPanel, 0, ctx->stream>>>(linv + kb * kPanel * kPanel, nk, y + k0, ldy, yd, 1);
+            TrsvDiagKernel<T><<<1, 1024, 0, ctx->stream>>>(linv + kb * kPanel * kPanel, nk, y + k0, ldy, yd, 1);
             if (k0 > 0) { TrsvUpdateAboveKernel<T><<<static_cast<unsigned>(CeilDiv(k0, 8)), 256, 0, ctx->stream>>>(l, ld, k0, nk, y, ldy, yd); }
             ctx->launches += k0 > 0 ? 2 : 1;
         }
@@ -674,7 +769,7 @@ namespace erl_gp {
     }
 
 #define ERL_GP_INSTANTIATE_DENSE(T)                                                                                            \
-    template int Gemm<T>(Context *, int, int, long, long, long, T, const T *, long, const T *, long, T, T *, long, bool);      \
+    template int Gemm<T>(Context *, int, int, long, long, long, T, const T *, long, const T *, long, T, T *, long, int);      \
     template int Potrf<T>(Context *, long, T *, long, T *, T *, int *);                                                        \
     template int TrsmLower<T>(Context *, long, long, const T *, long, const T *, T *, long, T *, T *, bool);                   \
     template int TrsmLowerTrans<T>(Context *, long, long, const T *, long, const T *, T *, long, T *);                         \

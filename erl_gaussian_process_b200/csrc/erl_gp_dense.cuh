@@ -17,7 +17,7 @@ namespace erl_gp {
 
     template<typename T>
     int
-    Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, bool lower_only);
+    Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, int lower_only);  // lower_only: 0 full, 1 lower tiles, 2 lower tiles except tile (0, 0)
 
     // Factor the n x n lower triangle at `l` (ld) in place; linv receives ceil(n/128) inverses of the
     // 128 x 128 diagonal blocks (each 128 x 128 col-major, identity-padded); panel is an n x 128 workspace;

@@ -16,6 +16,9 @@ struct erl_gp_context {
     int max_smem_optin = 0;
     long launches = 0;
     char last_error[512] = {0};
+    // look-ahead of the blocked Cholesky (erl_gp_dense.cu): side stream + events, created on first use
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_panel = nullptr, ev_diag = nullptr;
 };
 
 namespace erl_gp {

@@ -4,7 +4,7 @@ ExistentialRobotics/erl_gaussian_process behind the C ABI of include/erl_gp_b200
 Python here is only the thin host-side mirror used by tests and bench.py; the product is the
 CUDA library (csrc/) and the C++ drop-in headers (cpp/).
 """
-from . import _capi
+from . import _capi, sharding
 from ._capi import ErlGpError, KERNELS, load
 from .host import (
     BatchGp,
@@ -29,4 +29,5 @@ __all__ = [
     "compute_ktest",
     "compute_ktrain",
     "load",
+    "sharding",
 ]

@@ -343,7 +343,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt_e2e = float(tt.item())
         assert np.isfinite(h_mean).all() and h_valid.all() and (h_info == 0).all()
-        h2d = host["n_train"].nbytes + host["x"].nbytes + host["y"].nbytes + host["var"].nbytes + host["q_offsets"].nbytes + host["q_x"].nbytes + h_mean.nbytes + h_var.nbytes
+        h2d = host["n_train"].nbytes + host["x"].nbytes + host["y"].nbytes + host["var"].nbytes + host["q_offsets"].nbytes + host["q_x"].nbytes
         d2h = h_mean.nbytes + h_var.nbytes + h_valid.nbytes + h_info.nbytes
         e2e = {"value": world * tq / dt_e2e, "unit": "test-points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": dt_e2e * 1e3,
                "api": "erl_gp_batch_train_predict_f32 (C ABI, pinned host buffers; L stays device-resident, materialised on demand by erl_gp_batch_download)"}

@@ -146,6 +146,17 @@ namespace erl_gp {
         DeviceBuffer<long> q_offsets;
         DeviceBuffer<T> q_x, mean, variance;
         DeviceBuffer<uint8_t> valid;
+        // host-buffer pipeline (BatchTrainPredictHost): copy streams and per-chunk events, created on first use
+        cudaStream_t copy_in = nullptr, copy_out = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_kernel;
+        PinnedBuffer<int> info_host;
+
+        ~Batch() {
+            if (copy_in != nullptr) { cudaStreamDestroy(copy_in); }
+            if (copy_out != nullptr) { cudaStreamDestroy(copy_out); }
+            for (cudaEvent_t e: ev_in) { cudaEventDestroy(e); }
+            for (cudaEvent_t e: ev_kernel) { cudaEventDestroy(e); }
+        }
 
         BatchParams<T>
         Params(const long min_num_samples, const int write_l) const {

@@ -138,7 +138,7 @@ namespace erl_gp {
             float *al = smem + Lay::kAl;
             const float *sv = smem + Lay::kVar;
             const int tid = threadIdx.x;
-            const int warp = tid >> 5;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction: role branches need no reconvergence code
             const int lane = tid & 31;
             const int h = tid & 1;
             const int npr = nblk * 16;
@@ -319,7 +319,7 @@ namespace erl_gp {
             const float *rs = smem + Lay::kRs;
             float *al = smem + Lay::kAl;
             const int tid = threadIdx.x;
-            const int warp = tid >> 5;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction: role branches need no reconvergence code
             const int lane = tid & 31;
             float s = 0.f;
             for (int kb = nblk - 1; kb >= 0; --kb) {
@@ -558,7 +558,7 @@ namespace erl_gp {
 
             const int g = blockIdx.x;
             const int tid = threadIdx.x;
-            const int warp = tid >> 5;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction: role branches need no reconvergence code
             const int lane = tid & 31;
             const int n = p.n_train[g];
             const long q0 = (MODE & kBatchPredict) ? p.q_offsets[g] : 0;

@@ -146,8 +146,8 @@ def cpu_baseline(w, sample_gps, threads=None, min_seconds=10.0):
     `sample_gps` GPs of the workload, repeated until at least `min_seconds` of CPU work have been timed."""
     import oracle
 
-    if threads:
-        oracle.set_num_threads(threads)
+    # all host threads: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently time one core
+    oracle.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = oracle.num_threads()
     ww = dict(w, num_gps=sample_gps)
     n_train, x, y, var, q_offsets, q_x = synth_batch(ww, 0)

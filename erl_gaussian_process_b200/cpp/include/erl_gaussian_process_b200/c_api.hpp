@@ -84,6 +84,7 @@ namespace erl::gaussian_process::b200 {
         static constexpr auto range3d_train = erl_gp_range3d_train_##SFX;                \
         static constexpr auto range3d_test = erl_gp_range3d_test_##SFX;                  \
         static constexpr auto range3d_get_gp = erl_gp_range3d_get_gp_##SFX;              \
+        static constexpr auto range3d_compute_occ = erl_gp_range3d_compute_occ_##SFX;    \
     };
     ERL_GP_API_STRUCT(float, f32)
     ERL_GP_API_STRUCT(double, f64)

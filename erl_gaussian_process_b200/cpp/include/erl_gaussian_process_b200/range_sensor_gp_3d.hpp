@@ -199,6 +199,34 @@ namespace erl::gaussian_process {
             if (!m_trained_) { return nullptr; }
             return std::make_shared<TestResult>(this, directions, directions_are_local, un_map);
         }
+
+        [[nodiscard]] bool
+        ComputeOcc(const Vector3 &pos_local, Dtype &dist_pos, Dtype &range_pred, Dtype &occ) const {  // src/range_sensor_gp_3d.cpp:409-439
+            if (!m_trained_) { return false; }
+            Dtype coords[2] = {0, 0};
+            unsigned char coords_ok = m_sensor_frame_->ComputeFrameCoords(pos_local.data(), dist_pos, coords) ? 1 : 0;  // + CoordsIsInFrame: the partition search rejects the rest
+            unsigned char ok = 0;
+            m_ctx_->Check(Api::range3d_compute_occ(m_handle_, coords, &coords_ok, &dist_pos, 1, m_setting_->max_valid_range_var, m_setting_->occ_test_temperature, &range_pred, &occ, &ok),
+                          "erl_gp_range3d_compute_occ");
+            return ok != 0;
+        }
+
+        // batched form for the per-voxel caller pattern: pos_local is 3 x T
+        [[nodiscard]] Eigen::VectorXb
+        ComputeOcc(const Matrix3X &pos_local, VectorX &dist_pos, VectorX &range_pred, VectorX &occ) const {
+            const long n = pos_local.cols();
+            Eigen::VectorXb ok(n);
+            ok.setZero();
+            if (!m_trained_) { return ok; }
+            dist_pos.resize(n), range_pred.resize(n), occ.resize(n);
+            MatrixX coords(2, n);
+            Eigen::VectorXb coords_ok(n);
+            for (long i = 0; i < n; ++i) { coords_ok[i] = m_sensor_frame_->ComputeFrameCoords(&pos_local(0, i), dist_pos[i], &coords(0, i)) ? 1 : 0; }
+            m_ctx_->Check(Api::range3d_compute_occ(m_handle_, coords.data(), coords_ok.data(), dist_pos.data(), n, m_setting_->max_valid_range_var, m_setting_->occ_test_temperature,
+                                                   range_pred.data(), occ.data(), ok.data()),
+                          "erl_gp_range3d_compute_occ");
+            return ok;
+        }
     };
 
     using RangeSensorGaussianProcess3Dd = RangeSensorGaussianProcess3D<double>;

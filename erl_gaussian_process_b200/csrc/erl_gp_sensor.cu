@@ -324,7 +324,7 @@ namespace erl_gp {
     template<typename T>
     __global__ void
     OccEpilogueKernel(const long num, const T *__restrict__ dist, const uint8_t *__restrict__ valid, const T *__restrict__ variance, const T max_valid_range_var, const T temperature,
-                      const int mapping, const T mapping_scale, T *__restrict__ range_pred, T *__restrict__ occ, uint8_t *__restrict__ ok) {
+                      const int mapping, const T mapping_scale, T *__restrict__ range_pred, T *__restrict__ occ, uint8_t *__restrict__ ok, const T *__restrict__ prefill) {
         const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
         if (i >= num) { return; }
         bool good = valid[i] != 0 && !(variance[i] > max_valid_range_var);
@@ -333,6 +333,8 @@ namespace erl_gp {
             const T a = dist[i] * temperature;
             occ[i] = T(2) / (T(1) + exp(a * (f - MappingMap<T>(mapping, mapping_scale, dist[i])))) - T(1);
             range_pred[i] = MappingInv<T>(mapping, mapping_scale, f);
+        } else if (prefill != nullptr) {
+            range_pred[i] = prefill[i];  // rejected by the variance gate: the reference returns before it assigns range_pred
         }
         ok[i] = good ? 1 : 0;
     }
@@ -524,8 +526,13 @@ namespace erl_gp {
         // occ lives in sorted_x's slot-free twin: reuse q_local (dead after the scatter) as the occ buffer
         T *d_occ = ws.q_local.ptr;
         if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_occ, occ, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream)); }
+        T *d_prefill = nullptr;
+        if (range_pred != nullptr) {  // sorted_x is dead after the predict: keeps the caller's values for the gated-out positions
+            d_prefill = ws.sorted_x.ptr;
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_prefill, range_pred, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream));
+        }
         OccEpilogueKernel<T><<<static_cast<unsigned>(CeilDiv(num, 256)), 256, 0, ctx->stream>>>(num, ws.q_dist.ptr, ws.valid.ptr, ws.variance.ptr, max_valid_range_var, temperature, gp->setting.mapping,
-                                                                                               static_cast<T>(gp->setting.mapping_scale), ws.mean.ptr, d_occ, ws.ok.ptr);
+                                                                                               static_cast<T>(gp->setting.mapping_scale), ws.mean.ptr, d_occ, ws.ok.ptr, d_prefill);
         ctx->launches += 1;
         ERL_GP_CUDA_OK(ctx, cudaGetLastError());
         if (dist != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(dist, ws.q_dist.ptr, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream)); }
@@ -605,6 +612,44 @@ namespace erl_gp {
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         gp->trained = true;
+        return ERL_GP_STATUS_OK;
+    }
+
+    // Batched RangeSensorGaussianProcess3D::ComputeOcc (src/range_sensor_gp_3d.cpp:409-439).  ComputeFrameCoords /
+    // CoordsIsInFrame belong to erl_geometry and stay on the caller's side: coords (2 x num), coords_ok (their combined bool)
+    // and dist (the distance ComputeFrameCoords returns) are the inputs.
+    template<typename T>
+    static int
+    Range3dTest(Range3d<T> *gp, const T *coords, const uint8_t *coords_ok, long num_test, int un_map, T *mean, T *var, uint8_t *valid);
+
+    template<typename T>
+    static int
+    Range3dComputeOcc(Range3d<T> *gp, const T *coords, const uint8_t *coords_ok, const T *dist, long num, T max_valid_range_var, T temperature, T *range_pred, T *occ, uint8_t *ok) {
+        if (gp == nullptr || coords == nullptr || dist == nullptr || num < 0 || ok == nullptr || range_pred == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        if (!gp->trained) { return SetError(ctx, ERL_GP_STATUS_NOT_TRAINED, "range3d: ComputeOcc() before Train()"); }
+        if (num == 0) { return ERL_GP_STATUS_OK; }
+        // the caller's range_pred values come back for every rejected position: keep them on the device first
+        QueryWorkspace<T> &ws = gp->ws;
+        ERL_GP_CUDA_OK(ctx, ws.Reserve(num, gp->batch->num_gps, 2, 2));
+        ERL_GP_CUDA_OK(ctx, ws.q_local.Reserve(2 * num));
+        T *d_prefill = ws.q_local.ptr + num;  // q_local is unused by the 3-D query: [0, num) = occ, [num, 2 num) = prefill
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_prefill, range_pred, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream));
+        // mapped mean + variance of every position (results stay in the workspace; the host copy of mean is re-written below)
+        std::vector<T> var_host(static_cast<size_t>(num));
+        int rc = Range3dTest<T>(gp, coords, coords_ok, num, 0, range_pred, var_host.data(), nullptr);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_dist.ptr, dist, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream));
+        T *d_occ = ws.q_local.ptr;
+        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_occ, occ, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream)); }
+        OccEpilogueKernel<T><<<static_cast<unsigned>(CeilDiv(num, 256)), 256, 0, ctx->stream>>>(num, ws.q_dist.ptr, ws.valid.ptr, ws.variance.ptr, max_valid_range_var, temperature, gp->setting.mapping,
+                                                                                               static_cast<T>(gp->setting.mapping_scale), ws.mean.ptr, d_occ, ws.ok.ptr, d_prefill);
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(range_pred, ws.mean.ptr, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream));
+        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(occ, d_occ, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ok, ws.ok.ptr, num, cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }
 
@@ -724,6 +769,10 @@ extern "C" {
     int erl_gp_range3d_train_##SFX(erl_gp_range3d_##SFX *gp, const T *ranges, const uint8_t *mask_hit) { return Range3dTrain<T>(gp, ranges, mask_hit); }                        \
     int erl_gp_range3d_test_##SFX(erl_gp_range3d_##SFX *gp, const T *coords, const uint8_t *coords_ok, long num_test, int un_map, T *mean, T *var, uint8_t *valid) {            \
         return Range3dTest<T>(gp, coords, coords_ok, num_test, un_map, mean, var, valid);                                                                                       \
+    }                                                                                                                                                                           \
+    int erl_gp_range3d_compute_occ_##SFX(erl_gp_range3d_##SFX *gp, const T *coords, const uint8_t *coords_ok, const T *dist, long num, T max_valid_range_var,                   \
+                                         T occ_test_temperature, T *range_pred, T *occ, uint8_t *ok) {                                                                          \
+        return Range3dComputeOcc<T>(gp, coords, coords_ok, dist, num, max_valid_range_var, occ_test_temperature, range_pred, occ, ok);                                          \
     }                                                                                                                                                                           \
     int erl_gp_range3d_get_gp_##SFX(erl_gp_range3d_##SFX *gp, long row_part, long col_part, int *info, long *n, T *l, long ld_l, T *alpha) {                                    \
         if (gp == nullptr || row_part < 0 || col_part < 0 || row_part >= gp->row_parts.Size() || col_part >= gp->col_parts.Size()) { return ERL_GP_STATUS_INVALID_ARGUMENT; }   \

@@ -627,6 +627,25 @@ class RangeSensorGaussianProcess3D:
         res._init_from_coords(self, coords, coords_ok, un_map)
         return res
 
+    def compute_occ(self, pos_local):
+        """Batched ComputeOcc (src/range_sensor_gp_3d.cpp:409-439). pos_local: (T, 3) in the sensor frame.
+        Returns ok, dist, range_pred, occ (range_pred / occ of rejected positions stay NaN)."""
+        if not self.is_trained:
+            return None
+        pos = np.asarray(pos_local, dtype=self.dtype)
+        ok_c, dist, coords = self.sensor_frame.compute_frame_coords(pos)  # ComputeFrameCoords + CoordsIsInFrame stay on the host side
+        t = pos.shape[0]
+        _, ct = _sfx(self.dtype)
+        coords = np.ascontiguousarray(coords, dtype=self.dtype)
+        dist = np.ascontiguousarray(dist, dtype=self.dtype)
+        okb = np.ascontiguousarray(ok_c, dtype=np.uint8)
+        rp = np.full(t, np.nan, dtype=self.dtype)
+        occ = np.full(t, np.nan, dtype=self.dtype)
+        ok = np.zeros(t, dtype=np.uint8)
+        check(self.ctx.fn("erl_gp_range3d_compute_occ", self.dtype)(self.handle, _p(coords), _p(okb), _p(dist), C.c_long(t), ct(self.setting.max_valid_range_var),
+                                                                   ct(self.setting.occ_test_temperature), _p(rp), _p(occ), _p(ok)), "range3d_compute_occ", self.ctx.handle)
+        return ok.astype(bool), dist, rp, occ
+
     def get_gp(self, row_part, col_part):
         mn = self.setting.row_group_size * self.setting.col_group_size
         info, n = C.c_int(0), C.c_long(0)

@@ -325,6 +325,16 @@ int erl_gp_range3d_test_f32(erl_gp_range3d_f32 *gp, const float *coords, const u
                             int un_map, float *mean, float *var, uint8_t *valid);
 int erl_gp_range3d_test_f64(erl_gp_range3d_f64 *gp, const double *coords, const uint8_t *coords_ok, long num_test,
                             int un_map, double *mean, double *var, uint8_t *valid);
+/* Batched ComputeOcc (src/range_sensor_gp_3d.cpp:409-439).  coords (2 x num), coords_ok and dist are what
+ * RangeSensorFrame3D::ComputeFrameCoords (+ CoordsIsInFrame) returns for the positions; ok[i] = 0 where the reference
+ * returns false (bad coords / no partition / untrained / var > max_valid_range_var); range_pred / occ of those stay
+ * untouched. */
+int erl_gp_range3d_compute_occ_f32(erl_gp_range3d_f32 *gp, const float *coords, const uint8_t *coords_ok, const float *dist,
+                                   long num, float max_valid_range_var, float occ_test_temperature, float *range_pred,
+                                   float *occ, uint8_t *ok);
+int erl_gp_range3d_compute_occ_f64(erl_gp_range3d_f64 *gp, const double *coords, const uint8_t *coords_ok,
+                                   const double *dist, long num, double max_valid_range_var, double occ_test_temperature,
+                                   double *range_pred, double *occ, uint8_t *ok);
 int erl_gp_range3d_get_gp_f32(erl_gp_range3d_f32 *gp, long row_part, long col_part, int *info, long *n, float *l,
                               long ld_l, float *alpha);
 int erl_gp_range3d_get_gp_f64(erl_gp_range3d_f64 *gp, long row_part, long col_part, int *info, long *n, double *l,

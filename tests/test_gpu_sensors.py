@@ -230,3 +230,46 @@ def test_range_sensor_3d_limits(gp):
     s.row_group_size, s.col_group_size = 24, 12  # 288 samples per GP > one-CTA limit
     with pytest.raises(gp.ErlGpError):
         gp.RangeSensorGaussianProcess3D(s, np.float32)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_range_sensor_3d_compute_occ(gp, oracle, dtype):
+    """Batched 3-D ComputeOcc (src/range_sensor_gp_3d.cpp:409-439): variance gate, mapped mean, occ, un-mapped range."""
+    rng = np.random.default_rng(21)
+    rows, cols = 64, 96
+    s = gp.RangeSensorGaussianProcess3D.Setting()
+    s.row_group_size, s.row_overlap_size, s.col_group_size, s.col_overlap_size = 12, 2, 10, 4
+    s.sensor_frame.azimuth_min, s.sensor_frame.azimuth_max, s.sensor_frame.num_azimuth_lines = -0.5, 0.5, rows
+    s.sensor_frame.elevation_min, s.sensor_frame.elevation_max, s.sensor_frame.num_elevation_lines = -0.3, 0.3, cols
+    s.sensor_frame.valid_range_min, s.sensor_frame.valid_range_max = 0.1, 30.0
+    s.gp.kernel_type, s.gp.scale = "matern32", 0.05
+    s.max_valid_range_var = 0.02
+    rg3 = gp.RangeSensorGaussianProcess3D(s, dtype)
+    fc = rg3.sensor_frame.frame_coords
+    og = oracle.RangeSensorGp3D(fc, oracle.KERNELS["matern32"], 0.05, 12, 2, 0, 10, 4, 0, 32, 0.01, 2, 1.0, dtype)
+    img = _range_image(rng, rows, cols, dtype)
+    assert rg3.train(np.eye(3), np.zeros(3), img)
+    assert og.train(rg3.sensor_frame.ranges, rg3.sensor_frame.mask_hit)
+    t = 3000
+    az = rng.uniform(-0.6, 0.6, t)
+    el = rng.uniform(-0.36, 0.36, t)
+    d = rng.uniform(0.5, 8.0, t)
+    pos = np.stack([d * np.cos(el) * np.cos(az), d * np.cos(el) * np.sin(az), d * np.sin(el)], axis=1).astype(dtype)
+    pos[5] = 0  # zero vector: ComputeFrameCoords fails
+    ok, dist, rp, occ = rg3.compute_occ(pos)
+    ok_c, dist_ref, coords = rg3.sensor_frame.compute_frame_coords(pos)
+    m_ref, v_ref, valid_ref = og.test(coords, ok_c, False)  # mapped mean + variance
+    with np.errstate(invalid="ignore", over="ignore"):
+        good_ref = valid_ref & ~(v_ref > s.max_valid_range_var)
+        occ_ref = 2.0 / (1.0 + np.exp(dist_ref.astype(np.float64) * s.occ_test_temperature * (m_ref.astype(np.float64) - 1.0 / np.sqrt(dist_ref.astype(np.float64))))) - 1.0
+        rp_ref = 1.0 / (m_ref.astype(np.float64) ** 2)
+    # positions whose variance sits within rounding of the gate may flip
+    near_gate = valid_ref & (np.abs(v_ref - s.max_valid_range_var) < (1e-5 if dtype == np.float32 else 1e-11))
+    sel = ~near_gate
+    assert np.array_equal(ok[sel], good_ref[sel])
+    assert not ok[5] and ok.sum() > 300 and (~ok).sum() > 100
+    both = ok & good_ref
+    tol = 2e-4 if dtype == np.float32 else 1e-9
+    assert np.abs(rp[both] - rp_ref[both]).max() / np.abs(rp_ref[both]).max() < tol
+    assert np.abs(occ[both] - occ_ref[both]).max() < (2e-2 if dtype == np.float32 else 1e-7)  # steep sigmoid of 30 d (f - map(d))
+    assert np.isnan(rp[~ok]).all() and np.isnan(occ[~ok]).all()  # untouched

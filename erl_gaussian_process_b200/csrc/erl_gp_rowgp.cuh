@@ -125,6 +125,40 @@ namespace erl_gp {
             }
         };
 
+        // 16 x 16 pivot block of a panel, factorised by one warp with shuffles.  LDL^T-style elimination: the update of column
+        // cc uses acc[c] / d (reciprocal) and the RAW column entries of the pivot rows, which can be shuffled before the
+        // reciprocal is known; the Cholesky entries l[c] = acc[c] / sqrt(d) are formed off the dependency chain.
+        template<bool STATIC_SRC>
+        __device__ __forceinline__ void
+        PivotBlock(float (&acc)[16], float &zacc, float (&l)[16], const int half, const int c0, const int lane, int &fail, float *__restrict__ rs, float *__restrict__ al) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int src = STATIC_SRC ? 2 * c : (c < half ? 2 * c : 2 * (c - half) + 1);
+                const float d = __shfl_sync(kFull, acc[c], src);
+                const float zc = __shfl_sync(kFull, zacc, src);
+                float t[16];
+#pragma unroll
+                for (int cc = c + 1; cc < 16; ++cc) {
+                    const int src2 = STATIC_SRC ? 2 * cc : (cc < half ? 2 * cc : 2 * (cc - half) + 1);
+                    t[cc] = __shfl_sync(kFull, acc[c], src2);
+                }
+                if (!(d > 0.f) && fail == 0) { fail = c0 + c + 1; }
+                float invd;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invd) : "f"(d));
+                invd = invd * fmaf(-d, invd, 2.0f);  // one Newton step on MUFU.RCP
+                const float rsv = RsqrtRefined(d);
+                const float sc = acc[c] * invd;
+#pragma unroll
+                for (int cc = c + 1; cc < 16; ++cc) { acc[cc] = fmaf(-sc, t[cc], acc[cc]); }
+                zacc = fmaf(-sc, zc, zacc);
+                l[c] = acc[c] * rsv;
+                if (lane == 0) {
+                    rs[c0 + c] = rsv;
+                    al[c0 + c] = zc * rsv;
+                }
+            }
+        }
+
         // --------------------------------------------------------------------------------------
         // train: blocked left-looking Cholesky with the Gram panel generated on the fly
         // --------------------------------------------------------------------------------------
@@ -232,30 +266,13 @@ namespace erl_gp {
                     float l[16];
 
                     if (warp == 0) {
-                        // (c) pivot block: rows c0 + c live in lanes src(c); every lane's row follows along
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const int src = c < half ? 2 * c : 2 * (c - half) + 1;
-                            const float d = __shfl_sync(kFull, acc[c], src);
-                            const float zc = __shfl_sync(kFull, zacc, src);
-                            float t[16];
-#pragma unroll
-                            for (int cc = c + 1; cc < 16; ++cc) {
-                                const int src2 = cc < half ? 2 * cc : 2 * (cc - half) + 1;
-                                t[cc] = __shfl_sync(kFull, acc[c], src2);
-                            }
-                            if (!(d > 0.f) && fail == 0) { fail = c0 + c + 1; }
-                            const float invd = __frcp_rn(d);
-                            const float rsv = RsqrtRefined(d);
-                            const float sc = acc[c] * invd;
-#pragma unroll
-                            for (int cc = c + 1; cc < 16; ++cc) { acc[cc] = fmaf(-sc, t[cc], acc[cc]); }
-                            zacc = fmaf(-sc, zc, zacc);
-                            l[c] = acc[c] * rsv;
-                            if (lane == 0) {
-                                rs[c0 + c] = rsv;
-                                al[c0 + c] = zc * rsv;
-                            }
+                        // (c) pivot block: rows c0 + c live in lanes src(c); every lane's row follows along.  While the panel has
+                        // at least 32 rows the pivot rows sit in the even lanes (static shuffle sources); only the last panel
+                        // (16 rows: pairs q < 8 hold rows q and q + 8) needs the general mapping.
+                        if (half >= 16) {
+                            PivotBlock<true>(acc, zacc, l, half, c0, lane, fail, rs, al);
+                        } else {
+                            PivotBlock<false>(acc, zacc, l, half, c0, lane, fail, rs, al);
                         }
                     }
                     if (warp == 0 && active) {

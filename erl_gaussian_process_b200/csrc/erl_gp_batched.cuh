@@ -128,11 +128,24 @@ namespace erl_gp {
         static_assert(kNpad <= kNB * kTq, "var scratch aliases the R buffer");
     };
 
+    // 1 / sqrt(v) off the slow paths: FP64 sqrt + division are ~40 dependent instructions each and sat on the critical
+    // path of every pivot (16 per block); rsqrt(double) is MUFU.RSQ64H + Newton (<= 1 ulp), the diagonal is v * rsqrt(v).
+    __device__ __forceinline__ float
+    InvSqrt(float v) {
+        return 1.0f / sqrtf(v);
+    }
+
+    __device__ __forceinline__ double
+    InvSqrt(double v) {
+        const double r = rsqrt(v);
+        return fma(fma(-v * r, r, 1.0), 0.5 * r, r);  // one more Newton step: correctly rounded in practice
+    }
+
     // ---- 16x16 diagonal block: Cholesky in registers of one warp --------------------------
-    // Lane r (< 16) owns row r.  Returns 0 or the 1-based failing column (warp-uniform).
+    // Lane r (< 16) owns row r.  Returns 0 or the 1-based failing column (warp-uniform); invs[k] = 1 / L_kk (every lane).
     template<typename T>
     __device__ __forceinline__ int
-    DiagCholesky(T *d, const int lane) {
+    DiagCholesky(T *d, const int lane, T (&invs)[kNB]) {
         constexpr unsigned kFull = 0xffffffffu;
         T a[kNB];
 #pragma unroll
@@ -142,9 +155,9 @@ namespace erl_gp {
         for (int k = 0; k < kNB; ++k) {
             const T akk = __shfl_sync(kFull, a[k], k);
             if (!(akk > T(0)) && fail == 0) { fail = k + 1; }
-            const T diag = Sqrt(akk);
-            const T inv = T(1) / diag;
-            const T lk = lane == k ? diag : a[k] * inv;
+            const T inv = InvSqrt(akk);
+            invs[k] = inv;
+            const T lk = lane == k ? akk * inv : a[k] * inv;
             a[k] = lk;
 #pragma unroll
             for (int j = k + 1; j < kNB; ++j) {
@@ -160,10 +173,10 @@ namespace erl_gp {
     }
 
     // inverse of a factored lower 16x16 block (col-major d) into row-major dinv (stride DinvLd);
-    // lane c computes column c of the inverse by forward substitution on e_c.
+    // lane c computes column c of the inverse by forward substitution on e_c; invs[i] = 1 / d[i, i].
     template<typename T>
     __device__ __forceinline__ void
-    DiagInverse(const T *d, T *dinv, const int lane) {
+    DiagInverse(const T *d, T *dinv, const int lane, const T (&invs)[kNB]) {
         constexpr int kLd = DinvLd<T>::value;
         if (lane < kNB) {
             T xc[kNB];
@@ -172,11 +185,22 @@ namespace erl_gp {
                 T s = i == lane ? T(1) : T(0);
 #pragma unroll
                 for (int p = 0; p < i; ++p) { s -= d[i + kNB * p] * xc[p]; }
-                xc[i] = s / d[i + kNB * i];
+                xc[i] = s * invs[i];
             }
 #pragma unroll
             for (int i = 0; i < kNB; ++i) { dinv[i * kLd + lane] = xc[i]; }
         }
+    }
+
+    // same, reciprocals of the diagonal computed here (one division per lane, shared by shuffles); whole warp must call
+    template<typename T>
+    __device__ __forceinline__ void
+    DiagInverse(const T *d, T *dinv, const int lane) {
+        const T mine = T(1) / d[(lane & (kNB - 1)) * (kNB + 1)];
+        T invs[kNB];
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) { invs[i] = __shfl_sync(0xffffffffu, mine, i); }
+        DiagInverse(d, dinv, lane, invs);
     }
 
     // ---- blocked right-looking Cholesky of the block-packed lower triangle in smem ---------
@@ -193,10 +217,11 @@ namespace erl_gp {
             T *dkk = lp + LowerBlock(kb, kb);
             T *dinv_k = dinv + kb * kNB * kLd;
             if (warp == 0) {
-                const int fail = DiagCholesky(dkk, lane);
+                T invs[kNB];
+                const int fail = DiagCholesky(dkk, lane, invs);
                 if (fail != 0 && lane == 0 && *s_fail == 0) { *s_fail = kb * kNB + fail; }
                 __syncwarp();
-                DiagInverse(dkk, dinv_k, lane);
+                DiagInverse(dkk, dinv_k, lane, invs);
             }
             __syncthreads();
             const int m = nblk - kb - 1;  // block rows below the diagonal block

@@ -390,8 +390,14 @@ erl_gp_context_destroy(erl_gp_context *c) {
         cudaStreamSynchronize(ctx->side_stream);
         cudaStreamDestroy(ctx->side_stream);
     }
-    if (ctx->ev_panel != nullptr) { cudaEventDestroy(ctx->ev_panel); }
-    if (ctx->ev_diag != nullptr) { cudaEventDestroy(ctx->ev_diag); }
+    if (ctx->sync_ints != nullptr) { cudaFree(ctx->sync_ints); }
+    if (ctx->side_stream2 != nullptr) {
+        cudaStreamSynchronize(ctx->side_stream2);
+        cudaStreamDestroy(ctx->side_stream2);
+    }
+    for (cudaEvent_t ev: {ctx->ev_panel, ctx->ev_diag, ctx->ev_la_start, ctx->ev_la_done}) {
+        if (ev != nullptr) { cudaEventDestroy(ev); }
+    }
     delete ctx;
     return ERL_GP_STATUS_OK;
 }

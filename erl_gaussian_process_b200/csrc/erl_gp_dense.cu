@@ -296,7 +296,7 @@ namespace erl_gp {
 #pragma unroll
             for (int j = 0; j < kQpt; ++j) { v[m][j] = (tr + kNB * m == col0 + qbase + j) ? T(1) : T(0); }
         }
-        for (int kb = 0; kb < nblk; ++kb) {
+        for (int kb = col0 / kNB; kb < nblk; ++kb) {  // rows above col0 of these columns of the inverse are zero
             T rk[kQpt];
 #pragma unroll
             for (int m = 0; m < kDiagBlocks; ++m) {
@@ -390,15 +390,25 @@ namespace erl_gp {
         const int nblk = (nk + kNB - 1) / kNB;
         const int npad = nblk * kNB;
         if (tid == 0) { *s_fail = 0; }
-        for (int c = warp; c < npad; c += kBatchThreads / 32) {
-            for (int r = (c & ~15) + lane; r < npad; r += 32) {
-                T val;
+        // 8 loads in flight per thread (one load per loop trip left the single CTA waiting ~1 us of L2 / HBM latency per
+        // column: 17 % of the kernel); a warp reads 32 consecutive rows of one column
+        for (int i0 = 0; i0 < kPanel * kPanel / kBatchThreads; i0 += 8) {
+            T val[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + kBatchThreads * (i0 + u);
+                const int r = e % kPanel, c = e / kPanel;
                 if (r < nk && c < nk) {
-                    val = r >= c ? a[r + static_cast<long>(c) * ld] : T(0);
+                    val[u] = r >= c ? a[r + static_cast<long>(c) * ld] : T(0);
                 } else {
-                    val = r == c ? T(1) : T(0);
+                    val[u] = r == c ? T(1) : T(0);
                 }
-                lp[LowerBlock(r >> 4, c >> 4) + (r & 15) + kNB * (c & 15)] = val;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + kBatchThreads * (i0 + u);
+                const int r = e % kPanel, c = e / kPanel;
+                if ((r >> 4) >= (c >> 4) && r < npad) { lp[LowerBlock(r >> 4, c >> 4) + (r & 15) + kNB * (c & 15)] = val[u]; }
             }
         }
         __syncthreads();
@@ -438,93 +448,189 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // C[0:nt, 0:nt] (lower triangle, nt <= 128) -= A[0:nt, 0:k] A[0:nt, 0:k]^T, spread over up to 10 CTAs of 32 x 32 outputs.
+    // This is the tile that the next diagonal factorisation waits for: as one 128 x 128 GEMM tile it is a single CTA on
+    // a single SM (30 us at k = 128, 89 us at k = 512); cut in 32 x 32 pieces it takes a few microseconds.
+    template<typename T>
+    __global__ void __launch_bounds__(256)
+    SyrkTileKernel(const int nt, const long k, const T *__restrict__ a, const long lda, T *__restrict__ c, const long ldc) {
+        constexpr int kSub = 32, kChunk = 64, kLdS = kSub + 2;
+        __shared__ __align__(16) T as[kChunk][kLdS];
+        __shared__ __align__(16) T bs[kChunk][kLdS];
+        const int r0 = kSub * blockIdx.x, c0 = kSub * blockIdx.y;
+        if (c0 > r0 || r0 >= nt) { return; }
+        const int tid = threadIdx.x;
+        const int tx = tid & 15, ty = tid >> 4;
+        T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+        for (long k0 = 0; k0 < k; k0 += kChunk) {
+            T va[8], vb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + 256 * u;
+                const int rr = e & 31;
+                const long kk = k0 + (e >> 5);
+                va[u] = (r0 + rr < nt && kk < k) ? a[(r0 + rr) + kk * lda] : T(0);
+                vb[u] = (c0 + rr < nt && kk < k) ? a[(c0 + rr) + kk * lda] : T(0);
+            }
+            __syncthreads();  // the previous chunk has been consumed
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + 256 * u;
+                as[e >> 5][e & 31] = va[u];
+                bs[e >> 5][e & 31] = vb[u];
+            }
+            __syncthreads();
+#pragma unroll 16
+            for (int kk = 0; kk < kChunk; ++kk) {
+                T a2[2], b2[2];
+                Load2(&as[kk][2 * tx], a2);
+                Load2(&bs[kk][2 * ty], b2);
+                acc[0][0] += a2[0] * b2[0];
+                acc[0][1] += a2[0] * b2[1];
+                acc[1][0] += a2[1] * b2[0];
+                acc[1][1] += a2[1] * b2[1];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int row = r0 + 2 * tx + i, col = c0 + 2 * ty + j;
+                if (row < nt && col < nt && row >= col) { c[row + static_cast<long>(col) * ldc] -= acc[i][j]; }
+            }
+        }
+    }
+
+    // Look-ahead of one diagonal block on the stream `la`: once `chain` has produced the k columns at `a` (rows of the
+    // block), update the nt x nt diagonal tile `c` with them and factor it; ev_la_done fires when L11 and its inverse exist.
+    template<typename T>
+    static int
+    LookaheadDiag(Context *ctx, cudaStream_t chain, cudaStream_t la, const int nt, const long k, const T *a, const long lda, T *c, const long ldc, T *linv_k, int *info, const long col) {
+        using Smem = BatchSmem<T, 1, kDiagBlocks>;
+        ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_la_start, chain));
+        ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(la, ctx->ev_la_start, 0));
+        SyrkTileKernel<T><<<dim3(4, 4), 256, 0, la>>>(nt, k, a, lda, c, ldc);
+        DiagFactorKernel<T><<<1, kBatchThreads, Smem::kBytes, la>>>(c, ldc, nt, linv_k, info, static_cast<int>(col));
+        ctx->launches += 2;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_la_done, la));
+        return ERL_GP_STATUS_OK;
+    }
+
+    // Factor the block column [j0, j1) (rows j0 .. n) right-looking with 128-column panels on ctx->stream:
+    // DiagFactorKernel (L11 and its inverse), panel solve L21 <- A21 L11^-T as an IN-PLACE GEMM against the inverse (one
+    // column tile: every CTA has consumed its 128 rows of A21 before its epilogue overwrites them), rank-128 update of the
+    // columns of the block column to the right of the panel with L21 itself as the operand.
+    // Panel look-ahead: the diagonal tile of the next panel is updated and factored on ctx->side_stream2 (LookaheadDiag)
+    // while ctx->stream runs the rest of the rank-128 update, so the chain per panel is diag + solve + a few microseconds
+    // instead of diag + solve + whole update.  first_diag_pending: the caller already did that for the first panel.
+    template<typename T>
+    static int
+    FactorBlockColumn(Context *ctx, const long n, const long j0, const long j1, T *l, const long ld, T *linv, int *info, const bool first_diag_pending) {
+        using Smem = BatchSmem<T, 1, kDiagBlocks>;
+        static const bool no_panel_la = std::getenv("ERL_GP_POTRF_NO_PANEL_LOOKAHEAD") != nullptr;  // A/B measurements
+        cudaStream_t chain = ctx->stream;
+        cudaStream_t la = ctx->side_stream2;
+        bool diag_done = first_diag_pending;  // the diagonal block of the panel about to be processed is factored on `la`
+        int rc = ERL_GP_STATUS_OK;
+        for (long k0 = j0; k0 < j1; k0 += kPanel) {
+            const long nk = n - k0 < kPanel ? n - k0 : kPanel;
+            T *linv_k = linv + (k0 / kPanel) * kPanel * kPanel;
+            if (diag_done) {
+                ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(chain, ctx->ev_la_done, 0));
+                diag_done = false;
+            } else {
+                DiagFactorKernel<T><<<1, kBatchThreads, Smem::kBytes, chain>>>(l + k0 + k0 * ld, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
+                ctx->launches += 1;
+                ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            }
+            const long k1 = k0 + nk;
+            const long m = n - k1;
+            if (m <= 0) { break; }
+            T *l21 = l + k1 + k0 * ld;
+            rc = Gemm<T>(ctx, kOpN, kOpT, m, nk, nk, T(1), l21, ld, linv_k, kPanel, T(0), l21, ld, 0);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            const long rest = j1 - k1;  // columns of the block column still to the right of this panel
+            if (rest <= 0) { break; }
+            T *c = l + k1 + k1 * ld;
+            int skip_first_tile = 1;
+            if (!no_panel_la) {
+                const long next_nk = m < kPanel ? m : kPanel;
+                rc = LookaheadDiag<T>(ctx, chain, la, static_cast<int>(next_nk), nk, l21, ld, c, ld, linv + (k1 / kPanel) * kPanel * kPanel, info, k1);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+                diag_done = true;
+                skip_first_tile = 2;
+            }
+            rc = Gemm<T>(ctx, kOpN, kOpT, m, rest, nk, T(-1), l21, ld, l21, ld, T(1), c, ld, skip_first_tile);  // 2: all lower tiles but (0, 0)
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+        }
+        if (diag_done) { ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(chain, ctx->ev_la_done, 0)); }
+        return ERL_GP_STATUS_OK;
+    }
+
     template<typename T>
     int
     Potrf(Context *ctx, long n, T *l, long ld, T *linv, T *panel, int *info) {
         using Smem = BatchSmem<T, 1, kDiagBlocks>;
-        auto diag = DiagFactorKernel<T>;
-        ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(diag, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Smem::kBytes)));
+        ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(DiagFactorKernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Smem::kBytes)));
         ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(info, 0, sizeof(int), ctx->stream));
-        // Two-level blocking: inside an outer block of kOuter columns the 128-column panels are factored right-looking,
-        // but their rank-128 updates are applied to the rest of the OUTER BLOCK only; everything to the right of it gets
-        // one rank-kOuter update per outer block (4x less read-modify-write traffic on the trailing matrix and 4x longer
-        // reduction loops than a rank-128 SYRK per panel, which ran at 19 of 37 TFLOP/s).
-        // Look-ahead: the 128 x 128 diagonal block of the NEXT panel is updated and factored (a one-CTA kernel, ~140 us)
-        // on a side stream while the main stream runs the bulk of the current update (which skips that tile).
+        // Two-level blocking: a block column of kOuter columns is factored with 128-column panels whose rank-128 updates
+        // stay inside the block column; everything to its right gets ONE rank-kOuter update per block column (4x less
+        // read-modify-write traffic on the trailing matrix and 4x longer reduction loops than a rank-128 SYRK per panel:
+        // the rank-512 SYRK runs at 26.5 of 37 TFLOP/s, the rank-128 one at 19).
+        // Look-ahead over block columns: the panel chain of a block column is a sequence of small latency-bound kernels
+        // (4 x (one-CTA diagonal factorisation + panel solve + rank-128 update), ~0.7 ms) that left the GPU idle for a third
+        // of the factorisation.  So, once block column b is final, the update of block column b + 1 and its panel chain run
+        // on a high-priority side stream while the main stream applies the rank-kOuter update to the columns right of block
+        // column b + 1; the two join before the next step.  The first diagonal block of block column b + 1 is itself looked
+        // ahead (LookaheadDiag) while the side stream updates the rest of that block column.
         constexpr long kOuter = 4 * kPanel;
         if (ctx->side_stream == nullptr) {
-            // highest priority: its one-CTA kernels must get the first SM slot that frees up while the bulk update still has
-            // thousands of CTAs queued (with equal priorities they only start when the bulk kernel has drained)
+            // highest priority: the chain's small kernels must get the first SM slots that free up while the bulk update still
+            // has thousands of CTAs queued (with equal priorities they only start when the bulk kernel has drained)
             int prio_lo = 0, prio_hi = 0;
             ERL_GP_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
-            ERL_GP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming));
-            ERL_GP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_diag, cudaEventDisableTiming));
+            ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream2, cudaStreamNonBlocking, prio_hi));
+            for (cudaEvent_t *ev: {&ctx->ev_panel, &ctx->ev_diag, &ctx->ev_la_start, &ctx->ev_la_done}) { ERL_GP_CUDA_OK(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming)); }
         }
+        (void) panel;  // workspace of the former out-of-place panel solve
         cudaStream_t main_stream = ctx->stream;
         cudaStream_t side = ctx->side_stream;
-        bool diag_pending = false;  // the diagonal block of the panel about to be processed was factored on the side stream
-        for (long j0 = 0; j0 < n; j0 += kOuter) {
-            const long j1 = j0 + kOuter < n ? j0 + kOuter : n;  // end of the outer block
-            for (long k0 = j0; k0 < j1; k0 += kPanel) {
-                const long kb = k0 / kPanel;
-                const long nk = n - k0 < kPanel ? n - k0 : kPanel;
-                T *l11 = l + k0 + k0 * ld;
-                T *linv_k = linv + kb * kPanel * kPanel;
-                if (diag_pending) {
-                    ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_diag, 0));
-                    diag_pending = false;
-                } else {
-                    diag<<<1, kBatchThreads, Smem::kBytes, main_stream>>>(l11, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
-                    ctx->launches += 1;
-                    ERL_GP_CUDA_OK(ctx, cudaGetLastError());
-                }
-                const long m = n - k0 - nk;
-                if (m <= 0) { break; }
-                const long k1 = k0 + nk;
-                T *l21 = l + k1 + k0 * ld;
-                // panel solve: P = A21 * L11^-T  (GEMM N,T against the kept inverse), then L21 <- P
-                int rc = Gemm<T>(ctx, kOpN, kOpT, m, nk, nk, T(1), l21, ld, linv_k, kPanel, T(0), panel, m, 0);
-                if (rc != ERL_GP_STATUS_OK) { return rc; }
-                ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l21, sizeof(T) * ld, panel, sizeof(T) * m, sizeof(T) * m, nk, cudaMemcpyDeviceToDevice, main_stream));
-                const long rest = j1 - k1;  // columns of the outer block still to the right of this panel
-                // the update that touches the next diagonal block: the rank-128 one inside the outer block, or the
-                // rank-kOuter one when this was the last panel of the block
-                const bool inner = rest > 0;
-                const T *upd_a = inner ? panel : l + j1 + j0 * ld;
-                const long upd_lda = inner ? m : ld;
-                const long upd_k = inner ? nk : j1 - j0;
-                const long upd_m = inner ? m : n - j1;
-                const long upd_n = inner ? rest : n - j1;
-                T *upd_c = inner ? l + k1 + k1 * ld : l + j1 + j1 * ld;
-                // look-ahead pays only while the bulk update is long enough to hide (tile update + factorisation) of one CTA
-                const bool lookahead = upd_m >= 6 * 1024;
-                if (upd_m > 0 && !lookahead) {
-                    rc = Gemm<T>(ctx, kOpN, kOpT, upd_m, upd_n, upd_k, T(-1), upd_a, upd_lda, upd_a, upd_lda, T(1), upd_c, ld, 1);
-                    if (rc != ERL_GP_STATUS_OK) { return rc; }
-                }
-                if (upd_m > 0 && lookahead) {
-                    const long next_nk = upd_m < kPanel ? upd_m : kPanel;
-                    // side stream: tile (0, 0) of the update, then the next diagonal factorisation
-                    ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_panel, main_stream));
-                    ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(side, ctx->ev_panel, 0));
-                    ctx->stream = side;
-                    rc = Gemm<T>(ctx, kOpN, kOpT, next_nk, next_nk, upd_k, T(-1), upd_a, upd_lda, upd_a, upd_lda, T(1), upd_c, ld, 1);
-                    ctx->stream = main_stream;
-                    if (rc != ERL_GP_STATUS_OK) { return rc; }
-                    const long next_k0 = inner ? k1 : j1;
-                    diag<<<1, kBatchThreads, Smem::kBytes, side>>>(upd_c, ld, static_cast<int>(next_nk), linv + (next_k0 / kPanel) * kPanel * kPanel, info, static_cast<int>(next_k0));
-                    ctx->launches += 1;
-                    ERL_GP_CUDA_OK(ctx, cudaGetLastError());
-                    ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_diag, side));
-                    diag_pending = true;
-                    // main stream: the rest of the update (lower tiles only, diagonal tile (0, 0) skipped)
-                    rc = Gemm<T>(ctx, kOpN, kOpT, upd_m, upd_n, upd_k, T(-1), upd_a, upd_lda, upd_a, upd_lda, T(1), upd_c, ld, 2);
-                    if (rc != ERL_GP_STATUS_OK) { return rc; }
-                }
+        static const bool no_lookahead = std::getenv("ERL_GP_POTRF_NO_LOOKAHEAD") != nullptr;  // A/B measurements
+        int rc = FactorBlockColumn<T>(ctx, n, 0, kOuter < n ? kOuter : n, l, ld, linv, info, false);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        for (long j0 = 0; j0 + kOuter < n; j0 += kOuter) {
+            // block column [j0, j1) is final and visible to the main stream
+            const long j1 = j0 + kOuter;
+            const long m = n - j1;                     // rows / columns of the trailing matrix
+            const long w = kOuter < m ? kOuter : m;    // width of the next block column
+            const T *a1 = l + j1 + j0 * ld;            // L[j1:, j0:j1]
+            T *c1 = l + j1 + j1 * ld;
+            const bool fork = m > w && !no_lookahead;
+            cudaStream_t chain = fork ? side : main_stream;
+            if (fork) {
+                ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_panel, main_stream));
+                ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(side, ctx->ev_panel, 0));
             }
+            // next block column: A[j1:, j1:j1+w] -= L[j1:, j0:j1] L[j1:j1+w, j0:j1]^T (lower tiles; its diagonal tile (0, 0) on
+            // the look-ahead stream, followed by the first diagonal factorisation), then its panel chain
+            rc = LookaheadDiag<T>(ctx, chain, ctx->side_stream2, static_cast<int>(m < kPanel ? m : kPanel), kOuter, a1, ld, c1, ld, linv + (j1 / kPanel) * kPanel * kPanel, info, j1);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            ctx->stream = chain;
+            rc = Gemm<T>(ctx, kOpN, kOpT, m, w, kOuter, T(-1), a1, ld, a1, ld, T(1), c1, ld, 2);
+            if (rc == ERL_GP_STATUS_OK) { rc = FactorBlockColumn<T>(ctx, n, j1, j1 + w, l, ld, linv, info, true); }
+            if (fork && rc == ERL_GP_STATUS_OK && cudaEventRecord(ctx->ev_diag, side) != cudaSuccess) { rc = ERL_GP_STATUS_CUDA_ERROR; }
+            ctx->stream = main_stream;
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+            if (m > w) {
+                // the rest of the trailing matrix: A[j1+w:, j1+w:] -= L[j1+w:, j0:j1] L[j1+w:, j0:j1]^T (lower tiles)
+                const T *a2 = a1 + w;
+                rc = Gemm<T>(ctx, kOpN, kOpT, m - w, m - w, kOuter, T(-1), a2, ld, a2, ld, T(1), c1 + w + w * ld, ld, 1);
+                if (rc != ERL_GP_STATUS_OK) { return rc; }
+            }
+            if (fork) { ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_diag, 0)); }
         }
-        if (diag_pending) { ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_diag, 0)); }
         return ERL_GP_STATUS_OK;
     }
 
@@ -703,10 +809,243 @@ namespace erl_gp {
         }
     }
 
+    // ---- wavefront TRSV: the whole substitution in ONE launch per direction -------------------------------------------------
+    // One CTA per 128-row block.  Forward (TRANS = false): CTA i accumulates sum_{k < i} L[i, k] z_k as the z_k appear
+    // (a flag per block, set by the CTA that produced it), then z_i = Linv_i (y_i - sum) and raises its own flag; backward
+    // (TRANS = true) is the mirror image with the column blocks L[k, i]^T, k > i.  The critical path per block is one flag
+    // round trip + two 128 x 128 mat-vecs (~2-3 us) instead of two dependent kernel launches (~16 us); the off-critical
+    // blocks of L stream in behind the wavefront (register double buffering, one block ahead).
+    // Blocks are handed out by a ticket counter in the order the CTAs actually start, and a CTA only ever waits for blocks
+    // with smaller tickets, so the spin loops cannot deadlock however many CTAs are resident.
+    constexpr int kWaveThreads = 512;
+
+    template<typename T, bool TRANS>
+    struct WaveFrag {  // this thread's 32 entries of a 128 x 128 block M (leading dimension ldm): out = M v (or M^T v)
+        T m[32];
+
+        // non-TRANS: thread (r = tid & 127, q = tid >> 7) holds M[r, 32 q + j];  TRANS: lane c, warp w hold M[c + 32 i, w + 16 j] (slot 4 j + i)
+        __device__ __forceinline__ void
+        Load(const T *__restrict__ mat, const long ldm, const long row_lim, const long col_lim, const int tid) {
+            if (!TRANS) {
+                const int r = tid & 127, q = tid >> 7;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { m[j] = (r < row_lim && 32 * q + j < col_lim) ? mat[r + (32 * q + j) * ldm] : T(0); }
+            } else {
+                const int c = tid & 31, w = tid >> 5;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { m[4 * j + i] = (c + 32 * i < row_lim && w + 16 * j < col_lim) ? mat[(c + 32 * i) + (w + 16 * j) * ldm] : T(0); }
+                }
+            }
+        }
+
+        // adds this block's contribution to acc_s[yy][r] (shared, TRANS) or to the thread's partial sums (non-TRANS)
+        __device__ __forceinline__ void
+        Apply(const T (*vs)[kPanel], const int y_dim, T (&acc)[kTrsvYmax], T (*acc_s)[kPanel], const int tid) const {
+            if (!TRANS) {
+                const int q = tid >> 7;
+#pragma unroll
+                for (int yy = 0; yy < kTrsvYmax; ++yy) {
+                    if (yy < y_dim) {
+                        T s0 = T(0), s1 = T(0);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            s0 += m[j] * vs[yy][32 * q + j];
+                            s1 += m[j + 1] * vs[yy][32 * q + j + 1];
+                        }
+                        acc[yy] += s0 + s1;
+                    }
+                }
+            } else {
+                const int c = tid & 31, w = tid >> 5;
+#pragma unroll
+                for (int yy = 0; yy < kTrsvYmax; ++yy) {
+                    if (yy < y_dim) {
+                        T v4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { v4[i] = vs[yy][c + 32 * i]; }
+                        T mine = T(0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            T sj = (m[4 * j] * v4[0] + m[4 * j + 1] * v4[1]) + (m[4 * j + 2] * v4[2] + m[4 * j + 3] * v4[3]);
+#pragma unroll
+                            for (int off = 16; off > 0; off >>= 1) { sj += __shfl_xor_sync(0xffffffffu, sj, off); }
+                            if (c == j) { mine = sj; }
+                        }
+                        if (c < 8) { acc_s[yy][w + 16 * c] += mine; }  // column w + 16 c belongs to this warp only
+                    }
+                }
+            }
+        }
+    };
+
+    template<typename T, bool TRANS>
+    __global__ void __launch_bounds__(kWaveThreads, 1)
+    TrsvWavefrontKernel(const T *__restrict__ l, const long ld, const T *__restrict__ linv, const long n, T *y, const long ldy, const int y_dim, int *sync_buf) {
+        __shared__ int s_step;
+        __shared__ T vs[kTrsvYmax][kPanel];        // the vector the current block is applied to
+        __shared__ T acc_s[kTrsvYmax][kPanel];     // TRANS: running sums; non-TRANS: reduction scratch
+        __shared__ T red[3][kTrsvYmax][kPanel];    // non-TRANS: partial sums of the column quarters 1..3
+        const int tid = threadIdx.x;
+        if (tid == 0) { s_step = atomicAdd(sync_buf, 1); }
+        for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) { acc_s[e / kPanel][e % kPanel] = T(0); }
+        __syncthreads();
+        const int nblk = static_cast<int>((n + kPanel - 1) / kPanel);
+        const int step = s_step;
+        if (step >= nblk) { return; }
+        volatile int *ready = sync_buf + 1;
+        const int blk = TRANS ? nblk - 1 - step : step;
+        const long r0 = static_cast<long>(blk) * kPanel;
+        const long nr = n - r0 < kPanel ? n - r0 : kPanel;  // rows of this block
+
+        T acc[kTrsvYmax];
+#pragma unroll
+        for (int yy = 0; yy < kTrsvYmax; ++yy) { acc[yy] = T(0); }
+
+        // FP32: the next block is loaded into a second register set before waiting for the current flag; FP64 (64 doubles would
+        // not fit the 128-register budget of 512 threads) pulls the next block into L2 with prefetch instructions instead
+        constexpr bool kDoubleBuffer = sizeof(T) == 4;
+        WaveFrag<T, TRANS> cur;
+        WaveFrag<T, (kDoubleBuffer ? TRANS : false)> nxt_storage[kDoubleBuffer ? 1 : 0 + 1];
+        auto block_ptr = [&](const int kk) {
+            const int kb = TRANS ? nblk - 1 - kk : kk;
+            const long k0 = static_cast<long>(kb) * kPanel;
+            return TRANS ? l + k0 + r0 * ld : l + r0 + k0 * ld;  // L[kb rows, blk columns]^T : L[blk rows, kb columns]
+        };
+        auto load_block = [&](WaveFrag<T, TRANS> &f, const int kk) {
+            const int kb = TRANS ? nblk - 1 - kk : kk;
+            const long k0 = static_cast<long>(kb) * kPanel;
+            // non-TRANS: kb < blk is a full block, my rows may be short; TRANS: the last row block may be short
+            f.Load(block_ptr(kk), ld, TRANS ? n - k0 : nr, kPanel, tid);
+        };
+        auto prefetch_block = [&](const int kk) {  // 128 columns x 1 KiB: 2 lines per thread
+            const int kb = TRANS ? nblk - 1 - kk : kk;
+            const long rows = TRANS ? n - static_cast<long>(kb) * kPanel : nr;
+            const T *base = block_ptr(kk);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = tid + kWaveThreads * u;  // 0 .. 1023
+                const int col = e >> 3, seg = (e & 7) * 16;
+                if (seg < rows) { asm volatile("prefetch.global.L2 [%0];" ::"l"(base + seg + col * ld)); }
+            }
+        };
+        if (step > 0) { load_block(cur, 0); }
+        for (int kk = 0; kk < step; ++kk) {
+            if (kk + 1 < step) {
+                if constexpr (kDoubleBuffer) {
+                    load_block(nxt_storage[0], kk + 1);
+                } else {
+                    prefetch_block(kk + 1);
+                }
+            }
+            const int kb = TRANS ? nblk - 1 - kk : kk;
+            if (tid == 0) {
+                while (ready[kb] == 0) {}
+                __threadfence();
+            }
+            __syncthreads();  // also: everybody is done with vs of the previous block
+            const long k0 = static_cast<long>(kb) * kPanel;
+            for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) {
+                const int yy = e / kPanel, c = e % kPanel;
+                vs[yy][c] = (yy < y_dim && k0 + c < n) ? __ldcg(y + k0 + c + yy * ldy) : T(0);
+            }
+            __syncthreads();
+            cur.Apply(vs, y_dim, acc, acc_s, tid);
+            if (kk + 1 < step) {
+                if constexpr (kDoubleBuffer) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { cur.m[j] = nxt_storage[0].m[j]; }
+                } else {
+                    load_block(cur, kk + 1);
+                }
+            }
+        }
+        // v = y_blk - sum, then z_blk = Linv_blk v (forward) / Linv_blk^T v (backward)
+        cur.Load(linv + static_cast<long>(blk) * kPanel * kPanel, kPanel, kPanel, kPanel, tid);
+        __syncthreads();
+        if (!TRANS) {
+            const int r = tid & 127, q = tid >> 7;
+#pragma unroll
+            for (int yy = 0; yy < kTrsvYmax; ++yy) {
+                if (q > 0) {
+                    red[q - 1][yy][r] = acc[yy];
+                } else {
+                    acc_s[yy][r] = acc[yy];
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) {
+                const int yy = e / kPanel, c = e % kPanel;
+                acc_s[yy][c] += (red[0][yy][c] + red[1][yy][c]) + red[2][yy][c];
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) {
+            const int yy = e / kPanel, c = e % kPanel;
+            vs[yy][c] = (yy < y_dim && c < nr) ? y[r0 + c + yy * ldy] - acc_s[yy][c] : T(0);
+        }
+        __syncthreads();
+        for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) { acc_s[e / kPanel][e % kPanel] = T(0); }
+#pragma unroll
+        for (int yy = 0; yy < kTrsvYmax; ++yy) { acc[yy] = T(0); }
+        __syncthreads();
+        cur.Apply(vs, y_dim, acc, acc_s, tid);
+        __syncthreads();
+        if (!TRANS) {
+            const int r = tid & 127, q = tid >> 7;
+#pragma unroll
+            for (int yy = 0; yy < kTrsvYmax; ++yy) {
+                if (q > 0) {
+                    red[q - 1][yy][r] = acc[yy];
+                } else {
+                    acc_s[yy][r] = acc[yy];
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) {
+                const int yy = e / kPanel, c = e % kPanel;
+                acc_s[yy][c] += (red[0][yy][c] + red[1][yy][c]) + red[2][yy][c];
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < kTrsvYmax * kPanel; e += kWaveThreads) {
+            const int yy = e / kPanel, c = e % kPanel;
+            if (yy < y_dim && c < nr) { y[r0 + c + yy * ldy] = acc_s[yy][c]; }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            ready[blk] = 1;
+        }
+    }
+
     template<typename T>
     int
     TrsvSolve(Context *ctx, long n, long y_dim, const T *l, long ld, const T *linv, T *y, long ldy) {
         if (y_dim < 1 || y_dim > kTrsvYmax) { return ERL_GP_STATUS_UNSUPPORTED; }
+        static const bool legacy_trsv = std::getenv("ERL_GP_TRSV_LEGACY") != nullptr;  // A/B measurements: two launches per panel
+        if (!legacy_trsv) {
+            const int nblk = static_cast<int>(CeilDiv(n, kPanel));
+            if (ctx->sync_ints_capacity < 2 * (nblk + 1)) {
+                if (ctx->sync_ints != nullptr) {
+                    ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+                    ERL_GP_CUDA_OK(ctx, cudaFree(ctx->sync_ints));
+                    ctx->sync_ints = nullptr;
+                    ctx->sync_ints_capacity = 0;
+                }
+                const int cap = 2 * (nblk + 1) < 1024 ? 1024 : 2 * (nblk + 1);
+                ERL_GP_CUDA_OK(ctx, cudaMalloc(&ctx->sync_ints, sizeof(int) * cap));
+                ctx->sync_ints_capacity = cap;
+            }
+            ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(ctx->sync_ints, 0, sizeof(int) * 2 * (nblk + 1), ctx->stream));
+            TrsvWavefrontKernel<T, false><<<nblk, kWaveThreads, 0, ctx->stream>>>(l, ld, linv, n, y, ldy, static_cast<int>(y_dim), ctx->sync_ints);
+            TrsvWavefrontKernel<T, true><<<nblk, kWaveThreads, 0, ctx->stream>>>(l, ld, linv, n, y, ldy, static_cast<int>(y_dim), ctx->sync_ints + nblk + 1);
+            ctx->launches += 2;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            return ERL_GP_STATUS_OK;
+        }
         const long num_panels = CeilDiv(n, kPanel);
         const int yd = static_cast<int>(y_dim);
         for (long kb = 0; kb < num_panels; ++kb) {  // z = L^-1 y

@@ -16,9 +16,12 @@ struct erl_gp_context {
     int max_smem_optin = 0;
     long launches = 0;
     char last_error[512] = {0};
-    // look-ahead of the blocked Cholesky (erl_gp_dense.cu): side stream + events, created on first use
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_panel = nullptr, ev_diag = nullptr;
+    // look-ahead of the blocked Cholesky (erl_gp_dense.cu): side streams + events, created on first use
+    cudaStream_t side_stream = nullptr, side_stream2 = nullptr;
+    cudaEvent_t ev_panel = nullptr, ev_diag = nullptr, ev_la_start = nullptr, ev_la_done = nullptr;
+    // ticket counter + per-block flags of the wavefront TRSV (erl_gp_dense.cu), grow-only
+    int *sync_ints = nullptr;
+    int sync_ints_capacity = 0;
 };
 
 namespace erl_gp {

@@ -72,7 +72,9 @@ namespace erl_gp {
             static constexpr int kAl = kRs + kNp;       // y -> z -> alpha
             static constexpr int kVar = kAl + kNp;      // noise variances
             static constexpr int kMisc = kVar + kNp;    // int fail flag
-            static constexpr int kEnd = kMisc + 4;
+            static constexpr int kDinvLd = 20;          // column stride of a 16 x 16 inverse block (== 4 mod 16, like the L columns)
+            static constexpr int kDinv = kMisc + 4;     // inverses of the 16 x 16 diagonal blocks of L, column-major (tensor-path predict)
+            static constexpr int kEnd = kDinv + NBLK * 16 * kDinvLd;
             static constexpr size_t kBytes = static_cast<size_t>(kEnd) * sizeof(float);
         };
 
@@ -561,6 +563,207 @@ namespace erl_gp {
             }
         }
 
+        // --------------------------------------------------------------------------------------
+        // Tensor-path predict (3xTF32 on mma.sync.m16n8k8): V^T = Kt^T L^-T, one warp per 16 queries.
+        //
+        // The substitution is written for the TRANSPOSED system so that a finished 16-column block of V^T, which the MMA
+        // leaves in the accumulator ("C") layout, is directly the A operand of the next products: C holds (row g, columns
+        // 2t, 2t+1), A wants (row g, k-slots t, t+4), and since the order of the reduction index is free the two columns of
+        // C simply become the slots t and t+4 - the B fragment is loaded with the matching permutation, b0 = B[2t][g],
+        // b1 = B[2t+1][g].  No shuffle, no shared-memory round trip, no barrier: a warp walks the 16-column blocks of L
+        //     V^T_j = X_j Dinv_j^T          (X_j = the accumulated block, Dinv_j = inverse of the 16 x 16 diagonal block)
+        //     X_i  -= V^T_j L_ij^T          for every block row i below j
+        // with all 16 x 128 accumulators (64 registers) resident.  L stays in the packed column-major layout of the
+        // factorisation: b0 / b1 are two LDS.32 whose 32 lanes hit 32 different banks (column stride == 4 mod 16).
+        // FP32 accuracy comes from the 3xTF32 split a = hi + lo (hi = cvt.rna.tf32, lo = a - hi exact): a b ~ hi_a hi_b +
+        // lo_a hi_b + hi_a lo_b, error ~2^-21 relative per product (measured against the oracle in tests/test_gpu_batch.py).
+        // One m16n8k8 is 1024 FMAs per issue slot instead of 64 for a warp-wide FFMA2: the FMA / issue pipes that bound the
+        // previous predict are left to the factorisations of the other resident CTAs.
+        // --------------------------------------------------------------------------------------
+        __device__ __forceinline__ uint32_t
+        Tf32Hi(const float x) {
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+            return r;
+        }
+
+        __device__ __forceinline__ void
+        MmaTf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        }
+
+        // d += A B with A = ahi + alo (pre-split) and the two B entries of this lane split here
+        __device__ __forceinline__ void
+        Mma3(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float bf0, const float bf1) {
+            const uint32_t bh0 = Tf32Hi(bf0), bh1 = Tf32Hi(bf1);
+            const uint32_t bl0 = __float_as_uint(bf0 - __uint_as_float(bh0));
+            const uint32_t bl1 = __float_as_uint(bf1 - __uint_as_float(bh1));
+            MmaTf32(d, alo, bh0, bh1);
+            MmaTf32(d, ahi, bl0, bl1);
+            MmaTf32(d, ahi, bh0, bh1);
+        }
+
+        // accumulator tile (columns 2t, 2t+1 of rows g, g+8) -> A fragment (k-slots t, t+4), scaled by sgn, split in hi + lo
+        __device__ __forceinline__ void
+        AccToA(const float (&c)[4], const float sgn, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+            const float a[4] = {sgn * c[0], sgn * c[2], sgn * c[1], sgn * c[3]};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                hi[k] = Tf32Hi(a[k]);
+                lo[k] = __float_as_uint(a[k] - __uint_as_float(hi[k]));
+            }
+        }
+
+        // inverses of the 16 x 16 diagonal blocks of L (lane c < 16 of a warp: column c by forward substitution on e_c)
+        template<int NBLK>
+        __device__ __forceinline__ void
+        ComputeDinv(float *__restrict__ smem, const int nblk) {
+            using Lay = Layout<NBLK>;
+            const float *lp = smem + Lay::kL;
+            const float *rs = smem + Lay::kRs;
+            float *dinv = smem + Lay::kDinv;
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+            if (lane >= 16) { return; }
+            for (int kb = warp; kb < nblk; kb += kThreads / 32) {
+                const float *blk = lp + Lay::Base(kb);
+                const int stride = Lay::Stride(kb);
+                float sres[16], x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { sres[i] = i == lane ? 1.0f : 0.f; }
+#pragma unroll
+                for (int pc = 0; pc < 16; ++pc) {
+                    x[pc] = sres[pc] * rs[16 * kb + pc];
+                    float col[16];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 v4 = *reinterpret_cast<const float4 *>(blk + pc * stride + 4 * k4);  // warp-uniform address
+                        col[4 * k4] = v4.x, col[4 * k4 + 1] = v4.y, col[4 * k4 + 2] = v4.z, col[4 * k4 + 3] = v4.w;
+                    }
+#pragma unroll
+                    for (int i = pc + 1; i < 16; ++i) { sres[i] = fmaf(-col[i], x[pc], sres[i]); }
+                }
+                float *dst = dinv + kb * 16 * Lay::kDinvLd + lane * Lay::kDinvLd;  // column `lane` of the inverse
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(x[4 * k4], x[4 * k4 + 1], x[4 * k4 + 2], x[4 * k4 + 3]); }
+            }
+        }
+
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ void
+        PredictTileMma(const BatchParams<float> &p, const CovCoef cov, const float *__restrict__ smem, const int n, const int nblk, const long q_begin, const int nq) {
+            using Lay = Layout<NBLK>;
+            const float *lp = smem + Lay::kL;
+            const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
+            const float *dinv = smem + Lay::kDinv;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            const int g = lane >> 2, t = lane & 3;
+            if (16 * warp >= nq) { return; }  // warp-uniform; PredictTileMma has no barrier
+            const int qrow[2] = {16 * warp + g, 16 * warp + g + 8};
+
+            float xq[2][XDIM];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int d = 0; d < XDIM; ++d) { xq[k][d] = qrow[k] < nq ? p.q_x[(q_begin + qrow[k]) * XDIM + d] : 0.f; }
+            }
+
+            // Ktest^T tile in the accumulator layout: acc[j] = columns 8 j + 2 t, + 1 of query rows g (slots 0, 1) and g + 8 (slots 2, 3)
+            float acc[2 * NBLK][4];
+            float mean[2] = {0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 2 * NBLK; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * j + 2 * t + e;
+                    const float4 pt = pts[col];
+                    float ka = cov(Dist2<XDIM>(pt, xq[0]));
+                    float kb = cov(Dist2<XDIM>(pt, xq[1]));
+                    if (col >= n) { ka = kb = 0.f; }
+                    mean[0] = fmaf(ka, pt.w, mean[0]);
+                    mean[1] = fmaf(kb, pt.w, mean[1]);
+                    acc[j][e] = ka;
+                    acc[j][2 + e] = kb;
+                }
+            }
+
+            float ss[2] = {0.f, 0.f};
+            StaticFor<0, NBLK>([&](auto jb_c) {
+                constexpr int jb = decltype(jb_c)::value;
+                if (jb < nblk) {
+                    // V^T_jb = X_jb Dinv_jb^T  (Dinv lower triangular: the (k-tile 1, n-tile 0) product is zero)
+                    uint32_t xhi[2][4], xlo[2][4];
+                    AccToA(acc[2 * jb], 1.0f, xhi[0], xlo[0]);
+                    AccToA(acc[2 * jb + 1], 1.0f, xhi[1], xlo[1]);
+                    float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                    const float *dv = dinv + jb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;  // Dinv[g][2 t]
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                        for (int kt = 0; kt <= nt; ++kt) { Mma3(v[nt], xhi[kt], xlo[kt], dv[8 * kt * Lay::kDinvLd + 8 * nt], dv[(8 * kt + 1) * Lay::kDinvLd + 8 * nt]); }
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        ss[0] = fmaf(v[nt][0], v[nt][0], ss[0]);
+                        ss[0] = fmaf(v[nt][1], v[nt][1], ss[0]);
+                        ss[1] = fmaf(v[nt][2], v[nt][2], ss[1]);
+                        ss[1] = fmaf(v[nt][3], v[nt][3], ss[1]);
+                    }
+                    if (jb + 1 < nblk) {
+                        // X_i -= V^T_jb L_{i,jb}^T for the block rows below
+                        uint32_t ahi[2][4], alo[2][4];
+                        AccToA(v[0], -1.0f, ahi[0], alo[0]);
+                        AccToA(v[1], -1.0f, ahi[1], alo[1]);
+                        constexpr int stride = Lay::Stride(jb);
+                        const float *lb = lp + Lay::Base(jb) + 2 * t * stride + g;  // L[16 jb + g][16 jb + 2 t]
+                        StaticFor<jb + 1, NBLK>([&](auto i_c) {
+                            constexpr int i = decltype(i_c)::value;
+                            if (i < nblk) {
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                                    for (int kt = 0; kt < 2; ++kt) {
+                                        const float *bp = lb + 8 * kt * stride + 16 * (i - jb) + 8 * nt;  // L[16 i + 8 nt + g][16 jb + 8 kt + 2 t (+ 1)]
+                                        Mma3(acc[2 * i + nt], ahi[kt], alo[kt], bp[0], bp[stride]);
+                                    }
+                                }
+                            }
+                        });
+                    }
+                }
+            });
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                mean[k] += __shfl_xor_sync(kFull, mean[k], 1);
+                mean[k] += __shfl_xor_sync(kFull, mean[k], 2);
+                ss[k] += __shfl_xor_sync(kFull, ss[k], 1);
+                ss[k] += __shfl_xor_sync(kFull, ss[k], 2);
+            }
+            if (t < 2 && qrow[t] < nq) {
+                const long src = q_begin + qrow[t];
+                const long dst = p.q_out_index != nullptr ? p.q_out_index[src] : src;
+                const float mk = t == 0 ? mean[0] : mean[1];
+                const float sk = t == 0 ? ss[0] : ss[1];
+                if (p.mean != nullptr) {
+                    float f = mk;
+                    if (p.mapping != ERL_GP_MAPPING_NONE) { f = MappingInv<float>(p.mapping, p.mapping_scale, f); }
+                    p.mean[dst] = f;
+                }
+                if (p.variance != nullptr) { p.variance[dst] = 1.0f - sk; }  // literal prior 1.0f, src/vanilla_gp.cpp:121
+                if (p.valid != nullptr) { p.valid[dst] = 1; }
+            }
+        }
+
+#ifndef ERL_GP_ROWGP_FFMA_PREDICT
+        constexpr bool kMmaPredict = true;
+#else
+        constexpr bool kMmaPredict = false;  // A/B builds of the FFMA2 predict (PredictTile)
+#endif
+
         template<int XDIM, int NBLK, int MODE>
         __global__ void __launch_bounds__(kThreads, 4)
         RowGpKernel(const BatchParams<float> p) {
@@ -668,6 +871,7 @@ namespace erl_gp {
                     smem[Lay::kPts + 4 * e + 3] = a;
                 }
                 if (tid == 0) { p.info[g] = 0; }
+                if constexpr (kMmaPredict && (MODE & kBatchPredict) != 0) { ComputeDinv<NBLK>(smem, nblk); }
             } else {
                 // ---- predict-only: reload L (float4 along the rows when the layout allows), rebuild 1 / L_jj ----
                 __syncthreads();
@@ -708,13 +912,21 @@ namespace erl_gp {
                         }
                     }
                 }
+                if constexpr (kMmaPredict) {
+                    __syncthreads();
+                    ComputeDinv<NBLK>(smem, nblk);
+                }
             }
 
             if constexpr ((MODE & kBatchPredict) != 0) {
                 __syncthreads();
                 for (long qb = q0 + static_cast<long>(blockIdx.y) * kTileQ; qb < q1; qb += static_cast<long>(gridDim.y) * kTileQ) {
                     const int nq = static_cast<int>(q1 - qb < kTileQ ? q1 - qb : kTileQ);
-                    PredictTile<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
+                    if constexpr (kMmaPredict) {
+                        PredictTileMma<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
+                    } else {
+                        PredictTile<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
+                    }
                 }
             }
         }

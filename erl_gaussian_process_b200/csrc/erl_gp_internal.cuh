@@ -123,6 +123,9 @@ namespace erl_gp {
         uint8_t *valid;
         int mapping;  // ERL_GP_MAPPING_NONE = no un-map
         T mapping_scale;
+        // row-GP kernel, fused train + predict: CTA slot k of an SM (first wave only) starts k * stagger_cycles late
+        int stagger_cycles = 0;
+        int sm_count = 148;
     };
 
     enum BatchMode : int { kBatchTrain = 1, kBatchPredict = 2, kBatchTrainPredict = 3 };

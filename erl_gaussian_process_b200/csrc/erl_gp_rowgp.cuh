@@ -32,6 +32,7 @@
 
 #include "erl_gp_internal.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace erl_gp {
@@ -50,6 +51,7 @@ namespace erl_gp {
 
         constexpr int kThreads = 128;
         constexpr unsigned kFull = 0xffffffffu;
+        constexpr int kDefaultStaggerCycles = 0;  // per CTA slot, see RowGpKernel
 
         template<int NBLK>
         struct Layout {
@@ -575,16 +577,17 @@ namespace erl_gp {
         //     X_i  -= V^T_j L_ij^T          for every block row i below j
         // with all 16 x 128 accumulators (64 registers) resident.  L stays in the packed column-major layout of the
         // factorisation: b0 / b1 are two LDS.32 whose 32 lanes hit 32 different banks (column stride == 4 mod 16).
-        // FP32 accuracy comes from the 3xTF32 split a = hi + lo (hi = cvt.rna.tf32, lo = a - hi exact): a b ~ hi_a hi_b +
-        // lo_a hi_b + hi_a lo_b, error ~2^-21 relative per product (measured against the oracle in tests/test_gpu_batch.py).
+        // FP32 accuracy comes from the 3xTF32 split a = hi + lo (hi = a truncated to TF32, lo = a - hi exact): a b ~ hi_a hi_b +
+        // lo_a hi_b + hi_a lo_b, error ~2^-20 relative per product (measured against the oracle in tests/test_gpu_batch.py).
         // One m16n8k8 is 1024 FMAs per issue slot instead of 64 for a warp-wide FFMA2: the FMA / issue pipes that bound the
         // previous predict are left to the factorisations of the other resident CTAs.
         // --------------------------------------------------------------------------------------
+        // The tensor core reads only the upper 19 bits of a TF32 operand, so "hi" is the FP32 value itself (truncation is
+        // implicit) and lo = x - trunc(x) is exact: one LOP3 + one FADD per split.  (cvt.rna.tf32.f32 is emulated on sm_100a
+        // with IADD + FSETP + SEL + LOP3 - it made up 27 % of the instructions of the first version of this kernel.)
         __device__ __forceinline__ uint32_t
-        Tf32Hi(const float x) {
-            uint32_t r;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-            return r;
+        Tf32Lo(const float x) {
+            return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
         }
 
         __device__ __forceinline__ void
@@ -597,11 +600,9 @@ namespace erl_gp {
         // d += A B with A = ahi + alo (pre-split) and the two B entries of this lane split here
         __device__ __forceinline__ void
         Mma3(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float bf0, const float bf1) {
-            const uint32_t bh0 = Tf32Hi(bf0), bh1 = Tf32Hi(bf1);
-            const uint32_t bl0 = __float_as_uint(bf0 - __uint_as_float(bh0));
-            const uint32_t bl1 = __float_as_uint(bf1 - __uint_as_float(bh1));
+            const uint32_t bh0 = __float_as_uint(bf0), bh1 = __float_as_uint(bf1);
             MmaTf32(d, alo, bh0, bh1);
-            MmaTf32(d, ahi, bl0, bl1);
+            MmaTf32(d, ahi, Tf32Lo(bf0), Tf32Lo(bf1));
             MmaTf32(d, ahi, bh0, bh1);
         }
 
@@ -611,8 +612,8 @@ namespace erl_gp {
             const float a[4] = {sgn * c[0], sgn * c[2], sgn * c[1], sgn * c[3]};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                hi[k] = Tf32Hi(a[k]);
-                lo[k] = __float_as_uint(a[k] - __uint_as_float(hi[k]));
+                hi[k] = __float_as_uint(a[k]);
+                lo[k] = Tf32Lo(a[k]);
             }
         }
 
@@ -691,20 +692,39 @@ namespace erl_gp {
                 }
             }
 
+            // The loop over the blocks is fully unrolled (static register indices).  (A runtime loop with the accumulators
+            // rotated down by one block per step halves the code size but ran 25 % slower: no overlap across the back edge.)
+            // Issue order inside a step: the three products of the 3xTF32 split go to the same accumulator and a dependent
+            // HMMA waits ~20 cycles for its predecessor, so the products are issued term by term over a GROUP of accumulator
+            // tiles (two block rows = 4 tiles) - consecutive HMMAs never touch the same accumulator.
             float ss[2] = {0.f, 0.f};
             StaticFor<0, NBLK>([&](auto jb_c) {
                 constexpr int jb = decltype(jb_c)::value;
                 if (jb < nblk) {
-                    // V^T_jb = X_jb Dinv_jb^T  (Dinv lower triangular: the (k-tile 1, n-tile 0) product is zero)
+                    // V^T_jb = X_jb Dinv_jb^T  (Dinv lower triangular: the (k-tile 1, n-tile 0) product is zero); three
+                    // independent accumulators (n-tile 0; n-tile 1 by k-tile), interleaved term by term
                     uint32_t xhi[2][4], xlo[2][4];
                     AccToA(acc[2 * jb], 1.0f, xhi[0], xlo[0]);
                     AccToA(acc[2 * jb + 1], 1.0f, xhi[1], xlo[1]);
                     float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                    const float *dv = dinv + jb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;  // Dinv[g][2 t]
+                    {
+                        const float *dv = dinv + jb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;  // Dinv[g][2 t]
+                        float w[4] = {0.f, 0.f, 0.f, 0.f};  // n-tile 1, k-tile 1
+                        const float d00[2] = {dv[0], dv[Lay::kDinvLd]};                                            // n-tile 0, k-tile 0
+                        const float d10[2] = {dv[8], dv[Lay::kDinvLd + 8]};                                        // n-tile 1, k-tile 0
+                        const float d11[2] = {dv[8 * Lay::kDinvLd + 8], dv[9 * Lay::kDinvLd + 8]};                 // n-tile 1, k-tile 1
+                        const uint32_t l00[2] = {Tf32Lo(d00[0]), Tf32Lo(d00[1])}, l10[2] = {Tf32Lo(d10[0]), Tf32Lo(d10[1])}, l11[2] = {Tf32Lo(d11[0]), Tf32Lo(d11[1])};
+                        MmaTf32(v[0], xlo[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
+                        MmaTf32(v[1], xlo[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
+                        MmaTf32(w, xlo[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
+                        MmaTf32(v[0], xhi[0], l00[0], l00[1]);
+                        MmaTf32(v[1], xhi[0], l10[0], l10[1]);
+                        MmaTf32(w, xhi[1], l11[0], l11[1]);
+                        MmaTf32(v[0], xhi[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
+                        MmaTf32(v[1], xhi[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
+                        MmaTf32(w, xhi[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-                        for (int kt = 0; kt <= nt; ++kt) { Mma3(v[nt], xhi[kt], xlo[kt], dv[8 * kt * Lay::kDinvLd + 8 * nt], dv[(8 * kt + 1) * Lay::kDinvLd + 8 * nt]); }
+                        for (int c = 0; c < 4; ++c) { v[1][c] += w[c]; }
                     }
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
@@ -714,23 +734,45 @@ namespace erl_gp {
                         ss[1] = fmaf(v[nt][3], v[nt][3], ss[1]);
                     }
                     if (jb + 1 < nblk) {
-                        // X_i -= V^T_jb L_{i,jb}^T for the block rows below
+                        // X_i -= V^T_jb L_{i,jb}^T for the block rows below, two block rows (4 accumulator tiles) per group
                         uint32_t ahi[2][4], alo[2][4];
                         AccToA(v[0], -1.0f, ahi[0], alo[0]);
                         AccToA(v[1], -1.0f, ahi[1], alo[1]);
                         constexpr int stride = Lay::Stride(jb);
-                        const float *lb = lp + Lay::Base(jb) + 2 * t * stride + g;  // L[16 jb + g][16 jb + 2 t]
-                        StaticFor<jb + 1, NBLK>([&](auto i_c) {
+                        const float *lb = lp + Lay::Base(jb) + 2 * t * stride + g - 16 * jb;  // + row: L[row + g][16 jb + 2 t]
+                        auto update = [&](auto i_c, auto cnt_c) {  // block rows i .. i + cnt - 1
                             constexpr int i = decltype(i_c)::value;
-                            if (i < nblk) {
+                            constexpr int kTiles = 2 * decltype(cnt_c)::value;
 #pragma unroll
-                                for (int nt = 0; nt < 2; ++nt) {
+                            for (int kt = 0; kt < 2; ++kt) {
+                                float b[kTiles][2];
+                                uint32_t bl[kTiles][2];
 #pragma unroll
-                                    for (int kt = 0; kt < 2; ++kt) {
-                                        const float *bp = lb + 8 * kt * stride + 16 * (i - jb) + 8 * nt;  // L[16 i + 8 nt + g][16 jb + 8 kt + 2 t (+ 1)]
-                                        Mma3(acc[2 * i + nt], ahi[kt], alo[kt], bp[0], bp[stride]);
-                                    }
+                                for (int u = 0; u < kTiles; ++u) {
+                                    const float *bp = lb + 8 * kt * stride + 16 * i + 8 * u;  // L[16 i + 8 u + g][16 jb + 8 kt + 2 t (+ 1)]
+                                    b[u][0] = bp[0];
+                                    b[u][1] = bp[stride];
                                 }
+#pragma unroll
+                                for (int u = 0; u < kTiles; ++u) { bl[u][0] = Tf32Lo(b[u][0]), bl[u][1] = Tf32Lo(b[u][1]); }
+#pragma unroll
+                                for (int u = 0; u < kTiles; ++u) { MmaTf32(acc[2 * i + u], alo[kt], __float_as_uint(b[u][0]), __float_as_uint(b[u][1])); }
+#pragma unroll
+                                for (int u = 0; u < kTiles; ++u) { MmaTf32(acc[2 * i + u], ahi[kt], bl[u][0], bl[u][1]); }
+#pragma unroll
+                                for (int u = 0; u < kTiles; ++u) { MmaTf32(acc[2 * i + u], ahi[kt], __float_as_uint(b[u][0]), __float_as_uint(b[u][1])); }
+                            }
+                        };
+                        StaticFor<0, (NBLK - jb) / 2>([&](auto grp_c) {
+                            constexpr int i = jb + 1 + 2 * decltype(grp_c)::value;
+                            if constexpr (i + 1 < NBLK) {
+                                if (i + 1 < nblk) {
+                                    update(std::integral_constant<int, i>{}, std::integral_constant<int, 2>{});
+                                } else if (i < nblk) {
+                                    update(std::integral_constant<int, i>{}, std::integral_constant<int, 1>{});
+                                }
+                            } else if constexpr (i < NBLK) {
+                                if (i < nblk) { update(std::integral_constant<int, i>{}, std::integral_constant<int, 1>{}); }
                             }
                         });
                     }
@@ -780,6 +822,17 @@ namespace erl_gp {
             const int tid = threadIdx.x;
             const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction: role branches need no reconvergence code
             const int lane = tid & 31;
+            if constexpr (MODE == kBatchTrainPredict) {
+                // The CTAs of one SM start together and do identical work, so they would stay in lock-step: all four in the
+                // barrier-bound factorisation, then all four on the tensor pipe.  Delaying the slots of the first wave by a
+                // fraction of the per-GP time keeps them out of phase for the rest of the launch (the hardware refills a
+                // slot when its CTA retires), so that factorisations overlap with tensor-path predicts.
+                if (p.stagger_cycles > 0 && g < 4 * p.sm_count) {
+                    const long long wait = static_cast<long long>(g / p.sm_count) * p.stagger_cycles;
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < wait) { __nanosleep(500); }
+                }
+            }
             const int n = p.n_train[g];
             const long q0 = (MODE & kBatchPredict) ? p.q_offsets[g] : 0;
             const long q1 = (MODE & kBatchPredict) ? p.q_offsets[g + 1] : 0;
@@ -941,7 +994,13 @@ namespace erl_gp {
             }
             ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Lay::kBytes)));
             const dim3 grid(static_cast<unsigned>(params.num_gps), static_cast<unsigned>(tiles_per_gp < 1 ? 1 : tiles_per_gp));
-            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(params);
+            BatchParams<float> launch_params = params;
+            if (MODE == kBatchTrainPredict) {
+                static const char *env = std::getenv("ERL_GP_ROWGP_STAGGER");
+                launch_params.stagger_cycles = env != nullptr ? std::atoi(env) : kDefaultStaggerCycles;
+                launch_params.sm_count = ctx->sm_count;
+            }
+            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(launch_params);
             ctx->launches += 1;
             ERL_GP_CUDA_OK(ctx, cudaGetLastError());
             return ERL_GP_STATUS_OK;

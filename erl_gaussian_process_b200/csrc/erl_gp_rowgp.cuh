@@ -52,6 +52,11 @@ namespace erl_gp {
         constexpr int kThreads = 128;
         constexpr unsigned kFull = 0xffffffffu;
         constexpr int kDefaultStaggerCycles = 0;  // per CTA slot, see RowGpKernel
+#ifndef ERL_GP_ROWGP_FFMA_TRAIN
+        constexpr bool kMmaTrain = true;
+#else
+        constexpr bool kMmaTrain = false;  // A/B builds of the FFMA2 factorisation (Factorize)
+#endif
 
         template<int NBLK>
         struct Layout {
@@ -132,18 +137,19 @@ namespace erl_gp {
         // 16 x 16 pivot block of a panel, factorised by one warp with shuffles.  LDL^T-style elimination: the update of column
         // cc uses acc[c] / d (reciprocal) and the RAW column entries of the pivot rows, which can be shuffled before the
         // reciprocal is known; the Cholesky entries l[c] = acc[c] / sqrt(d) are formed off the dependency chain.
-        template<bool STATIC_SRC>
+        // SRC: which lane owns pivot row c: 0 = pair layout, general (last panel); 1 = pair layout, even lanes (2 c); 2 = lane c
+        template<int SRC>
         __device__ __forceinline__ void
         PivotBlock(float (&acc)[16], float &zacc, float (&l)[16], const int half, const int c0, const int lane, int &fail, float *__restrict__ rs, float *__restrict__ al) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const int src = STATIC_SRC ? 2 * c : (c < half ? 2 * c : 2 * (c - half) + 1);
+                const int src = SRC == 2 ? c : SRC == 1 ? 2 * c : (c < half ? 2 * c : 2 * (c - half) + 1);
                 const float d = __shfl_sync(kFull, acc[c], src);
                 const float zc = __shfl_sync(kFull, zacc, src);
                 float t[16];
 #pragma unroll
                 for (int cc = c + 1; cc < 16; ++cc) {
-                    const int src2 = STATIC_SRC ? 2 * cc : (cc < half ? 2 * cc : 2 * (cc - half) + 1);
+                    const int src2 = SRC == 2 ? cc : SRC == 1 ? 2 * cc : (cc < half ? 2 * cc : 2 * (cc - half) + 1);
                     t[cc] = __shfl_sync(kFull, acc[c], src2);
                 }
                 if (!(d > 0.f) && fail == 0) { fail = c0 + c + 1; }
@@ -161,6 +167,71 @@ namespace erl_gp {
                     al[c0 + c] = zc * rsv;
                 }
             }
+        }
+
+        // The tensor core reads only the upper 19 bits of a TF32 operand, so "hi" is the FP32 value itself (truncation is
+        // implicit) and lo = x - trunc(x) is exact: one LOP3 + one FADD per split.  (cvt.rna.tf32.f32 is emulated on sm_100a
+        // with IADD + FSETP + SEL + LOP3 - it made up 27 % of the instructions of the first version of this kernel.)
+        __device__ __forceinline__ uint32_t
+        Tf32Lo(const float x) {
+            return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+        }
+
+        __device__ __forceinline__ void
+        MmaTf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        }
+
+        // d += A B with A = ahi + alo (pre-split) and the two B entries of this lane split here
+        __device__ __forceinline__ void
+        Mma3(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float bf0, const float bf1) {
+            const uint32_t bh0 = __float_as_uint(bf0), bh1 = __float_as_uint(bf1);
+            MmaTf32(d, alo, bh0, bh1);
+            MmaTf32(d, ahi, Tf32Lo(bf0), Tf32Lo(bf1));
+            MmaTf32(d, ahi, bh0, bh1);
+        }
+
+        // accumulator tile (columns 2t, 2t+1 of rows g, g+8) -> A fragment (k-slots t, t+4), scaled by sgn, split in hi + lo
+        __device__ __forceinline__ void
+        AccToA(const float (&c)[4], const float sgn, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+            const float a[4] = {sgn * c[0], sgn * c[2], sgn * c[1], sgn * c[3]};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                hi[k] = __float_as_uint(a[k]);
+                lo[k] = Tf32Lo(a[k]);
+            }
+        }
+
+        // v (two 8-column accumulator tiles) = X Dinv^T for a 16 x 16 tile X held in the accumulator layout (x[0], x[1] = its two
+        // 8-column halves) and the inverse Dinv of a 16 x 16 diagonal block of L (lower triangular: the (k-tile 1, n-tile 0)
+        // product is zero).  dv = address of Dinv[g][2 t] in the column-major block (stride Layout::kDinvLd).  Three independent
+        // accumulators, products issued term by term: consecutive HMMAs never wait for each other.
+        template<int LD>
+        __device__ __forceinline__ void
+        MulDinvT(const float (&x0)[4], const float (&x1)[4], const float *__restrict__ dv, float (&v)[2][4]) {
+            uint32_t xhi[2][4], xlo[2][4];
+            AccToA(x0, 1.0f, xhi[0], xlo[0]);
+            AccToA(x1, 1.0f, xhi[1], xlo[1]);
+            float w[4] = {0.f, 0.f, 0.f, 0.f};  // n-tile 1, k-tile 1
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { v[0][c] = v[1][c] = 0.f; }
+            const float d00[2] = {dv[0], dv[LD]};                    // n-tile 0, k-tile 0
+            const float d10[2] = {dv[8], dv[LD + 8]};                // n-tile 1, k-tile 0
+            const float d11[2] = {dv[8 * LD + 8], dv[9 * LD + 8]};   // n-tile 1, k-tile 1
+            const uint32_t l00[2] = {Tf32Lo(d00[0]), Tf32Lo(d00[1])}, l10[2] = {Tf32Lo(d10[0]), Tf32Lo(d10[1])}, l11[2] = {Tf32Lo(d11[0]), Tf32Lo(d11[1])};
+            MmaTf32(v[0], xlo[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
+            MmaTf32(v[1], xlo[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
+            MmaTf32(w, xlo[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
+            MmaTf32(v[0], xhi[0], l00[0], l00[1]);
+            MmaTf32(v[1], xhi[0], l10[0], l10[1]);
+            MmaTf32(w, xhi[1], l11[0], l11[1]);
+            MmaTf32(v[0], xhi[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
+            MmaTf32(v[1], xhi[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
+            MmaTf32(w, xhi[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { v[1][c] += w[c]; }
         }
 
         // --------------------------------------------------------------------------------------
@@ -274,9 +345,9 @@ namespace erl_gp {
                         // at least 32 rows the pivot rows sit in the even lanes (static shuffle sources); only the last panel
                         // (16 rows: pairs q < 8 hold rows q and q + 8) needs the general mapping.
                         if (half >= 16) {
-                            PivotBlock<true>(acc, zacc, l, half, c0, lane, fail, rs, al);
+                            PivotBlock<1>(acc, zacc, l, half, c0, lane, fail, rs, al);
                         } else {
-                            PivotBlock<false>(acc, zacc, l, half, c0, lane, fail, rs, al);
+                            PivotBlock<0>(acc, zacc, l, half, c0, lane, fail, rs, al);
                         }
                     }
                     if (warp == 0 && active) {
@@ -326,6 +397,213 @@ namespace erl_gp {
                 } else {
                     __syncthreads();  // #1
                     if (half > 16) { __syncthreads(); }  // #2
+                }
+            }
+            return fail;
+        }
+
+        // --------------------------------------------------------------------------------------
+        // train on the tensor path: the same left-looking blocked Cholesky, but every product is a 3xTF32 mma.sync.
+        //
+        // Panel kb (16 columns, rows c0 = 16 kb .. npr) is cut in 16-row tiles; tile i goes to warp i % 4.  Per panel:
+        //   A. update: P_i = K[tile i, panel] - L[tile i, 0:c0] L[panel rows, 0:c0]^T.  A fragments are rows of L, B fragments the
+        //      pivot rows of L, both read from the packed column-major L with the k-slot permutation (slot t <-> column 2 t,
+        //      slot t + 4 <-> column 2 t + 1) that makes the LDS.32 bank-conflict free; the Gram entries are generated in the
+        //      accumulator layout (never stored).
+        //   B. warp 0 owns tile 0 = the 16 x 16 pivot block: it goes through shared memory once to get "lane r owns row r",
+        //      is factorised with shuffles (PivotBlock; z = L^-1 y rides along), and its inverse Dinv is formed (lane c = column c).
+        //   C. the other tiles become L_i = P_i Dinv^T: the accumulators ARE the A operand (same trick as in the predict), so the
+        //      in-thread elimination of the FFMA version (136 dependent FMAs + broadcast loads per row) is 9 HMMAs per tile.
+        // Two barriers per panel as before, but ~2.5x fewer instructions between them and no idle "finished rows" threads in
+        // phase A (tiles are dealt to all four warps).  Accuracy: tests/test_gpu_batch.py; a numpy emulation of the split
+        // (tools/emulate_3xtf32.py) gives mean / variance errors of 4e-6 / 1e-6 against 1e-6 / 6e-7 for plain FP32.
+        // --------------------------------------------------------------------------------------
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ int
+        FactorizeMma(const CovCoef cov, float *__restrict__ smem, const int n, const int nblk) {
+            using Lay = Layout<NBLK>;
+            constexpr int kSlots = (NBLK + 3) / 4;  // tiles per warp and panel
+            float *lp = smem + Lay::kL;
+            const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
+            float *rs = smem + Lay::kRs;
+            float *al = smem + Lay::kAl;
+            const float *sv = smem + Lay::kVar;
+            float *dinv = smem + Lay::kDinv;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            const int g = lane >> 2, t = lane & 3;
+            int fail = 0;
+
+            for (int kb = 0; kb < nblk; ++kb) {
+                const int c0 = 16 * kb;
+                const int mt = nblk - kb;  // tiles of this panel
+                const int stride_k = Lay::kNp - 16 * kb + 4;
+                float *panel = lp + (16 * kb * (Lay::kNp + 4) - 128 * kb * (kb - 1));  // element (row c0, column c0)
+
+                // ---- A: update of my tiles -------------------------------------------------------------------------
+                float acc[kSlots][2][4];
+#pragma unroll
+                for (int sl = 0; sl < kSlots; ++sl) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) { acc[sl][nt][0] = acc[sl][nt][1] = acc[sl][nt][2] = acc[sl][nt][3] = 0.f; }
+                }
+                if (warp < mt) {
+                    for (int jb = 0; jb < kb; ++jb) {
+                        const int stride = Lay::kNp - 16 * jb + 4;
+                        // element (row 16 jb + g, column 16 jb + 2 t) of column block jb; rows are added relative to 16 jb
+                        const float *cb = lp + (16 * jb * (Lay::kNp + 4) - 128 * jb * (jb - 1)) + 2 * t * stride + g;
+                        const float *brow = cb + (c0 - 16 * jb);
+#pragma unroll
+                        for (int kt = 0; kt < 2; ++kt) {
+                            float b[2][2];
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+                                b[nt][0] = brow[8 * kt * stride + 8 * nt];           // L[c0 + 8 nt + g][16 jb + 8 kt + 2 t]
+                                b[nt][1] = brow[(8 * kt + 1) * stride + 8 * nt];     // ... + 1
+                            }
+                            uint32_t bl[2][2];
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) { bl[nt][0] = Tf32Lo(b[nt][0]), bl[nt][1] = Tf32Lo(b[nt][1]); }
+#pragma unroll
+                            for (int sl = 0; sl < kSlots; ++sl) {
+                                const int ti = warp + 4 * sl;
+                                if (ti < mt) {
+                                    const float *arow = brow + 16 * ti + 8 * kt * stride;
+                                    // slots (row g, k t), (row g + 8, k t), (row g, k t + 4), (row g + 8, k t + 4)
+                                    const float a[4] = {arow[0], arow[8], arow[stride], arow[stride + 8]};
+                                    uint32_t ahi[4], alo[4];
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) { ahi[k] = __float_as_uint(a[k]), alo[k] = Tf32Lo(a[k]); }
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], alo, __float_as_uint(b[nt][0]), __float_as_uint(b[nt][1])); }
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], ahi, bl[nt][0], bl[nt][1]); }
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], ahi, __float_as_uint(b[nt][0]), __float_as_uint(b[nt][1])); }
+                                }
+                            }
+                        }
+                    }
+                    // P = Gram tile - update (Gram entries in the accumulator layout, fused noise diagonal, identity padding)
+                    float pcx[2][2][XDIM];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float4 pc = pts[c0 + 8 * nt + 2 * t + e];
+                            pcx[nt][e][0] = pc.x;
+                            if (XDIM > 1) { pcx[nt][e][XDIM > 1 ? 1 : 0] = pc.y; }
+                            if (XDIM > 2) { pcx[nt][e][XDIM > 2 ? 2 : 0] = pc.z; }
+                        }
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < kSlots; ++sl) {
+                        const int ti = warp + 4 * sl;
+                        if (ti < mt) {
+#pragma unroll
+                            for (int hr = 0; hr < 2; ++hr) {
+                                const int row = c0 + 16 * ti + g + 8 * hr;
+                                const float4 pr = pts[row];
+                                const float diag = row < n ? 1.0f + sv[row] : 1.0f;
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        const int col = c0 + 8 * nt + 2 * t + e;
+                                        float kv = cov(Dist2<XDIM>(pr, pcx[nt][e]));
+                                        if (row >= n || col >= n) { kv = 0.f; }
+                                        if (row == col) { kv = diag; }
+                                        acc[sl][nt][2 * hr + e] = kv - acc[sl][nt][2 * hr + e];
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+
+                // ---- B: pivot block (warp 0 holds tile 0 in slot 0) --------------------------------------------------
+                if (warp == 0) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            panel[(8 * nt + 2 * t + e) * stride_k + g] = acc[0][nt][e];
+                            panel[(8 * nt + 2 * t + e) * stride_k + g + 8] = acc[0][nt][2 + e];
+                        }
+                    }
+                    // z: y_r - sum_{j < c0} L[r][j] z_j for the pivot rows, two lanes per row (even / odd column blocks)
+                    const int r = lane & 15, hh = lane >> 4;
+                    float zs = 0.f;
+                    for (int jb = hh; jb < kb; jb += 2) {
+                        const int stride = Lay::kNp - 16 * jb + 4;
+                        const float *rowp = lp + (16 * jb * (Lay::kNp + 4) - 128 * jb * (jb - 1)) + (c0 + r - 16 * jb);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 z4 = *reinterpret_cast<const float4 *>(al + 16 * jb + 4 * j4);
+                            zs = fmaf(rowp[(4 * j4) * stride], z4.x, zs);
+                            zs = fmaf(rowp[(4 * j4 + 1) * stride], z4.y, zs);
+                            zs = fmaf(rowp[(4 * j4 + 2) * stride], z4.z, zs);
+                            zs = fmaf(rowp[(4 * j4 + 3) * stride], z4.w, zs);
+                        }
+                    }
+                    zs += __shfl_xor_sync(kFull, zs, 16);
+                    float zacc = al[c0 + r] - zs;  // al[c0 + r] still holds y
+                    __syncwarp();
+                    float prow[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { prow[c] = panel[c * stride_k + r]; }  // lanes 16 .. 31 duplicate lanes 0 .. 15
+                    PivotBlock<2>(prow, zacc, l, 0, c0, lane, fail, rs, al);
+                    __syncwarp();  // everybody has read the raw tile
+                    if (lane < 16) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { panel[c * stride_k + r] = c > r ? 0.f : l[c]; }
+                    }
+                    __syncwarp();
+                    // Dinv: lane c = column c by forward substitution on e_c (1 / L_jj = rs, written by lane 0 above)
+                    if (lane < 16) {
+                        float sres[16], x[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { sres[i] = i == lane ? 1.0f : 0.f; }
+#pragma unroll
+                        for (int pc = 0; pc < 16; ++pc) {
+                            x[pc] = sres[pc] * rs[c0 + pc];
+                            float col[16];
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 v4 = *reinterpret_cast<const float4 *>(panel + pc * stride_k + 4 * k4);  // warp-uniform address
+                                col[4 * k4] = v4.x, col[4 * k4 + 1] = v4.y, col[4 * k4 + 2] = v4.z, col[4 * k4 + 3] = v4.w;
+                            }
+#pragma unroll
+                            for (int i = pc + 1; i < 16; ++i) { sres[i] = fmaf(-col[i], x[pc], sres[i]); }
+                        }
+                        float *dst = dinv + kb * 16 * Lay::kDinvLd + lane * Lay::kDinvLd;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(x[4 * k4], x[4 * k4 + 1], x[4 * k4 + 2], x[4 * k4 + 3]); }
+                    }
+                }
+                __syncthreads();  // #1: pivot block, Dinv, rs, z of this panel are published
+                if (mt > 1) {
+                    // ---- C: L_i = P_i Dinv^T for the tiles below the pivot block ----------------------------------------
+                    const float *dv = dinv + kb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;
+#pragma unroll
+                    for (int sl = 0; sl < kSlots; ++sl) {
+                        const int ti = warp + 4 * sl;
+                        if (ti > 0 && ti < mt) {
+                            float v[2][4];
+                            MulDinvT<Lay::kDinvLd>(acc[sl][0], acc[sl][1], dv, v);
+                            float *dst = panel + 16 * ti + g;
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    dst[(8 * nt + 2 * t + e) * stride_k] = v[nt][e];
+                                    dst[(8 * nt + 2 * t + e) * stride_k + 8] = v[nt][2 + e];
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();  // #2: the whole panel is published
                 }
             }
             return fail;
@@ -582,41 +860,6 @@ namespace erl_gp {
         // One m16n8k8 is 1024 FMAs per issue slot instead of 64 for a warp-wide FFMA2: the FMA / issue pipes that bound the
         // previous predict are left to the factorisations of the other resident CTAs.
         // --------------------------------------------------------------------------------------
-        // The tensor core reads only the upper 19 bits of a TF32 operand, so "hi" is the FP32 value itself (truncation is
-        // implicit) and lo = x - trunc(x) is exact: one LOP3 + one FADD per split.  (cvt.rna.tf32.f32 is emulated on sm_100a
-        // with IADD + FSETP + SEL + LOP3 - it made up 27 % of the instructions of the first version of this kernel.)
-        __device__ __forceinline__ uint32_t
-        Tf32Lo(const float x) {
-            return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-        }
-
-        __device__ __forceinline__ void
-        MmaTf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
-            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-        }
-
-        // d += A B with A = ahi + alo (pre-split) and the two B entries of this lane split here
-        __device__ __forceinline__ void
-        Mma3(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float bf0, const float bf1) {
-            const uint32_t bh0 = __float_as_uint(bf0), bh1 = __float_as_uint(bf1);
-            MmaTf32(d, alo, bh0, bh1);
-            MmaTf32(d, ahi, Tf32Lo(bf0), Tf32Lo(bf1));
-            MmaTf32(d, ahi, bh0, bh1);
-        }
-
-        // accumulator tile (columns 2t, 2t+1 of rows g, g+8) -> A fragment (k-slots t, t+4), scaled by sgn, split in hi + lo
-        __device__ __forceinline__ void
-        AccToA(const float (&c)[4], const float sgn, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
-            const float a[4] = {sgn * c[0], sgn * c[2], sgn * c[1], sgn * c[3]};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                hi[k] = __float_as_uint(a[k]);
-                lo[k] = Tf32Lo(a[k]);
-            }
-        }
-
         // inverses of the 16 x 16 diagonal blocks of L (lane c < 16 of a warp: column c by forward substitution on e_c)
         template<int NBLK>
         __device__ __forceinline__ void
@@ -701,31 +944,9 @@ namespace erl_gp {
             StaticFor<0, NBLK>([&](auto jb_c) {
                 constexpr int jb = decltype(jb_c)::value;
                 if (jb < nblk) {
-                    // V^T_jb = X_jb Dinv_jb^T  (Dinv lower triangular: the (k-tile 1, n-tile 0) product is zero); three
-                    // independent accumulators (n-tile 0; n-tile 1 by k-tile), interleaved term by term
-                    uint32_t xhi[2][4], xlo[2][4];
-                    AccToA(acc[2 * jb], 1.0f, xhi[0], xlo[0]);
-                    AccToA(acc[2 * jb + 1], 1.0f, xhi[1], xlo[1]);
-                    float v[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                    {
-                        const float *dv = dinv + jb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;  // Dinv[g][2 t]
-                        float w[4] = {0.f, 0.f, 0.f, 0.f};  // n-tile 1, k-tile 1
-                        const float d00[2] = {dv[0], dv[Lay::kDinvLd]};                                            // n-tile 0, k-tile 0
-                        const float d10[2] = {dv[8], dv[Lay::kDinvLd + 8]};                                        // n-tile 1, k-tile 0
-                        const float d11[2] = {dv[8 * Lay::kDinvLd + 8], dv[9 * Lay::kDinvLd + 8]};                 // n-tile 1, k-tile 1
-                        const uint32_t l00[2] = {Tf32Lo(d00[0]), Tf32Lo(d00[1])}, l10[2] = {Tf32Lo(d10[0]), Tf32Lo(d10[1])}, l11[2] = {Tf32Lo(d11[0]), Tf32Lo(d11[1])};
-                        MmaTf32(v[0], xlo[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
-                        MmaTf32(v[1], xlo[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
-                        MmaTf32(w, xlo[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
-                        MmaTf32(v[0], xhi[0], l00[0], l00[1]);
-                        MmaTf32(v[1], xhi[0], l10[0], l10[1]);
-                        MmaTf32(w, xhi[1], l11[0], l11[1]);
-                        MmaTf32(v[0], xhi[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
-                        MmaTf32(v[1], xhi[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
-                        MmaTf32(w, xhi[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) { v[1][c] += w[c]; }
-                    }
+                    // V^T_jb = X_jb Dinv_jb^T
+                    float v[2][4];
+                    MulDinvT<Lay::kDinvLd>(acc[2 * jb], acc[2 * jb + 1], dinv + jb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g, v);
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
                         ss[0] = fmaf(v[nt][0], v[nt][0], ss[0]);
@@ -874,7 +1095,7 @@ namespace erl_gp {
                     sv[e] = e < n ? gv[e] : 0.f;
                 }
                 __syncthreads();
-                const int fail = Factorize<XDIM, NBLK>(cov, smem, n, nblk);
+                const int fail = kMmaTrain ? FactorizeMma<XDIM, NBLK>(cov, smem, n, nblk) : Factorize<XDIM, NBLK>(cov, smem, n, nblk);
                 int *s_fail = reinterpret_cast<int *>(smem + Lay::kMisc);
                 if (tid == 0) { *s_fail = fail; }  // warp 0 tracked every pivot
                 __syncthreads();
@@ -924,7 +1145,7 @@ namespace erl_gp {
                     smem[Lay::kPts + 4 * e + 3] = a;
                 }
                 if (tid == 0) { p.info[g] = 0; }
-                if constexpr (kMmaPredict && (MODE & kBatchPredict) != 0) { ComputeDinv<NBLK>(smem, nblk); }
+                if constexpr (kMmaPredict && !kMmaTrain && (MODE & kBatchPredict) != 0) { ComputeDinv<NBLK>(smem, nblk); }  // FactorizeMma leaves Dinv behind
             } else {
                 // ---- predict-only: reload L (float4 along the rows when the layout allows), rebuild 1 / L_jj ----
                 __syncthreads();

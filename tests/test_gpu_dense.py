@@ -84,7 +84,9 @@ def test_vanilla_c1(gp, oracle):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("n,t,d,kernel,scale,ydim", [(5, 3, 1, "ou", 0.5, 1), (129, 300, 3, "matern32", 0.5, 1), (700, 1000, 2, "matern32", 0.3, 2), (384, 130, 2, "ou", 0.2, 1)])
+@pytest.mark.parametrize("n,t,d,kernel,scale,ydim", [(5, 3, 1, "ou", 0.5, 1), (129, 300, 3, "matern32", 0.5, 1), (700, 1000, 2, "matern32", 0.3, 2), (384, 130, 2, "ou", 0.2, 1),
+                                                     # several 512-column block columns with a ragged tail (look-ahead streams) and 3 / 4 right-hand sides (wavefront TRSV)
+                                                     (1100, 200, 2, "matern32", 0.3, 4), (2500, 257, 3, "matern32", 0.4, 3)])
 def test_vanilla_shapes(gp, oracle, dtype, n, t, d, kernel, scale, ydim):
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, (n, d)).astype(dtype)

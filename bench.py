@@ -364,7 +364,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
                          "kernel": "rowgp::RowGpKernel<x_dim=3, NBLK=8, train+predict> (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu (FFMA2 with fresh operands sustains ~55, tools/fma_lds_rate.cu); the factorisation runs on the FP32 pipe, the predict on the tensor pipe as 3xTF32 mma.sync (276 TFLOP/s TF32 peak = 92 FP32-equivalent); the kernel is latency / issue bound, not HBM bound, see DESIGN.md"}},
+                         "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu (FFMA2 with fresh operands sustains ~55, tools/fma_lds_rate.cu); factorisation and predict run on the tensor pipe as 3xTF32 mma.sync (276 TFLOP/s TF32 peak = 92 FP32-equivalent), pivot blocks / back-substitution / covariance entries on the FP32 pipe; the kernel is latency / issue bound, not HBM bound, see DESIGN.md"}},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -672,7 +672,9 @@ namespace erl_gp {
             // FP32, n <= 128: the register-resident "row GP" kernel (erl_gp_rowgp.cuh); ERL_GP_BATCH_LEGACY=1 keeps the
             // generic shared-memory kernel below (A/B measurements and tests of the generic path)
             static const bool legacy = std::getenv("ERL_GP_BATCH_LEGACY") != nullptr;
+            static const bool legacy_large = std::getenv("ERL_GP_BATCH_LEGACY_LARGE") != nullptr;  // generic kernel for 128 < n <= 256 only
             if (max_n <= 128 && !legacy) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
+            if (max_n <= 256 && !legacy && !legacy_large) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
         }
         if (max_n <= 64) { return LaunchBatchMode<T, XDIM, 4>(ctx, params, mode, tiles_per_gp); }
         if (max_n <= 128) { return LaunchBatchMode<T, XDIM, 8>(ctx, params, mode, tiles_per_gp); }

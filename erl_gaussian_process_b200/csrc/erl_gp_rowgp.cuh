@@ -620,10 +620,13 @@ namespace erl_gp {
             const int tid = threadIdx.x;
             const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction: role branches need no reconvergence code
             const int lane = tid & 31;
-            float s = 0.f;
+            constexpr int kColSlots = (Lay::kNp + kThreads - 1) / kThreads;  // columns per thread: column = tid + kThreads * slot
+            float s[kColSlots];
+#pragma unroll
+            for (int sl = 0; sl < kColSlots; ++sl) { s[sl] = 0.f; }
             for (int kb = nblk - 1; kb >= 0; --kb) {
                 const int c0 = 16 * kb;
-                if (warp == (c0 >> 5)) {
+                if (warp == ((c0 & (kThreads - 1)) >> 5)) {
                     const int lb = c0 & 31;
                     const bool mine = lane >= lb && lane < lb + 16;
                     const int jj = mine ? lane - lb : 0;
@@ -636,28 +639,37 @@ namespace erl_gp {
                     }
                     const float zj = al[c0 + jj];
                     const float rsj = rs[c0 + jj];
+                    float sj = s[0];
+#pragma unroll
+                    for (int sl = 1; sl < kColSlots; ++sl) {
+                        if (c0 >= kThreads * sl) { sj = s[sl]; }
+                    }
                     float amine = 0.f;
 #pragma unroll
                     for (int c = 15; c >= 0; --c) {
-                        const float a = (zj - s) * rsj;
+                        const float a = (zj - sj) * rsj;
                         const float ac = __shfl_sync(kFull, a, lb + c);
                         if (jj == c) { amine = a; }
-                        if (mine && jj < c) { s = fmaf(lblk[c], ac, s); }  // L(c0 + c, c0 + jj) * alpha_c
+                        if (mine && jj < c) { sj = fmaf(lblk[c], ac, sj); }  // L(c0 + c, c0 + jj) * alpha_c
                     }
                     if (mine) { al[c0 + jj] = amine; }
                 }
                 __syncthreads();
-                if (tid < c0) {
-                    const int cb = tid >> 4;
-                    const float *colp = lp + Lay::Base(cb) + (tid & 15) * Lay::Stride(cb) + (c0 - 16 * cb);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float4 lv = *reinterpret_cast<const float4 *>(colp + 4 * k);
-                        const float4 av = *reinterpret_cast<const float4 *>(al + c0 + 4 * k);
-                        s = fmaf(lv.x, av.x, s);
-                        s = fmaf(lv.y, av.y, s);
-                        s = fmaf(lv.z, av.z, s);
-                        s = fmaf(lv.w, av.w, s);
+                for (int sl = 0; sl < kColSlots; ++sl) {
+                    const int col = tid + kThreads * sl;
+                    if (col < c0) {
+                        const int cb = col >> 4;
+                        const float *colp = lp + Lay::Base(cb) + (col & 15) * Lay::Stride(cb) + (c0 - 16 * cb);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 lv = *reinterpret_cast<const float4 *>(colp + 4 * k);
+                            const float4 av = *reinterpret_cast<const float4 *>(al + c0 + 4 * k);
+                            s[sl] = fmaf(lv.x, av.x, s[sl]);
+                            s[sl] = fmaf(lv.y, av.y, s[sl]);
+                            s[sl] = fmaf(lv.z, av.z, s[sl]);
+                            s[sl] = fmaf(lv.w, av.w, s[sl]);
+                        }
                     }
                 }
             }
@@ -1028,7 +1040,7 @@ namespace erl_gp {
 #endif
 
         template<int XDIM, int NBLK, int MODE>
-        __global__ void __launch_bounds__(kThreads, 4)
+        __global__ void __launch_bounds__(kThreads, NBLK <= 8 ? 4 : (NBLK <= 12 ? 2 : 1))
         RowGpKernel(const BatchParams<float> p) {
             using Lay = Layout<NBLK>;
             extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1095,7 +1107,12 @@ namespace erl_gp {
                     sv[e] = e < n ? gv[e] : 0.f;
                 }
                 __syncthreads();
-                const int fail = kMmaTrain ? FactorizeMma<XDIM, NBLK>(cov, smem, n, nblk) : Factorize<XDIM, NBLK>(cov, smem, n, nblk);
+                int fail;
+                if constexpr (kMmaTrain || NBLK > 8) {  // the FFMA version is thread-per-row: n <= 128 only
+                    fail = FactorizeMma<XDIM, NBLK>(cov, smem, n, nblk);
+                } else {
+                    fail = Factorize<XDIM, NBLK>(cov, smem, n, nblk);
+                }
                 int *s_fail = reinterpret_cast<int *>(smem + Lay::kMisc);
                 if (tid == 0) { *s_fail = fail; }  // warp 0 tracked every pivot
                 __syncthreads();
@@ -1111,8 +1128,9 @@ namespace erl_gp {
                 if (p.write_l) {
                     float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                     if ((p.max_n & 3) == 0) {
-                        const int r4 = 4 * lane;
-                        for (int c = warp; c < n; c += kThreads / 32) {
+                        for (int cc = warp; cc < n * ((Lay::kNp + 127) / 128); cc += kThreads / 32) {
+                            const int c = cc % n;
+                            const int r4 = 4 * lane + 128 * (cc / n);  // 128 rows per warp and step
                             const int cb = c >> 4;
                             if (r4 < n) {
                                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1145,19 +1163,21 @@ namespace erl_gp {
                     smem[Lay::kPts + 4 * e + 3] = a;
                 }
                 if (tid == 0) { p.info[g] = 0; }
-                if constexpr (kMmaPredict && !kMmaTrain && (MODE & kBatchPredict) != 0) { ComputeDinv<NBLK>(smem, nblk); }  // FactorizeMma leaves Dinv behind
+                if constexpr ((kMmaPredict || NBLK > 8) && !(kMmaTrain || NBLK > 8) && (MODE & kBatchPredict) != 0) { ComputeDinv<NBLK>(smem, nblk); }  // FactorizeMma leaves Dinv behind
             } else {
                 // ---- predict-only: reload L (float4 along the rows when the layout allows), rebuild 1 / L_jj ----
                 __syncthreads();
                 const float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                 const bool vec_ok = (p.max_n & 3) == 0;
                 constexpr int kBatch = 8;  // columns in flight per warp: the loads of a batch are all issued before the first store
-                for (int c0 = warp * kBatch; c0 < npr; c0 += (kThreads / 32) * kBatch) {
+                for (int cc0 = warp * kBatch; cc0 < npr * ((Lay::kNp + 127) / 128); cc0 += (kThreads / 32) * kBatch) {
+                    const int c0 = cc0 % npr;             // npr is a multiple of 16, kBatch divides 16: a batch never straddles the wrap
+                    const int rchunk = 128 * (cc0 / npr);  // rows [16 cb + rchunk, + 128) of the column
                     float val[kBatch][4];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
                         const int c = c0 + u;
-                        const int r4 = 16 * (c >> 4) + 4 * lane;
+                        const int r4 = 16 * (c >> 4) + 4 * lane + rchunk;
                         const float *gcol = gl + static_cast<long>(c) * p.max_n;
                         if (vec_ok && c < n && r4 + 3 < n) {
                             const float4 t = *reinterpret_cast<const float4 *>(gcol + r4);
@@ -1171,7 +1191,7 @@ namespace erl_gp {
                     for (int u = 0; u < kBatch; ++u) {
                         const int c = c0 + u;
                         const int cb = c >> 4;
-                        const int r4 = 16 * cb + 4 * lane;
+                        const int r4 = 16 * cb + 4 * lane + rchunk;
                         if (c < npr && r4 < npr) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -1186,7 +1206,7 @@ namespace erl_gp {
                         }
                     }
                 }
-                if constexpr (kMmaPredict) {
+                if constexpr (kMmaPredict || NBLK > 8) {
                     __syncthreads();
                     ComputeDinv<NBLK>(smem, nblk);
                 }
@@ -1196,7 +1216,7 @@ namespace erl_gp {
                 __syncthreads();
                 for (long qb = q0 + static_cast<long>(blockIdx.y) * kTileQ; qb < q1; qb += static_cast<long>(gridDim.y) * kTileQ) {
                     const int nq = static_cast<int>(q1 - qb < kTileQ ? q1 - qb : kTileQ);
-                    if constexpr (kMmaPredict) {
+                    if constexpr (kMmaPredict || NBLK > 8) {
                         PredictTileMma<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
                     } else {
                         PredictTile<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
@@ -1238,7 +1258,7 @@ namespace erl_gp {
             }
         }
 
-        // max_n <= 128 only
+        // max_n <= 256
         template<int XDIM>
         int
         Launch(Context *ctx, const BatchParams<float> &params, const int mode, const int tiles_per_gp) {
@@ -1246,7 +1266,9 @@ namespace erl_gp {
             if (max_n <= 32) { return LaunchMode<XDIM, 2>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 64) { return LaunchMode<XDIM, 4>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 96) { return LaunchMode<XDIM, 6>(ctx, params, mode, tiles_per_gp); }
-            return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp);
+            if (max_n <= 128) { return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp); }
+            if (max_n <= 192) { return LaunchMode<XDIM, 12>(ctx, params, mode, tiles_per_gp); }  // 104 KB of shared memory, 2 CTAs / SM
+            return LaunchMode<XDIM, 16>(ctx, params, mode, tiles_per_gp);                        // 171 KB, 1 CTA / SM
         }
 
     }  // namespace rowgp

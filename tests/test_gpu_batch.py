@@ -85,6 +85,8 @@ def test_batch_ragged(gp, oracle, dtype, max_n, x_dim, kernel, scale):
 
 def test_batch_max_n_256_f32(gp, oracle):
     _check_batch(gp, oracle, np.float32, "matern32", 0.3, 12, 256, 2, seed=3, n_lo=200, n_hi=256, q_lo=1, q_hi=200)
+    _check_batch(gp, oracle, np.float32, "ou", 0.1, 9, 250, 1, seed=4, n_lo=130, n_hi=250, q_lo=0, q_hi=150)
+    _check_batch(gp, oracle, np.float32, "matern32", 0.4, 7, 256, 3, seed=5, n_lo=256, n_hi=256, q_lo=64, q_hi=64)
 
 
 def test_batch_min_num_samples_gate(gp, oracle):
@@ -112,15 +114,16 @@ def test_batch_not_spd_reports_info(gp):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_batch_device_path_train_then_predict(gp, oracle, dtype):
-    """Device-resident buffers: train kernel, then the predict-only kernel with scatter index."""
+@pytest.mark.parametrize("max_n,x_dim,kernel,scale", [(64, 1, "ou", 0.05), (192, 2, "matern32", 0.3)])
+def test_batch_device_path_train_then_predict(gp, oracle, dtype, max_n, x_dim, kernel, scale):
+    """Device-resident buffers: train kernel, then the predict-only kernel (L reloaded from HBM) with scatter index."""
     import torch
 
     rng = np.random.default_rng(21)
-    num_gps, max_n, x_dim = 24, 64, 1
-    n_train, x, y, var, q_offsets, q_x = make_batch(rng, num_gps, max_n, x_dim, dtype, n_lo=30, n_hi=64, q_lo=100, q_hi=900)
+    num_gps = 24
+    n_train, x, y, var, q_offsets, q_x = make_batch(rng, num_gps, max_n, x_dim, dtype, n_lo=max_n // 2, n_hi=max_n, q_lo=100, q_hi=900)
     t = q_x.shape[0]
-    b = gp.BatchGp(num_gps, max_n, x_dim, "ou", 0.05, dtype)
+    b = gp.BatchGp(num_gps, max_n, x_dim, kernel, scale, dtype)
     b.upload(n_train, x, y, var)
     b.train_dev(write_l=True)
     perm = rng.permutation(t).astype(np.int32)
@@ -134,7 +137,7 @@ def test_batch_device_path_train_then_predict(gp, oracle, dtype):
     torch.cuda.synchronize()
     b.predict_dev(d_off, d_qx, t, d_mean, d_var, d_valid, q_out_index=d_perm)
     b.ctx.synchronize()
-    ref = oracle.batched_train_predict(oracle.OU, 0.05, n_train, x, y, var, q_offsets, q_x)
+    ref = oracle.batched_train_predict({"ou": oracle.OU, "matern32": oracle.MATERN32}[kernel], scale, n_train, x, y, var, q_offsets, q_x)
     mean = d_mean.cpu().numpy()
     varo = d_var.cpu().numpy()
     assert d_valid.cpu().numpy().all()

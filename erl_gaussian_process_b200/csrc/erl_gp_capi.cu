@@ -1,6 +1,8 @@
 // C ABI: context, covariance and batched small-GP entry points (see include/erl_gp_b200.h).
 #include "erl_gp_internal.cuh"
 
+#include <cstdlib>
+
 namespace erl_gp {
 
     int
@@ -62,6 +64,8 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->var.ptr, var, sizeof(T) * bn, cudaMemcpyHostToDevice, ctx->stream));
         return ERL_GP_STATUS_OK;
     }
+
+    constexpr long kDefaultHostChunks = 8;  // chunks of the host-buffer pipeline (BatchTrainPredictHost)
 
     template<typename T>
     int
@@ -154,7 +158,9 @@ namespace erl_gp {
         // Pipeline: the GP stream is cut into chunks; chunk c+1 is uploaded (copy-in stream) and chunk c-1 downloaded
         // (copy-out stream) while chunk c is computed (the context's stream).  H2D, the kernel and D2H of a 50k-GP batch
         // cost 4.7 + 7.6 + 1.0 ms back to back; overlapped the step is bounded by the kernel.
-        const long num_chunks = num_gps >= 8 * 1024 ? 8 : 1;
+        static const long env_chunks = std::getenv("ERL_GP_BATCH_CHUNKS") != nullptr ? std::atol(std::getenv("ERL_GP_BATCH_CHUNKS")) : 0;
+        const long want_chunks = env_chunks > 0 ? env_chunks : kDefaultHostChunks;
+        const long num_chunks = num_gps >= 1024 * want_chunks ? want_chunks : (num_gps >= 8 * 1024 ? 8 : 1);
         if (b->copy_in == nullptr) {
             ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
             ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));

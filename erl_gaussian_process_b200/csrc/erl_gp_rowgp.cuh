@@ -52,6 +52,18 @@ namespace erl_gp {
         constexpr int kThreads = 128;
         constexpr unsigned kFull = 0xffffffffu;
         constexpr int kDefaultStaggerCycles = 0;  // per CTA slot, see RowGpKernel
+        // A/B switches (measured on the B200, C4, fused / train-only ms): z-dot hoisted before the update 5.80 / 2.76, in phase B
+        // 5.56 / 2.74; back-substitution through Dinv 5.56 / 2.74, as a 16-step shuffle chain 5.47 / 2.98.
+#ifdef ERL_GP_V_ZDOT_EARLY
+        constexpr bool kZdotEarly = true;
+#else
+        constexpr bool kZdotEarly = false;
+#endif
+#ifdef ERL_GP_V_BACKSOLVE_CHAIN
+        constexpr bool kBackSolveDinv = false;
+#else
+        constexpr bool kBackSolveDinv = true;
+#endif
 #ifndef ERL_GP_ROWGP_FFMA_TRAIN
         constexpr bool kMmaTrain = true;
 #else
@@ -153,10 +165,17 @@ namespace erl_gp {
                     t[cc] = __shfl_sync(kFull, acc[c], src2);
                 }
                 if (!(d > 0.f) && fail == 0) { fail = c0 + c + 1; }
-                float invd;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invd) : "f"(d));
-                invd = invd * fmaf(-d, invd, 2.0f);  // one Newton step on MUFU.RCP
-                const float rsv = RsqrtRefined(d);
+                float invd, rsv;
+                if (SRC == 2) {
+                    // tensor-path factorisation: one MUFU.RSQ + one Newton step, 1 / d = rsv^2 (the products around it carry
+                    // 2^-20 already; saves a MUFU and 3 dependent instructions per pivot on the serial chain of the kernel)
+                    rsv = RsqrtRefined(d);
+                    invd = rsv * rsv;
+                } else {
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invd) : "f"(d));
+                    invd = invd * fmaf(-d, invd, 2.0f);  // one Newton step on MUFU.RCP
+                    rsv = RsqrtRefined(d);
+                }
                 const float sc = acc[c] * invd;
 #pragma unroll
                 for (int cc = c + 1; cc < 16; ++cc) { acc[cc] = fmaf(-sc, t[cc], acc[cc]); }
@@ -410,8 +429,9 @@ namespace erl_gp {
         //      pivot rows of L, both read from the packed column-major L with the k-slot permutation (slot t <-> column 2 t,
         //      slot t + 4 <-> column 2 t + 1) that makes the LDS.32 bank-conflict free; the Gram entries are generated in the
         //      accumulator layout (never stored).
-        //   B. warp 0 owns tile 0 = the 16 x 16 pivot block: it goes through shared memory once to get "lane r owns row r",
-        //      is factorised with shuffles (PivotBlock; z = L^-1 y rides along), and its inverse Dinv is formed (lane c = column c).
+        //   B. warp 0 owns tile 0 = the 16 x 16 pivot block: it goes through shared memory once to get "lane r owns row r" and
+        //      is factorised with shuffles (PivotBlock; z = L^-1 y rides along); lanes 16 .. 31 run the same instructions on the
+        //      unit vectors and end up with the columns of its inverse Dinv.
         //   C. the other tiles become L_i = P_i Dinv^T: the accumulators ARE the A operand (same trick as in the predict), so the
         //      in-thread elimination of the FFMA version (136 dependent FMAs + broadcast loads per row) is 9 HMMAs per tile.
         // Two barriers per panel as before, but ~2.5x fewer instructions between them and no idle "finished rows" threads in
@@ -440,6 +460,28 @@ namespace erl_gp {
                 const int mt = nblk - kb;  // tiles of this panel
                 const int stride_k = Lay::kNp - 16 * kb + 4;
                 float *panel = lp + (16 * kb * (Lay::kNp + 4) - 128 * kb * (kb - 1));  // element (row c0, column c0)
+
+                // z: sum_{j < c0} L[r][j] z_j for the pivot rows r (warp 0; two lanes per row: even / odd column blocks)
+                auto pivot_row_dot_z = [&]() {
+                    const int r = lane & 15, hh = lane >> 4;
+                    float zp[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int jb = hh; jb < kb; jb += 2) {
+                        const int stride = Lay::kNp - 16 * jb + 4;
+                        const float *rowp = lp + (16 * jb * (Lay::kNp + 4) - 128 * jb * (jb - 1)) + (c0 + r - 16 * jb);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 z4 = *reinterpret_cast<const float4 *>(al + 16 * jb + 4 * j4);
+                            zp[0] = fmaf(rowp[(4 * j4) * stride], z4.x, zp[0]);
+                            zp[1] = fmaf(rowp[(4 * j4 + 1) * stride], z4.y, zp[1]);
+                            zp[2] = fmaf(rowp[(4 * j4 + 2) * stride], z4.z, zp[2]);
+                            zp[3] = fmaf(rowp[(4 * j4 + 3) * stride], z4.w, zp[3]);
+                        }
+                    }
+                    const float zsum = (zp[0] + zp[1]) + (zp[2] + zp[3]);
+                    return zsum + __shfl_xor_sync(kFull, zsum, 16);
+                };
+                float zs = 0.f;
+                if (kZdotEarly && warp == 0) { zs = pivot_row_dot_z(); }  // before the update: the FMA chain overlaps with the HMMAs
 
                 // ---- A: update of my tiles -------------------------------------------------------------------------
                 float acc[kSlots][2][4];
@@ -532,54 +574,29 @@ namespace erl_gp {
                             panel[(8 * nt + 2 * t + e) * stride_k + g + 8] = acc[0][nt][2 + e];
                         }
                     }
-                    // z: y_r - sum_{j < c0} L[r][j] z_j for the pivot rows, two lanes per row (even / odd column blocks)
-                    const int r = lane & 15, hh = lane >> 4;
-                    float zs = 0.f;
-                    for (int jb = hh; jb < kb; jb += 2) {
-                        const int stride = Lay::kNp - 16 * jb + 4;
-                        const float *rowp = lp + (16 * jb * (Lay::kNp + 4) - 128 * jb * (jb - 1)) + (c0 + r - 16 * jb);
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 z4 = *reinterpret_cast<const float4 *>(al + 16 * jb + 4 * j4);
-                            zs = fmaf(rowp[(4 * j4) * stride], z4.x, zs);
-                            zs = fmaf(rowp[(4 * j4 + 1) * stride], z4.y, zs);
-                            zs = fmaf(rowp[(4 * j4 + 2) * stride], z4.z, zs);
-                            zs = fmaf(rowp[(4 * j4 + 3) * stride], z4.w, zs);
-                        }
-                    }
-                    zs += __shfl_xor_sync(kFull, zs, 16);
+                    const int r = lane & 15;
+                    if (!kZdotEarly) { zs = pivot_row_dot_z(); }
                     float zacc = al[c0 + r] - zs;  // al[c0 + r] still holds y
                     __syncwarp();
+                    // Lanes 0 .. 15 own the rows of the pivot tile.  Lanes 16 + j start from the unit vector e_j instead and run
+                    // the very same elimination: with t[i] = L[i][c] L[c][c] and sc = acc[c] / d the update acc[i] -= sc t[i] is the
+                    // forward substitution of L x = e_j, and the scaled entries l[c] = acc[c] / L[c][c] that lanes 0 .. 15 read as row
+                    // r of L are, in lane 16 + j, column j of Dinv = L^-1.  The inverse costs no instruction at all.
                     float prow[16], l[16];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) { prow[c] = panel[c * stride_k + r]; }  // lanes 16 .. 31 duplicate lanes 0 .. 15
+                    for (int c = 0; c < 16; ++c) {
+                        const float pv = panel[c * stride_k + r];
+                        prow[c] = lane < 16 ? pv : (c == r ? 1.0f : 0.f);
+                    }
                     PivotBlock<2>(prow, zacc, l, 0, c0, lane, fail, rs, al);
                     __syncwarp();  // everybody has read the raw tile
                     if (lane < 16) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) { panel[c * stride_k + r] = c > r ? 0.f : l[c]; }
-                    }
-                    __syncwarp();
-                    // Dinv: lane c = column c by forward substitution on e_c (1 / L_jj = rs, written by lane 0 above)
-                    if (lane < 16) {
-                        float sres[16], x[16];
+                    } else {
+                        float *dst = dinv + kb * 16 * Lay::kDinvLd + r * Lay::kDinvLd;  // column r of Dinv (zero above the diagonal)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { sres[i] = i == lane ? 1.0f : 0.f; }
-#pragma unroll
-                        for (int pc = 0; pc < 16; ++pc) {
-                            x[pc] = sres[pc] * rs[c0 + pc];
-                            float col[16];
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const float4 v4 = *reinterpret_cast<const float4 *>(panel + pc * stride_k + 4 * k4);  // warp-uniform address
-                                col[4 * k4] = v4.x, col[4 * k4 + 1] = v4.y, col[4 * k4 + 2] = v4.z, col[4 * k4 + 3] = v4.w;
-                            }
-#pragma unroll
-                            for (int i = pc + 1; i < 16; ++i) { sres[i] = fmaf(-col[i], x[pc], sres[i]); }
-                        }
-                        float *dst = dinv + kb * 16 * Lay::kDinvLd + lane * Lay::kDinvLd;
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(x[4 * k4], x[4 * k4 + 1], x[4 * k4 + 2], x[4 * k4 + 3]); }
+                        for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]); }
                     }
                 }
                 __syncthreads();  // #1: pivot block, Dinv, rs, z of this panel are published
@@ -610,7 +627,8 @@ namespace erl_gp {
         }
 
         // alpha = L^-T z (al holds z on entry, alpha on exit); thread = column, blocked from the bottom
-        template<int NBLK>
+        // USE_DINV: the inverses of the diagonal blocks are in shared memory (FactorizeMma)
+        template<int NBLK, bool USE_DINV>
         __device__ __forceinline__ void
         BackSolve(float *__restrict__ smem, const int nblk) {
             using Lay = Layout<NBLK>;
@@ -630,27 +648,47 @@ namespace erl_gp {
                     const int lb = c0 & 31;
                     const bool mine = lane >= lb && lane < lb + 16;
                     const int jj = mine ? lane - lb : 0;
-                    const float *colp = lp + Lay::Base(kb) + jj * Lay::Stride(kb);  // rows c0.. of column c0 + jj
-                    float lblk[16];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float4 v = *reinterpret_cast<const float4 *>(colp + 4 * k);
-                        lblk[4 * k] = v.x, lblk[4 * k + 1] = v.y, lblk[4 * k + 2] = v.z, lblk[4 * k + 3] = v.w;
-                    }
-                    const float zj = al[c0 + jj];
-                    const float rsj = rs[c0 + jj];
                     float sj = s[0];
 #pragma unroll
                     for (int sl = 1; sl < kColSlots; ++sl) {
                         if (c0 >= kThreads * sl) { sj = s[sl]; }
                     }
-                    float amine = 0.f;
+                    float amine;
+                    if constexpr (USE_DINV) {
+                        // alpha_blk = Dinv^T (z_blk - s_blk): 16 independent shuffles + FMAs instead of a 16-step substitution chain
+                        const float vj = al[c0 + jj] - sj;
+                        const float *dcol = smem + Lay::kDinv + kb * 16 * Lay::kDinvLd + jj * Lay::kDinvLd;  // column jj of Dinv: Dinv[r][jj]
+                        float dr[16];
 #pragma unroll
-                    for (int c = 15; c >= 0; --c) {
-                        const float a = (zj - sj) * rsj;
-                        const float ac = __shfl_sync(kFull, a, lb + c);
-                        if (jj == c) { amine = a; }
-                        if (mine && jj < c) { sj = fmaf(lblk[c], ac, sj); }  // L(c0 + c, c0 + jj) * alpha_c
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 v = *reinterpret_cast<const float4 *>(dcol + 4 * k);
+                            dr[4 * k] = v.x, dr[4 * k + 1] = v.y, dr[4 * k + 2] = v.z, dr[4 * k + 3] = v.w;
+                        }
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 16; r += 2) {
+                            a0 = fmaf(dr[r], __shfl_sync(kFull, vj, lb + r), a0);  // rows r < jj of the column are zero
+                            a1 = fmaf(dr[r + 1], __shfl_sync(kFull, vj, lb + r + 1), a1);
+                        }
+                        amine = a0 + a1;
+                    } else {
+                        const float *colp = lp + Lay::Base(kb) + jj * Lay::Stride(kb);  // rows c0.. of column c0 + jj
+                        float lblk[16];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 v = *reinterpret_cast<const float4 *>(colp + 4 * k);
+                            lblk[4 * k] = v.x, lblk[4 * k + 1] = v.y, lblk[4 * k + 2] = v.z, lblk[4 * k + 3] = v.w;
+                        }
+                        const float zj = al[c0 + jj];
+                        const float rsj = rs[c0 + jj];
+                        amine = 0.f;
+#pragma unroll
+                        for (int c = 15; c >= 0; --c) {
+                            const float a = (zj - sj) * rsj;
+                            const float ac = __shfl_sync(kFull, a, lb + c);
+                            if (jj == c) { amine = a; }
+                            if (mine && jj < c) { sj = fmaf(lblk[c], ac, sj); }  // L(c0 + c, c0 + jj) * alpha_c
+                        }
                     }
                     if (mine) { al[c0 + jj] = amine; }
                 }
@@ -1128,9 +1166,10 @@ namespace erl_gp {
                 if (p.write_l) {
                     float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                     if ((p.max_n & 3) == 0) {
-                        for (int cc = warp; cc < n * ((Lay::kNp + 127) / 128); cc += kThreads / 32) {
-                            const int c = cc % n;
-                            const int r4 = 4 * lane + 128 * (cc / n);  // 128 rows per warp and step
+                        constexpr int kRowChunks = (Lay::kNp + 127) / 128;  // 128 rows per warp and step
+                        for (int cc = warp; cc < n * kRowChunks; cc += kThreads / 32) {
+                            const int c = kRowChunks == 1 ? cc : cc % n;
+                            const int r4 = 4 * lane + (kRowChunks == 1 ? 0 : 128 * (cc / n));
                             const int cb = c >> 4;
                             if (r4 < n) {
                                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1154,7 +1193,7 @@ namespace erl_gp {
                         }
                     }
                 }
-                BackSolve<NBLK>(smem, nblk);
+                BackSolve<NBLK, (kBackSolveDinv && (kMmaTrain || NBLK > 8))>(smem, nblk);
                 __syncthreads();
                 float *ga = p.alpha + static_cast<long>(g) * p.max_n;
                 for (int e = tid; e < n; e += kThreads) {
@@ -1170,9 +1209,10 @@ namespace erl_gp {
                 const float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                 const bool vec_ok = (p.max_n & 3) == 0;
                 constexpr int kBatch = 8;  // columns in flight per warp: the loads of a batch are all issued before the first store
-                for (int cc0 = warp * kBatch; cc0 < npr * ((Lay::kNp + 127) / 128); cc0 += (kThreads / 32) * kBatch) {
-                    const int c0 = cc0 % npr;             // npr is a multiple of 16, kBatch divides 16: a batch never straddles the wrap
-                    const int rchunk = 128 * (cc0 / npr);  // rows [16 cb + rchunk, + 128) of the column
+                constexpr int kRowChunks = (Lay::kNp + 127) / 128;
+                for (int cc0 = warp * kBatch; cc0 < npr * kRowChunks; cc0 += (kThreads / 32) * kBatch) {
+                    const int c0 = kRowChunks == 1 ? cc0 : cc0 % npr;             // npr is a multiple of 16, kBatch divides 16: a batch never straddles the wrap
+                    const int rchunk = kRowChunks == 1 ? 0 : 128 * (cc0 / npr);  // rows [16 cb + rchunk, + 128) of the column
                     float val[kBatch][4];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
@@ -1263,12 +1303,17 @@ namespace erl_gp {
         int
         Launch(Context *ctx, const BatchParams<float> &params, const int mode, const int tiles_per_gp) {
             const int max_n = params.max_n;
+#ifdef ERL_GP_ROWGP_FAST_BUILD  // kernel experiments only (make EXTRA=-DERL_GP_ROWGP_FAST_BUILD): one instance, n <= 128
+            if (max_n <= 128) { return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp); }
+            return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "fast build: max_n=%d > 128", max_n);
+#else
             if (max_n <= 32) { return LaunchMode<XDIM, 2>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 64) { return LaunchMode<XDIM, 4>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 96) { return LaunchMode<XDIM, 6>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 128) { return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 192) { return LaunchMode<XDIM, 12>(ctx, params, mode, tiles_per_gp); }  // 104 KB of shared memory, 2 CTAs / SM
             return LaunchMode<XDIM, 16>(ctx, params, mode, tiles_per_gp);                        // 171 KB, 1 CTA / SM
+#endif
         }
 
     }  // namespace rowgp

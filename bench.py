@@ -38,6 +38,9 @@ WORKLOADS = {
     # name: (description, num_gps per GPU, n, x_dim, queries per GP, kernel, scale, dtype)
     "c4": dict(desc="batched small-GP stream: 50k independent GPs per GPU, n=128, x_dim=3, Matern32(0.3), 128 test points per GP, f32 (BASELINE.json configs[3])",
                num_gps=50_000, n=128, x_dim=3, q_per_gp=128, kernel="matern32", scale=0.3, dtype="f32"),
+    # diagnostic: the same stream in double (generic one-CTA-per-GP kernel); not the bench line
+    "c4f64": dict(desc="batched small-GP stream in double: 50k independent GPs per GPU, n=128, x_dim=3, Matern32(0.3), 128 test points per GP, f64 (diagnostic)",
+                  num_gps=50_000, n=128, x_dim=3, q_per_gp=128, kernel="matern32", scale=0.3, dtype="f64"),
 }
 
 
@@ -363,7 +366,7 @@ def main():
                        "l2": f"per-step inputs+outputs {alg_bytes / 1e9:.2f} GB >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                         "kernel": "rowgp::RowGpKernel<x_dim=3, NBLK=8, train+predict> (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": ("rowgp::RowGpKernel<x_dim=3, NBLK=8, train+predict>" if w["dtype"] == "f32" else "BatchedGpKernel<double, x_dim=3, MROWS=8, train+predict>") + " (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
                          "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu (FFMA2 with fresh operands sustains ~55, tools/fma_lds_rate.cu); factorisation and predict run on the tensor pipe as 3xTF32 mma.sync (276 TFLOP/s TF32 peak = 92 FP32-equivalent), pivot blocks / back-substitution / covariance entries on the FP32 pipe; the kernel is latency / issue bound, not HBM bound, see DESIGN.md"}},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }

@@ -93,7 +93,8 @@ namespace erl_gp {
             static constexpr int kMisc = kVar + kNp;    // int fail flag
             static constexpr int kDinvLd = 20;          // column stride of a 16 x 16 inverse block (== 4 mod 16, like the L columns)
             static constexpr int kDinv = kMisc + 4;     // inverses of the 16 x 16 diagonal blocks of L, column-major (tensor-path predict)
-            static constexpr int kEnd = kDinv + NBLK * 16 * kDinvLd;
+            static constexpr int kSoa = kDinv + NBLK * 16 * kDinvLd;  // x[kNp], y[kNp], z[kNp], alpha[kNp]: pairs of neighbouring points for the packed (f32x2) covariance code
+            static constexpr int kEnd = kSoa + 4 * kNp;
             static constexpr size_t kBytes = static_cast<size_t>(kEnd) * sizeof(float);
         };
 
@@ -146,6 +147,33 @@ namespace erl_gp {
             }
         };
 
+        // Two covariance entries at a time on the packed FP32 pipe (add / mul / fma.f32x2): the entries of two neighbouring
+        // training points against one query / row.  17 instructions per pair instead of 30 (the Gram / Ktest entries were 17 % of
+        // the instructions of the fused kernel, all of it straight-line code the instruction fetch has to stream).
+        template<int XDIM>
+        __device__ __forceinline__ float2
+        Dist2Pair(const float2 (&pc)[XDIM], const float (&negq)[XDIM]) {
+            float2 d = __fadd2_rn(pc[0], make_float2(negq[0], negq[0]));
+            float2 r2 = __fmul2_rn(d, d);
+#pragma unroll
+            for (int k = 1; k < XDIM; ++k) {
+                d = __fadd2_rn(pc[k], make_float2(negq[k], negq[k]));
+                r2 = __ffma2_rn(d, d, r2);
+            }
+            return r2;
+        }
+
+        __device__ __forceinline__ float2
+        CovPair(const CovCoef &cov, const float2 r2) {
+            float2 sq, e;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.x) : "f"(r2.x));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq.y) : "f"(r2.y));
+            const float2 arg = __ffma2_rn(make_float2(cov.b, cov.b), sq, __fmul2_rn(make_float2(cov.c, cov.c), r2));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+            return __ffma2_rn(__fmul2_rn(make_float2(cov.a, cov.a), sq), e, e);
+        }
+
         // 16 x 16 pivot block of a panel, factorised by one warp with shuffles.  LDL^T-style elimination: the update of column
         // cc uses acc[c] / d (reciprocal) and the RAW column entries of the pivot rows, which can be shuffled before the
         // reciprocal is known; the Cholesky entries l[c] = acc[c] / sqrt(d) are formed off the dependency chain.
@@ -196,6 +224,13 @@ namespace erl_gp {
             return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
         }
 
+        // two values (a packed add.f32x2 for the subtraction was measured slower: the operands have to be moved into pairs)
+        __device__ __forceinline__ void
+        Tf32LoPair(const float x0, const float x1, uint32_t &lo0, uint32_t &lo1) {
+            lo0 = Tf32Lo(x0);
+            lo1 = Tf32Lo(x1);
+        }
+
         __device__ __forceinline__ void
         MmaTf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
             asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -217,10 +252,9 @@ namespace erl_gp {
         AccToA(const float (&c)[4], const float sgn, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
             const float a[4] = {sgn * c[0], sgn * c[2], sgn * c[1], sgn * c[3]};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                hi[k] = __float_as_uint(a[k]);
-                lo[k] = Tf32Lo(a[k]);
-            }
+            for (int k = 0; k < 4; ++k) { hi[k] = __float_as_uint(a[k]); }
+            Tf32LoPair(a[0], a[1], lo[0], lo[1]);
+            Tf32LoPair(a[2], a[3], lo[2], lo[3]);
         }
 
         // v (two 8-column accumulator tiles) = X Dinv^T for a 16 x 16 tile X held in the accumulator layout (x[0], x[1] = its two
@@ -239,7 +273,10 @@ namespace erl_gp {
             const float d00[2] = {dv[0], dv[LD]};                    // n-tile 0, k-tile 0
             const float d10[2] = {dv[8], dv[LD + 8]};                // n-tile 1, k-tile 0
             const float d11[2] = {dv[8 * LD + 8], dv[9 * LD + 8]};   // n-tile 1, k-tile 1
-            const uint32_t l00[2] = {Tf32Lo(d00[0]), Tf32Lo(d00[1])}, l10[2] = {Tf32Lo(d10[0]), Tf32Lo(d10[1])}, l11[2] = {Tf32Lo(d11[0]), Tf32Lo(d11[1])};
+            uint32_t l00[2], l10[2], l11[2];
+            Tf32LoPair(d00[0], d00[1], l00[0], l00[1]);
+            Tf32LoPair(d10[0], d10[1], l10[0], l10[1]);
+            Tf32LoPair(d11[0], d11[1], l11[0], l11[1]);
             MmaTf32(v[0], xlo[0], __float_as_uint(d00[0]), __float_as_uint(d00[1]));
             MmaTf32(v[1], xlo[0], __float_as_uint(d10[0]), __float_as_uint(d10[1]));
             MmaTf32(w, xlo[1], __float_as_uint(d11[0]), __float_as_uint(d11[1]));
@@ -506,7 +543,7 @@ namespace erl_gp {
                             }
                             uint32_t bl[2][2];
 #pragma unroll
-                            for (int nt = 0; nt < 2; ++nt) { bl[nt][0] = Tf32Lo(b[nt][0]), bl[nt][1] = Tf32Lo(b[nt][1]); }
+                            for (int nt = 0; nt < 2; ++nt) { Tf32LoPair(b[nt][0], b[nt][1], bl[nt][0], bl[nt][1]); }
 #pragma unroll
                             for (int sl = 0; sl < kSlots; ++sl) {
                                 const int ti = warp + 4 * sl;
@@ -516,7 +553,9 @@ namespace erl_gp {
                                     const float a[4] = {arow[0], arow[8], arow[stride], arow[stride + 8]};
                                     uint32_t ahi[4], alo[4];
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) { ahi[k] = __float_as_uint(a[k]), alo[k] = Tf32Lo(a[k]); }
+                                    for (int k = 0; k < 4; ++k) { ahi[k] = __float_as_uint(a[k]); }
+                                    Tf32LoPair(a[0], a[1], alo[0], alo[1]);
+                                    Tf32LoPair(a[2], a[3], alo[2], alo[3]);
 #pragma unroll
                                     for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], alo, __float_as_uint(b[nt][0]), __float_as_uint(b[nt][1])); }
 #pragma unroll
@@ -527,18 +566,16 @@ namespace erl_gp {
                             }
                         }
                     }
-                    // P = Gram tile - update (Gram entries in the accumulator layout, fused noise diagonal, identity padding)
-                    float pcx[2][2][XDIM];
+                    // P = Gram tile - update (Gram entries in the accumulator layout, two neighbouring columns per packed
+                    // operation, fused noise diagonal, identity padding)
+                    const float2 *soa = reinterpret_cast<const float2 *>(smem + Lay::kSoa);
+                    float2 pcx[2][XDIM];
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float4 pc = pts[c0 + 8 * nt + 2 * t + e];
-                            pcx[nt][e][0] = pc.x;
-                            if (XDIM > 1) { pcx[nt][e][XDIM > 1 ? 1 : 0] = pc.y; }
-                            if (XDIM > 2) { pcx[nt][e][XDIM > 2 ? 2 : 0] = pc.z; }
-                        }
+                        for (int d = 0; d < XDIM; ++d) { pcx[nt][d] = soa[d * (Lay::kNp / 2) + (c0 + 8 * nt) / 2 + t]; }
                     }
+                    const bool ragged = c0 + 16 > n;  // padding columns in this panel (warp-uniform)
 #pragma unroll
                     for (int sl = 0; sl < kSlots; ++sl) {
                         const int ti = warp + 4 * sl;
@@ -547,17 +584,24 @@ namespace erl_gp {
                             for (int hr = 0; hr < 2; ++hr) {
                                 const int row = c0 + 16 * ti + g + 8 * hr;
                                 const float4 pr = pts[row];
+                                float negr[XDIM];
+                                negr[0] = -pr.x;
+                                if (XDIM > 1) { negr[XDIM > 1 ? 1 : 0] = -pr.y; }
+                                if (XDIM > 2) { negr[XDIM > 2 ? 2 : 0] = -pr.z; }
                                 const float diag = row < n ? 1.0f + sv[row] : 1.0f;
 #pragma unroll
                                 for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-                                    for (int e = 0; e < 2; ++e) {
-                                        const int col = c0 + 8 * nt + 2 * t + e;
-                                        float kv = cov(Dist2<XDIM>(pr, pcx[nt][e]));
-                                        if (row >= n || col >= n) { kv = 0.f; }
-                                        if (row == col) { kv = diag; }
-                                        acc[sl][nt][2 * hr + e] = kv - acc[sl][nt][2 * hr + e];
+                                    const int col = c0 + 8 * nt + 2 * t;
+                                    float2 kv = CovPair(cov, Dist2Pair<XDIM>(pcx[nt], negr));
+                                    if (row >= n) { kv = make_float2(0.f, 0.f); }
+                                    if (ragged) {
+                                        if (col >= n) { kv.x = 0.f; }
+                                        if (col + 1 >= n) { kv.y = 0.f; }
                                     }
+                                    if (row == col) { kv.x = diag; }
+                                    if (row == col + 1) { kv.y = diag; }
+                                    acc[sl][nt][2 * hr] = kv.x - acc[sl][nt][2 * hr];
+                                    acc[sl][nt][2 * hr + 1] = kv.y - acc[sl][nt][2 * hr + 1];
                                 }
                             }
                         }
@@ -945,10 +989,14 @@ namespace erl_gp {
             }
         }
 
-        template<int XDIM, int NBLK>
+        // FULL: nblk == NBLK is known at compile time (every "is this block row active" test folds away: the common case of a
+        // full GP then runs branch-free straight-line code; with the runtime tests every group of HMMAs ends in a taken branch
+        // over its short-row variant, and the fused kernel spent 18 % of its warp samples waiting for instructions)
+        template<int XDIM, int NBLK, bool FULL>
         __device__ __forceinline__ void
-        PredictTileMma(const BatchParams<float> &p, const CovCoef cov, const float *__restrict__ smem, const int n, const int nblk, const long q_begin, const int nq) {
+        PredictTileMma(const BatchParams<float> &p, const CovCoef cov, const float *__restrict__ smem, const int n, const int nblk_rt, const long q_begin, const int nq) {
             using Lay = Layout<NBLK>;
+            const int nblk = FULL ? NBLK : nblk_rt;
             const float *lp = smem + Lay::kL;
             const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
             const float *dinv = smem + Lay::kDinv;
@@ -966,23 +1014,43 @@ namespace erl_gp {
                 for (int d = 0; d < XDIM; ++d) { xq[k][d] = qrow[k] < nq ? p.q_x[(q_begin + qrow[k]) * XDIM + d] : 0.f; }
             }
 
-            // Ktest^T tile in the accumulator layout: acc[j] = columns 8 j + 2 t, + 1 of query rows g (slots 0, 1) and g + 8 (slots 2, 3)
+            // Ktest^T tile in the accumulator layout: acc[j] = columns 8 j + 2 t, + 1 of query rows g (slots 0, 1) and g + 8 (slots 2, 3);
+            // the two neighbouring columns of a query are one packed (f32x2) evaluation
             float acc[2 * NBLK][4];
-            float mean[2] = {0.f, 0.f};
+            float mean[2];
+            {
+                const float2 *soa = reinterpret_cast<const float2 *>(smem + Lay::kSoa);
+                float negq[2][XDIM];
 #pragma unroll
-            for (int j = 0; j < 2 * NBLK; ++j) {
+                for (int k = 0; k < 2; ++k) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = 8 * j + 2 * t + e;
-                    const float4 pt = pts[col];
-                    float ka = cov(Dist2<XDIM>(pt, xq[0]));
-                    float kb = cov(Dist2<XDIM>(pt, xq[1]));
-                    if (col >= n) { ka = kb = 0.f; }
-                    mean[0] = fmaf(ka, pt.w, mean[0]);
-                    mean[1] = fmaf(kb, pt.w, mean[1]);
-                    acc[j][e] = ka;
-                    acc[j][2 + e] = kb;
+                    for (int d = 0; d < XDIM; ++d) { negq[k][d] = -xq[k][d]; }
                 }
+                float2 mean2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int j = 0; j < 2 * NBLK; ++j) {
+                    if (FULL || 8 * j < 16 * nblk) {
+                        float2 pc[XDIM];
+#pragma unroll
+                        for (int d = 0; d < XDIM; ++d) { pc[d] = soa[d * (Lay::kNp / 2) + 4 * j + t]; }
+                        const float2 av = soa[3 * (Lay::kNp / 2) + 4 * j + t];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            float2 kv = CovPair(cov, Dist2Pair<XDIM>(pc, negq[k]));
+                            if (8 * j + 8 > n) {  // padding columns (warp-uniform test)
+                                if (8 * j + 2 * t >= n) { kv.x = 0.f; }
+                                if (8 * j + 2 * t + 1 >= n) { kv.y = 0.f; }
+                            }
+                            mean2[k] = __ffma2_rn(kv, av, mean2[k]);
+                            acc[j][2 * k] = kv.x;
+                            acc[j][2 * k + 1] = kv.y;
+                        }
+                    } else {
+                        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+                    }
+                }
+                mean[0] = mean2[0].x + mean2[0].y;
+                mean[1] = mean2[1].x + mean2[1].y;
             }
 
             // The loop over the blocks is fully unrolled (static register indices).  (A runtime loop with the accumulators
@@ -1025,7 +1093,7 @@ namespace erl_gp {
                                     b[u][1] = bp[stride];
                                 }
 #pragma unroll
-                                for (int u = 0; u < kTiles; ++u) { bl[u][0] = Tf32Lo(b[u][0]), bl[u][1] = Tf32Lo(b[u][1]); }
+                                for (int u = 0; u < kTiles; ++u) { Tf32LoPair(b[u][0], b[u][1], bl[u][0], bl[u][1]); }
 #pragma unroll
                                 for (int u = 0; u < kTiles; ++u) { MmaTf32(acc[2 * i + u], alo[kt], __float_as_uint(b[u][0]), __float_as_uint(b[u][1])); }
 #pragma unroll
@@ -1135,6 +1203,10 @@ namespace erl_gp {
                 }
                 pts[e] = pt;
                 rs[e] = 1.0f;
+                smem[Lay::kSoa + e] = pt.x;
+                smem[Lay::kSoa + Lay::kNp + e] = pt.y;
+                smem[Lay::kSoa + 2 * Lay::kNp + e] = pt.z;
+                smem[Lay::kSoa + 3 * Lay::kNp + e] = pt.w;  // alpha (predict-only mode; the train modes fill it after the back-substitution)
             }
 
             if constexpr ((MODE & kBatchTrain) != 0) {
@@ -1200,6 +1272,7 @@ namespace erl_gp {
                     const float a = al[e];
                     ga[e] = a;
                     smem[Lay::kPts + 4 * e + 3] = a;
+                    smem[Lay::kSoa + 3 * Lay::kNp + e] = a;
                 }
                 if (tid == 0) { p.info[g] = 0; }
                 if constexpr ((kMmaPredict || NBLK > 8) && !(kMmaTrain || NBLK > 8) && (MODE & kBatchPredict) != 0) { ComputeDinv<NBLK>(smem, nblk); }  // FactorizeMma leaves Dinv behind
@@ -1257,7 +1330,11 @@ namespace erl_gp {
                 for (long qb = q0 + static_cast<long>(blockIdx.y) * kTileQ; qb < q1; qb += static_cast<long>(gridDim.y) * kTileQ) {
                     const int nq = static_cast<int>(q1 - qb < kTileQ ? q1 - qb : kTileQ);
                     if constexpr (kMmaPredict || NBLK > 8) {
-                        PredictTileMma<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
+                        if (nblk == NBLK) {
+                            PredictTileMma<XDIM, NBLK, true>(p, cov, smem, n, nblk, qb, nq);
+                        } else {
+                            PredictTileMma<XDIM, NBLK, false>(p, cov, smem, n, nblk, qb, nq);
+                        }
                     } else {
                         PredictTile<XDIM, NBLK>(p, cov, smem, n, nblk, qb, nq);
                     }

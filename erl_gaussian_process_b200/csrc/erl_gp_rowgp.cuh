@@ -1037,7 +1037,7 @@ namespace erl_gp {
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             float2 kv = CovPair(cov, Dist2Pair<XDIM>(pc, negq[k]));
-                            if (8 * j + 8 > n) {  // padding columns (warp-uniform test)
+                            if ((!FULL || j >= 2 * NBLK - 2) && 8 * j + 8 > n) {  // padding columns (warp-uniform test; FULL: only the last block can have any)
                                 if (8 * j + 2 * t >= n) { kv.x = 0.f; }
                                 if (8 * j + 2 * t + 1 >= n) { kv.y = 0.f; }
                             }
@@ -1239,20 +1239,51 @@ namespace erl_gp {
                     float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                     if ((p.max_n & 3) == 0) {
                         constexpr int kRowChunks = (Lay::kNp + 127) / 128;  // 128 rows per warp and step
-                        for (int cc = warp; cc < n * kRowChunks; cc += kThreads / 32) {
-                            const int c = kRowChunks == 1 ? cc : cc % n;
-                            const int r4 = 4 * lane + (kRowChunks == 1 ? 0 : 128 * (cc / n));
-                            const int cb = c >> 4;
-                            if (r4 < n) {
-                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (r4 >= 16 * cb) { v = *reinterpret_cast<const float4 *>(lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) + (r4 - 16 * cb)); }
-                                float *dst = gl + r4 + static_cast<long>(c) * p.max_n;
-                                if (r4 + 3 < n) {
-                                    *reinterpret_cast<float4 *>(dst) = v;
-                                } else {
-                                    dst[0] = v.x;
-                                    if (r4 + 1 < n) { dst[1] = v.y; }
-                                    if (r4 + 2 < n) { dst[2] = v.z; }
+                        if ((n & 3) == 0) {
+                            // fast path (no ragged float4): one LDS.128 + one STG.128 per lane and column, nothing else
+                            for (int cb = 0; cb < nblk; ++cb) {
+                                const float *blk = lp + Lay::Base(cb) - 16 * cb + warp * Lay::Stride(cb);
+                                const int stride4 = (kThreads / 32) * Lay::Stride(cb);
+                                float *gcol = gl + static_cast<long>(16 * cb + warp) * p.max_n;
+#pragma unroll
+                                for (int k = 0; k < 16 / (kThreads / 32); ++k) {
+                                    if (16 * cb + warp + (kThreads / 32) * k < n) {
+#pragma unroll
+                                        for (int ch = 0; ch < kRowChunks; ++ch) {
+                                            const int r4 = 4 * lane + 128 * ch;
+                                            if (r4 < n) {
+                                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                                if (r4 >= 16 * cb) { v = *reinterpret_cast<const float4 *>(blk + k * stride4 + r4); }
+                                                *reinterpret_cast<float4 *>(gcol + static_cast<long>((kThreads / 32) * k) * p.max_n + r4) = v;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        } else
+                        for (int cb = 0; cb < nblk; ++cb) {  // per column block: base / stride of the packed layout once
+                            const float *blk = lp + Lay::Base(cb) - 16 * cb;
+                            const int stride = Lay::Stride(cb);
+#pragma unroll
+                            for (int k = 0; k < 16 / (kThreads / 32); ++k) {
+                                const int c = 16 * cb + warp + (kThreads / 32) * k;
+                                if (c < n) {
+                                    float *gcol = gl + static_cast<long>(c) * p.max_n;
+#pragma unroll
+                                    for (int ch = 0; ch < kRowChunks; ++ch) {
+                                        const int r4 = 4 * lane + 128 * ch;
+                                        if (r4 < n) {
+                                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                            if (r4 >= 16 * cb) { v = *reinterpret_cast<const float4 *>(blk + (c & 15) * stride + r4); }
+                                            if (r4 + 3 < n) {
+                                                *reinterpret_cast<float4 *>(gcol + r4) = v;
+                                            } else {
+                                                gcol[r4] = v.x;
+                                                if (r4 + 1 < n) { gcol[r4 + 1] = v.y; }
+                                                if (r4 + 2 < n) { gcol[r4 + 2] = v.z; }
+                                            }
+                                        }
+                                    }
                                 }
                             }
                         }

@@ -950,7 +950,7 @@ namespace erl_gp {
         // with all 16 x 128 accumulators (64 registers) resident.  L stays in the packed column-major layout of the
         // factorisation: b0 / b1 are two LDS.32 whose 32 lanes hit 32 different banks (column stride == 4 mod 16).
         // FP32 accuracy comes from the 3xTF32 split a = hi + lo (hi = a truncated to TF32, lo = a - hi exact): a b ~ hi_a hi_b +
-        // lo_a hi_b + hi_a lo_b, error ~2^-20 relative per product (measured against the oracle in tests/test_gpu_batch.py).
+        // lo_a hi_b + hi_a lo_b, error ~2^-20 relative per product (measured in tests/test_gpu_batch.py).
         // One m16n8k8 is 1024 FMAs per issue slot instead of 64 for a warp-wide FFMA2: the FMA / issue pipes that bound the
         // previous predict are left to the factorisations of the other resident CTAs.
         // --------------------------------------------------------------------------------------
@@ -1361,8 +1361,8 @@ namespace erl_gp {
                 for (long qb = q0 + static_cast<long>(blockIdx.y) * kTileQ; qb < q1; qb += static_cast<long>(gridDim.y) * kTileQ) {
                     const int nq = static_cast<int>(q1 - qb < kTileQ ? q1 - qb : kTileQ);
                     if constexpr (kMmaPredict || NBLK > 8) {
-                        if (nblk == NBLK) {
-                            PredictTileMma<XDIM, NBLK, true>(p, cov, smem, n, nblk, qb, nq);
+                        if (NBLK <= 8 && nblk == NBLK) {  // (the larger instances keep one variant: build time)
+                            PredictTileMma<XDIM, (NBLK <= 8 ? NBLK : 2), (NBLK <= 8)>(p, cov, smem, n, nblk, qb, nq);
                         } else {
                             PredictTileMma<XDIM, NBLK, false>(p, cov, smem, n, nblk, qb, nq);
                         }
@@ -1396,7 +1396,7 @@ namespace erl_gp {
         }
 
         template<int XDIM, int NBLK>
-        static int
+        int
         LaunchMode(Context *ctx, const BatchParams<float> &params, const int mode, const int tiles_per_gp) {
             switch (mode) {
                 case kBatchTrain: return LaunchInstance<XDIM, NBLK, kBatchTrain>(ctx, params, 1);
@@ -1405,6 +1405,22 @@ namespace erl_gp {
                 default: return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: bad mode %d", mode);
             }
         }
+
+        // The kernels are instantiated in their own translation units (erl_gp_rowgp_x<dim>_<a|b|c>.cu: n <= 128 / 192 / 256), so that
+        // a clean build compiles them in parallel; everybody else only sees these declarations.
+#ifdef ERL_GP_ROWGP_EXTERN_INSTANCES
+#define ERL_GP_ROWGP_EXTERN(XD)                                                                          \
+    extern template int LaunchMode<XD, 2>(Context *, const BatchParams<float> &, int, int);           \
+    extern template int LaunchMode<XD, 4>(Context *, const BatchParams<float> &, int, int);           \
+    extern template int LaunchMode<XD, 6>(Context *, const BatchParams<float> &, int, int);           \
+    extern template int LaunchMode<XD, 8>(Context *, const BatchParams<float> &, int, int);           \
+    extern template int LaunchMode<XD, 12>(Context *, const BatchParams<float> &, int, int);          \
+    extern template int LaunchMode<XD, 16>(Context *, const BatchParams<float> &, int, int);
+        ERL_GP_ROWGP_EXTERN(1)
+        ERL_GP_ROWGP_EXTERN(2)
+        ERL_GP_ROWGP_EXTERN(3)
+#undef ERL_GP_ROWGP_EXTERN
+#endif
 
         // max_n <= 256
         template<int XDIM>

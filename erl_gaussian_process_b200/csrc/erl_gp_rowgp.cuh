@@ -472,7 +472,12 @@ namespace erl_gp {
         //   C. the other tiles become L_i = P_i Dinv^T: the accumulators ARE the A operand (same trick as in the predict), so the
         //      in-thread elimination of the FFMA version (136 dependent FMAs + broadcast loads per row) is 9 HMMAs per tile.
         // Two barriers per panel as before, but ~2.5x fewer instructions between them and no idle "finished rows" threads in
-        // phase A (tiles are dealt to all four warps).  Accuracy: tests/test_gpu_batch.py; a numpy emulation of the split
+        // phase A (tiles are dealt to all four warps).  Cycle counters (-DERL_GP_ROWGP_TIMING, C4, 4 CTAs / SM): a factorisation
+        // takes ~62 k cycles, all of it on warp 0's path: 27 k in phase A (two tiles per panel while mt > 4, one of them the pivot
+        // tile) and 32 k in phase B (8 pivot blocks, ~4 k each: 16 dependent shuffle + MUFU.RSQ + FMA steps at the latency the
+        // loaded SM gives them); the other warps are busy 14 - 19 k cycles.  Tried and measured slower: warp 0 on the pivot tile
+        // only (5.95 vs 5.58 ms fused), and splitting the pivot tile's update over the four warps by column block with the
+        // shares summed through shared memory behind a third barrier (5.43 vs 4.97 ms).  Accuracy: tests/test_gpu_batch.py; a numpy emulation of the split
         // (tools/emulate_3xtf32.py) gives mean / variance errors of 4e-6 / 1e-6 against 1e-6 / 6e-7 for plain FP32.
         // --------------------------------------------------------------------------------------
         template<int XDIM, int NBLK>
@@ -492,6 +497,13 @@ namespace erl_gp {
             const int g = lane >> 2, t = lane & 3;
             int fail = 0;
 
+            // -DERL_GP_ROWGP_TIMING: cycle counters per phase and warp, printed by two CTAs (kernel experiments only)
+#ifdef ERL_GP_ROWGP_TIMING
+            long long tm_a = 0, tm_b = 0, tm_w1 = 0, tm_c = 0, tm_w2 = 0, tm_t = clock64();
+#define ERL_GP_TICK(acc_) { const long long now_ = clock64(); acc_ += now_ - tm_t; tm_t = now_; }
+#else
+#define ERL_GP_TICK(acc_)
+#endif
             for (int kb = 0; kb < nblk; ++kb) {
                 const int c0 = 16 * kb;
                 const int mt = nblk - kb;  // tiles of this panel
@@ -608,6 +620,7 @@ namespace erl_gp {
                     }
                 }
 
+                ERL_GP_TICK(tm_a)
                 // ---- B: pivot block (warp 0 holds tile 0 in slot 0) --------------------------------------------------
                 if (warp == 0) {
 #pragma unroll
@@ -643,7 +656,9 @@ namespace erl_gp {
                         for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]); }
                     }
                 }
+                ERL_GP_TICK(tm_b)
                 __syncthreads();  // #1: pivot block, Dinv, rs, z of this panel are published
+                ERL_GP_TICK(tm_w1)
                 if (mt > 1) {
                     // ---- C: L_i = P_i Dinv^T for the tiles below the pivot block ----------------------------------------
                     const float *dv = dinv + kb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;
@@ -664,9 +679,16 @@ namespace erl_gp {
                             }
                         }
                     }
+                    ERL_GP_TICK(tm_c)
                     __syncthreads();  // #2: the whole panel is published
+                    ERL_GP_TICK(tm_w2)
                 }
             }
+#ifdef ERL_GP_ROWGP_TIMING
+            if ((blockIdx.x == 20000 || blockIdx.x == 31111) && lane == 0) {
+                printf("cta %d warp %d: A %lld  B %lld  wait1 %lld  C %lld  wait2 %lld\n", blockIdx.x, warp, tm_a, tm_b, tm_w1, tm_c, tm_w2);
+            }
+#endif
             return fail;
         }
 

@@ -477,7 +477,11 @@ namespace erl_gp {
         // tile) and 32 k in phase B (8 pivot blocks, ~4 k each: 16 dependent shuffle + MUFU.RSQ + FMA steps at the latency the
         // loaded SM gives them); the other warps are busy 14 - 19 k cycles.  Tried and measured slower: warp 0 on the pivot tile
         // only (5.95 vs 5.58 ms fused), and splitting the pivot tile's update over the four warps by column block with the
-        // shares summed through shared memory behind a third barrier (5.43 vs 4.97 ms).  Accuracy: tests/test_gpu_batch.py; a numpy emulation of the split
+        // shares summed through shared memory behind a third barrier (5.43 vs 4.97 ms); keeping the 16 pivot diagonals up to date
+        // in every lane so that the MUFU.RSQ chain does not run through the shuffles (+240 independent instructions per pivot
+        // block: train alone 2.65 -> 2.71 ms, fused 4.97 -> 5.30 ms).  Every change that ADDED instructions made the fused kernel
+        // slower and every one that removed some made it faster: with 4 warps per scheduler the fused kernel behaves as
+        // issue-throughput bound, not as bound by the latency of warp 0's chain.  Accuracy: tests/test_gpu_batch.py; a numpy emulation of the split
         // (tools/emulate_3xtf32.py) gives mean / variance errors of 4e-6 / 1e-6 against 1e-6 / 6e-7 for plain FP32.
         // --------------------------------------------------------------------------------------
         template<int XDIM, int NBLK>

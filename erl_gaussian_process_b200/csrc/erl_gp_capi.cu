@@ -177,7 +177,15 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(b->copy_in, b->ev_kernel[0], 0));
         ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(b->copy_out, b->ev_kernel[0], 0));
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->q_offsets.ptr, q_offsets, sizeof(long) * (num_gps + 1), cudaMemcpyHostToDevice, b->copy_in));
-        auto chunk_begin = [&](long c) { return c * num_gps / num_chunks; };
+        // Uneven cut: a short first chunk (the first kernel starts after 1/4 of a nominal chunk's upload instead of a whole one)
+        // and a short last chunk (a short download after the last kernel); the interior is cut evenly.
+        const long edge = num_chunks >= 4 ? num_gps / (4 * num_chunks) : 0;
+        auto chunk_begin = [&](long c) {
+            if (edge == 0) { return c * num_gps / num_chunks; }
+            if (c <= 0) { return 0L; }
+            if (c >= num_chunks) { return num_gps; }
+            return edge + (c - 1) * (num_gps - 2 * edge) / (num_chunks - 2);
+        };
         // ---- enqueue every upload and every kernel ----
         for (long c = 0; c < num_chunks; ++c) {
             const long g0 = chunk_begin(c), g1 = chunk_begin(c + 1);

@@ -49,3 +49,23 @@ def sharded_train_predict(compute, n_train, x, y, var, q_offsets, q_x, rank: int
         return None
     # ranks hold contiguous, ascending GP ranges: concatenation in rank order restores the batch order
     return {k: np.concatenate([g[k] for g in gathered], axis=0) for k in part}
+
+
+def sharded_dense_predict(predict, x_test, rank: int = 0, world: int = 1, group=None):
+    """Dense VanillaGaussianProcess predict over several GPUs: every rank holds a replica of the
+    trained GP (L, alpha, x_train: the factorisation itself is "replicas only"), the test points are split into contiguous
+    ranges, `predict(x_test_slice) -> (mean, variance)` runs on this rank's slice and the slices are gathered on rank 0 in
+    rank order (host gather, no data-path collective).  Returns (mean, variance) on rank 0 and None elsewhere."""
+    x_test = np.asarray(x_test)
+    t0, t1 = shard_range(x_test.shape[0], rank, world)
+    mean, variance = predict(np.ascontiguousarray(x_test[t0:t1]))
+    part = (np.asarray(mean), np.asarray(variance))
+    if world == 1:
+        return part
+    import torch.distributed as dist
+
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(part, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    return np.concatenate([g[0] for g in gathered], axis=0), np.concatenate([g[1] for g in gathered], axis=0)

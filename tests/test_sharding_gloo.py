@@ -57,9 +57,25 @@ def _worker(rank, world, port, tmpdir):
         ref = compute(*batch)
         for k in ("mean", "var", "info", "alpha"):
             np.testing.assert_array_equal(full[k], np.asarray(ref[k]), err_msg=k)
-        np.save(os.path.join(tmpdir, "ok.npy"), np.array([1]))
     else:
         assert full is None
+
+    # dense VanillaGaussianProcess predict: replicas of the trained GP, test points split across ranks, host gather
+    n, t = 60, 101
+    xd = rng.uniform(-1, 1, (n, 2))
+    yd = np.sin(3 * xd).sum(axis=1)
+    vd = np.full(n, 1e-3)
+    xt = rng.uniform(-1, 1, (t, 2))
+    van = oracle.VanillaGp(oracle.MATERN32, 0.4, np.float64, max_num_samples=n)
+    assert van.train(xd, yd, vd) == 0
+    res = sharding.sharded_dense_predict(lambda xs: van.test(xs), xt, rank=rank, world=world)
+    if rank == 0:
+        m_ref, v_ref = van.test(xt)
+        np.testing.assert_array_equal(res[0], m_ref)
+        np.testing.assert_array_equal(res[1], v_ref)
+        np.save(os.path.join(tmpdir, "ok.npy"), np.array([1]))
+    else:
+        assert res is None
     dist.barrier()
     dist.destroy_process_group()
 

@@ -22,8 +22,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=16384)
-    ap.add_argument("--t", type=int, default=131072)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=16384)  # --size / --tests: torchrun's own parser trips over --n
+    ap.add_argument("--t", "--tests", dest="t", type=int, default=131072)
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--scale", type=float, default=0.1)
     ap.add_argument("--reps", type=int, default=3)
@@ -39,7 +39,21 @@ def main():
     var = np.full(args.n, 1e-3, dtype=dt)
     xt = np.random.default_rng(2).uniform(-1, 1, (args.t, 2)).astype(dt)
 
-    ctx = gp.Context(0)
+    # several GPUs (torchrun, one process per GPU): every rank factors its own replica (the factorisation is "replicas only",
+    # SURVEY.md 8e) and predicts a contiguous range of the test points; rank 0 reports the aggregate (max over ranks of the time)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        from erl_gaussian_process_b200 import sharding
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl")
+        t_begin, t_end = sharding.shard_range(args.t, rank, world)
+        xt = np.ascontiguousarray(xt[t_begin:t_end])
+    ctx = gp.Context(local)
     g = gp.VanillaGaussianProcess(gp.VanillaGaussianProcess.Setting("matern32", args.scale, -1), dt, ctx)
     train_ms, test_ms = [], []
     for _ in range(args.reps + 1):
@@ -55,7 +69,15 @@ def main():
         test_ms.append(1e3 * (time.perf_counter() - t0))
     train = min(train_ms[1:])
     test = min(test_ms[1:])
-    out = {"n": args.n, "t": args.t, "dtype": args.dtype, "info": g.info, "train_ms": train, "potrf_tflops": args.n ** 3 / 3 / (train * 1e-3) / 1e12, "test_ms": test,
+    if world > 1:
+        tt = torch.tensor([train, test], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        train, test = float(tt[0]), float(tt[1])
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    out = {"n": args.n, "t": args.t, "n_gpus": world, "dtype": args.dtype, "info": g.info, "train_ms": train, "potrf_tflops": args.n ** 3 / 3 / (train * 1e-3) / 1e12, "test_ms": test,
            "predict_tflops": args.t * (args.n ** 2 + 2 * args.n) / (test * 1e-3) / 1e12, "test_points_per_s": args.t / (test * 1e-3), "train_ms_all": train_ms, "test_ms_all": test_ms,
            "launches": ctx.kernel_launches}
     if args.check:

@@ -227,6 +227,147 @@ namespace erl_gp {
         }
     }
 
+    // ---- the same GEMM with a 3-stage cp.async pipeline ---------------------------------------------------------------
+    // ncu on the rank-512 update (profiles/r01k_dense_syrk_*): tensor pipe 73.5 % of the active cycles, the rest long-scoreboard
+    // (the operand loads of slab k+1 are issued one slab = 1 us ahead, L2 hit rate 60 %) and fixed-latency stalls.  cp.async
+    // (LDGSTS) keeps two slabs in flight, needs no staging registers and leaves one barrier per slab.  Measured slower than the
+    // register-staged kernel (see GemmUseCpAsync): kept for A/B runs only.
+    constexpr int kGemmStages = 3;
+
+    __device__ __forceinline__ void
+    CpAsync8(double *smem_dst, const double *gmem_src, const bool pred) {
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+        const int src_bytes = pred ? 8 : 0;  // 0: zero-fill, the source is not read
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+    }
+
+    __device__ __forceinline__ void
+    CpAsync16(double *smem_dst, const double *gmem_src, const bool pred) {
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+        const int src_bytes = pred ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+    }
+
+    // one (128 x BK) operand slab: same element -> thread mapping as GemmLoadTile / GemmStoreTile.  vec16: the operand allows
+    // 16-byte copies along the outer index (even leading dimension, 16-byte aligned base, even tile origin)
+    template<bool K_CONTIG>
+    __device__ __forceinline__ void
+    GemmCpAsyncTile(double *__restrict__ dst /* [BK][kLd] */, const double *__restrict__ src, const long ld, const long o0, const long o_lim, const long k0, const long k_lim, const int tid,
+                    const bool vec16) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        if (!K_CONTIG) {
+            const int o = (tid & 31) * 4;
+            const int kk = tid >> 5;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long k = k0 + kk + 8 * i;
+                if (vec16) {
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2) {
+                        const long oo = o0 + o + j;
+                        if (oo + 1 < o_lim || oo >= o_lim) {
+                            const bool ok = oo < o_lim && k < k_lim;
+                            CpAsync16(dst + (kk + 8 * i) * kLd + o + j, ok ? src + oo + k * ld : src, ok);
+                        } else {  // the pair straddles the edge
+                            CpAsync8(dst + (kk + 8 * i) * kLd + o + j, k < k_lim ? src + oo + k * ld : src, k < k_lim);
+                            CpAsync8(dst + (kk + 8 * i) * kLd + o + j + 1, src, false);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long oo = o0 + o + j;
+                        const bool ok = oo < o_lim && k < k_lim;
+                        CpAsync8(dst + (kk + 8 * i) * kLd + o + j, ok ? src + oo + k * ld : src, ok);
+                    }
+                }
+            }
+        } else {
+            const int kk = tid & 15;
+            const int o = tid >> 4;
+            const long k = k0 + kk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long oo = o0 + o + 16 * i;
+                const bool ok = oo < o_lim && k < k_lim;
+                CpAsync8(dst + kk * kLd + o + 16 * i, ok ? src + k + oo * ld : src, ok);
+            }
+        }
+    }
+
+    template<bool A_KC, bool B_KC>
+    __global__ void __launch_bounds__(kGemmThreads, 1)
+    GemmKernelDmmaAsync(const long m, const long n, const long k, const double alpha, const double *__restrict__ a, const long lda, const double *__restrict__ b, const long ldb, const double beta,
+                        double *__restrict__ c, const long ldc, const int lower_only) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        constexpr int kSlab = kGemmBK * kLd;
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        double *as = reinterpret_cast<double *>(smem_raw);  // [stages][BK][kLd]
+        double *bs = as + kGemmStages * kSlab;
+        const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
+        const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
+        if (lower_only && col0 > row0 + kGemmBM - 1) { return; }
+        if (lower_only == 2 && blockIdx.x == 0 && blockIdx.y == 0) { return; }
+        const int tid = threadIdx.x;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wm = warp & 1, wn = warp >> 1;
+        const int g = lane >> 2, kq = lane & 3;
+        double acc[8][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = acc[mi][ni][1] = 0.0; }
+        }
+        const long num_kt = (k + kGemmBK - 1) / kGemmBK;
+        const bool va = !A_KC && (lda & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0;  // row0 / col0 are multiples of 128
+        const bool vb = !B_KC && (ldb & 1) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+#pragma unroll
+        for (int st = 0; st < kGemmStages - 1; ++st) {
+            if (st < num_kt) {
+                GemmCpAsyncTile<A_KC>(as + st * kSlab, a, lda, row0, m, st * kGemmBK, k, tid, va);
+                GemmCpAsyncTile<B_KC>(bs + st * kSlab, b, ldb, col0, n, st * kGemmBK, k, tid, vb);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (long kt = 0; kt < num_kt; ++kt) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kGemmStages - 2) : "memory");  // slab kt has landed (for this thread)
+            __syncthreads();                                                              // ... for everybody; slab kt - 1 is consumed
+            const long nxt = kt + kGemmStages - 1;
+            if (nxt < num_kt) {
+                const int st = static_cast<int>(nxt % kGemmStages);
+                GemmCpAsyncTile<A_KC>(as + st * kSlab, a, lda, row0, m, nxt * kGemmBK, k, tid, va);
+                GemmCpAsyncTile<B_KC>(bs + st * kSlab, b, ldb, col0, n, nxt * kGemmBK, k, tid, vb);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            const int cur = static_cast<int>(kt % kGemmStages);
+            SlabMma(acc, as + cur * kSlab, bs + cur * kSlab, wm, wn, lane);
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long col = col0 + 32 * wn + 8 * ni + 2 * kq + e;
+                if (col >= n) { continue; }
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) {
+                    const long row = row0 + 64 * wm + 8 * mi + g;
+                    if (row >= m || (lower_only && row < col)) { continue; }
+                    double *dst = c + row + col * ldc;
+                    const double prev = beta == 0.0 ? 0.0 : beta * (*dst);
+                    *dst = alpha * acc[mi][ni][e] + prev;
+                }
+            }
+        }
+    }
+
+    // ERL_GP_DENSE_CP_ASYNC=1 selects the cp.async kernel.  Measured on the B200 at n = 16384 (Potrf, 63.9 ms with the
+    // register-staged kernel): 69.7 ms with 8-byte copies, 66.5 ms with 16-byte copies - slower, so it is off by default.
+    static bool
+    GemmUseCpAsync() {
+        static const bool on = std::getenv("ERL_GP_DENSE_CP_ASYNC") != nullptr;
+        return on;
+    }
+
     template<typename T, bool A_KC, bool B_KC>
     struct GemmSelect {
         static auto
@@ -238,8 +379,8 @@ namespace erl_gp {
     struct GemmSelect<double, A_KC, B_KC> {
         static auto
         Get() {
-            static const bool fma = std::getenv("ERL_GP_DENSE_FMA") != nullptr;  // A/B measurements of the DFMA loop
-            return fma ? GemmKernel<double, A_KC, B_KC> : GemmKernelDmma<A_KC, B_KC>;
+            static const bool fma = std::getenv("ERL_GP_DENSE_FMA") != nullptr;      // A/B measurements of the DFMA loop
+            return fma ? GemmKernel<double, A_KC, B_KC> : (GemmUseCpAsync() ? GemmKernelDmmaAsync<A_KC, B_KC> : GemmKernelDmma<A_KC, B_KC>);
         }
     };
 
@@ -248,7 +389,8 @@ namespace erl_gp {
     Gemm(Context *ctx, int op_a, int op_b, long m, long n, long k, T alpha, const T *a, long lda, const T *b, long ldb, T beta, T *c, long ldc, int lower_only) {
         if (m <= 0 || n <= 0) { return ERL_GP_STATUS_OK; }
         const dim3 grid(static_cast<unsigned>(CeilDiv(m, kGemmBM)), static_cast<unsigned>(CeilDiv(n, kGemmBN)));
-        const size_t smem = sizeof(T) * 4 * kGemmBK * (kGemmBM + kGemmPad);
+        // two stages of two operand slabs; the cp.async FP64 kernel uses kGemmStages
+        const size_t smem = sizeof(T) * ((sizeof(T) == 8 && GemmUseCpAsync()) ? 2 * kGemmStages : 4) * kGemmBK * (kGemmBM + kGemmPad);
         // op(A)(m,k): N -> a[m + k lda] (outer contiguous), T -> a[k + m lda] (k contiguous)
         // op(B)(k,n): N -> b[k + n ldb] (k contiguous),     T -> b[n + k ldb] (outer contiguous)
 #define ERL_GP_GEMM_LAUNCH(AKC, BKC)                                                                                          \

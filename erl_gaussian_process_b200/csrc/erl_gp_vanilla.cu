@@ -323,32 +323,32 @@ namespace erl_gp {
         int rc = SpgpPrepareLqm(gp);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         const long m = gp->m, d = gp->x_dim;
-        const long tile = std::min(TestTile(m, sizeof(T)), ((num_test + 127) / 128) * 128);
-        ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(tile) * d));
-        ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(m) * tile));
-        ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * tile));
-        ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(tile));
-        ERL_GP_CUDA_OK(ctx, gp->sumsq2.Reserve(tile));
-        ERL_GP_CUDA_OK(ctx, gp->mean.Reserve(tile));
-        ERL_GP_CUDA_OK(ctx, gp->variance.Reserve(tile));
-        for (long t0 = 0; t0 < num_test; t0 += tile) {
-            const long tt = std::min(tile, num_test - t0);
+        // Fused path (erl_gp_predict_dense.cu), as in VanillaTest: Ktest(Z, x*) is generated where it is consumed - once for
+        // the mean (k*^T Q_M^-1 alpha, :150-162) and inside each of the two left-looking solves of the variance
+        //   var = 1 - ||L_KM^-1 kt||^2 + ||L_QM^-1 kt||^2   (:288-292, :304-309)
+        // instead of a materialised M x tile Ktest, two GEMM-based TRSMs and a regenerated Ktest in between (same 7.5 ms per
+        // 10 000 points at M = 2048 - 79 tiles of 128 points do not fill the GPU - but no M x T buffer and 27 TFLOP/s for large T).
+        const long chunk = std::min<long>(num_test, 1L << 20);
+        ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(chunk) * d));
+        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, gp->mean.Reserve(chunk)); }
+        if (var != nullptr) {
+            ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(chunk));
+            ERL_GP_CUDA_OK(ctx, gp->sumsq2.Reserve(chunk));
+            ERL_GP_CUDA_OK(ctx, gp->variance.Reserve(chunk));
+            ERL_GP_CUDA_OK(ctx, gp->w.Reserve(PredictVarianceSlabElems<T>(ctx, m, chunk)));
+        }
+        for (long t0 = 0; t0 < num_test; t0 += chunk) {
+            const long tt = std::min(chunk, num_test - t0);
             ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test + t0 * ld_xt, sizeof(T) * ld_xt, sizeof(T) * d, tt, cudaMemcpyHostToDevice, ctx->stream));
-            rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->z.ptr, d, m, gp->xt.ptr, d, tt, gp->w.ptr, m);
-            if (rc != ERL_GP_STATUS_OK) { return rc; }
-            if (mean != nullptr) {  // mean = Kt^T Q_M^-1 alpha (:150-162)
-                rc = GemvT<T>(ctx, m, tt, gp->w.ptr, m, gp->alpha_solved.ptr, m, 1, gp->mean.ptr, tt);
+            if (mean != nullptr) {
+                rc = PredictMean<T>(ctx, gp->kernel, gp->scale, d, m, tt, gp->z.ptr, gp->xt.ptr, gp->alpha_solved.ptr, m, 1, gp->mean.ptr, tt);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
                 ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean + t0, gp->mean.ptr, sizeof(T) * tt, cudaMemcpyDeviceToHost, ctx->stream));
             }
-            if (var != nullptr) {  // var = 1 - ||L_KM^-1 kt||^2 + ||L_QM^-1 kt||^2 (:288-292, :304-309)
-                ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq.ptr, 0, sizeof(T) * tt, ctx->stream));
-                ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq2.ptr, 0, sizeof(T) * tt, ctx->stream));
-                rc = TrsmLower<T>(ctx, m, tt, gp->l_km.ptr, m, gp->linv_km.ptr, gp->w.ptr, m, gp->s_buf.ptr, gp->sumsq.ptr, false);
+            if (var != nullptr) {
+                rc = PredictVariance<T>(ctx, gp->kernel, gp->scale, d, m, tt, gp->z.ptr, gp->xt.ptr, gp->l_km.ptr, m, gp->linv_km.ptr, gp->w.ptr, gp->sumsq.ptr);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
-                rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->z.ptr, d, m, gp->xt.ptr, d, tt, gp->w.ptr, m);  // the solve consumed Kt: regenerate
-                if (rc != ERL_GP_STATUS_OK) { return rc; }
-                rc = TrsmLower<T>(ctx, m, tt, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->w.ptr, m, gp->s_buf.ptr, gp->sumsq2.ptr, false);
+                rc = PredictVariance<T>(ctx, gp->kernel, gp->scale, d, m, tt, gp->z.ptr, gp->xt.ptr, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->w.ptr, gp->sumsq2.ptr);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
                 rc = VarianceFinalize<T>(ctx, tt, gp->sumsq.ptr, gp->sumsq2.ptr, gp->variance.ptr);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }

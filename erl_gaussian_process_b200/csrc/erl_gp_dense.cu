@@ -360,6 +360,131 @@ namespace erl_gp {
         }
     }
 
+    // ---- the same GEMM with 16 warps per CTA (32 x 32 warp tiles) --------------------------------------------------------
+    // The 8-warp kernel keeps 2 warps per scheduler and its tensor pipe is 73.5 % active (ncu, rank-512 update): the rest are
+    // fixed-latency and scoreboard stalls that nothing covers.  512 threads halve the accumulators per thread (32 doubles, <= 128
+    // registers) and give every scheduler 4 warps; the operand fragments are read twice as often from shared memory (8 LDS.64
+    // per 16 DMMAs instead of 12 per 32), which the shared-memory pipe has room for.
+    constexpr int kGemmThreads512 = 512;
+
+    template<bool K_CONTIG>
+    __device__ __forceinline__ void
+    GemmLoadTile512(const double *__restrict__ src, const long ld, const long o0, const long o_lim, const long k0, const long k_lim, const int tid, double (&reg)[4]) {
+        if (!K_CONTIG) {
+            const int o = (tid & 31) * 4;
+            const long k = k0 + (tid >> 5);  // 0 .. 15
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long oo = o0 + o + j;
+                reg[j] = (oo < o_lim && k < k_lim) ? src[oo + k * ld] : 0.0;
+            }
+        } else {
+            const long k = k0 + (tid & 15);
+            const int o = tid >> 4;  // 0 .. 31
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long oo = o0 + o + 32 * i;
+                reg[i] = (oo < o_lim && k < k_lim) ? src[k + oo * ld] : 0.0;
+            }
+        }
+    }
+
+    template<bool K_CONTIG>
+    __device__ __forceinline__ void
+    GemmStoreTile512(double *__restrict__ dst /* [BK][128 + pad] */, const int tid, const double (&reg)[4]) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        if (!K_CONTIG) {
+            Store4(dst + (tid >> 5) * kLd + (tid & 31) * 4, reg);
+        } else {
+            const int kk = tid & 15;
+            const int o = tid >> 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { dst[kk * kLd + o + 32 * i] = reg[i]; }
+        }
+    }
+
+    template<bool A_KC, bool B_KC>
+    __global__ void __launch_bounds__(kGemmThreads512, 1)
+    GemmKernelDmma512(const long m, const long n, const long k, const double alpha, const double *__restrict__ a, const long lda, const double *__restrict__ b, const long ldb, const double beta,
+                      double *__restrict__ c, const long ldc, const int lower_only) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        double *as = reinterpret_cast<double *>(smem_raw);
+        double *bs = as + 2 * kGemmBK * kLd;
+        const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
+        const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
+        if (lower_only && col0 > row0 + kGemmBM - 1) { return; }
+        if (lower_only == 2 && blockIdx.x == 0 && blockIdx.y == 0) { return; }
+        const int tid = threadIdx.x;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wm = warp & 3, wn = warp >> 2;
+        const int g = lane >> 2, kq = lane & 3;
+        double acc[4][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = acc[mi][ni][1] = 0.0; }
+        }
+        double ra[4], rb[4];
+        GemmLoadTile512<A_KC>(a, lda, row0, m, 0, k, tid, ra);
+        GemmLoadTile512<B_KC>(b, ldb, col0, n, 0, k, tid, rb);
+        GemmStoreTile512<A_KC>(as, tid, ra);
+        GemmStoreTile512<B_KC>(bs, tid, rb);
+        __syncthreads();
+        const long num_kt = (k + kGemmBK - 1) / kGemmBK;
+        for (long kt = 0; kt < num_kt; ++kt) {
+            const int cur = static_cast<int>(kt & 1);
+            if (kt + 1 < num_kt) {
+                GemmLoadTile512<A_KC>(a, lda, row0, m, (kt + 1) * kGemmBK, k, tid, ra);
+                GemmLoadTile512<B_KC>(b, ldb, col0, n, (kt + 1) * kGemmBK, k, tid, rb);
+            }
+            const double *at = as + cur * kGemmBK * kLd;
+            const double *bt = bs + cur * kGemmBK * kLd;
+#pragma unroll
+            for (int k4 = 0; k4 < kGemmBK / 4; ++k4) {
+                const double *ap = at + (4 * k4 + kq) * kLd + 32 * wm + g;
+                const double *bp = bt + (4 * k4 + kq) * kLd + 32 * wn + g;
+                double av[4], bv[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) { av[mi] = ap[8 * mi]; }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) { bv[ni] = bp[8 * ni]; }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) { Dmma884(acc[mi][ni], av[mi], bv[ni]); }
+                }
+            }
+            if (kt + 1 < num_kt) {
+                GemmStoreTile512<A_KC>(as + (cur ^ 1) * kGemmBK * kLd, tid, ra);
+                GemmStoreTile512<B_KC>(bs + (cur ^ 1) * kGemmBK * kLd, tid, rb);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long col = col0 + 32 * wn + 8 * ni + 2 * kq + e;
+                if (col >= n) { continue; }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const long row = row0 + 32 * wm + 8 * mi + g;
+                    if (row >= m || (lower_only && row < col)) { continue; }
+                    double *dst = c + row + col * ldc;
+                    const double prev = beta == 0.0 ? 0.0 : beta * (*dst);
+                    *dst = alpha * acc[mi][ni][e] + prev;
+                }
+            }
+        }
+    }
+
+    static bool
+    GemmUse512() {
+        static const bool off = std::getenv("ERL_GP_DENSE_256") != nullptr;  // A/B: the 8-warp kernel (Potrf n = 16384: 63.9 ms vs 61.9 ms)
+        return !off;
+    }
+
     // ERL_GP_DENSE_CP_ASYNC=1 selects the cp.async kernel.  Measured on the B200 at n = 16384 (Potrf, 63.9 ms with the
     // register-staged kernel): 69.7 ms with 8-byte copies, 66.5 ms with 16-byte copies - slower, so it is off by default.
     static bool
@@ -380,7 +505,7 @@ namespace erl_gp {
         static auto
         Get() {
             static const bool fma = std::getenv("ERL_GP_DENSE_FMA") != nullptr;      // A/B measurements of the DFMA loop
-            return fma ? GemmKernel<double, A_KC, B_KC> : (GemmUseCpAsync() ? GemmKernelDmmaAsync<A_KC, B_KC> : GemmKernelDmma<A_KC, B_KC>);
+            return fma ? GemmKernel<double, A_KC, B_KC> : (GemmUseCpAsync() ? GemmKernelDmmaAsync<A_KC, B_KC> : (GemmUse512() ? GemmKernelDmma512<A_KC, B_KC> : GemmKernelDmma<A_KC, B_KC>));
         }
     };
 
@@ -397,7 +522,7 @@ namespace erl_gp {
     {                                                                                                                         \
         auto kern = GemmSelect<T, AKC, BKC>::Get();                                                                               \
         ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-        kern<<<grid, kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only);    \
+        kern<<<grid, (sizeof(T) == 8 && GemmUse512() && !GemmUseCpAsync() && std::getenv("ERL_GP_DENSE_FMA") == nullptr) ? kGemmThreads512 : kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only);    \
     }
         if (op_a == kOpN && op_b == kOpT) {
             ERL_GP_GEMM_LAUNCH(false, false)

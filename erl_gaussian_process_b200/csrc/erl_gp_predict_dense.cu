@@ -440,6 +440,214 @@ namespace erl_gp {
             }
         }
 
+        // ---- 16-warp variant of the DMMA kernel: 32 x 32 warp tiles, 4 warps per scheduler instead of 2 (the 8-warp kernel keeps the
+        // tensor pipe 70.6 % active; the same change took the GEMM of the factorisation from 73.5 % upwards) -----------------------
+        constexpr int kThreads16 = 512;
+
+        template<typename T>
+        __device__ __forceinline__ void
+        LoadA16(const T *__restrict__ a, const long lda, const long row0, const long row_lim, const long k0, const long k_lim, const bool vec, const int tid, T (&reg)[4]) {
+            const long row = row0 + (tid & 31) * 4;
+            const long k = k0 + (tid >> 5);  // 0 .. 15
+            T v4[4] = {T(0), T(0), T(0), T(0)};
+            if (k < k_lim) {
+                if (vec && row + 3 < row_lim) {
+                    LdVec4<T>(a + row + k * lda, v4);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (row + j < row_lim) { v4[j] = a[row + j + k * lda]; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { reg[j] = v4[j]; }
+        }
+
+        template<typename T>
+        __device__ __forceinline__ void
+        StoreA16(T *__restrict__ dst /* [16][kLd] */, const int tid, const T (&reg)[4]) {
+            StVec4<T>(dst + (tid >> 5) * kLd + (tid & 31) * 4, reg);
+        }
+
+        template<typename T>
+        __device__ __forceinline__ void
+        LoadB16(const T *__restrict__ v, const long ldv, const long k0, const int tid, T (&reg)[4]) {
+            LdVec4<T>(v + k0 + (tid & 3) * 4 + static_cast<long>(tid >> 2) * ldv, reg);  // column tid / 4 (0 .. 127), 4 consecutive k
+        }
+
+        template<typename T>
+        __device__ __forceinline__ void
+        StoreB16(T *__restrict__ dst /* [16][kLd] */, const int tid, const T (&reg)[4]) {
+            const int k4 = (tid & 3) * 4;
+            const int c = tid >> 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { dst[(k4 + j) * kLd + c] = reg[j]; }
+        }
+
+        __device__ __forceinline__ void
+        SlabMma16(double (&acc)[4][4][2], const double *__restrict__ at, const double *__restrict__ bt, const int wm, const int wn, const int lane) {
+            const int kq = lane & 3;
+            const int g = lane >> 2;
+#pragma unroll
+            for (int k4 = 0; k4 < kBk / 4; ++k4) {
+                const double *ap = at + (4 * k4 + kq) * kLd + 32 * wm + g;
+                const double *bp = bt + (4 * k4 + kq) * kLd + 32 * wn + g;
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) { a[mi] = ap[8 * mi]; }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) { b[ni] = bp[8 * ni]; }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) { Dmma884(acc[mi][ni], a[mi], b[ni]); }
+                }
+            }
+        }
+
+        template<int XDIM>
+        __global__ void __launch_bounds__(kThreads16, 1)
+        PredictVarianceKernelDmma16(
+            const Covariance<double> cov,
+            const long n,
+            const long t,
+            const double *__restrict__ x_train,
+            const double *__restrict__ x_test,
+            const double *__restrict__ l,
+            const long ldl,
+            const double *__restrict__ linv,
+            double *__restrict__ v_slabs,
+            const long n_pad,
+            double *__restrict__ sumsq) {
+            using T = double;
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            T *as = reinterpret_cast<T *>(smem_raw);  // [2][16][kLd]
+            T *bs = as + 2 * kBk * kLd;               // [2][16][kLd]
+            T *wt = bs + 2 * kBk * kLd;               // [128][kLd]  W tile, row (k) major
+            T *xqs = wt + kTile * kLd;                // [128][XDIM]
+            T *ssq_s = xqs + kTile * 3;               // [128] column sums of the tile
+            const int tid = threadIdx.x;
+            const int lane = tid & 31;
+            const int warp = tid >> 5;
+            const int wm = warp & 3, wn = warp >> 2;  // 16 warps: rows 32 wm .. + 31, columns 32 wn .. + 31
+            const int g = lane >> 2, kq = lane & 3;
+            T *vs = v_slabs + static_cast<long>(blockIdx.x) * n_pad * kTile;
+            const long num_panels = (n + kTile - 1) / kTile;
+            const bool vec_l = (ldl & 3) == 0 && (reinterpret_cast<uintptr_t>(l) & 31) == 0;
+            const long num_ct = (t + kTile - 1) / kTile;
+
+            for (long ct = blockIdx.x; ct < num_ct; ct += gridDim.x) {
+                const long col0 = ct * kTile;
+                __syncthreads();
+                for (int e = tid; e < kTile * XDIM; e += kThreads16) { xqs[e] = col0 * XDIM + e < t * XDIM ? x_test[col0 * XDIM + e] : T(0); }
+                if (tid < kTile) { ssq_s[tid] = T(0); }
+                __syncthreads();
+                T ssq[4][2];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) { ssq[ni][0] = ssq[ni][1] = T(0); }
+
+                for (long p = 0; p < num_panels; ++p) {
+                    const long k0 = p * kTile;
+                    T acc[4][4][2];
+                    // ---- acc = -Ktest[panel rows, my points] ----
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const long row = k0 + 32 * wm + 8 * mi + g;
+                        T xi[XDIM];
+#pragma unroll
+                        for (int d = 0; d < XDIM; ++d) { xi[d] = row < n ? x_train[row * XDIM + d] : T(0); }
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = 32 * wn + 8 * ni + 2 * kq + e;
+                                acc[mi][ni][e] = (row < n && col0 + c < t) ? -cov(SquaredDistance<T, XDIM>(xi, xqs + c * XDIM)) : T(0);
+                            }
+                        }
+                    }
+                    // ---- acc += L[panel rows, 0:k0] * V[0:k0, my points] ----
+                    if (k0 > 0) {
+                        T ra[4], rb[4];
+                        LoadA16<T>(l, ldl, k0, n, 0, k0, vec_l, tid, ra);
+                        LoadB16<T>(vs, n_pad, 0, tid, rb);
+                        StoreA16<T>(as, tid, ra);
+                        StoreB16<T>(bs, tid, rb);
+                        __syncthreads();
+                        const long num_kt = k0 / kBk;
+                        for (long kt = 0; kt < num_kt; ++kt) {
+                            const int cur = static_cast<int>(kt & 1);
+                            if (kt + 1 < num_kt) {
+                                LoadA16<T>(l, ldl, k0, n, (kt + 1) * kBk, k0, vec_l, tid, ra);
+                                LoadB16<T>(vs, n_pad, (kt + 1) * kBk, tid, rb);
+                            }
+                            SlabMma16(acc, as + cur * kBk * kLd, bs + cur * kBk * kLd, wm, wn, lane);
+                            if (kt + 1 < num_kt) {
+                                StoreA16<T>(as + (cur ^ 1) * kBk * kLd, tid, ra);
+                                StoreB16<T>(bs + (cur ^ 1) * kBk * kLd, tid, rb);
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    // ---- W tile -> shared, negated back ----
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) {
+                            *reinterpret_cast<double2 *>(wt + (32 * wm + 8 * mi + g) * kLd + 32 * wn + 8 * ni + 2 * kq) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+                            acc[mi][ni][0] = acc[mi][ni][1] = T(0);
+                        }
+                    }
+                    // ---- V_p = Linv_p * W ----
+                    {
+                        const T *lip = linv + p * kTile * kTile;
+                        T ra[4];
+                        LoadA16<T>(lip, kTile, 0, kTile, 0, kTile, true, tid, ra);
+                        StoreA16<T>(as, tid, ra);
+                        __syncthreads();  // also publishes the W tile
+                        for (int kt = 0; kt < kTile / kBk; ++kt) {
+                            const int cur = kt & 1;
+                            if (kt + 1 < kTile / kBk) { LoadA16<T>(lip, kTile, 0, kTile, (kt + 1) * kBk, kTile, true, tid, ra); }
+                            SlabMma16(acc, as + cur * kBk * kLd, wt + kt * kBk * kLd, wm, wn, lane);
+                            if (kt + 1 < kTile / kBk) { StoreA16<T>(as + (cur ^ 1) * kBk * kLd, tid, ra); }
+                            __syncthreads();
+                        }
+                    }
+                    // ---- column sums of squares; V_p -> my slab ----
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = 32 * wn + 8 * ni + 2 * kq + e;
+                            T s = T(0);
+#pragma unroll
+                            for (int mi = 0; mi < 4; ++mi) { s += acc[mi][ni][e] * acc[mi][ni][e]; }
+                            ssq[ni][e] += s;
+                            if (p + 1 < num_panels) {
+#pragma unroll
+                                for (int mi = 0; mi < 4; ++mi) { vs[k0 + 32 * wm + 8 * mi + g + static_cast<long>(c) * n_pad] = acc[mi][ni][e]; }
+                            }
+                        }
+                    }
+                    __syncthreads();  // the slab rows written above are read by this CTA in the next panel
+                }
+                // ---- reduce the column sums over the 8 row groups of the warp (lane / 4) and the two row-halves (wm) ----
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        T s = ssq[ni][e];
+                        s += __shfl_xor_sync(0xffffffffu, s, 4);
+                        s += __shfl_xor_sync(0xffffffffu, s, 8);
+                        s += __shfl_xor_sync(0xffffffffu, s, 16);
+                        if (g == 0) { atomicAdd(ssq_s + 32 * wn + 8 * ni + 2 * kq + e, s); }
+                    }
+                }
+                __syncthreads();
+                if (tid < kTile && col0 + tid < t) { sumsq[col0 + tid] = ssq_s[tid]; }
+            }
+        }
+
         // mean[j + c * ld_out] = sum_i k(x_i, x*_j) alpha[i + c * ld_a]; one thread per test point and split of the
         // training set (blockIdx.y), partial sums combined with atomics only when the set is split
         template<typename T, int XDIM, int YMAX>
@@ -483,6 +691,13 @@ namespace erl_gp {
             }
         }
 
+        // ERL_GP_DENSE_256=1: the 8-warp kernels (A/B measurements)
+        static bool
+        PredictUse16Warps() {
+            static const bool on = std::getenv("ERL_GP_DENSE_256") == nullptr && std::getenv("ERL_GP_DENSE_FMA") == nullptr;
+            return on;
+        }
+
         // float: FFMA tile kernel; double: DMMA tile kernel (ERL_GP_DENSE_FMA=1 keeps the DFMA loop for A/B measurements)
         template<typename T, int XDIM>
         struct PredictVarianceSelect {
@@ -496,7 +711,7 @@ namespace erl_gp {
             static auto
             Get() {
                 static const bool fma = std::getenv("ERL_GP_DENSE_FMA") != nullptr;
-                return fma ? PredictVarianceKernel<double, XDIM> : PredictVarianceKernelDmma<XDIM>;
+                return fma ? PredictVarianceKernel<double, XDIM> : (PredictUse16Warps() ? PredictVarianceKernelDmma16<XDIM> : PredictVarianceKernelDmma<XDIM>);
             }
         };
 
@@ -524,7 +739,7 @@ namespace erl_gp {
     {                                                                                                                            \
         auto kern = PredictVarianceSelect<T, XD>::Get();                                                                         \
         ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));    \
-        kern<<<ctas, kThreads, smem, ctx->stream>>>(cov, n, t, x_train, x_test, l, ldl, linv, v_slabs, n_pad, sumsq);            \
+        kern<<<ctas, (sizeof(T) == 8 && PredictUse16Warps()) ? kThreads16 : kThreads, smem, ctx->stream>>>(cov, n, t, x_train, x_test, l, ldl, linv, v_slabs, n_pad, sumsq); \
     }
         switch (x_dim) {
             case 1: ERL_GP_LAUNCH_PV(1) break;

@@ -506,7 +506,7 @@ namespace erl_gp {
     }
 
     template<typename T, int XDIM, int MROWS, int MODE>
-    __global__ void __launch_bounds__(kBatchThreads, (sizeof(T) == 4 && MROWS <= 8) ? 2 : 1)
+    __global__ void __launch_bounds__(kBatchThreads, (MROWS <= 8) ? 2 : 1)
     BatchedGpKernel(const BatchParams<T> p) {
         using Smem = BatchSmem<T, XDIM, MROWS>;
         extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -3,16 +3,17 @@
 // Replaces Eigen's `llt()` and `triangularView::solve` as used at src/vanilla_gp.cpp:499-502,
 // :139-149 and src/sparse_pseudo_input_gp.cpp:341, 100-106, 304-309, 768-774, 840.
 //
-// Blocked right-looking Cholesky with a 128-wide panel:
+// Blocked right-looking Cholesky, 128-column panels inside 512-column block columns (Potrf):
 //   1. DiagFactorKernel: one CTA factors the 128x128 diagonal block entirely in shared memory (the same
-//      block-packed 16x16 machinery as the batched small-GP kernel) and also produces its INVERSE, so that
-//   2. the panel solve  L21 = A21 * L11^-T  and every later triangular solve (alpha, predictive variance)
+//      block-packed 16x16 machinery as the generic batched small-GP kernel) and also produces its INVERSE, so that
+//   2. the panel solve  L21 = A21 * L11^-T  (in place) and every later triangular solve (predictive variance, SPGP)
 //      are plain GEMMs against the kept 128x128 inverses, and
-//   3. the trailing update A22 -= L21 L21^T is a lower-triangle-only GEMM (SYRK).
-// The GEMM is a register-tiled (8x8 per thread), double-buffered FMA kernel: on B200 the FP64 tensor
-// path (DMMA m8n8k4, 37.0 TFLOP/s measured) has the same peak as the FP64 FMA pipe (36.2 TFLOP/s
-// measured, tools/mma_rate.cu), and the FP32 path must stay true FP32 (3xTF32 mma.sync measures only
-// 92 TFLOP/s-equivalent vs 71 TFLOP/s FFMA, and plain TF32 breaks the 1e-4 parity).
+//   3. the trailing updates are lower-triangle-only GEMMs (rank 128 inside the block column, rank 512 to its right);
+//   4. the latency-bound panel chain is looked ahead on two high-priority side streams (block column and next diagonal tile).
+// FP64 GEMMs run on the tensor path (mma.sync.m8n8k4.f64, SASS DMMA; 16 warps per CTA, 32 x 32 warp tiles): the DFMA loop
+// (GemmKernel<double>, ERL_GP_DENSE_FMA=1) has the same peak (36.2 vs 37.0 TFLOP/s measured, tools/mma_rate.cu) but is
+// register-file bound at 52 % of it.  FP32 GEMMs are true-FP32 FFMA tiles (GemmKernel<float>).
+// alpha = L^-T L^-1 y for a few right-hand sides is one wavefront kernel per direction (TrsvWavefrontKernel).
 #include "erl_gp_dense.cuh"
 #include "erl_gp_dense_mma.cuh"
 

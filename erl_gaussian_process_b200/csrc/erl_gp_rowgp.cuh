@@ -1,4 +1,4 @@
-// FP32 fast path of the one-CTA-per-GP batched train / predict kernel for n <= 128 ("row GP" kernel).
+// FP32 one-CTA-per-GP batched train / predict kernel for n <= 256 ("row GP" kernel), sm_100a.
 //
 // Same contract as BatchedGpKernel (erl_gp_batched.cuh) and the same reference code replaced:
 //   VanillaGaussianProcess::UpdateKtrain + Solve        src/vanilla_gp.cpp:476-505
@@ -6,28 +6,24 @@
 //   TestResult::GetMean / GetVariance                   src/vanilla_gp.cpp:61-150
 // driven per partition by src/lidar_gp_2d.cpp:366-392 / src/range_sensor_gp_3d.cpp:334-360.
 //
-// Design, from the measurements in tools/fma_lds_rate.cu (B200): a plain FFMA with two fresh register
-// operands sustains only ~37 TFLOP/s, FFMA2 (fma.rn.f32x2, scalar-broadcast operand form) ~55 TFLOP/s when every
-// LDS.128 feeds >= 8 FMAs; a warp-uniform LDS.128 costs 2 shared-memory cycles per SM.  Hence:
-//   * 128 threads per GP, ~42 KB of shared memory, 3 CTAs per SM: the serial parts of one GP (pivot-block
-//     factorisation, alpha back-substitution) overlap with the FMA-bound parts of the other two;
-//   * the Gram matrix is never stored: every 16-column panel of K is generated in registers right
-//     before it is eliminated (fused distance + covariance + noise diagonal);
-//   * left-looking blocked Cholesky, 16-column panels.  A thread PAIR accumulates the update of two
-//     rows (each thread 8 of the 16 panel columns, FFMA2 against warp-uniform broadcasts of the 16
-//     pivot rows), the pair then swaps halves so that each thread owns one row; the 16 x 16 pivot block
-//     is factorised by one warp with shuffles (rows of the same warp follow along), the other rows
-//     are eliminated in-thread against the published pivot block.  z = L^-1 y rides along as a 17th
-//     column, alpha = L^-T z is a blocked back-substitution with thread = column;
-//   * L lives in shared memory column-major, packed by 16-column blocks (column block b keeps rows
-//     >= 16 b) with a 4-float pad per column, so that "one row per lane", "one column per lane" and
-//     warp-uniform float4 accesses are all bank-conflict free;
-//   * predict: a thread pair owns 2 queries; each thread keeps 64 of the 128 rows of both V = L^-1 k*
-//     columns in registers (rows 8m + 4h .. +3), Ktest entries are generated in registers, the
-//     right-looking substitution is fully unrolled (column index static => register-resident V, no
-//     barrier at all), v_j is exchanged inside the pair with one shuffle per query and column, every
-//     LDS.128 of L feeds 4 FFMA2.  mean = k*^T alpha and ||v||^2 are accumulated on the way.
-// HBM traffic per GP is the algorithmic minimum (x, y, var in; L, alpha out; queries in; mean/var out).
+// Design (measured history in DESIGN.md 4.1):
+//   * 128 threads per GP; n <= 128: 55 KB of shared memory and 128 registers, 4 CTAs per SM, so that the serial parts of one GP
+//     (pivot blocks, back-substitution) overlap with the tensor-pipe parts of the others;
+//   * the Gram matrix is never stored: the entries of a 16-column panel are generated in the MMA accumulator layout right
+//     when the panel is updated (fused distance + covariance + noise diagonal, two entries per packed f32x2 operation);
+//   * train (FactorizeMma): left-looking blocked Cholesky, 16-column panels, 16-row tiles, every product a 3xTF32
+//     mma.sync.m16n8k8; the 16 x 16 pivot block is factorised by one warp with shuffles while its lanes 16 .. 31 eliminate
+//     the unit vectors (= the inverse of the block, for free); the tiles below become L = P Dinv^T straight from the
+//     accumulators; z = L^-1 y rides along, alpha = L^-T z is a blocked back-substitution through the block inverses;
+//   * L lives in shared memory column-major, packed by 16-column blocks (column block b keeps rows >= 16 b) with a 4-float
+//     pad per column, so that "one row per lane", "one column per lane", warp-uniform float4 and both MMA fragment patterns
+//     (with the k-slot permutation slot t <-> column 2t, slot t + 4 <-> column 2t + 1) are bank-conflict free;
+//   * predict (PredictTileMma): transposed substitution V^T = Kt^T L^-T, one warp per 16 queries, all 16 x n accumulators
+//     resident, finished blocks reused as A operands without data movement, no barrier; mean = k*^T alpha and ||v||^2 on the way.
+// The FFMA2 versions of both halves (Factorize, PredictTile; n <= 128) are kept for A/B builds
+// (-DERL_GP_ROWGP_FFMA_TRAIN / _PREDICT); they were designed from the measurements in tools/fma_lds_rate.cu (a plain FFMA with
+// two fresh register operands sustains ~37 TFLOP/s, FFMA2 with a scalar-broadcast operand ~55 when every LDS.128 feeds >= 8 FMAs).
+// HBM traffic per GP is the algorithmic minimum (x, y, var in; L, alpha out; queries in; mean / var out).
 #pragma once
 
 #include "erl_gp_internal.cuh"

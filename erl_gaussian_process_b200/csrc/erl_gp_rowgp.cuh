@@ -45,7 +45,13 @@ namespace erl_gp {
             }
         }
 
-        constexpr int kThreads = 128;
+        constexpr int kThreads = 128;  // n <= 192 (and the FFMA2 versions)
+
+        // threads per CTA of an instance: the n <= 256 instances need 171 KB of shared memory (one CTA per SM), so they run 8 warps
+        template<int NBLK>
+        struct ThreadsFor {
+            static constexpr int value = NBLK > 12 ? 256 : 128;
+        };
         constexpr unsigned kFull = 0xffffffffu;
         constexpr int kDefaultStaggerCycles = 0;  // per CTA slot, see RowGpKernel
         // A/B switches (measured on the B200, C4, fused / train-only ms): z-dot hoisted before the update 5.80 / 2.76, in phase B
@@ -484,7 +490,8 @@ namespace erl_gp {
         __device__ __forceinline__ int
         FactorizeMma(const CovCoef cov, float *__restrict__ smem, const int n, const int nblk) {
             using Lay = Layout<NBLK>;
-            constexpr int kSlots = (NBLK + 3) / 4;  // tiles per warp and panel
+            constexpr int kWarps = ThreadsFor<NBLK>::value / 32;
+            constexpr int kSlots = (NBLK + kWarps - 1) / kWarps;  // tiles per warp and panel
             float *lp = smem + Lay::kL;
             const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
             float *rs = smem + Lay::kRs;
@@ -558,7 +565,7 @@ namespace erl_gp {
                             for (int nt = 0; nt < 2; ++nt) { Tf32LoPair(b[nt][0], b[nt][1], bl[nt][0], bl[nt][1]); }
 #pragma unroll
                             for (int sl = 0; sl < kSlots; ++sl) {
-                                const int ti = warp + 4 * sl;
+                                const int ti = warp + kWarps * sl;
                                 if (ti < mt) {
                                     const float *arow = brow + 16 * ti + 8 * kt * stride;
                                     // slots (row g, k t), (row g + 8, k t), (row g, k t + 4), (row g + 8, k t + 4)
@@ -590,7 +597,7 @@ namespace erl_gp {
                     const bool ragged = c0 + 16 > n;  // padding columns in this panel (warp-uniform)
 #pragma unroll
                     for (int sl = 0; sl < kSlots; ++sl) {
-                        const int ti = warp + 4 * sl;
+                        const int ti = warp + kWarps * sl;
                         if (ti < mt) {
 #pragma unroll
                             for (int hr = 0; hr < 2; ++hr) {
@@ -664,7 +671,7 @@ namespace erl_gp {
                     const float *dv = dinv + kb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;
 #pragma unroll
                     for (int sl = 0; sl < kSlots; ++sl) {
-                        const int ti = warp + 4 * sl;
+                        const int ti = warp + kWarps * sl;
                         if (ti > 0 && ti < mt) {
                             float v[2][4];
                             MulDinvT<Lay::kDinvLd>(acc[sl][0], acc[sl][1], dv, v);
@@ -698,26 +705,27 @@ namespace erl_gp {
         __device__ __forceinline__ void
         BackSolve(float *__restrict__ smem, const int nblk) {
             using Lay = Layout<NBLK>;
+            constexpr int kThr = ThreadsFor<NBLK>::value;
             const float *lp = smem + Lay::kL;
             const float *rs = smem + Lay::kRs;
             float *al = smem + Lay::kAl;
             const int tid = threadIdx.x;
             const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction: role branches need no reconvergence code
             const int lane = tid & 31;
-            constexpr int kColSlots = (Lay::kNp + kThreads - 1) / kThreads;  // columns per thread: column = tid + kThreads * slot
+            constexpr int kColSlots = (Lay::kNp + kThr - 1) / kThr;  // columns per thread: column = tid + kThr * slot
             float s[kColSlots];
 #pragma unroll
             for (int sl = 0; sl < kColSlots; ++sl) { s[sl] = 0.f; }
             for (int kb = nblk - 1; kb >= 0; --kb) {
                 const int c0 = 16 * kb;
-                if (warp == ((c0 & (kThreads - 1)) >> 5)) {
+                if (warp == ((c0 & (kThr - 1)) >> 5)) {
                     const int lb = c0 & 31;
                     const bool mine = lane >= lb && lane < lb + 16;
                     const int jj = mine ? lane - lb : 0;
                     float sj = s[0];
 #pragma unroll
                     for (int sl = 1; sl < kColSlots; ++sl) {
-                        if (c0 >= kThreads * sl) { sj = s[sl]; }
+                        if (c0 >= kThr * sl) { sj = s[sl]; }
                     }
                     float amine;
                     if constexpr (USE_DINV) {
@@ -761,7 +769,7 @@ namespace erl_gp {
                 __syncthreads();
 #pragma unroll
                 for (int sl = 0; sl < kColSlots; ++sl) {
-                    const int col = tid + kThreads * sl;
+                    const int col = tid + kThr * sl;
                     if (col < c0) {
                         const int cb = col >> 4;
                         const float *colp = lp + Lay::Base(cb) + (col & 15) * Lay::Stride(cb) + (c0 - 16 * cb);
@@ -987,7 +995,7 @@ namespace erl_gp {
             const int warp = threadIdx.x >> 5;
             const int lane = threadIdx.x & 31;
             if (lane >= 16) { return; }
-            for (int kb = warp; kb < nblk; kb += kThreads / 32) {
+            for (int kb = warp; kb < nblk; kb += ThreadsFor<NBLK>::value / 32) {
                 const float *blk = lp + Lay::Base(kb);
                 const int stride = Lay::Stride(kb);
                 float sres[16], x[16];
@@ -1168,9 +1176,11 @@ namespace erl_gp {
 #endif
 
         template<int XDIM, int NBLK, int MODE>
-        __global__ void __launch_bounds__(kThreads, NBLK <= 8 ? 4 : (NBLK <= 12 ? 2 : 1))
+        __global__ void __launch_bounds__(ThreadsFor<NBLK>::value, NBLK <= 8 ? 4 : (NBLK <= 12 ? 2 : 1))
         RowGpKernel(const BatchParams<float> p) {
             using Lay = Layout<NBLK>;
+            constexpr int kThr = ThreadsFor<NBLK>::value;  // threads of this instance
+            constexpr int kQTile = kThr / 2;                 // queries per predict pass: 16 per warp
             extern __shared__ __align__(16) unsigned char smem_raw[];
             float *smem = reinterpret_cast<float *>(smem_raw);
             float *lp = smem + Lay::kL;
@@ -1202,7 +1212,7 @@ namespace erl_gp {
                 if (n <= p.min_train || n <= 0) {  // the reference's `cnt > min_num_samples_per_group` / `cnt > 0` gate
                     if (tid == 0) { p.info[g] = -1; }
                     if ((MODE & kBatchPredict) && p.valid != nullptr) {
-                        for (long q = q0 + tid; q < q1; q += kThreads) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
+                        for (long q = q0 + tid; q < q1; q += kThr) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
                     }
                     return;
                 }
@@ -1215,7 +1225,7 @@ namespace erl_gp {
 
             // ---- stage the training inputs (everything below works on the first 16 * nblk rows / columns only) ----
             const float *gx = p.x + static_cast<long>(g) * p.max_n * XDIM;
-            for (int e = tid; e < Lay::kNp; e += kThreads) {
+            for (int e = tid; e < Lay::kNp; e += kThr) {
                 float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (e < n) {
                     pt.x = gx[e * XDIM];
@@ -1234,7 +1244,7 @@ namespace erl_gp {
             if constexpr ((MODE & kBatchTrain) != 0) {
                 const float *gy = p.y + static_cast<long>(g) * p.max_n;
                 const float *gv = p.var + static_cast<long>(g) * p.max_n;
-                for (int e = tid; e < Lay::kNp; e += kThreads) {
+                for (int e = tid; e < Lay::kNp; e += kThr) {
                     al[e] = e < n ? gy[e] : 0.f;
                     sv[e] = e < n ? gv[e] : 0.f;
                 }
@@ -1252,7 +1262,7 @@ namespace erl_gp {
                 if (failed != 0) {
                     if (tid == 0) { p.info[g] = failed; }
                     if ((MODE & kBatchPredict) && p.valid != nullptr) {
-                        for (long q = q0 + tid; q < q1; q += kThreads) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
+                        for (long q = q0 + tid; q < q1; q += kThr) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
                     }
                     return;
                 }
@@ -1265,18 +1275,18 @@ namespace erl_gp {
                             // fast path (no ragged float4): one LDS.128 + one STG.128 per lane and column, nothing else
                             for (int cb = 0; cb < nblk; ++cb) {
                                 const float *blk = lp + Lay::Base(cb) - 16 * cb + warp * Lay::Stride(cb);
-                                const int stride4 = (kThreads / 32) * Lay::Stride(cb);
+                                const int stride4 = (kThr / 32) * Lay::Stride(cb);
                                 float *gcol = gl + static_cast<long>(16 * cb + warp) * p.max_n;
 #pragma unroll
-                                for (int k = 0; k < 16 / (kThreads / 32); ++k) {
-                                    if (16 * cb + warp + (kThreads / 32) * k < n) {
+                                for (int k = 0; k < 16 / (kThr / 32); ++k) {
+                                    if (16 * cb + warp + (kThr / 32) * k < n) {
 #pragma unroll
                                         for (int ch = 0; ch < kRowChunks; ++ch) {
                                             const int r4 = 4 * lane + 128 * ch;
                                             if (r4 < n) {
                                                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                                                 if (r4 >= 16 * cb) { v = *reinterpret_cast<const float4 *>(blk + k * stride4 + r4); }
-                                                *reinterpret_cast<float4 *>(gcol + static_cast<long>((kThreads / 32) * k) * p.max_n + r4) = v;
+                                                *reinterpret_cast<float4 *>(gcol + static_cast<long>((kThr / 32) * k) * p.max_n + r4) = v;
                                             }
                                         }
                                     }
@@ -1287,8 +1297,8 @@ namespace erl_gp {
                             const float *blk = lp + Lay::Base(cb) - 16 * cb;
                             const int stride = Lay::Stride(cb);
 #pragma unroll
-                            for (int k = 0; k < 16 / (kThreads / 32); ++k) {
-                                const int c = 16 * cb + warp + (kThreads / 32) * k;
+                            for (int k = 0; k < 16 / (kThr / 32); ++k) {
+                                const int c = 16 * cb + warp + (kThr / 32) * k;
                                 if (c < n) {
                                     float *gcol = gl + static_cast<long>(c) * p.max_n;
 #pragma unroll
@@ -1310,7 +1320,7 @@ namespace erl_gp {
                             }
                         }
                     } else {
-                        for (int c = warp; c < n; c += kThreads / 32) {
+                        for (int c = warp; c < n; c += kThr / 32) {
                             const int cb = c >> 4;
                             for (int r = lane; r < n; r += 32) {
                                 gl[r + static_cast<long>(c) * p.max_n] = r >= 16 * cb ? lp[Lay::Base(cb) + (c & 15) * Lay::Stride(cb) + (r - 16 * cb)] : 0.f;
@@ -1321,7 +1331,7 @@ namespace erl_gp {
                 BackSolve<NBLK, (kBackSolveDinv && (kMmaTrain || NBLK > 8))>(smem, nblk);
                 __syncthreads();
                 float *ga = p.alpha + static_cast<long>(g) * p.max_n;
-                for (int e = tid; e < n; e += kThreads) {
+                for (int e = tid; e < n; e += kThr) {
                     const float a = al[e];
                     ga[e] = a;
                     smem[Lay::kPts + 4 * e + 3] = a;
@@ -1336,7 +1346,7 @@ namespace erl_gp {
                 const bool vec_ok = (p.max_n & 3) == 0;
                 constexpr int kBatch = 8;  // columns in flight per warp: the loads of a batch are all issued before the first store
                 constexpr int kRowChunks = (Lay::kNp + 127) / 128;
-                for (int cc0 = warp * kBatch; cc0 < npr * kRowChunks; cc0 += (kThreads / 32) * kBatch) {
+                for (int cc0 = warp * kBatch; cc0 < npr * kRowChunks; cc0 += (kThr / 32) * kBatch) {
                     const int c0 = kRowChunks == 1 ? cc0 : cc0 % npr;             // npr is a multiple of 16, kBatch divides 16: a batch never straddles the wrap
                     const int rchunk = kRowChunks == 1 ? 0 : 128 * (cc0 / npr);  // rows [16 cb + rchunk, + 128) of the column
                     float val[kBatch][4];
@@ -1380,8 +1390,8 @@ namespace erl_gp {
 
             if constexpr ((MODE & kBatchPredict) != 0) {
                 __syncthreads();
-                for (long qb = q0 + static_cast<long>(blockIdx.y) * kTileQ; qb < q1; qb += static_cast<long>(gridDim.y) * kTileQ) {
-                    const int nq = static_cast<int>(q1 - qb < kTileQ ? q1 - qb : kTileQ);
+                for (long qb = q0 + static_cast<long>(blockIdx.y) * kQTile; qb < q1; qb += static_cast<long>(gridDim.y) * kQTile) {
+                    const int nq = static_cast<int>(q1 - qb < kQTile ? q1 - qb : kQTile);
                     if constexpr (kMmaPredict || NBLK > 8) {
                         if (NBLK <= 8 && nblk == NBLK) {  // (the larger instances keep one variant: build time)
                             PredictTileMma<XDIM, (NBLK <= 8 ? NBLK : 2), (NBLK <= 8)>(p, cov, smem, n, nblk, qb, nq);
@@ -1411,7 +1421,7 @@ namespace erl_gp {
                 launch_params.stagger_cycles = env != nullptr ? std::atoi(env) : kDefaultStaggerCycles;
                 launch_params.sm_count = ctx->sm_count;
             }
-            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(launch_params);
+            kernel<<<grid, ThreadsFor<NBLK>::value, Lay::kBytes, ctx->stream>>>(launch_params);
             ctx->launches += 1;
             ERL_GP_CUDA_OK(ctx, cudaGetLastError());
             return ERL_GP_STATUS_OK;

@@ -144,3 +144,21 @@ def test_batch_device_path_train_then_predict(gp, oracle, dtype, max_n, x_dim, k
     tol = TOL[np.dtype(dtype)]
     assert err_mean(mean[perm], ref["mean"]) < tol
     assert err_var(varo[perm], ref["var"]) < tol
+
+
+@pytest.mark.parametrize("max_n", [128, 192])
+def test_batch_is_deterministic(gp, max_n):
+    """Warp-level hand-offs inside the row-GP kernel (pivot tile through shared memory, Dinv from lanes 16-31): every output
+    must be bit-identical from run to run."""
+    rng = np.random.default_rng(17)
+    batch = make_batch(rng, 300, max_n, 3, np.float32, n_lo=1, n_hi=max_n, q_lo=0, q_hi=150)
+    b = gp.BatchGp(300, max_n, 3, "matern32", 0.3, np.float32)
+    ref = None
+    for _ in range(3):
+        out = b.train_predict(*batch)
+        cur = {k: np.array(out[k], copy=True) for k in ("mean", "var", "valid", "info", "alpha")}
+        if ref is None:
+            ref = cur
+        else:
+            for k in ref:
+                assert np.array_equal(ref[k], cur[k], equal_nan=True), k

@@ -159,3 +159,22 @@ def test_spgp_2d_incremental(gp, oracle, dtype):
     assert np.abs(q - q_ref).max() / np.abs(q_ref).max() < rel
     assert np.abs(a - a_ref).max() / np.abs(a_ref).max() < rel
     assert np.abs(lk - lk_ref).max() / np.abs(lk_ref).max() < (1e-3 if dtype == np.float32 else 1e-10)
+
+
+def test_vanilla_train_is_deterministic(gp):
+    """The factorisation runs on three streams (block-column / panel look-ahead) and the alpha solve spins on flags: two
+    trainings of the same data must give bit-identical L and alpha (a missing dependency shows up as a difference)."""
+    n = 1664  # 3 block columns + a ragged tail
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, (n, 2))
+    y = np.stack([np.sin(3 * x).sum(axis=1), np.cos(2 * x).sum(axis=1)], axis=1)
+    var = rng.uniform(0.005, 0.02, n)
+    g = gp.VanillaGaussianProcess(gp.VanillaGaussianProcess.Setting("matern32", 0.3, max_num_samples=n), np.float64)
+    ref = None
+    for _ in range(3):
+        assert g.train(x, y, var) and g.info == 0
+        _, l, a = g.get()
+        if ref is None:
+            ref = (l.copy(), a.copy())
+        else:
+            assert np.array_equal(ref[0], l) and np.array_equal(ref[1], a)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — GP train+predict test-points/sec on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c3|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c1|c2|c3|c3n256|c5|spgp|...]
 
 Default workload = BASELINE.json configs[3] ("c4"): the batched small-GP stream, 50 000 independent
 GPs per GPU (n = 128, 3-D inputs, Matern32, 128 test points each, float32) — the configuration
@@ -14,6 +14,9 @@ only for the barrier and the max-over-ranks of the device time).
 `e2e`    : the same metric through the C-ABI host-buffer call erl_gp_batch_train_predict_f32
            (pinned host buffers; H2D of the training sets and queries and D2H of mean /
            variance / valid / info inside the timed region).
+`--workload c1|c2|c3|c3n256|c5|spgp`: the other BASELINE.json configurations (bench_workloads.py), same line schema: `value` with
+           device-resident inputs, `e2e` through the C-ABI calls with pinned host buffers, `roofline` of the dominant kernel
+           (HBM for the partitioned sensor GPs, FP64 tensor peak for the dense / SPGP paths), `cpu_baseline`, `clocks`.
 `--impl reference`: the reference's CPU path (the OpenMP oracle restatement — the reference
            itself cannot be built here) on all host cores, bounded sample.
 """
@@ -32,6 +35,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+import bench_workloads  # noqa: E402  (numpy only at import time)
 
 SEED = 6
 WORKLOADS = {
@@ -195,6 +200,127 @@ def run_reference(args, w, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_generic(args):
+    """c1 / c2 / c3 / c5 / spgp: same contract as the c4 line (see the module docstring of bench_workloads.py)."""
+    wl = bench_workloads.make(args.workload)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "gp_train_predict_test_points_per_sec"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals, base = [], None
+        for i in range(args.warmup + args.steps):
+            base = wl.cpu_baseline(args.ref_seconds)
+            if i >= args.warmup:
+                vals.append(base["value"])
+        value = sum(vals) / len(vals)
+        base["value"] = value
+        print(json.dumps({"impl": "reference", "metric": metric, "value": value, "unit": "test-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": base["seconds"] * 1e3, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+                          "config": {"workload": wl.desc, "sample": base["sample"], "note": "CPU reference path = OpenMP oracle port (the reference cannot be built in this image)"},
+                          "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": value, "unit": "test-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import erl_gaussian_process_b200 as gp
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = gp.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    wl.setup(gp, torch, ctx, dev, stream, rank, world)
+    for _ in range(args.warmup):
+        wl.step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first_sample()
+    wl.step_dev()
+    barrier()
+    wl.dom_events.clear()
+    if hasattr(wl, "train_events"):
+        wl.train_events.clear()
+    launches0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        wl.step_dev()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - launches0
+    ms_dom = wl.dominant_ms()
+    if len(sampler.lines) < 3:
+        t_s = time.perf_counter()
+        while len(sampler.lines) < 3 and time.perf_counter() - t_s < 3.0:
+            wl.step_dev()
+            torch.cuda.synchronize()
+    clocks = sampler.stop()
+    wl.check()
+    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / args.steps
+    units = torch.tensor([float(wl.units)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    total_units = float(units.item())
+    value = total_units / (ms_step * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            wl.step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            wl.step_e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        wl.check_e2e()
+        e2e = {"value": total_units / dt, "unit": "test-points/s", "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h), "ms_per_step": dt * 1e3,
+               "api": "C-ABI train + test calls with pinned host buffers (copies inside the timed region)"}
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        roof = wl.roofline(ms_dom, peaks)
+        roof.setdefault("peak_source", peak_kind)
+        line = {"metric": metric, "value": value, "unit": "test-points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+                "config": {"workload": wl.desc, "test_points_per_step": total_units, "sharding": wl.sharding,
+                           "l2": "every step re-reads its inputs from HBM-resident buffers and rewrites K / L / slabs larger than L2 for c5; c1 / c2 / c3 / spgp working sets (8 MB - 0.5 GB) are "
+                                 "not flushed between steps: they are latency / launch bound, not bandwidth bound (see roofline.note)"},
+                "roofline": roof, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e}
+        if world == 1 and not args.no_cpu_baseline:
+            base = wl.cpu_baseline(10.0)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this rank to the CPUs NVML reports as local to GPU `index` (several ranks per box: every rank uploads 205 MB per
     step from pinned host memory; first-touch on the GPU's own NUMA node keeps the copies off the inter-socket link)."""
@@ -219,17 +345,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + list(bench_workloads.NAMES))
     ap.add_argument("--num-gps", type=int, default=None, help="override GPs per GPU (smoke runs)")
     ap.add_argument("--ref-sample", type=int, default=4000, help="GPs in the CPU reference sample")
     ap.add_argument("--ref-seconds", type=float, default=2.0, help="--impl reference: CPU seconds per step (the sample is repeated)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-variants", action="store_true", help="N=1: also time the host-buffer call with alpha and with L + alpha written back to the host")
     ap.add_argument("--phase", default="fused", choices=["fused", "train", "predict", "split"],
                     help="diagnostics only: time the train kernel, the predict kernel or both as separate launches (the reported metric is always the fused step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.workload in bench_workloads.NAMES:
+        run_generic(args)
+        return
     w = dict(WORKLOADS[args.workload])
     if args.num_gps:
         w["num_gps"] = args.num_gps
@@ -375,6 +505,30 @@ def main():
         d2h = h_mean.nbytes + h_var.nbytes + h_valid.nbytes + h_info.nbytes
         e2e = {"value": world * tq / dt_e2e, "unit": "test-points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": dt_e2e * 1e3,
                "api": "erl_gp_batch_train_predict_f32 (C ABI, pinned host buffers; L stays device-resident, materialised on demand by erl_gp_batch_download)"}
+        if world == 1 and args.e2e_variants:
+            # the reference's Train() materialises alpha (and L) on the host (BatchGaussianProcessUpdateTorch::GetGpResult,
+            # src/batch_gp_update_torch.cpp:86-98): the same call with alpha / L + alpha written back, so that the PCIe cost of
+            # those semantics is on record beside the predict-only e2e
+            variants = {}
+            h_alpha_t, h_alpha = pinned(np.zeros((b, n), dtype=np_dt))
+            h_l_t, h_l = pinned(np.zeros((b, n, n), dtype=np_dt))
+            for name, lp, ap_ in (("alpha_back", None, h_alpha), ("l_alpha_back", h_l, h_alpha)):
+                def var_step():
+                    rc = fn(batch.handle, C.c_long(0), _p(host["n_train"]), _p(host["x"]), _p(host["y"]), _p(host["var"]), _p(host["q_offsets"]), _p(host["q_x"]), C.c_long(tq), _p(lp), _p(ap_),
+                            _p(h_info), _p(h_mean), _p(h_var), _p(h_valid))
+                    assert rc == 0, rc
+                var_step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    var_step()
+                torch.cuda.synchronize()
+                dtv = (time.perf_counter() - t0) / 3
+                extra = h_alpha.nbytes + (h_l.nbytes if lp is not None else 0)
+                variants[name] = {"value": tq / dtv, "unit": "test-points/s", "ms_per_step": dtv * 1e3, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + extra)}
+            assert np.isfinite(h_alpha).all() and np.isfinite(h_l[:: max(1, b // 64)]).all()
+            e2e["variants"] = variants
+            del h_l_t, h_alpha_t
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -391,7 +545,7 @@ def main():
                        "l2": f"per-step inputs+outputs {alg_bytes / 1e9:.2f} GB >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                         "kernel": ("rowgp::RowGpKernel<x_dim=3, NBLK=8, train+predict>" if w["dtype"] == "f32" else "BatchedGpKernel<double, x_dim=3, MROWS=8, train+predict>") + " (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": (f"rowgp::RowGpKernel<x_dim={d}, NBLK={(n + 15) // 16}, train+predict>" if w["dtype"] == "f32" else f"BatchedGpKernel<double, x_dim={d}, n<={n}, train+predict>") + " (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
                          # the kernel's real bound: 3xTF32 mma.sync work (3 HMMA products per FP32 product; 276 TFLOP/s TF32 measured
                          # => 92 TFLOP/s FP32-equivalent); 590 HMMA.1688 per 16 queries and GP at n = t = 128
                          "tensor_pipe": {"useful_tflops_fp32_equiv": fl / (ms_step * 1e-3) / 1e12, "peak_tflops_fp32_equiv": 276.46 / 3,

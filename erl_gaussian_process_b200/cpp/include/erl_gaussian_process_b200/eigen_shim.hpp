@@ -1,11 +1,22 @@
 // Minimal column-major Matrix / Vector / Ref subset with Eigen's spelling, used when Eigen is not on the
-// include path (it is absent from this image).  Define ERL_GP_USE_EIGEN to build the same headers against
-// real Eigen: only the subset below is used by the drop-in classes.
+// include path (it is absent from this image).  With real Eigen on the include path (detected with __has_include,
+// or forced with -DERL_GP_USE_EIGEN) the same headers build against it: only the subset below is used by the
+// drop-in classes.  The shim lives in its own namespace and is aliased to `Eigen` only when Eigen itself is absent, so
+// a translation unit can never see two definitions of Eigen::MatrixX.  -DERL_GP_NO_EIGEN forces the shim.
 #pragma once
+
+#include <cstdint>
+
+#if !defined(ERL_GP_USE_EIGEN) && !defined(ERL_GP_NO_EIGEN) && defined(__has_include)
+    #if __has_include(<Eigen/Dense>)
+        #define ERL_GP_USE_EIGEN 1
+    #endif
+#endif
 
 #ifdef ERL_GP_USE_EIGEN
     #include <Eigen/Dense>
 namespace Eigen {
+    // erl_common's typedefs (the reference's masks are Eigen matrices of bool)
     using VectorXb = Matrix<bool, Dynamic, 1>;
     using MatrixXb = Matrix<bool, Dynamic, Dynamic>;
 }  // namespace Eigen
@@ -15,7 +26,7 @@ namespace Eigen {
     #include <cstddef>
     #include <vector>
 
-namespace Eigen {
+namespace erl_gp_eigen_shim {
 
     template<typename T>
     class MatrixX {
@@ -133,5 +144,25 @@ namespace Eigen {
     template<typename M>
     using Ref = M &;
 
-}  // namespace Eigen
+}  // namespace erl_gp_eigen_shim
+
+namespace Eigen = erl_gp_eigen_shim;
 #endif
+
+namespace erl::gaussian_process::b200 {
+    // The C ABI takes masks as uint8_t*.  The reference's masks are Eigen::VectorX<bool> (real Eigen) or the shim's
+    // VectorX<unsigned char>: both are one byte per element holding 0 / 1.
+    template<typename MaskVector>
+    inline std::uint8_t *
+    MaskData(MaskVector &v) {
+        static_assert(sizeof(*v.data()) == 1, "mask elements must be one byte");
+        return reinterpret_cast<std::uint8_t *>(v.data());
+    }
+
+    template<typename MaskVector>
+    inline const std::uint8_t *
+    MaskData(const MaskVector &v) {
+        static_assert(sizeof(*v.data()) == 1, "mask elements must be one byte");
+        return reinterpret_cast<const std::uint8_t *>(v.data());
+    }
+}  // namespace erl::gaussian_process::b200

@@ -59,7 +59,7 @@ namespace erl::gaussian_process {
                 m_mean_.resize(n);
                 m_var_.resize(n);
                 m_valid_.resize(n);
-                gp->m_ctx_->Check(Api::lidar2d_test(gp->m_handle_, angles.data(), n, angles_are_local, un_map, m_mean_.data(), m_var_.data(), m_valid_.data()), "erl_gp_lidar2d_test");
+                gp->m_ctx_->Check(Api::lidar2d_test(gp->m_handle_, angles.data(), n, angles_are_local, un_map, m_mean_.data(), m_var_.data(), b200::MaskData(m_valid_)), "erl_gp_lidar2d_test");
             }
 
             [[nodiscard]] long
@@ -195,7 +195,7 @@ namespace erl::gaussian_process {
             m_sensor_frame_->UpdateRanges(rotation, translation, std::move(ranges));
             if (!m_sensor_frame_->IsValid()) { return false; }
             m_ctx_->Check(
-                Api::lidar2d_train(m_handle_, rotation.data(), m_sensor_frame_->GetRanges().data(), m_sensor_frame_->GetHitMask().data(), m_sensor_frame_->GetContinuityMask().data()),
+                Api::lidar2d_train(m_handle_, rotation.data(), m_sensor_frame_->GetRanges().data(), b200::MaskData(m_sensor_frame_->GetHitMask()), b200::MaskData(m_sensor_frame_->GetContinuityMask())),
                 "erl_gp_lidar2d_train");
             m_trained_ = true;
             return true;
@@ -226,7 +226,7 @@ namespace erl::gaussian_process {
             if (!m_trained_) { return ok; }
             dist_pos.resize(n), range_pred.resize(n), occ.resize(n);
             m_ctx_->Check(Api::lidar2d_compute_occ(m_handle_, pos_local.data(), n, m_setting_->max_valid_range_var, m_setting_->occ_test_temperature, dist_pos.data(), range_pred.data(),
-                                                   occ.data(), ok.data()),
+                                                   occ.data(), b200::MaskData(ok)),
                           "erl_gp_lidar2d_compute_occ");
             return ok;
         }

@@ -70,7 +70,7 @@ namespace erl::gaussian_process {
                 m_mean_.resize(n);
                 m_var_.resize(n);
                 m_valid_.resize(n);
-                gp->m_ctx_->Check(Api::range3d_test(gp->m_handle_, coords.data(), coords_ok.data(), n, un_map, m_mean_.data(), m_var_.data(), m_valid_.data()), "erl_gp_range3d_test");
+                gp->m_ctx_->Check(Api::range3d_test(gp->m_handle_, coords.data(), b200::MaskData(coords_ok), n, un_map, m_mean_.data(), m_var_.data(), b200::MaskData(m_valid_)), "erl_gp_range3d_test");
             }
 
             [[nodiscard]] long
@@ -189,7 +189,7 @@ namespace erl::gaussian_process {
             Reset();
             m_sensor_frame_->UpdateRanges(rotation, translation, std::move(ranges));
             if (!m_sensor_frame_->IsValid()) { return false; }
-            m_ctx_->Check(Api::range3d_train(m_handle_, m_sensor_frame_->GetRanges().data(), m_sensor_frame_->GetHitMask().data()), "erl_gp_range3d_train");
+            m_ctx_->Check(Api::range3d_train(m_handle_, m_sensor_frame_->GetRanges().data(), b200::MaskData(m_sensor_frame_->GetHitMask())), "erl_gp_range3d_train");
             m_trained_ = true;
             return true;
         }
@@ -222,8 +222,8 @@ namespace erl::gaussian_process {
             MatrixX coords(2, n);
             Eigen::VectorXb coords_ok(n);
             for (long i = 0; i < n; ++i) { coords_ok[i] = m_sensor_frame_->ComputeFrameCoords(&pos_local(0, i), dist_pos[i], &coords(0, i)) ? 1 : 0; }
-            m_ctx_->Check(Api::range3d_compute_occ(m_handle_, coords.data(), coords_ok.data(), dist_pos.data(), n, m_setting_->max_valid_range_var, m_setting_->occ_test_temperature,
-                                                   range_pred.data(), occ.data(), ok.data()),
+            m_ctx_->Check(Api::range3d_compute_occ(m_handle_, coords.data(), b200::MaskData(coords_ok), dist_pos.data(), n, m_setting_->max_valid_range_var, m_setting_->occ_test_temperature,
+                                                   range_pred.data(), occ.data(), b200::MaskData(ok)),
                           "erl_gp_range3d_compute_occ");
             return ok;
         }

@@ -52,11 +52,32 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // O(num_gps) host checks of caller metadata: a training-set size beyond the capacity would index past the per-GP slices
+    // (and the kernel's shared memory), an inconsistent CSR query list past the query / output buffers
+    static bool
+    TrainSizesOk(const int *n_train, long num_gps, long max_n) {
+        for (long g = 0; g < num_gps; ++g) {
+            if (n_train[g] < 0 || n_train[g] > max_n) { return false; }
+        }
+        return true;
+    }
+
+    static bool
+    QueryOffsetsOk(const long *q_offsets, long num_gps, long num_q) {
+        if (q_offsets[0] != 0 || q_offsets[num_gps] != num_q) { return false; }
+        for (long g = 0; g < num_gps; ++g) {
+            if (q_offsets[g + 1] < q_offsets[g]) { return false; }
+        }
+        return true;
+    }
+
     template<typename T>
     int
     BatchUpload(Batch<T> *b, const int *n_train, const T *x, const T *y, const T *var) {
         if (b == nullptr || n_train == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
+        if (!TrainSizesOk(n_train, b->num_gps, b->max_n)) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: n_train[g] must lie in [0, max_n = %ld]", b->max_n); }
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         const size_t bn = static_cast<size_t>(b->num_gps) * b->max_n;
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->n_train.ptr, n_train, sizeof(int) * b->num_gps, cudaMemcpyHostToDevice, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->x.ptr, x, sizeof(T) * bn * b->x_dim, cudaMemcpyHostToDevice, ctx->stream));
@@ -71,6 +92,7 @@ namespace erl_gp {
     int
     BatchTrainDev(Batch<T> *b, long min_num_samples, int write_l) {
         if (b == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        ERL_GP_CUDA_OK(b->ctx, cudaSetDevice(b->ctx->device));
         const BatchParams<T> p = b->Params(min_num_samples, write_l);
         return LaunchBatch<T>(b->ctx, p, static_cast<int>(b->x_dim), kBatchTrain, 1);
     }
@@ -80,6 +102,7 @@ namespace erl_gp {
     BatchPredictDev(Batch<T> *b, const long *q_offsets, const T *q_x, const int *q_out_index, long num_q, int mapping, T mapping_scale, T *mean, T *var, uint8_t *valid) {
         if (b == nullptr || q_offsets == nullptr || q_x == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         if (num_q <= 0) { return ERL_GP_STATUS_OK; }
+        ERL_GP_CUDA_OK(b->ctx, cudaSetDevice(b->ctx->device));
         BatchParams<T> p = b->Params(0, 0);
         p.q_offsets = q_offsets;
         p.q_x = q_x;
@@ -103,6 +126,7 @@ namespace erl_gp {
     int
     BatchTrainPredictDev(Batch<T> *b, long min_num_samples, int write_l, const long *q_offsets, const T *q_x, long num_q, T *mean, T *var, uint8_t *valid) {
         if (b == nullptr || q_offsets == nullptr || (num_q > 0 && q_x == nullptr)) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        ERL_GP_CUDA_OK(b->ctx, cudaSetDevice(b->ctx->device));
         BatchParams<T> p = b->Params(min_num_samples, write_l);
         p.q_offsets = q_offsets;
         p.q_x = q_x;
@@ -117,6 +141,7 @@ namespace erl_gp {
     BatchDownload(Batch<T> *b, T *l, T *alpha, int *info) {
         if (b == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         const size_t bn = static_cast<size_t>(b->num_gps) * b->max_n;
         if (l != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(l, b->l.ptr, sizeof(T) * bn * b->max_n, cudaMemcpyDeviceToHost, ctx->stream)); }
         if (alpha != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(alpha, b->alpha.ptr, sizeof(T) * bn, cudaMemcpyDeviceToHost, ctx->stream)); }
@@ -146,6 +171,10 @@ namespace erl_gp {
         if (b == nullptr || q_offsets == nullptr || num_q < 0 || n_train == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         if (num_q > 0 && q_x == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
+        if (!TrainSizesOk(n_train, b->num_gps, b->max_n)) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: n_train[g] must lie in [0, max_n = %ld]", b->max_n); }
+        if (!QueryOffsetsOk(q_offsets, b->num_gps, num_q)) {
+            return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: q_offsets must start at 0, be non-decreasing and end at num_q = %ld", num_q);
+        }
         ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         const long num_gps = b->num_gps, max_n = b->max_n, d = b->x_dim;
         const size_t nq = static_cast<size_t>(num_q > 0 ? num_q : 1);
@@ -269,6 +298,7 @@ namespace erl_gp {
     BatchGetGp(Batch<T> *b, long g, int *info, long *n, T *l, long ld_l, T *alpha) {
         if (b == nullptr || g < 0 || g >= b->num_gps) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = b->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         int h_info = -1, h_n = 0;
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(&h_info, b->info.ptr + g, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(&h_n, b->n_train.ptr + g, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -460,11 +490,13 @@ erl_gp_context_kernel_launches(const erl_gp_context *ctx, long *count) {
     }                                                                                                                                                                        \
     int erl_gp_compute_ktrain_dev_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, const T *x, long ld_x, const T *var, long n, T *k, long ld_k) {                \
         if (ctx == nullptr || x == nullptr || var == nullptr || k == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                     \
+        ERL_GP_CUDA_OK(Ctx(ctx), cudaSetDevice(ctx->device));                                                                                                                \
         return LaunchKtrain<T>(Ctx(ctx), kernel, scale, x_dim, x, ld_x, var, n, k, ld_k);                                                                                    \
     }                                                                                                                                                                        \
     int erl_gp_compute_ktest_dev_##SFX(erl_gp_context *ctx, int kernel, T scale, long x_dim, const T *x1, long ld_x1, long n1, const T *x2, long ld_x2, long n2, T *k,       \
                                        long ld_k) {                                                                                                                          \
         if (ctx == nullptr || x1 == nullptr || x2 == nullptr || k == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }                                                     \
+        ERL_GP_CUDA_OK(Ctx(ctx), cudaSetDevice(ctx->device));                                                                                                                \
         return LaunchKtest<T>(Ctx(ctx), kernel, scale, x_dim, x1, ld_x1, n1, x2, ld_x2, n2, k, ld_k);                                                                        \
     }                                                                                                                                                                        \
     int erl_gp_batch_create_##SFX(erl_gp_context *ctx, long num_gps, long max_n, long x_dim, int kernel, T scale, erl_gp_batch_##SFX **batch) {                              \

@@ -36,7 +36,7 @@ namespace erl_gp {
     template<typename T>
     struct Covariance {
         int type;
-        T c0;  // OU: 1/l   Matern32: sqrt(3)/l   RBF: 2 l^2
+        T c0;  // OU: l   Matern32: sqrt(3)/l   RBF: 2 l^2
 
         __host__ static Covariance
         Make(int type, T scale) {

@@ -18,6 +18,8 @@ namespace erl_gp {
         std::vector<long> index_left, index_right;
         std::vector<T> coord_left, coord_right;
 
+        bool bad = false;  // a coordinate index fell outside the frame while the table was built
+
         long
         Size() const {
             return static_cast<long>(index_left.size());
@@ -37,7 +39,15 @@ namespace erl_gp {
     static PartitionTable<T>
     MakePartitionTable(const T *coords, long stride, long n, long group_size, long overlap_size, long margin, bool symmetric) {
         PartitionTable<T> t;
-        auto c = [&](long i) { return coords[i * stride]; };
+        // the reference indexes its coordinate vector unchecked (latent out-of-bounds reads for margin >= n or
+        // overlap_size > group_size - overlap_size); here an index outside [0, n) marks the table as bad instead
+        auto c = [&](long i) {
+            if (i < 0 || i >= n) {
+                t.bad = true;
+                i = i < 0 ? 0 : n - 1;
+            }
+            return coords[i * stride];
+        };
         const long step = group_size - overlap_size;
         const long num_groups = std::max(1l, n / step) + 1;
         const long gs2 = (n - (num_groups - 2) * step) / 2;
@@ -68,6 +78,7 @@ namespace erl_gp {
     template<typename T>
     static bool
     PartitionsFit(const PartitionTable<T> &t, long n, long capacity) {
+        if (t.bad) { return false; }
         for (long i = 0; i < t.Size(); ++i) {
             if (t.index_left[i] < 0 || t.index_right[i] > n || t.index_right[i] - t.index_left[i] > capacity || t.index_right[i] < t.index_left[i]) { return false; }
         }
@@ -406,7 +417,9 @@ namespace erl_gp {
         Context *ctx = Ctx(c);
         if (ctx == nullptr || s == nullptr || angles == nullptr || out == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         *out = nullptr;
-        if (s->group_size <= s->overlap_size || s->overlap_size < 0 || s->margin < 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "lidar2d: group_size must exceed overlap_size"); }
+        if (s->group_size <= s->overlap_size || s->overlap_size < 0 || s->margin < 0 || s->margin >= num_rays) {
+            return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "lidar2d: group_size must exceed overlap_size and 0 <= margin < num_rays");
+        }
         if (num_rays <= s->overlap_size) {  // "no enough samples to perform partition", src/lidar_gp_2d.cpp:177-180
             return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "lidar2d: num_rays=%ld <= overlap_size=%ld", num_rays, s->overlap_size);
         }
@@ -445,14 +458,15 @@ namespace erl_gp {
     Lidar2dTrain(Lidar2d<T> *gp, const T *rotation, const T *ranges, const uint8_t *hit, const uint8_t *con) {
         if (gp == nullptr || ranges == nullptr || hit == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         const auto &s = gp->setting;
         gp->trained = false;
         if (rotation != nullptr) { std::memcpy(gp->rotation, rotation, sizeof(gp->rotation)); }
         const long n = gp->num_rays;
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_ranges.ptr, ranges, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_hit.ptr, hit, n, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_ranges.ptr, ranges, sizeof(T) * n, cudaMemcpyDefault, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_hit.ptr, hit, n, cudaMemcpyDefault, ctx->stream));
         if (con != nullptr) {
-            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_con.ptr, con, n, cudaMemcpyHostToDevice, ctx->stream));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_con.ptr, con, n, cudaMemcpyDefault, ctx->stream));
         } else {
             ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->d_con.ptr, 1, n, ctx->stream));
         }
@@ -476,15 +490,16 @@ namespace erl_gp {
     static int
     Lidar2dQuery(Lidar2d<T> *gp, const T *q_host, long num_q, int mode, int angles_are_local, int mapping, const T *mean_seed, const T *var_seed) {
         Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         Batch<T> *b = gp->batch;
         QueryWorkspace<T> &ws = gp->ws;
         const int in_dim = mode == 0 ? 1 : 2;
         ERL_GP_CUDA_OK(ctx, ws.Reserve(num_q, b->num_gps, in_dim, 1));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_in.ptr, q_host, sizeof(T) * num_q * in_dim, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_in.ptr, q_host, sizeof(T) * num_q * in_dim, cudaMemcpyDefault, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(ws.counts.ptr, 0, sizeof(int) * b->num_gps, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(ws.valid.ptr, 0, num_q, ctx->stream));
-        if (mean_seed != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.mean.ptr, mean_seed, sizeof(T) * num_q, cudaMemcpyHostToDevice, ctx->stream)); }
-        if (var_seed != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.variance.ptr, var_seed, sizeof(T) * num_q, cudaMemcpyHostToDevice, ctx->stream)); }
+        if (mean_seed != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.mean.ptr, mean_seed, sizeof(T) * num_q, cudaMemcpyDefault, ctx->stream)); }
+        if (var_seed != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.variance.ptr, var_seed, sizeof(T) * num_q, cudaMemcpyDefault, ctx->stream)); }
         const unsigned blocks = static_cast<unsigned>(CeilDiv(num_q, 256));
         const T *r = gp->rotation;  // col-major: r[0]=R00 r[1]=R10 r[2]=R01 r[3]=R11
         LidarAssignKernel<T><<<blocks, 256, 0, ctx->stream>>>(num_q, ws.q_in.ptr, mode, angles_are_local, r[0], r[1], r[2], r[3], gp->d_parts.count, gp->d_parts.cl.ptr, gp->d_parts.cr.ptr,
@@ -506,9 +521,9 @@ namespace erl_gp {
         const int rc = Lidar2dQuery<T>(gp, angles, num_test, 0, angles_are_local, un_map ? gp->setting.mapping : ERL_GP_MAPPING_NONE, mean, var);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         QueryWorkspace<T> &ws = gp->ws;
-        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean, ws.mean.ptr, sizeof(T) * num_test, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (var != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var, ws.variance.ptr, sizeof(T) * num_test, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (valid != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(valid, ws.valid.ptr, num_test, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean, ws.mean.ptr, sizeof(T) * num_test, cudaMemcpyDefault, ctx->stream)); }
+        if (var != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var, ws.variance.ptr, sizeof(T) * num_test, cudaMemcpyDefault, ctx->stream)); }
+        if (valid != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(valid, ws.valid.ptr, num_test, cudaMemcpyDefault, ctx->stream)); }
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }
@@ -525,20 +540,20 @@ namespace erl_gp {
         QueryWorkspace<T> &ws = gp->ws;
         // occ lives in sorted_x's slot-free twin: reuse q_local (dead after the scatter) as the occ buffer
         T *d_occ = ws.q_local.ptr;
-        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_occ, occ, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream)); }
+        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_occ, occ, sizeof(T) * num, cudaMemcpyDefault, ctx->stream)); }
         T *d_prefill = nullptr;
         if (range_pred != nullptr) {  // sorted_x is dead after the predict: keeps the caller's values for the gated-out positions
             d_prefill = ws.sorted_x.ptr;
-            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_prefill, range_pred, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_prefill, range_pred, sizeof(T) * num, cudaMemcpyDefault, ctx->stream));
         }
         OccEpilogueKernel<T><<<static_cast<unsigned>(CeilDiv(num, 256)), 256, 0, ctx->stream>>>(num, ws.q_dist.ptr, ws.valid.ptr, ws.variance.ptr, max_valid_range_var, temperature, gp->setting.mapping,
                                                                                                static_cast<T>(gp->setting.mapping_scale), ws.mean.ptr, d_occ, ws.ok.ptr, d_prefill);
         ctx->launches += 1;
         ERL_GP_CUDA_OK(ctx, cudaGetLastError());
-        if (dist != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(dist, ws.q_dist.ptr, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (range_pred != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(range_pred, ws.mean.ptr, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(occ, d_occ, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream)); }
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ok, ws.ok.ptr, num, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dist != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(dist, ws.q_dist.ptr, sizeof(T) * num, cudaMemcpyDefault, ctx->stream)); }
+        if (range_pred != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(range_pred, ws.mean.ptr, sizeof(T) * num, cudaMemcpyDefault, ctx->stream)); }
+        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(occ, d_occ, sizeof(T) * num, cudaMemcpyDefault, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ok, ws.ok.ptr, num, cudaMemcpyDefault, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }
@@ -551,6 +566,9 @@ namespace erl_gp {
         *out = nullptr;
         if (s->row_overlap_size % 2 != 0 || s->col_overlap_size % 2 != 0) {  // src/range_sensor_gp_3d.cpp:190-197
             return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "range3d: row_overlap_size / col_overlap_size must be even");
+        }
+        if (s->row_margin < 0 || s->row_margin >= rows || s->col_margin < 0 || s->col_margin >= cols || s->row_overlap_size < 0 || s->col_overlap_size < 0) {
+            return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "range3d: margins must lie inside the frame and overlaps must be >= 0");
         }
         if (s->row_group_size <= s->row_overlap_size || s->col_group_size <= s->col_overlap_size || rows <= s->row_overlap_size || cols <= s->col_overlap_size) {
             return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "range3d: group sizes must exceed overlap sizes and fit the frame");
@@ -595,11 +613,12 @@ namespace erl_gp {
     Range3dTrain(Range3d<T> *gp, const T *ranges, const uint8_t *hit) {
         if (gp == nullptr || ranges == nullptr || hit == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         const auto &s = gp->setting;
         gp->trained = false;
         const long pixels = gp->rows * gp->cols;
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_ranges.ptr, ranges, sizeof(T) * pixels, cudaMemcpyHostToDevice, ctx->stream));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_hit.ptr, hit, pixels, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_ranges.ptr, ranges, sizeof(T) * pixels, cudaMemcpyDefault, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->d_hit.ptr, hit, pixels, cudaMemcpyDefault, ctx->stream));
         Batch<T> *b = gp->batch;
         const int warps_per_block = 4;
         Range3dGatherKernel<T><<<static_cast<unsigned>(CeilDiv(b->num_gps, warps_per_block)), warps_per_block * 32, 0, ctx->stream>>>(
@@ -634,21 +653,21 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, ws.Reserve(num, gp->batch->num_gps, 2, 2));
         ERL_GP_CUDA_OK(ctx, ws.q_local.Reserve(2 * num));
         T *d_prefill = ws.q_local.ptr + num;  // q_local is unused by the 3-D query: [0, num) = occ, [num, 2 num) = prefill
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_prefill, range_pred, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_prefill, range_pred, sizeof(T) * num, cudaMemcpyDefault, ctx->stream));
         // mapped mean + variance of every position (results stay in the workspace; the host copy of mean is re-written below)
         std::vector<T> var_host(static_cast<size_t>(num));
         int rc = Range3dTest<T>(gp, coords, coords_ok, num, 0, range_pred, var_host.data(), nullptr);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_dist.ptr, dist, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_dist.ptr, dist, sizeof(T) * num, cudaMemcpyDefault, ctx->stream));
         T *d_occ = ws.q_local.ptr;
-        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_occ, occ, sizeof(T) * num, cudaMemcpyHostToDevice, ctx->stream)); }
+        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(d_occ, occ, sizeof(T) * num, cudaMemcpyDefault, ctx->stream)); }
         OccEpilogueKernel<T><<<static_cast<unsigned>(CeilDiv(num, 256)), 256, 0, ctx->stream>>>(num, ws.q_dist.ptr, ws.valid.ptr, ws.variance.ptr, max_valid_range_var, temperature, gp->setting.mapping,
                                                                                                static_cast<T>(gp->setting.mapping_scale), ws.mean.ptr, d_occ, ws.ok.ptr, d_prefill);
         ctx->launches += 1;
         ERL_GP_CUDA_OK(ctx, cudaGetLastError());
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(range_pred, ws.mean.ptr, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream));
-        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(occ, d_occ, sizeof(T) * num, cudaMemcpyDeviceToHost, ctx->stream)); }
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ok, ws.ok.ptr, num, cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(range_pred, ws.mean.ptr, sizeof(T) * num, cudaMemcpyDefault, ctx->stream));
+        if (occ != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(occ, d_occ, sizeof(T) * num, cudaMemcpyDefault, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ok, ws.ok.ptr, num, cudaMemcpyDefault, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }
@@ -658,17 +677,18 @@ namespace erl_gp {
     Range3dTest(Range3d<T> *gp, const T *coords, const uint8_t *coords_ok, long num_test, int un_map, T *mean, T *var, uint8_t *valid) {
         if (gp == nullptr || coords == nullptr || num_test < 0) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
         if (!gp->trained) { return SetError(ctx, ERL_GP_STATUS_NOT_TRAINED, "range3d: Test() before Train()"); }
         if (num_test == 0) { return ERL_GP_STATUS_OK; }
         Batch<T> *b = gp->batch;
         QueryWorkspace<T> &ws = gp->ws;
         ERL_GP_CUDA_OK(ctx, ws.Reserve(num_test, b->num_gps, 2, 2));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_in.ptr, coords, sizeof(T) * 2 * num_test, cudaMemcpyHostToDevice, ctx->stream));
-        if (coords_ok != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.coords_ok.ptr, coords_ok, num_test, cudaMemcpyHostToDevice, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.q_in.ptr, coords, sizeof(T) * 2 * num_test, cudaMemcpyDefault, ctx->stream));
+        if (coords_ok != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.coords_ok.ptr, coords_ok, num_test, cudaMemcpyDefault, ctx->stream)); }
         ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(ws.counts.ptr, 0, sizeof(int) * b->num_gps, ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(ws.valid.ptr, 0, num_test, ctx->stream));
-        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.mean.ptr, mean, sizeof(T) * num_test, cudaMemcpyHostToDevice, ctx->stream)); }
-        if (var != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.variance.ptr, var, sizeof(T) * num_test, cudaMemcpyHostToDevice, ctx->stream)); }
+        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.mean.ptr, mean, sizeof(T) * num_test, cudaMemcpyDefault, ctx->stream)); }
+        if (var != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(ws.variance.ptr, var, sizeof(T) * num_test, cudaMemcpyDefault, ctx->stream)); }
         const unsigned blocks = static_cast<unsigned>(CeilDiv(num_test, 256));
         Range3dAssignKernel<T><<<blocks, 256, 0, ctx->stream>>>(num_test, ws.q_in.ptr, coords_ok != nullptr ? ws.coords_ok.ptr : nullptr, gp->d_row_parts.count, gp->d_row_parts.cl.ptr,
                                                                 gp->d_row_parts.cr.ptr, gp->d_col_parts.count, gp->d_col_parts.cl.ptr, gp->d_col_parts.cr.ptr, b->info.ptr, ws.q_gp.ptr,
@@ -680,9 +700,9 @@ namespace erl_gp {
         const int rc = BatchPredictDev<T>(b, ws.offsets.ptr, ws.sorted_x.ptr, ws.out_index.ptr, num_test, un_map ? gp->setting.mapping : ERL_GP_MAPPING_NONE,
                                           static_cast<T>(gp->setting.mapping_scale), mean != nullptr ? ws.mean.ptr : nullptr, var != nullptr ? ws.variance.ptr : nullptr, ws.valid.ptr);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
-        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean, ws.mean.ptr, sizeof(T) * num_test, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (var != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var, ws.variance.ptr, sizeof(T) * num_test, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (valid != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(valid, ws.valid.ptr, num_test, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (mean != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean, ws.mean.ptr, sizeof(T) * num_test, cudaMemcpyDefault, ctx->stream)); }
+        if (var != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var, ws.variance.ptr, sizeof(T) * num_test, cudaMemcpyDefault, ctx->stream)); }
+        if (valid != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(valid, ws.valid.ptr, num_test, cudaMemcpyDefault, ctx->stream)); }
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }

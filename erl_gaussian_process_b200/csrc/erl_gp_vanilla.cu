@@ -270,9 +270,9 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(m) * n));
         ERL_GP_CUDA_OK(ctx, gp->s_buf.Reserve(static_cast<size_t>(kPanel) * n));
         ERL_GP_CUDA_OK(ctx, gp->sumsq.Reserve(n));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->x.ptr, sizeof(T) * d, x, sizeof(T) * ld_x, sizeof(T) * d, n, cudaMemcpyHostToDevice, ctx->stream));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->y.ptr, y, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
-        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->var.ptr, var, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->x.ptr, sizeof(T) * d, x, sizeof(T) * ld_x, sizeof(T) * d, n, cudaMemcpyDefault, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->y.ptr, y, sizeof(T) * n, cudaMemcpyDefault, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->var.ptr, var, sizeof(T) * n, cudaMemcpyDefault, ctx->stream));
         // K_MN (:759-762), kept; the triangular solve runs on a copy
         int rc = LaunchKtest<T>(ctx, gp->kernel, gp->scale, d, gp->z.ptr, d, m, gp->x.ptr, d, n, gp->k_mn.ptr, m);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
@@ -339,11 +339,11 @@ namespace erl_gp {
         }
         for (long t0 = 0; t0 < num_test; t0 += chunk) {
             const long tt = std::min(chunk, num_test - t0);
-            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test + t0 * ld_xt, sizeof(T) * ld_xt, sizeof(T) * d, tt, cudaMemcpyHostToDevice, ctx->stream));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test + t0 * ld_xt, sizeof(T) * ld_xt, sizeof(T) * d, tt, cudaMemcpyDefault, ctx->stream));
             if (mean != nullptr) {
                 rc = PredictMean<T>(ctx, gp->kernel, gp->scale, d, m, tt, gp->z.ptr, gp->xt.ptr, gp->alpha_solved.ptr, m, 1, gp->mean.ptr, tt);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
-                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean + t0, gp->mean.ptr, sizeof(T) * tt, cudaMemcpyDeviceToHost, ctx->stream));
+                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(mean + t0, gp->mean.ptr, sizeof(T) * tt, cudaMemcpyDefault, ctx->stream));
             }
             if (var != nullptr) {
                 rc = PredictVariance<T>(ctx, gp->kernel, gp->scale, d, m, tt, gp->z.ptr, gp->xt.ptr, gp->l_km.ptr, m, gp->linv_km.ptr, gp->w.ptr, gp->sumsq.ptr);
@@ -352,7 +352,7 @@ namespace erl_gp {
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
                 rc = VarianceFinalize<T>(ctx, tt, gp->sumsq.ptr, gp->sumsq2.ptr, gp->variance.ptr);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
-                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var + t0, gp->variance.ptr, sizeof(T) * tt, cudaMemcpyDeviceToHost, ctx->stream));
+                ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var + t0, gp->variance.ptr, sizeof(T) * tt, cudaMemcpyDefault, ctx->stream));
             }
         }
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -201,6 +201,25 @@ class VanillaGaussianProcess:
         self.is_trained = True
         return True
 
+    # ---- device-resident entry points (x, y, var, x_test, mean, var are device pointers, e.g. torch tensors) ----
+    def train_dev(self, x, y, var, n, x_dim, y_dim=1):
+        """erl_gp_vanilla_train_dev: asynchronous on the context's stream; `info` is read by vanilla_info()."""
+        s = self.setting
+        _, ct = _sfx(self.dtype)
+        check(self.ctx.fn("erl_gp_vanilla_train_dev", self.dtype)(self.handle, C.c_int(_kernel_id(s.kernel_type)), ct(s.scale), C.c_long(x_dim), C.c_long(y_dim), C.c_long(n), _p(x),
+                                                                  C.c_long(x_dim), _p(y), C.c_long(n), _p(var)), "vanilla_train_dev", self.ctx.handle)
+        self.n, self.y_dim = n, y_dim
+        self.is_trained = True
+
+    def vanilla_info(self):
+        info = C.c_int(0)
+        check(self.ctx.fn("erl_gp_vanilla_info", self.dtype)(self.handle, C.byref(info)), "vanilla_info", self.ctx.handle)
+        self.info = info.value
+        return info.value
+
+    def test_dev(self, x_test, num_test, x_dim, mean, var):
+        check(self.ctx.fn("erl_gp_vanilla_test_dev", self.dtype)(self.handle, C.c_long(num_test), _p(x_test), C.c_long(x_dim), _p(mean), _p(var)), "vanilla_test_dev", self.ctx.handle)
+
     def get(self):
         """(K, L, alpha) materialised on the host, as GetKtrain / GetCholeskyDecomposition / GetAlpha."""
         n = self.n

@@ -129,7 +129,7 @@ TestLidar(const char *name, const double tol) {
     ref.kernel_type = erl_gp_oracle::kOrnsteinUhlenbeck, ref.kernel_scale = Dtype(0.05);
     ref.sensor_range_var = setting->sensor_range_var, ref.max_valid_range_var = setting->max_valid_range_var, ref.occ_test_temperature = setting->occ_test_temperature;
     ref.Init(angles.data(), n);
-    ref.Train(rot.data(), frame->GetRanges().data(), frame->GetHitMask().data(), frame->GetContinuityMask().data(), true);
+    ref.Train(rot.data(), frame->GetRanges().data(), erl::gaussian_process::b200::MaskData(frame->GetHitMask()), erl::gaussian_process::b200::MaskData(frame->GetContinuityMask()), true);
 
     Eigen::VectorX<Dtype> q(n_test), mean(n_test), var(n_test);
     for (long i = 0; i < n_test; ++i) {
@@ -208,7 +208,7 @@ TestRangeSensor(const char *name, const double tol) {
     ref.sensor_range_var = setting->sensor_range_var;
     CHECK(ref.Init(frame->GetFrameCoordsData(), rows, cols), "oracle Init");
     CHECK(gp.GetRowPartitions().size() == ref.row_partitions.size() && gp.GetColPartitions().size() == ref.col_partitions.size(), "partition grid");
-    ref.Train(frame->GetRanges().data(), frame->GetHitMask().data(), true);
+    ref.Train(frame->GetRanges().data(), erl::gaussian_process::b200::MaskData(frame->GetHitMask()), true);
     constexpr long n_test = 5000;
     Eigen::MatrixX<Dtype> dirs(3, n_test), coords(2, n_test);
     for (long i = 0; i < n_test; ++i) {

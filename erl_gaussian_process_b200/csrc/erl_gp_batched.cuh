@@ -29,6 +29,18 @@
 #include "erl_gp_internal.cuh"
 #include "erl_gp_rowgp.cuh"
 
+namespace erl_gp {
+    namespace rowgp_tc {
+        // tcgen05 / TMEM fused train + predict kernel, n <= 128 (erl_gp_rowgp_tc.cuh, instantiated in erl_gp_rowgp_tc_x<dim>.cu)
+        template<int XDIM>
+        int
+        Launch(Context *ctx, const BatchParams<float> &params);
+        extern template int Launch<1>(Context *, const BatchParams<float> &);
+        extern template int Launch<2>(Context *, const BatchParams<float> &);
+        extern template int Launch<3>(Context *, const BatchParams<float> &);
+    }  // namespace rowgp_tc
+}  // namespace erl_gp
+
 #include <cstdlib>
 
 namespace erl_gp {
@@ -673,6 +685,11 @@ namespace erl_gp {
             // generic shared-memory kernel below (A/B measurements and tests of the generic path)
             static const bool legacy = std::getenv("ERL_GP_BATCH_LEGACY") != nullptr;
             static const bool legacy_large = std::getenv("ERL_GP_BATCH_LEGACY_LARGE") != nullptr;  // generic kernel for 128 < n <= 256 only
+            // fused train + predict, n <= 128: the tcgen05 / TMEM kernel (erl_gp_rowgp_tc.cuh); ERL_GP_ROWGP_TC=0 keeps the mma.sync kernel
+            static const bool tc_off = std::getenv("ERL_GP_ROWGP_TC") != nullptr && std::atoi(std::getenv("ERL_GP_ROWGP_TC")) == 0;
+            if (max_n <= 128 && !legacy && !tc_off && mode == kBatchTrainPredict && params.q_out_index == nullptr && params.mapping == ERL_GP_MAPPING_NONE) {
+                return rowgp_tc::Launch<XDIM>(ctx, params);
+            }
             if (max_n <= 128 && !legacy) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 256 && !legacy && !legacy_large) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
         }

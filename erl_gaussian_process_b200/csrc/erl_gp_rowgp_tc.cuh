@@ -78,27 +78,37 @@ namespace erl_gp {
             return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
         }
 
+        // The MMA warp executes the issue code convergently (all operands are warp-uniform, so they can live in uniform
+        // registers); `elected` (one lane, from elect.sync) predicates the instruction itself.  The probe measured ~52 cycles
+        // per MMA when a single divergent thread issues (tools/tcgen05_probe.cu).
+        __device__ __forceinline__ uint32_t
+        ElectOne() {
+            uint32_t pred;
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}\n" : "=r"(pred));
+            return pred;
+        }
+
         __device__ __forceinline__ void
-        MmaSS(const uint32_t d_tmem, const uint64_t a_desc, const uint64_t b_desc, const uint32_t idesc, const uint32_t accumulate) {
+        MmaSS(const uint32_t elected, const uint32_t d_tmem, const uint64_t a_desc, const uint64_t b_desc, const uint32_t idesc, const uint32_t accumulate) {
             asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+                "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
                 : "memory");
         }
 
         __device__ __forceinline__ void
-        MmaTS(const uint32_t d_tmem, const uint32_t a_tmem, const uint64_t b_desc, const uint32_t idesc, const uint32_t accumulate) {
+        MmaTS(const uint32_t elected, const uint32_t d_tmem, const uint32_t a_tmem, const uint64_t b_desc, const uint32_t idesc, const uint32_t accumulate) {
             asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+                "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
                 : "memory");
         }
 
         __device__ __forceinline__ void
-        Commit(const uint32_t bar) {
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        Commit(const uint32_t elected, const uint32_t bar) {
+            asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar), "r"(elected) : "memory");
         }
 
         __device__ __forceinline__ void
@@ -111,8 +121,12 @@ namespace erl_gp {
             asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
         }
 
+        // try_wait suspends the thread for a hardware-defined time per attempt; a protocol error would otherwise hang the GPU
+        // until the watchdog of the box fires, so the number of attempts is bounded and the kernel traps instead
+        // (-DERL_GP_TC_NO_WATCHDOG removes the counter).
         __device__ __forceinline__ void
         MbarWait(const uint32_t bar, const uint32_t parity) {
+#ifdef ERL_GP_TC_NO_WATCHDOG
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "WAIT_%=:\n\t"
@@ -122,6 +136,13 @@ namespace erl_gp {
                 "DONE_%=:\n\t}\n" ::"r"(bar),
                 "r"(parity)
                 : "memory");
+#else
+            uint32_t done = 0;
+            for (uint32_t tries = 0; !done; ++tries) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (!done && tries > (1u << 22)) { __trap(); }
+            }
+#endif
         }
 
         __device__ __forceinline__ void
@@ -367,7 +388,11 @@ namespace erl_gp {
                             }
                             // (b) minus the accumulated updates (the tensor core subtracted them from zero)
                             if (j > 0) {
-                                MbarWait(bars + 8 * kBarMma0, n_m0 & 1);
+                                if (is_t) {
+                                    MbarWait(bars + 8 * kBarMma0, n_m0 & 1);
+                                } else {
+                                    MbarWait(bars + 8 * kBarMma1, n_m1 & 1);
+                                }
                                 FenceAfter();
                                 float d[16];
                                 TmemLd16(my_tmem + c0, d);
@@ -381,7 +406,10 @@ namespace erl_gp {
                                 tile_y[row - c0] = yacc;
                             }
                         }
-                        if (j > 0) { n_m0 += 1; }
+                        if (j > 0) {
+                            n_m0 += 1;
+                            if (!is_t) { n_m1 += 1; }  // the query rows are done with this phase (waited above, or not needed: no queries)
+                        }
                         if (is_t && warp == (c0 >> 5)) { MbarArrive(bars + 8 * kBarTile); }
                         // (d) Dinv_j and z_j
                         MbarWait(bars + 8 * kBarDinv, n_dinv & 1);
@@ -428,7 +456,7 @@ namespace erl_gp {
                         }
                         // (f) operands of the trailing update
                         if (!last) {
-                            if (j > 0) {
+                            if (j > 0 && is_t) {
                                 MbarWait(bars + 8 * kBarMma1, n_m1 & 1);  // the previous update no longer reads the buffers / TMEM columns
                                 n_m1 += 1;
                                 FenceAfter();
@@ -494,44 +522,47 @@ namespace erl_gp {
                             MbarWait(bars + 8 * kBarFull, n_full & 1);
                             n_full += 1;
                             FenceAfter();
-                            if (lane == 0) {
+                            {
+                                // batch 0 (mbarrier Mma0): the training rows' columns of the NEXT panel - all the serial chain waits for;
+                                // batch 1 (mbarrier Mma1): the query rows' next-panel columns and everything to the right, both groups
+                                const uint32_t elected = ElectOne();
                                 const int n_rest = npr - c0 - 32;  // columns after the next panel
 #pragma unroll 1
-                                for (int part = 0; part < 2; ++part) {
+                                for (int batch = 0; batch < 4; ++batch) {  // (T, next), (Q, next), (T, rest), (Q, rest)
+                                    const int gq = batch & 1;
+                                    const int part = batch >> 1;
                                     const int ncols = part == 0 ? 16 : n_rest;
                                     const int col0 = c0 + 16 + 16 * part;
-                                    if (ncols > 0) {
+                                    if (ncols > 0 && (gq == 0 || has_q)) {
                                         const uint32_t idesc = InstrDesc(ncols);
                                         const uint32_t brow_off = static_cast<uint32_t>(col0 >> 3) * 128u;  // B = rows col0 .. of L_j
-#pragma unroll 1
-                                        for (int gq = 0; gq < (has_q ? 2 : 1); ++gq) {
-                                            const uint32_t dcol = tmem + 128u * gq + col0;
-                                            const uint32_t a_hi = tmem + 128u * gq + c0;
-                                            const uint32_t a_lo = tmem + 128u * gq + c0 - 16;
+                                        const uint32_t dcol = tmem + 128u * gq + col0;
+                                        const uint32_t a_hi = tmem + 128u * gq + c0;
+                                        const uint32_t a_lo = tmem + 128u * gq + c0 - 16;
 #pragma unroll
-                                            for (int ks = 0; ks < 2; ++ks) {
-                                                const uint64_t bhi = SmemDesc(s_bhi + brow_off + ks * 2 * kChunkBytes);
-                                                const uint64_t blo = SmemDesc(s_blo + brow_off + ks * 2 * kChunkBytes);
-                                                const uint32_t acc0 = (j > 0 || ks > 0) ? 1u : 0u;
-                                                if (j == 0) {
-                                                    MmaSS(dcol, SmemDesc((gq == 0 ? s_blo : s_aqlo) + ks * 2 * kChunkBytes), bhi, idesc, acc0);
-                                                } else {
-                                                    MmaTS(dcol, a_lo + 8 * ks, bhi, idesc, acc0);
-                                                }
-                                                MmaTS(dcol, a_hi + 8 * ks, blo, idesc, 1u);
-                                                MmaTS(dcol, a_hi + 8 * ks, bhi, idesc, 1u);
+                                        for (int ks = 0; ks < 2; ++ks) {
+                                            const uint64_t bhi = SmemDesc(s_bhi + brow_off + ks * 2 * kChunkBytes);
+                                            const uint64_t blo = SmemDesc(s_blo + brow_off + ks * 2 * kChunkBytes);
+                                            const uint32_t acc0 = (j > 0 || ks > 0) ? 1u : 0u;
+                                            if (j == 0) {
+                                                MmaSS(elected, dcol, SmemDesc((gq == 0 ? s_blo : s_aqlo) + ks * 2 * kChunkBytes), bhi, idesc, acc0);
+                                            } else {
+                                                MmaTS(elected, dcol, a_lo + 8 * ks, bhi, idesc, acc0);
                                             }
+                                            MmaTS(elected, dcol, a_hi + 8 * ks, blo, idesc, 1u);
+                                            MmaTS(elected, dcol, a_hi + 8 * ks, bhi, idesc, 1u);
                                         }
                                     }
-                                    Commit(bars + 8 * (part == 0 ? kBarMma0 : kBarMma1));
+                                    if (batch == 0) { Commit(elected, bars + 8 * kBarMma0); }
                                 }
+                                Commit(elected, bars + 8 * kBarMma1);
                             }
                             __syncwarp();
                         }
                     }
                 }
                 // the last update's second commit has not been consumed by the row threads yet
-                if (warp < 8 && nblk > 1) {
+                if (is_t && nblk > 1) {  // (the query rows consumed this phase in the last panel; the CTA barrier below covers them otherwise)
                     MbarWait(bars + 8 * kBarMma1, n_m1 & 1);
                     n_m1 += 1;
                 }

@@ -10,7 +10,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liberl_gp_b200.so")
+# ERL_GP_B200_LIB: another build of the same library (kernel experiments: timing / A-B variants), never a fallback
+LIB_PATH = os.environ.get("ERL_GP_B200_LIB") or os.path.join(_HERE, "lib", "liberl_gp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "erl_gp_b200.h")
 
 STATUS_OK = 0

@@ -530,6 +530,88 @@ def main():
             e2e["variants"] = variants
             del h_l_t, h_alpha_t
 
+    # ---- strong scaling: ONE stream of b GPs cut into `world` contiguous ranges (BASELINE configs[3]: "50k independent GPs ...
+    #      sharded across 1/2/4/8 GPUs").  (a) one process per GPU (this launch): rank r takes range r, device-timed and from host
+    #      buffers, max over ranks; (b) ONE process driving all the GPUs through erl_gp_batch_train_predict_multi_f32 (rank 0,
+    #      the other ranks wait): the host gather is the devices' copies into the caller's arrays, inside the timed region.
+    strong = None
+    if world > 1 and args.phase == "fused" and not args.no_e2e:
+        import ctypes as C
+
+        from erl_gaussian_process_b200.host import _p
+
+        bs = b // world
+        g0 = rank * bs
+        sl = slice(g0, g0 + bs)
+        q0 = int(q_offsets[g0])
+        off_s = np.ascontiguousarray(q_offsets[g0:g0 + bs + 1] - q0)
+        tqs = int(off_s[-1])
+        part = gp.BatchGp(bs, n, d, w["kernel"], w["scale"], np_dt, ctx)
+        part.upload(host["n_train"][sl], host["x"][sl], host["y"][sl], host["var"][sl])
+        d_off_s = torch.from_numpy(off_s).to(dev)
+
+        def strong_step():
+            part.train_predict_dev(d_off_s, d_qx[q0:q0 + tqs], tqs, d_mean[q0:q0 + tqs], d_var[q0:q0 + tqs], d_valid[q0:q0 + tqs], min_num_samples=0, write_l=True)
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            strong_step()
+        e1.record(stream)
+        barrier()
+        tms_s = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms_s, op=dist.ReduceOp.MAX)
+        off_host_t, off_host = pinned(off_s)
+        fn_s = ctx.fn("erl_gp_batch_train_predict", np_dt)
+
+        def strong_e2e_step():
+            rc = fn_s(part.handle, C.c_long(0), _p(host["n_train"][sl]), _p(host["x"][sl]), _p(host["y"][sl]), _p(host["var"][sl]), _p(off_host), _p(host["q_x"][q0:q0 + tqs]), C.c_long(tqs),
+                      None, None, _p(h_info[sl]), _p(h_mean[q0:q0 + tqs]), _p(h_var[q0:q0 + tqs]), _p(h_valid[q0:q0 + tqs]))
+            assert rc == 0, rc
+
+        for _ in range(2):
+            strong_e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            strong_e2e_step()
+        barrier()
+        tt = torch.tensor([(time.perf_counter() - t0) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "gps_total": bs * world, "gps_per_gpu": bs,
+                  "kernel": {"ms_per_step": float(tms_s.item()), "value": bs * world * t / (float(tms_s.item()) * 1e-3), "unit": "test-points/s"},
+                  "e2e": {"ms_per_step": float(tt.item()) * 1e3, "value": bs * world * t / float(tt.item()), "unit": "test-points/s",
+                          "api": "one process per GPU, erl_gp_batch_train_predict_f32 on the rank's contiguous range (pinned host buffers)"}}
+        del part
+        # (b) one process, all the GPUs
+        barrier()
+        if rank == 0:
+            try:
+                multi = gp.MultiDeviceBatchGp(bs * world, n, d, w["kernel"], w["scale"], np_dt, devices=list(range(world)))
+                nb = bs * world
+                tqm = int(q_offsets[nb])
+                off_m_t, off_m = pinned(np.ascontiguousarray(q_offsets[:nb + 1]))
+                out = {"mean": h_mean[:tqm], "var": h_var[:tqm], "valid": h_valid[:tqm], "info": h_info[:nb]}
+
+                def multi_step():
+                    multi.train_predict(host["n_train"][:nb], host["x"][:nb], host["y"][:nb], host["var"][:nb], off_m, host["q_x"][:tqm], want_l=False, want_alpha=False, out=out)
+
+                for _ in range(2):
+                    multi_step()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    multi_step()
+                dtm = (time.perf_counter() - t0) / 10
+                assert np.isfinite(h_mean[:tqm]).all() and h_valid[:tqm].all() and (h_info[:nb] == 0).all()
+                strong["single_process_multi_device"] = {"ms_per_step": dtm * 1e3, "value": nb * t / dtm, "unit": "test-points/s", "devices": world,
+                                                         "api": "erl_gp_batch_train_predict_multi_f32: one host thread + three streams per device, results written straight into the caller's pinned arrays"}
+                del multi
+            except Exception as exc:  # e.g. the launcher restricted this rank to one visible device
+                strong["single_process_multi_device"] = {"unavailable": repr(exc)[:200]}
+        barrier()
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         alg_bytes = algorithmic_bytes_per_gp(n, d, t, s) * b
@@ -553,6 +635,8 @@ def main():
                          "fp32_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 71.05, "note": "FFMA peak measured with tools/mma_rate.cu (FFMA2 with fresh operands sustains ~55, tools/fma_lds_rate.cu); factorisation and predict run on the tensor pipe as 3xTF32 mma.sync (276 TFLOP/s TF32 peak = 92 FP32-equivalent), pivot blocks / back-substitution / covariance entries on the FP32 pipe; the kernel is latency / issue bound, not HBM bound, see DESIGN.md"}},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_baseline(w, args.ref_sample)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -8,6 +8,7 @@ from . import _capi, sharding
 from ._capi import ErlGpError, KERNELS, load
 from .host import (
     BatchGp,
+    MultiDeviceBatchGp,
     Context,
     LidarGaussianProcess2D,
     RangeSensorGaussianProcess3D,
@@ -19,6 +20,7 @@ from .host import (
 
 __all__ = [
     "BatchGp",
+    "MultiDeviceBatchGp",
     "Context",
     "ErlGpError",
     "KERNELS",

@@ -2,6 +2,8 @@
 #include "erl_gp_internal.cuh"
 
 #include <cstdlib>
+#include <thread>
+#include <vector>
 
 namespace erl_gp {
 
@@ -293,6 +295,67 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // One process, several GPUs (src/lidar_gp_2d.cpp:366-392: the partitions are independent, the reference loops over them with
+    // OpenMP): batch i takes the next batches[i]->num_gps GPs of the caller's stream - contiguous GP ranges, no exchange between
+    // devices.  One host thread per batch drives that device's upload / kernel / download pipeline; every device writes its
+    // results straight into the caller's arrays, which is the whole "host gather".
+    template<typename T>
+    static int
+    BatchTrainPredictMulti(
+        Batch<T> *const *batches,
+        long num_batches,
+        long min_num_samples,
+        const int *n_train,
+        const T *x,
+        const T *y,
+        const T *var,
+        const long *q_offsets,
+        const T *q_x,
+        long num_q,
+        T *l,
+        T *alpha,
+        int *info,
+        T *mean,
+        T *variance,
+        uint8_t *valid) {
+        if (batches == nullptr || num_batches <= 0 || q_offsets == nullptr || n_train == nullptr || x == nullptr || y == nullptr || var == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        long total = 0;
+        for (long i = 0; i < num_batches; ++i) {
+            if (batches[i] == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+            if (batches[i]->max_n != batches[0]->max_n || batches[i]->x_dim != batches[0]->x_dim) {
+                return SetError(batches[0]->ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "multi: batch %ld has another max_n / x_dim than batch 0", i);
+            }
+            total += batches[i]->num_gps;
+        }
+        if (!QueryOffsetsOk(q_offsets, total, num_q)) {
+            return SetError(batches[0]->ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "multi: q_offsets must start at 0, be non-decreasing and end at num_q = %ld over the %ld GPs of all batches", num_q, total);
+        }
+        const long max_n = batches[0]->max_n, d = batches[0]->x_dim;
+        std::vector<int> status(static_cast<size_t>(num_batches), ERL_GP_STATUS_OK);
+        std::vector<std::vector<long>> offsets(static_cast<size_t>(num_batches));
+        std::vector<long> first(static_cast<size_t>(num_batches) + 1, 0);
+        for (long i = 0; i < num_batches; ++i) { first[i + 1] = first[i] + batches[i]->num_gps; }
+        auto run = [&](const long i) {
+            const long g0 = first[i], g1 = first[i + 1];
+            const long t0 = q_offsets[g0], t1 = q_offsets[g1];
+            std::vector<long> &off = offsets[i];  // the query lists of this range, re-based to 0
+            off.resize(static_cast<size_t>(g1 - g0) + 1);
+            for (long g = g0; g <= g1; ++g) { off[g - g0] = q_offsets[g] - t0; }
+            status[i] = BatchTrainPredictHost<T>(batches[i], min_num_samples, n_train + g0, x + g0 * max_n * d, y + g0 * max_n, var + g0 * max_n, off.data(),
+                                                 q_x != nullptr ? q_x + t0 * d : nullptr, t1 - t0, l != nullptr ? l + g0 * max_n * max_n : nullptr,
+                                                 alpha != nullptr ? alpha + g0 * max_n : nullptr, info != nullptr ? info + g0 : nullptr, mean != nullptr ? mean + t0 : nullptr,
+                                                 variance != nullptr ? variance + t0 : nullptr, valid != nullptr ? valid + t0 : nullptr);
+        };
+        std::vector<std::thread> workers;
+        for (long i = 1; i < num_batches; ++i) { workers.emplace_back(run, i); }
+        run(0);
+        for (std::thread &w : workers) { w.join(); }
+        for (long i = 0; i < num_batches; ++i) {
+            if (status[i] != ERL_GP_STATUS_OK) { return status[i]; }
+        }
+        return ERL_GP_STATUS_OK;
+    }
+
     template<typename T>
     int
     BatchGetGp(Batch<T> *b, long g, int *info, long *n, T *l, long ld_l, T *alpha) {
@@ -534,6 +597,11 @@ erl_gp_context_kernel_launches(const erl_gp_context *ctx, long *count) {
     int erl_gp_batch_train_predict_##SFX(erl_gp_batch_##SFX *batch, long min_num_samples, const int *n_train, const T *x, const T *y, const T *var, const long *q_offsets,   \
                                          const T *q_x, long num_q, T *l, T *alpha, int *info, T *mean, T *variance, uint8_t *valid) {                                        \
         return BatchTrainPredictHost<T>(batch, min_num_samples, n_train, x, y, var, q_offsets, q_x, num_q, l, alpha, info, mean, variance, valid);                           \
+    }                                                                                                                                                                        \
+    int erl_gp_batch_train_predict_multi_##SFX(erl_gp_batch_##SFX *const *batches, long num_batches, long min_num_samples, const int *n_train, const T *x, const T *y,        \
+                                               const T *var, const long *q_offsets, const T *q_x, long num_q, T *l, T *alpha, int *info, T *mean, T *variance, uint8_t *valid) { \
+        return BatchTrainPredictMulti<T>(reinterpret_cast<Batch<T> *const *>(batches), num_batches, min_num_samples, n_train, x, y, var, q_offsets, q_x, num_q, l, alpha, info,  \
+                                         mean, variance, valid);                                                                                                             \
     }                                                                                                                                                                        \
     int erl_gp_batch_download_##SFX(erl_gp_batch_##SFX *batch, T *l, T *alpha, int *info) { return BatchDownload<T>(batch, l, alpha, info); }                                \
     int erl_gp_batch_get_gp_##SFX(erl_gp_batch_##SFX *batch, long gp_index, int *info, long *n, T *l, long ld_l, T *alpha) {                                                 \

@@ -54,6 +54,9 @@ namespace erl_gp {
         constexpr int kOperandBytes = 128 * 16 * 4;  // 128 rows x 16 k x FP32
         constexpr int kBandLd = 36;  // floats per row of a band hand-over buffer: S (16), D (16), y (1), pad
         constexpr int kLbLd = 20;
+#ifndef ERL_GP_TC_SLEEP_NS
+#define ERL_GP_TC_SLEEP_NS 0  // back-off of the waits that are not on the critical path of a GP (A/B builds)
+#endif
 
         // shared memory (bytes): the row-GP layout, then the MMA operand buffers and the small hand-over buffers
         constexpr size_t kOffB = (Lay::kBytes + 127) / 128 * 128;      // rows of L_j: [panel parity][hi, lo] (B operands; T's A_lo at panel 0)
@@ -64,7 +67,8 @@ namespace erl_gp {
         constexpr size_t kOffLt = kOffLb + 16 * kLbLd * 4;             // rows of L_jj as the pivot warp leaves them, [panel parity][16][kLbLd]
         constexpr size_t kOffBars = kOffLt + 2 * 16 * kLbLd * 4;       // 9 mbarriers (16 slots)
         constexpr size_t kOffSlot = kOffBars + 16 * 8;                 // TMEM base address, fail flags [GP parity]
-        constexpr size_t kSmemBytes = kOffSlot + 16;
+        constexpr size_t kOffDbg = kOffSlot + 16;                      // -DERL_GP_TC_WATCHDOG_PRINT: one progress word per warp
+        constexpr size_t kSmemBytes = kOffDbg + 64;
         static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
 
         // mbarriers.  A waiter names a phase by its parity only, so a producer must never complete TWO phases of a barrier before
@@ -142,22 +146,35 @@ namespace erl_gp {
         // hang the GPU until the watchdog of the box fires, so the number of attempts is bounded and the kernel traps instead
         // (-DERL_GP_TC_WATCHDOG_PRINT names the barrier first: it costs ~25 instructions per wait, and the instruction cache
         // is what this kernel runs out of; -DERL_GP_TC_NO_WATCHDOG removes the counter).
+        template<int SLEEP_NS = 0>
         __device__ __forceinline__ void
         MbarWait(const uint32_t bar, const uint32_t parity) {
             uint32_t done = 0;
-#ifndef ERL_GP_TC_NO_WATCHDOG
+#ifdef ERL_GP_TC_WATCHDOG_PRINT
+            const long long t_start = clock64();
+#elif !defined(ERL_GP_TC_NO_WATCHDOG)
             uint32_t tries = 0;
 #endif
             while (true) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
                 if (done) { break; }
-#ifndef ERL_GP_TC_NO_WATCHDOG
-                if (++tries > (1u << 22)) {
+                if (SLEEP_NS > 0) { __nanosleep(SLEEP_NS); }  // waits off the critical path: keep the polling out of the issue slots
 #ifdef ERL_GP_TC_WATCHDOG_PRINT
-                    if ((threadIdx.x & 15) == 0) { printf("mbarrier time-out: CTA %d thread %d barrier %u parity %u\n", blockIdx.x, threadIdx.x, (bar >> 3) & 15u, parity); }
-#endif
+                if (clock64() - t_start > 1500000000ll) {  // debugging build: every waiter names its barrier, then the kernel traps
+                    if ((threadIdx.x & 31) == 0) {
+                        extern __shared__ __align__(1024) unsigned char smem_dbg[];
+                        const volatile int *dbg = reinterpret_cast<const volatile int *>(smem_dbg + kOffDbg);
+                        printf("mbarrier time-out: CTA %d warp %d barrier %u parity %u | progress (gp:panel:stage) %d:%d:%d %d:%d:%d %d:%d:%d %d:%d:%d | %d:%d:%d %d:%d:%d %d:%d:%d %d:%d:%d | %d:%d:%d %d:%d:%d\n",
+                               blockIdx.x, threadIdx.x >> 5, (bar >> 3) & 15u, parity, dbg[0] >> 8, (dbg[0] >> 4) & 15, dbg[0] & 15, dbg[1] >> 8, (dbg[1] >> 4) & 15, dbg[1] & 15, dbg[2] >> 8,
+                               (dbg[2] >> 4) & 15, dbg[2] & 15, dbg[3] >> 8, (dbg[3] >> 4) & 15, dbg[3] & 15, dbg[4] >> 8, (dbg[4] >> 4) & 15, dbg[4] & 15, dbg[5] >> 8, (dbg[5] >> 4) & 15, dbg[5] & 15,
+                               dbg[6] >> 8, (dbg[6] >> 4) & 15, dbg[6] & 15, dbg[7] >> 8, (dbg[7] >> 4) & 15, dbg[7] & 15, dbg[8] >> 8, (dbg[8] >> 4) & 15, dbg[8] & 15, dbg[9] >> 8, (dbg[9] >> 4) & 15,
+                               dbg[9] & 15);
+                    }
+                    for (int i = 0; i < 1000; ++i) { __nanosleep(1000000); }
                     asm volatile("trap;");
                 }
+#elif !defined(ERL_GP_TC_NO_WATCHDOG)
+                if (++tries > (1u << 22)) { asm volatile("trap;"); }
 #endif
             }
         }
@@ -223,7 +240,7 @@ namespace erl_gp {
         __device__ __forceinline__ void
         PanelEntries(const rowgp::CovCoef &cov, const float2 *__restrict__ soa, const int cb, const float (&negp)[XDIM], const bool train, const int row, const int n, const float diag,
                      float (&x)[16]) {
-#pragma unroll 1
+#pragma unroll 2
             for (int it = 0; it < 4; ++it) {
                 const int cq = cb + 4 * it;
                 float e[4];
@@ -381,6 +398,11 @@ namespace erl_gp {
 
         // -DERL_GP_TC_TIMING: per-role cycle counters (threads 96 / 128 / 256 / 288 / 320: last training warp, first query warp,
         // pivot, MMA, back-substitution warp), summed over the GPs of a CTA and printed by CTA 7 (kernel experiments only)
+#ifdef ERL_GP_TC_WATCHDOG_PRINT
+#define ERL_GP_TC_AT(j_, stage_) { if (lane == 0) { reinterpret_cast<volatile int *>(smem_raw + kOffDbg)[warp] = (g << 8) | ((j_) << 4) | (stage_); } }
+#else
+#define ERL_GP_TC_AT(j_, stage_)
+#endif
 #ifdef ERL_GP_TC_TIMING
 #define ERL_GP_TC_TICK(k_) { const long long now_ = clock64(); tm_acc[k_] += now_ - tm_t; tm_t = now_; }
 #else
@@ -502,6 +524,9 @@ namespace erl_gp {
                     }
                     continue;
                 }
+#ifdef ERL_GP_TC_TRACE
+                if (blockIdx.x == ERL_GP_TC_TRACE && lane == 0) { printf("trace: warp %d GP %d n %d q %ld..%ld tg %u\n", warp, g, n, q0, q1, tg); }
+#endif
                 const int nblk = (n + 15) >> 4;
                 const int npr = nblk * 16;
                 const int nq = static_cast<int>(q1 - q0 < 128 ? q1 - q0 : 128);  // queries that ride along with the factorisation
@@ -528,7 +553,9 @@ namespace erl_gp {
 #pragma unroll
                         for (int d = 0; d < XDIM; ++d) { negp[d] = -row_in[d]; }
                     }
+                    ERL_GP_TC_AT(0, 1)
                     NamedBarrier(2, kRowThreads);  // the staged points of this GP are visible to all row threads
+                    ERL_GP_TC_AT(0, 2)
                     ERL_GP_TC_TICK(0)              // staging
                     float mean = 0.f, ss = 0.f;
                     float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
@@ -548,6 +575,11 @@ namespace erl_gp {
                             float v[16];
 #pragma unroll
                             for (int c = 0; c < 16; ++c) { v[c] = 0.f; }
+                            // A wait names its phase by parity only, so every training warp has to see each phase of the "previous
+                            // back-substitution done" barrier: the live warps wait for it before their first store to L below, a warp
+                            // whose rows lie beyond the padded size does it here (it would otherwise reach the wait for THIS GP's
+                            // back-substitution, further query tiles, one phase early - or two phases late).
+                            if (j == 0 && is_t && !warp_live) { MbarWait(bars + 8 * kBarEpi, tg & 1); }
                             if (warp_live) {
                                 // (a) the entries of this panel: Gram (training rows) / Ktest (query rows), minus the accumulated
                                 //     updates (the tensor core subtracted them from zero).  Look-ahead: the warp that holds the rows of
@@ -563,7 +595,12 @@ namespace erl_gp {
                                     if (j > 0) {
                                         if (!waited) {
                                             ERL_GP_TC_TICK(1)  // entries
-                                            MbarWait(bars + 8 * (is_t ? kBarMmaT : kBarMmaQ), ((is_t ? upd_base : updq_base) + j - 1) & 1);
+                                            ERL_GP_TC_AT(j, 3)
+                                            if (is_t) {
+                                                MbarWait(bars + 8 * kBarMmaT, (upd_base + j - 1) & 1);
+                                            } else {
+                                                MbarWait<ERL_GP_TC_SLEEP_NS>(bars + 8 * kBarMmaQ, (updq_base + j - 1) & 1);
+                                            }
                                             FenceAfter();
                                             waited = true;
                                             ERL_GP_TC_TICK(8)  // wait for the MMAs
@@ -593,7 +630,12 @@ namespace erl_gp {
                                     MbarWait(bars + 8 * (kBarBand + ((pan_base + j + 1) & 1)), ((pan_base + j + 1) >> 1) & 1);
                                 }
 #endif
-                                MbarWait(bars + 8 * kBarDinv, (pan_base + j) & 1);
+                                ERL_GP_TC_AT(j, 4)
+                                if (is_t) {
+                                    MbarWait(bars + 8 * kBarDinv, (pan_base + j) & 1);
+                                } else {
+                                    MbarWait<ERL_GP_TC_SLEEP_NS>(bars + 8 * kBarDinv, (pan_base + j) & 1);
+                                }
                                 ERL_GP_TC_TICK(3)  // wait for the pivot warp
                                 // (c) v = x Dinv_j^T, then the z products; the rows of the tile take their row of L_jj from the pivot warp
                                 const bool in_tile = is_t && row >= c0 && row < c0 + 16;
@@ -663,15 +705,53 @@ namespace erl_gp {
                                     if (lane == 0) { MbarArrive(bars + 8 * (kBarBand + ((pan_base + j + 1) & 1))); }
                                     ERL_GP_TC_TICK(7)  // look-ahead update (band warp)
                                 }
-                                // (c'') the shared-memory copy of L (back-substitution, further query tiles)
+                                // (d) operands of the trailing update - before the stores of L: the tensor core waits for them (TMEM columns
+                                //     and operand buffers are free: this group's update j - 1 was awaited above, and its commit followed the
+                                //     other group's update j - 2)
+                                if (!last) {
+                                    uint32_t hi[16], lo[16];
+#pragma unroll
+                                    for (int c = 0; c < 16; ++c) {
+                                        hi[c] = __float_as_uint(v[c]);
+                                        lo[c] = rowgp::Tf32Lo(v[c]);
+                                    }
+                                    TmemSt16(my_tmem + c0, hi);                     // X_j's own columns are dead: V_hi
+                                    if (j > 0) { TmemSt16(my_tmem + c0 - 16, lo); }  // V_{j-1} hi is dead as well: V_lo
+                                    if (is_t) {
+                                        const uint32_t sb = s_b + static_cast<uint32_t>(j & 1) * 2u * kOperandBytes;
+                                        StoreOperandRow(sb, row, hi);
+                                        StoreOperandRow(sb + kOperandBytes, row, lo);
+                                    } else if (j == 0) {
+                                        StoreOperandRow(s_aqlo, row, lo);
+                                    }
+                                    TmemStWait();
+                                    FenceProxyAsync();
+                                    FenceBefore();
+                                    if (is_t) {
+                                        // dead warps (rows above the panel, or beyond the padded size) do not come here: the warp
+                                        // that is live in every panel arrives for them
+                                        int n_live = 0;
+#pragma unroll
+                                        for (int w = 0; w < 4; ++w) { n_live += (32 * w + 31 >= c0 && 32 * w < npr) ? 1 : 0; }
+                                        __syncwarp();
+                                        if (lane == 0) { MbarArriveCount(bars + 8 * kBarOpT, warp == w_last ? static_cast<uint32_t>(5 - n_live) : 1u); }
+                                    } else {
+                                        __syncwarp();
+                                        if (lane == 0) { MbarArrive(bars + 8 * kBarOpQ); }
+                                    }
+                                    ERL_GP_TC_TICK(5)  // operand split and stores
+                                }
+                                // (d') the shared-memory copy of L (back-substitution, further query tiles)
                                 if (is_t && (below || in_tile)) {
+                                    ERL_GP_TC_AT(j, 5)
                                     if (j == 0) { MbarWait(bars + 8 * kBarEpi, tg & 1); }  // the back-substitution of the previous GP has read L
+                                    ERL_GP_TC_AT(j, 6)
                                     float *lcol = lp + Lay::Base(j) + (row - c0);
 #pragma unroll
                                     for (int c = 0; c < 16; ++c) { lcol[c * Lay::Stride(j)] = v[c]; }
                                 }
                             }
-                            // (d) L to HBM straight from the registers: one 128-byte line per warp and column; the rows above the tile
+                            // (e) L to HBM straight from the registers: one 128-byte line per warp and column; the rows above the tile
                             //     write the zeros of the strict upper triangle (the rows of the tile are written by the pivot warp)
                             if (store_l) {  // (every row of the matrix: below the tile V, in the tile L_jj, above it zeros)
                                 float *gp = gl + row + c0 * p.max_n;
@@ -693,44 +773,9 @@ namespace erl_gp {
                                 }
                             }
                             ERL_GP_TC_TICK(4)  // V = X Dinv^T, z products, L stores
-                            if (!warp_live) { continue; }
-                            // (f) operands of the trailing update (TMEM columns and operand buffers are free: this group's
-                            //     update j - 1 was awaited above, and its commit followed the other group's update j - 2)
-                            if (!last) {
-                                uint32_t hi[16], lo[16];
-#pragma unroll
-                                for (int c = 0; c < 16; ++c) {
-                                    hi[c] = __float_as_uint(v[c]);
-                                    lo[c] = rowgp::Tf32Lo(v[c]);
-                                }
-                                TmemSt16(my_tmem + c0, hi);                     // X_j's own columns are dead: V_hi
-                                if (j > 0) { TmemSt16(my_tmem + c0 - 16, lo); }  // V_{j-1} hi is dead as well: V_lo
-                                if (is_t) {
-                                    const uint32_t sb = s_b + static_cast<uint32_t>(j & 1) * 2u * kOperandBytes;
-                                    StoreOperandRow(sb, row, hi);
-                                    StoreOperandRow(sb + kOperandBytes, row, lo);
-                                } else if (j == 0) {
-                                    StoreOperandRow(s_aqlo, row, lo);
-                                }
-                                TmemStWait();
-                                FenceProxyAsync();
-                                FenceBefore();
-                                if (is_t) {
-                                    // dead warps (rows above the panel, or beyond the padded size) do not come here: the warp
-                                    // that is live in every panel arrives for them
-                                    int n_live = 0;
-#pragma unroll
-                                    for (int w = 0; w < 4; ++w) { n_live += (32 * w + 31 >= c0 && 32 * w < npr) ? 1 : 0; }
-                                    __syncwarp();
-                                    if (lane == 0) { MbarArriveCount(bars + 8 * kBarOpT, warp == w_last ? static_cast<uint32_t>(5 - n_live) : 1u); }
-                                } else {
-                                    __syncwarp();
-                                    if (lane == 0) { MbarArrive(bars + 8 * kBarOpQ); }
-                                }
-                                ERL_GP_TC_TICK(5)  // operand split and stores
-                            }
                         }
                     }
+                    ERL_GP_TC_AT(15, 7)
                     if (is_t) {
                         __syncwarp();
                         if (lane == 0) { MbarArrive(bars + 8 * kBarFact); }
@@ -754,7 +799,11 @@ namespace erl_gp {
                     ERL_GP_TC_TICK(6)  // outputs
                     // ---- query tiles beyond the first 128: the mma.sync predict of erl_gp_rowgp.cuh on its shared-memory layout ----
                     if (is_t && q1 - q0 > 128) {
-                        MbarWait(bars + 8 * kBarEpi, (tg + 1) & 1);  // alpha of THIS GP is in shared memory
+                        ERL_GP_TC_AT(15, 8)
+                        // alpha of THIS GP is in shared memory (every training warp has seen the previous back-substitution complete
+                        // during panel 0, so the parity names the right phase)
+                        MbarWait(bars + 8 * kBarEpi, (tg + 1) & 1);
+                        ERL_GP_TC_AT(15, 9)
                         if (s_fail[par_g] == 0) {
                             float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
                             pt.x = -negp[0];
@@ -805,11 +854,13 @@ namespace erl_gp {
                         for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]); }
                         if (j == nblk - 1 && lane == 0) { s_fail[par_g] = fail; }
                         __syncwarp();
+                        // The pivot warp's "factorisation done" arrival comes BEFORE the last Dinv is published: no training warp can
+                        // leave this GP (and, with a short next GP, arrive for the NEXT phase of that barrier) ahead of it.  The phase
+                        // still completes only after the warp that waits for this Dinv has stored its rows and arrived.
+                        if (j == nblk - 1 && lane == 0) { MbarArrive(bars + 8 * kBarFact); }
                         if (lane == 0) { MbarArrive(bars + 8 * kBarDinv); }
                         ERL_GP_TC_TICK(2)  // pivot warp: pivot tile
                     }
-                    __syncwarp();
-                    if (lane == 0) { MbarArrive(bars + 8 * kBarFact); }
                 } else if (warp == 9) {
                     // ================= MMA warp =================
                     const uint32_t elected = ElectOne();
@@ -846,7 +897,7 @@ namespace erl_gp {
                     }
                     // ---- alpha = L^-T z of this GP: the MMA warp has nothing to issue until the next GP's first V is ready (about one
                     //      pivot tile + one V after its start), which is the time the back-substitution takes ----
-                    MbarWait(bars + 8 * kBarFact, tg & 1);
+                    MbarWait<ERL_GP_TC_SLEEP_NS>(bars + 8 * kBarFact, tg & 1);
                     ERL_GP_TC_TICK(5)  // MMA warp: wait for the end of the factorisation
                     const int failed = s_fail[par_g];
                     if (failed == 0) {
@@ -858,6 +909,7 @@ namespace erl_gp {
                     if (lane == 0) { MbarArrive(bars + 8 * kBarEpi); }
                     ERL_GP_TC_TICK(6)  // MMA warp: back-substitution
                 }
+                ERL_GP_TC_AT(15, 10)
                 tg += 1;
                 pan_base += static_cast<uint32_t>(nblk);
                 upd_base += static_cast<uint32_t>(nblk - 1);
@@ -868,6 +920,9 @@ namespace erl_gp {
                 printf("tc timing tid %3d total %lld: %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", tid, clock64() - tm_start, tm_acc[0], tm_acc[1], tm_acc[2], tm_acc[3], tm_acc[4], tm_acc[5],
                        tm_acc[6], tm_acc[7], tm_acc[8]);
             }
+#endif
+#ifdef ERL_GP_TC_TRACE
+            if (blockIdx.x == ERL_GP_TC_TRACE && lane == 0) { printf("trace: warp %d leaves the GP loop\n", warp); }
 #endif
             FenceBefore();
             __syncthreads();

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import check, load
+from ._capi import ErlGpError, check, load
 
 
 def _sfx(dtype):
@@ -315,6 +315,50 @@ class BatchGp:
         info = np.zeros(b, dtype=np.int32)
         check(self.ctx.fn("erl_gp_batch_download", self.dtype)(self.handle, _p(l), _p(alpha), _p(info)), "batch_download", self.ctx.handle)
         return dict(L=None if l is None else l.transpose(0, 2, 1), alpha=alpha, info=info)
+
+
+class MultiDeviceBatchGp:
+    """One GP stream over several GPUs from ONE process (erl_gp_batch_train_predict_multi_*): contiguous GP ranges per device,
+    no exchange between devices, every device writes straight into the caller's arrays (src/lidar_gp_2d.cpp:366-392: the
+    partitions are independent).  ``devices`` may name a device more than once (two pipelines on one GPU)."""
+
+    def __init__(self, num_gps, max_n, x_dim, kernel, scale, dtype=np.float32, devices=None):
+        devices = list(range(_capi.device_count())) if devices is None else list(devices)
+        if not devices:
+            raise ErlGpError(-1, "MultiDeviceBatchGp", "no CUDA device")
+        self.dtype = np.dtype(dtype)
+        self.num_gps, self.max_n, self.x_dim = int(num_gps), int(max_n), int(x_dim)
+        nd = len(devices)
+        # contiguous ranges, the first (num_gps % nd) devices take one GP more (the arithmetic of sharding.shard_range)
+        self.counts = [num_gps // nd + (1 if i < num_gps % nd else 0) for i in range(nd)]
+        if any(c == 0 for c in self.counts):
+            raise ErlGpError(-1, "MultiDeviceBatchGp", "fewer GPs than devices")
+        self.contexts = [Context(dev) for dev in devices]
+        self.parts = [BatchGp(c, max_n, x_dim, kernel, scale, dtype, ctx) for c, ctx in zip(self.counts, self.contexts)]
+
+    def train_predict(self, n_train, x, y, var, q_offsets, q_x, min_num_samples=0, want_l=False, want_alpha=True, out=None):
+        """``out``: optional dict of preallocated (pinned) arrays mean / var / valid / info / alpha / L to write into."""
+        b, mn, d = self.num_gps, self.max_n, self.x_dim
+        n_train = np.ascontiguousarray(n_train, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=self.dtype).reshape(b, mn, d)
+        y = np.ascontiguousarray(y, dtype=self.dtype).reshape(b, mn)
+        var = np.ascontiguousarray(var, dtype=self.dtype).reshape(b, mn)
+        q_offsets = np.ascontiguousarray(q_offsets, dtype=np.int64)
+        q_x = np.ascontiguousarray(q_x, dtype=self.dtype).reshape(-1, d)
+        t = q_x.shape[0]
+        out = out or {}
+        l = out.get("L", np.zeros((b, mn, mn), dtype=self.dtype) if want_l else None)
+        alpha = out.get("alpha", np.zeros((b, mn), dtype=self.dtype) if want_alpha else None)
+        info = out.get("info", np.zeros(b, dtype=np.int32))
+        mean = out.get("mean", np.full(t, np.nan, dtype=self.dtype))
+        variance = out.get("var", np.full(t, np.nan, dtype=self.dtype))
+        valid = out.get("valid", np.zeros(t, dtype=np.uint8))
+        handles = (C.c_void_p * len(self.parts))(*[part.handle for part in self.parts])
+        ctx0 = self.contexts[0]
+        check(ctx0.fn("erl_gp_batch_train_predict_multi", self.dtype)(handles, C.c_long(len(self.parts)), C.c_long(min_num_samples), _p(n_train), _p(x), _p(y), _p(var), _p(q_offsets),
+                                                                     _p(q_x), C.c_long(t), _p(l), _p(alpha), _p(info), _p(mean), _p(variance), _p(valid)), "batch_train_predict_multi",
+              ctx0.handle)
+        return dict(L=None if l is None else l.transpose(0, 2, 1), alpha=alpha, info=info, mean=mean, var=variance, valid=valid.astype(bool))
 
 
 # ------------------------------------------------------------------------------------------

@@ -211,6 +211,20 @@ int erl_gp_batch_train_predict_f64(erl_gp_batch_f64 *batch, long min_num_samples
                                    const double *x, const double *y, const double *var, const long *q_offsets,
                                    const double *q_x, long num_q, double *l, double *alpha, int *info, double *mean,
                                    double *variance, uint8_t *valid);
+/* The same call over SEVERAL GPUs from one process (north_star: "sharded across the 8 GPUs of one box with only a host
+ * gather"; the loop it replaces, src/lidar_gp_2d.cpp:366-392 / src/range_sensor_gp_3d.cpp:334-360, has no dependency
+ * between partitions).  batches[i] was created on a context of device i with its share of the GPs; batch i takes the next
+ * batches[i]->num_gps GPs of the arrays (contiguous ranges, sum = the number of GPs described by q_offsets).  One host
+ * thread per batch drives that device; every device writes straight into the caller's arrays.  Host buffers should be
+ * page-locked (cudaHostRegister / cudaHostAlloc) for the copies to overlap. */
+int erl_gp_batch_train_predict_multi_f32(erl_gp_batch_f32 *const *batches, long num_batches, long min_num_samples,
+                                         const int *n_train, const float *x, const float *y, const float *var,
+                                         const long *q_offsets, const float *q_x, long num_q, float *l, float *alpha,
+                                         int *info, float *mean, float *variance, uint8_t *valid);
+int erl_gp_batch_train_predict_multi_f64(erl_gp_batch_f64 *const *batches, long num_batches, long min_num_samples,
+                                         const int *n_train, const double *x, const double *y, const double *var,
+                                         const long *q_offsets, const double *q_x, long num_q, double *l, double *alpha,
+                                         int *info, double *mean, double *variance, uint8_t *valid);
 /* Device -> host download of results; any pointer may be NULL. */
 int erl_gp_batch_download_f32(erl_gp_batch_f32 *batch, float *l, float *alpha, int *info);
 int erl_gp_batch_download_f64(erl_gp_batch_f64 *batch, double *l, double *alpha, int *info);

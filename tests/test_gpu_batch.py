@@ -162,3 +162,33 @@ def test_batch_is_deterministic(gp, max_n):
         else:
             for k in ref:
                 assert np.array_equal(ref[k], cur[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("dtype,max_n", [(np.float32, 128), (np.float64, 64)])
+def test_multi_device_single_process(gp, oracle, dtype, max_n):
+    """erl_gp_batch_train_predict_multi_*: one process, one pipeline (host thread + streams) per device, contiguous GP ranges,
+    every device writes straight into the caller's arrays.  Runs with two pipelines on device 0 everywhere and over every
+    visible GPU where there is more than one; the result must be bit-identical to the single-batch call (the ranges are
+    independent) and within tolerance of the oracle; ragged training sets / query lists, untrained GPs."""
+    rng = np.random.default_rng(91)
+    num_gps, x_dim = 2311, 3
+    batch = make_batch(rng, num_gps, max_n, x_dim, dtype, n_lo=0, n_hi=max_n, q_lo=0, q_hi=200)
+    n_train, x, y, var, q_offsets, q_x = batch
+    single = gp.BatchGp(num_gps, max_n, x_dim, "matern32", 0.3, dtype).train_predict(*batch, min_num_samples=3, want_l=True)
+    device_sets = [[0, 0], [0, 0, 0]]
+    if gp._capi.device_count() > 1:
+        device_sets.append(list(range(gp._capi.device_count())))
+    for devices in device_sets:
+        multi = gp.MultiDeviceBatchGp(num_gps, max_n, x_dim, "matern32", 0.3, dtype, devices=devices)
+        assert sum(multi.counts) == num_gps and max(multi.counts) - min(multi.counts) <= 1
+        out = multi.train_predict(*batch, min_num_samples=3, want_l=True)
+        for k in ("info", "valid", "mean", "var", "alpha", "L"):
+            assert np.array_equal(single[k], out[k], equal_nan=True), (devices, k)
+    kid = oracle.KERNELS["matern32"]
+    nt_ref = np.where(n_train > 3, n_train, 0).astype(np.int32)
+    ref = oracle.batched_train_predict(kid, 0.3, nt_ref, x, y, var, q_offsets, q_x)
+    qmask = np.repeat(nt_ref > 0, np.diff(q_offsets))
+    tol = TOL[np.dtype(dtype)]
+    assert err_mean(out["mean"][qmask], ref["mean"][qmask]) < tol and err_var(out["var"][qmask], ref["var"][qmask]) < tol
+    with pytest.raises(gp.ErlGpError):  # fewer GPs than devices
+        gp.MultiDeviceBatchGp(1, max_n, x_dim, "matern32", 0.3, dtype, devices=[0, 0])

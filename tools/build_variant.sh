@@ -15,7 +15,7 @@ objs=""
 for f in *.cu; do
   tu=${f%.cu}
   if [[ " $* " == *" $tu "* ]]; then
-    $NVCC $ARCH -O3 -std=c++17 -lineinfo -ccbin $(command -v g++) -Xcompiler -fPIC,-Wall,-fvisibility=hidden -I../../include -I. --expt-relaxed-constexpr -Xptxas -v $flags -c $f -o $VDIR/$tu.o 2> $VDIR/$tu.ptxas.log || { cat $VDIR/$tu.ptxas.log; exit 1; }
+    $NVCC $ARCH -O3 -std=c++17 -lineinfo -ccbin $(command -v g++) -Xcompiler -fPIC,-Wall,-fvisibility=hidden -I../../include -I. --expt-relaxed-constexpr -Xptxas -v -Xfatbin=-compress-all $flags -c $f -o $VDIR/$tu.o 2> $VDIR/$tu.ptxas.log || { cat $VDIR/$tu.ptxas.log; exit 1; }
     objs="$objs $VDIR/$tu.o"
   else
     objs="$objs $OBJDIR/$tu.o"

@@ -352,6 +352,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-variants", action="store_true", help="N=1: also time the host-buffer call with alpha and with L + alpha written back to the host")
+    ap.add_argument("--rowgp-tc", type=int, default=-1, choices=[-1, 0, 1],
+                    help="fused FP32 kernel for n <= 128: 1 = tcgen05 / TMEM kernel, 0 = mma.sync kernel, -1 = library default (mma.sync)")
+    ap.add_argument("--no-tc-variant", action="store_true", help="N=1: do not time the tcgen05 kernel in a child process beside the default kernel")
     ap.add_argument("--phase", default="fused", choices=["fused", "train", "predict", "split"],
                     help="diagnostics only: time the train kernel, the predict kernel or both as separate launches (the reported metric is always the fused step)")
     args = ap.parse_args()
@@ -396,6 +399,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)  # our kernels run on torch's current stream: its events time them
+    ctx.set_rowgp_tc(args.rowgp_tc)
     batch = gp.BatchGp(b, n, d, w["kernel"], w["scale"], np_dt, ctx)
 
     # pinned host buffers (the e2e path reads / writes these)
@@ -637,6 +641,23 @@ def main():
         }
         if strong is not None:
             line["strong"] = strong
+        tc_now = args.rowgp_tc == 1 or (args.rowgp_tc < 0 and os.environ.get("ERL_GP_ROWGP_TC", "0") not in ("", "0"))
+        if w["dtype"] == "f32" and n <= 128 and tc_now:
+            line["roofline"]["kernel"] = f"rowgp_tc::RowGpTcKernel<x_dim={d}> (tcgen05.mma kind::tf32, TMEM accumulators; one launch per step)"
+        if world == 1 and w["dtype"] == "f32" and n <= 128 and not tc_now and not args.no_tc_variant and args.phase == "fused":
+            # the same step on the tcgen05 / TMEM kernel, in a child process (a kernel under development must not be able to
+            # take the measured process down with it); device-timed, inputs resident, like `value`
+            import subprocess
+
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--rowgp-tc", "1", "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-e2e",
+                   "--no-cpu-baseline"] + (["--num-gps", str(args.num_gps)] if args.num_gps else [])
+            try:
+                res = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+                child = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+                line["tcgen05_variant"] = {"kernel": child["roofline"]["kernel"], "ms_per_step": child["ms_per_step"], "value": child["value"], "unit": child["unit"],
+                                           "roofline_frac": child["roofline"]["frac"], "select": "erl_gp_context_set_rowgp_tc(ctx, 1) or ERL_GP_ROWGP_TC=1"}
+            except Exception as exc:
+                line["tcgen05_variant"] = {"unavailable": repr(exc)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_baseline(w, args.ref_sample)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -685,9 +685,12 @@ namespace erl_gp {
             // generic shared-memory kernel below (A/B measurements and tests of the generic path)
             static const bool legacy = std::getenv("ERL_GP_BATCH_LEGACY") != nullptr;
             static const bool legacy_large = std::getenv("ERL_GP_BATCH_LEGACY_LARGE") != nullptr;  // generic kernel for 128 < n <= 256 only
-            // fused train + predict, n <= 128: the tcgen05 / TMEM kernel (erl_gp_rowgp_tc.cuh); ERL_GP_ROWGP_TC=0 keeps the mma.sync kernel
-            static const bool tc_off = std::getenv("ERL_GP_ROWGP_TC") != nullptr && std::atoi(std::getenv("ERL_GP_ROWGP_TC")) == 0;
-            if (max_n <= 128 && !legacy && !tc_off && mode == kBatchTrainPredict && params.q_out_index == nullptr && params.mapping == ERL_GP_MAPPING_NONE) {
+            // fused train + predict, n <= 128: the tcgen05 / TMEM kernel (erl_gp_rowgp_tc.cuh) when the context asks for it
+            // (erl_gp_context_set_rowgp_tc) or ERL_GP_ROWGP_TC=1; the mma.sync kernel below is the default: it is the faster of
+            // the two on the C4 stream (4.90 vs 5.30 ms)
+            static const bool tc_env = std::getenv("ERL_GP_ROWGP_TC") != nullptr && std::atoi(std::getenv("ERL_GP_ROWGP_TC")) != 0;
+            const bool tc_on = ctx->rowgp_tc >= 0 ? ctx->rowgp_tc != 0 : tc_env;
+            if (max_n <= 128 && !legacy && tc_on && mode == kBatchTrainPredict && params.q_out_index == nullptr && params.mapping == ERL_GP_MAPPING_NONE) {
                 return rowgp_tc::Launch<XDIM>(ctx, params);
             }
             if (max_n <= 128 && !legacy) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }

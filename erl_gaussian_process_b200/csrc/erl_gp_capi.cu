@@ -537,6 +537,13 @@ erl_gp_context_last_error(const erl_gp_context *ctx) {
 }
 
 int
+erl_gp_context_set_rowgp_tc(erl_gp_context *ctx, int on) {
+    if (ctx == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+    ctx->rowgp_tc = on < 0 ? -1 : (on != 0 ? 1 : 0);
+    return ERL_GP_STATUS_OK;
+}
+
+int
 erl_gp_context_kernel_launches(const erl_gp_context *ctx, long *count) {
     if (ctx == nullptr || count == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
     *count = ctx->launches;

@@ -15,6 +15,7 @@ struct erl_gp_context {
     int sm_count = 148;
     int max_smem_optin = 0;
     long launches = 0;
+    int rowgp_tc = -1;  // fused FP32 train + predict, n <= 128, on the tcgen05 / TMEM kernel: 1 / 0, -1 = ERL_GP_ROWGP_TC or the default
     char last_error[512] = {0};
     // look-ahead of the blocked Cholesky (erl_gp_dense.cu): side streams + events, created on first use
     cudaStream_t side_stream = nullptr, side_stream2 = nullptr;

@@ -106,8 +106,9 @@ namespace erl_gp {
         }
 
         __device__ __forceinline__ float
-        RsqrtRefined(const float d) {  // MUFU.RSQ + one Newton step
-            const float r = rsqrtf(d);
+        RsqrtRefined(const float d) {  // MUFU.RSQ + one Newton step (rsqrtf() wraps the MUFU in a denormal range test: four more
+            float r;                   // instructions on the serial chain of every pivot; a pivot that small has failed anyway)
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
             return r * fmaf(-0.5f * d * r, r, 1.5f);
         }
 

@@ -72,9 +72,16 @@ namespace erl_gp {
         static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
 
         // mbarriers.  A waiter names a phase by its parity only, so a producer must never complete TWO phases of a barrier before
-        // a consumer has looked at the first one.  The band hand-overs of tile 0 and tile 1 both happen at panel 0 without any
-        // dependency in between, hence one barrier per tile parity (tile t: barrier t & 1, phase t >> 1).
-        enum Bar : int { kBarBand = 0 /* and 1 */, kBarDinv = 2, kBarOpT = 3, kBarOpQ = 4, kBarMmaT = 5, kBarMmaQ = 6, kBarFact = 7, kBarEpi = 8 };
+        // every consumer has looked at the first one (the wait would then block on the phase after).  Where the protocol lets the
+        // producer run further ahead, the barrier is replicated and used round-robin:
+        //   * band hand-over: tiles 0 and 1 are both handed over at panel 0 with nothing in between -> 2 barriers (tile t:
+        //     barrier t & 1, phase t >> 1);
+        //   * Dinv: with the look-ahead, pivot tile j + 1 only needs the BAND warp to have consumed Dinv_j; the other training
+        //     warps are only bound by update j (Dinv_{j+2} needs it), the query warps by update j + 1 -> 4 barriers (panel p:
+        //     barrier p & 3, phase p >> 2).
+        //   The other barriers are safe with one instance: operands-ready / MMA-done alternate strictly per group, "factorisation
+        //   done" and "back-substitution done" are chained through the pivot warp's wait at the start of a GP (see the kernel).
+        enum Bar : int { kBarBand = 0 /* and 1 */, kBarDinv = 2 /* .. 5 */, kBarOpT = 6, kBarOpQ = 7, kBarMmaT = 8, kBarMmaQ = 9, kBarFact = 10, kBarEpi = 11 };
 
         // ---- PTX wrappers (syntax as in CUTLASS's cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp, tmem_allocator_sm100.hpp) ----
         __device__ __forceinline__ uint32_t
@@ -239,7 +246,7 @@ namespace erl_gp {
         template<int XDIM>
         __device__ __forceinline__ void
         PanelEntries(const rowgp::CovCoef &cov, const float2 *__restrict__ soa, const int cb, const float (&negp)[XDIM], const bool train, const int row, const int n, const float diag,
-                     float (&x)[16]) {
+                     const bool need_mask, float (&x)[16]) {
 #pragma unroll 2
             for (int it = 0; it < 4; ++it) {
                 const int cq = cb + 4 * it;
@@ -253,11 +260,13 @@ namespace erl_gp {
                     e[2 * m] = kv.x;
                     e[2 * m + 1] = kv.y;
                 }
+                if (need_mask) {  // warp-uniform: padding in this GP, or the diagonal crosses this warp's rows in these columns
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int col = cq + i;
-                    if (col >= n || (train && row >= n)) { e[i] = 0.f; }
-                    if (train && row == col) { e[i] = diag; }
+                    for (int i = 0; i < 4; ++i) {
+                        const int col = cq + i;
+                        if (col >= n || (train && row >= n)) { e[i] = 0.f; }
+                        if (train && row == col) { e[i] = diag; }
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 12; ++i) { x[i] = x[i + 4]; }
@@ -438,7 +447,7 @@ namespace erl_gp {
                 // shuffles of the pivot chain go through.
                 MbarInit(bars + 8 * kBarBand, 1);
                 MbarInit(bars + 8 * (kBarBand + 1), 1);
-                MbarInit(bars + 8 * kBarDinv, 1);
+                for (int i = 0; i < 4; ++i) { MbarInit(bars + 8 * (kBarDinv + i), 1); }
                 MbarInit(bars + 8 * kBarOpT, 4);
                 MbarInit(bars + 8 * kBarOpQ, 4);
                 MbarInit(bars + 8 * kBarMmaT, 1);
@@ -591,7 +600,8 @@ namespace erl_gp {
 #pragma unroll 1
                                 for (int pass = band_warp ? 1 : 0; pass >= 0; --pass) {
                                     const int cb = c0 + 16 * pass;
-                                    PanelEntries<XDIM>(cov, soa, cb, negp, is_t, row, n, diag, x);  // (before the wait: it fills it)
+                                    const bool need_mask = n != npr || (is_t && 32 * warp <= cb + 15 && 32 * warp + 31 >= cb);
+                                    PanelEntries<XDIM>(cov, soa, cb, negp, is_t, row, n, diag, need_mask, x);  // (before the wait: it fills it)
                                     if (j > 0) {
                                         if (!waited) {
                                             ERL_GP_TC_TICK(1)  // entries
@@ -631,11 +641,7 @@ namespace erl_gp {
                                 }
 #endif
                                 ERL_GP_TC_AT(j, 4)
-                                if (is_t) {
-                                    MbarWait(bars + 8 * kBarDinv, (pan_base + j) & 1);
-                                } else {
-                                    MbarWait<ERL_GP_TC_SLEEP_NS>(bars + 8 * kBarDinv, (pan_base + j) & 1);
-                                }
+                                MbarWait(bars + 8 * (kBarDinv + ((pan_base + j) & 3)), ((pan_base + j) >> 2) & 1);
                                 ERL_GP_TC_TICK(3)  // wait for the pivot warp
                                 // (c) v = x Dinv_j^T, then the z products; the rows of the tile take their row of L_jj from the pivot warp
                                 const bool in_tile = is_t && row >= c0 && row < c0 + 16;
@@ -858,7 +864,7 @@ namespace erl_gp {
                         // leave this GP (and, with a short next GP, arrive for the NEXT phase of that barrier) ahead of it.  The phase
                         // still completes only after the warp that waits for this Dinv has stored its rows and arrived.
                         if (j == nblk - 1 && lane == 0) { MbarArrive(bars + 8 * kBarFact); }
-                        if (lane == 0) { MbarArrive(bars + 8 * kBarDinv); }
+                        if (lane == 0) { MbarArrive(bars + 8 * (kBarDinv + ((pan_base + j) & 3))); }
                         ERL_GP_TC_TICK(2)  // pivot warp: pivot tile
                     }
                 } else if (warp == 9) {

@@ -67,6 +67,10 @@ class Context:
     def synchronize(self):
         check(self.lib.erl_gp_context_synchronize(self.handle), "synchronize", self.handle)
 
+    def set_rowgp_tc(self, on: int):
+        """Fused FP32 train + predict, n <= 128: 1 = tcgen05 / TMEM kernel, 0 = mma.sync kernel, -1 = default."""
+        check(self.lib.erl_gp_context_set_rowgp_tc(self.handle, C.c_int(on)), "set_rowgp_tc", self.handle)
+
     @property
     def kernel_launches(self) -> int:
         n = C.c_long(0)
@@ -347,18 +351,22 @@ class MultiDeviceBatchGp:
         q_x = np.ascontiguousarray(q_x, dtype=self.dtype).reshape(-1, d)
         t = q_x.shape[0]
         out = out or {}
-        l = out.get("L", np.zeros((b, mn, mn), dtype=self.dtype) if want_l else None)
-        alpha = out.get("alpha", np.zeros((b, mn), dtype=self.dtype) if want_alpha else None)
-        info = out.get("info", np.zeros(b, dtype=np.int32))
-        mean = out.get("mean", np.full(t, np.nan, dtype=self.dtype))
-        variance = out.get("var", np.full(t, np.nan, dtype=self.dtype))
-        valid = out.get("valid", np.zeros(t, dtype=np.uint8))
+
+        def buf(name, make):  # (defaults are built only when the caller did not bring a buffer)
+            return out[name] if name in out else make()
+
+        l = buf("L", lambda: np.zeros((b, mn, mn), dtype=self.dtype) if want_l else None)
+        alpha = buf("alpha", lambda: np.zeros((b, mn), dtype=self.dtype) if want_alpha else None)
+        info = buf("info", lambda: np.zeros(b, dtype=np.int32))
+        mean = buf("mean", lambda: np.full(t, np.nan, dtype=self.dtype))
+        variance = buf("var", lambda: np.full(t, np.nan, dtype=self.dtype))
+        valid = buf("valid", lambda: np.zeros(t, dtype=np.uint8))
         handles = (C.c_void_p * len(self.parts))(*[part.handle for part in self.parts])
         ctx0 = self.contexts[0]
         check(ctx0.fn("erl_gp_batch_train_predict_multi", self.dtype)(handles, C.c_long(len(self.parts)), C.c_long(min_num_samples), _p(n_train), _p(x), _p(y), _p(var), _p(q_offsets),
                                                                      _p(q_x), C.c_long(t), _p(l), _p(alpha), _p(info), _p(mean), _p(variance), _p(valid)), "batch_train_predict_multi",
               ctx0.handle)
-        return dict(L=None if l is None else l.transpose(0, 2, 1), alpha=alpha, info=info, mean=mean, var=variance, valid=valid.astype(bool))
+        return dict(L=None if l is None else l.transpose(0, 2, 1), alpha=alpha, info=info, mean=mean, var=variance, valid=valid if "valid" in out else valid.astype(bool))
 
 
 # ------------------------------------------------------------------------------------------

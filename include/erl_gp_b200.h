@@ -78,6 +78,10 @@ int erl_gp_context_destroy(erl_gp_context *ctx);
 int erl_gp_context_set_stream(erl_gp_context *ctx, void *cuda_stream);
 int erl_gp_context_synchronize(erl_gp_context *ctx);
 const char *erl_gp_context_last_error(const erl_gp_context *ctx);
+/* Kernel choice for the fused FP32 train + predict of small GPs (n <= 128; replaces src/batch_gp_update_torch.cpp:74-82 and
+ * the per-partition loops src/lidar_gp_2d.cpp:366-392): on != 0 selects the tcgen05 / TMEM kernel (csrc/erl_gp_rowgp_tc.cuh),
+ * 0 the mma.sync kernel, a negative value the default (environment variable ERL_GP_ROWGP_TC, else the mma.sync kernel). */
+int erl_gp_context_set_rowgp_tc(erl_gp_context *ctx, int on);
 /* Number of this library's kernels launched through the context so far (bench.py `gpu_launches`). */
 int erl_gp_context_kernel_launches(const erl_gp_context *ctx, long *count);
 

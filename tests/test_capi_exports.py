@@ -2,6 +2,7 @@
 include/erl_gp_b200.h declares, and fails loudly (no CPU fallback) when no CUDA device is present."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 
 import pytest
@@ -56,3 +57,15 @@ def test_product_does_not_touch_the_oracle():
                 assert "oracle" not in text.lower(), f"{os.path.join(dirpath, f)} mentions the oracle"
     out = subprocess.run(["ldd", _capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_tc_sass_is_tcgen05():
+    """The fused kernel's tensor work is tcgen05.mma with TMEM accumulators: its SASS carries UTCHMMA, LDTM and STTM."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "csrc", "erl_gp_rowgp_tc_x3.o")
+    if not os.path.exists(cuobjdump) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available on this box")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, timeout=300).stdout
+    assert "RowGpTcKernel" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTCBAR"):
+        assert mnemonic in sass, mnemonic

@@ -589,8 +589,10 @@ def main():
                   "e2e": {"ms_per_step": float(tt.item()) * 1e3, "value": bs * world * t / float(tt.item()), "unit": "test-points/s",
                           "api": "one process per GPU, erl_gp_batch_train_predict_f32 on the rank's contiguous range (pinned host buffers)"}}
         del part
-        # (b) one process, all the GPUs
+        # (b) one process, all the GPUs.  The other ranks wait on a CPU (gloo) barrier: inside an NCCL barrier their GPUs would run
+        # a spinning collective kernel, and rank 0's kernels on those GPUs would be time-sliced against it.
         barrier()
+        cpu_group = dist.new_group(backend="gloo")
         if rank == 0:
             try:
                 multi = gp.MultiDeviceBatchGp(bs * world, n, d, w["kernel"], w["scale"], np_dt, devices=list(range(world)))
@@ -614,6 +616,7 @@ def main():
                 del multi
             except Exception as exc:  # e.g. the launcher restricted this rank to one visible device
                 strong["single_process_multi_device"] = {"unavailable": repr(exc)[:200]}
+        dist.barrier(group=cpu_group)
         barrier()
 
     if rank == 0:

@@ -101,9 +101,63 @@ namespace erl::gaussian_process {
             }
         };
 
+        // What the reference's GetGps()[p] (a VanillaGaussianProcess, include/erl_gaussian_process/lidar_gp_2d.hpp:132) exposes to
+        // the code that walks the partitions (erl_sdf_mapping): trained flag, number of samples, Cholesky factor, alpha.  The
+        // state lives on the device; a view is materialised on the host on first access after Train() (erl_gp_lidar2d_get_gp).
+        class PartitionGp {
+            const LidarGaussianProcess2D *m_owner_;
+            long m_index_;
+            mutable bool m_loaded_ = false, m_trained_ = false;
+            mutable long m_n_ = 0;
+            mutable MatrixX m_mat_l_;
+            mutable VectorX m_alpha_;
+
+            void
+            Load() const {
+                if (m_loaded_) { return; }
+                m_trained_ = m_owner_->GetGp(m_index_, m_n_, m_mat_l_, m_alpha_);
+                m_loaded_ = true;
+            }
+
+        public:
+            PartitionGp(const LidarGaussianProcess2D *owner, const long index)
+                : m_owner_(owner),
+                  m_index_(index) {}
+
+            void
+            Invalidate() const {
+                m_loaded_ = false;
+            }
+
+            [[nodiscard]] bool
+            IsTrained() const {
+                Load();
+                return m_trained_;
+            }
+
+            [[nodiscard]] long
+            GetNumTrainSamples() const {  // TrainSet::num_samples
+                Load();
+                return m_trained_ ? m_n_ : 0;
+            }
+
+            [[nodiscard]] const MatrixX &
+            GetCholeskyDecomposition() const {  // max_num_samples x max_num_samples buffer, the factor in its leading n x n block
+                Load();
+                return m_mat_l_;
+            }
+
+            [[nodiscard]] const VectorX &
+            GetAlpha() const {
+                Load();
+                return m_alpha_;
+            }
+        };
+
     protected:
         std::shared_ptr<Setting> m_setting_ = nullptr;
         std::shared_ptr<b200::DeviceContext> m_ctx_ = nullptr;
+        std::vector<std::shared_ptr<PartitionGp>> m_gps_;
         typename Api::Lidar2d *m_handle_ = nullptr;
         bool m_trained_ = false;
         std::vector<std::tuple<long, long, Dtype, Dtype>> m_angle_partitions_;
@@ -139,7 +193,10 @@ namespace erl::gaussian_process {
             std::vector<long> il(num), ir(num);
             std::vector<Dtype> cl(num), cr(num);
             m_ctx_->Check(Api::lidar2d_partitions(m_handle_, il.data(), ir.data(), cl.data(), cr.data()), "erl_gp_lidar2d_partitions");
-            for (long i = 0; i < num; ++i) { m_angle_partitions_.emplace_back(il[i], ir[i], cl[i], cr[i]); }
+            for (long i = 0; i < num; ++i) {
+                m_angle_partitions_.emplace_back(il[i], ir[i], cl[i], cr[i]);
+                m_gps_.push_back(std::make_shared<PartitionGp>(this, i));
+            }
         }
 
         LidarGaussianProcess2D(const LidarGaussianProcess2D &) = delete;
@@ -156,6 +213,11 @@ namespace erl::gaussian_process {
         [[nodiscard]] std::shared_ptr<Setting>
         GetSetting() const {
             return m_setting_;
+        }
+
+        [[nodiscard]] const std::vector<std::shared_ptr<PartitionGp>> &
+        GetGps() const {  // include/erl_gaussian_process/lidar_gp_2d.hpp:132
+            return m_gps_;
         }
 
         [[nodiscard]] const std::vector<std::tuple<long, long, Dtype, Dtype>> &
@@ -176,6 +238,7 @@ namespace erl::gaussian_process {
         void
         Reset() {
             m_trained_ = false;
+            for (const auto &gp: m_gps_) { gp->Invalidate(); }
         }
 
         // partition GP p as the reference's GetGps()[p] exposes it: trained flag, n, L (n x n), alpha

@@ -97,9 +97,105 @@ namespace erl::gaussian_process {
             }
         };
 
+        // What the reference's GetGps()(r, c) (a VanillaGaussianProcess, include/erl_gaussian_process/range_sensor_gp_3d.hpp:136)
+        // exposes to the code that walks the partition grid: trained flag, number of samples, Cholesky factor, alpha.  The state
+        // lives on the device; a view is materialised on the host on first access after Train() (erl_gp_range3d_get_gp).
+        class PartitionGp {
+            const RangeSensorGaussianProcess3D *m_owner_;
+            long m_row_, m_col_;
+            mutable bool m_loaded_ = false, m_trained_ = false;
+            mutable long m_n_ = 0;
+            mutable MatrixX m_mat_l_;
+            mutable VectorX m_alpha_;
+
+            void
+            Load() const {
+                if (m_loaded_) { return; }
+                m_trained_ = m_owner_->GetGp(m_row_, m_col_, m_n_, m_mat_l_, m_alpha_);
+                m_loaded_ = true;
+            }
+
+        public:
+            PartitionGp(const RangeSensorGaussianProcess3D *owner, const long row, const long col)
+                : m_owner_(owner),
+                  m_row_(row),
+                  m_col_(col) {}
+
+            void
+            Invalidate() const {
+                m_loaded_ = false;
+            }
+
+            [[nodiscard]] bool
+            IsTrained() const {
+                Load();
+                return m_trained_;
+            }
+
+            [[nodiscard]] long
+            GetNumTrainSamples() const {  // TrainSet::num_samples
+                Load();
+                return m_trained_ ? m_n_ : 0;
+            }
+
+            [[nodiscard]] const MatrixX &
+            GetCholeskyDecomposition() const {  // max_num_samples x max_num_samples buffer, the factor in its leading n x n block
+                Load();
+                return m_mat_l_;
+            }
+
+            [[nodiscard]] const VectorX &
+            GetAlpha() const {
+                Load();
+                return m_alpha_;
+            }
+        };
+
+        // stands in for Eigen::MatrixX<std::shared_ptr<Gp>> (column-major grid of partition GPs)
+        class GpGrid {
+            long m_rows_ = 0, m_cols_ = 0;
+            std::vector<std::shared_ptr<PartitionGp>> m_data_;
+
+        public:
+            void
+            Resize(const RangeSensorGaussianProcess3D *owner, const long rows, const long cols) {
+                m_rows_ = rows, m_cols_ = cols;
+                m_data_.clear();
+                for (long c = 0; c < cols; ++c) {
+                    for (long r = 0; r < rows; ++r) { m_data_.push_back(std::make_shared<PartitionGp>(owner, r, c)); }
+                }
+            }
+
+            [[nodiscard]] long
+            rows() const {
+                return m_rows_;
+            }
+
+            [[nodiscard]] long
+            cols() const {
+                return m_cols_;
+            }
+
+            [[nodiscard]] long
+            size() const {
+                return m_rows_ * m_cols_;
+            }
+
+            [[nodiscard]] const std::shared_ptr<PartitionGp> &
+            operator()(const long r, const long c) const {
+                return m_data_[static_cast<std::size_t>(r + c * m_rows_)];
+            }
+
+            [[nodiscard]] const std::shared_ptr<PartitionGp> *
+            data() const {
+                return m_data_.data();
+            }
+        };
+
     protected:
         std::shared_ptr<Setting> m_setting_ = nullptr;
         std::shared_ptr<b200::DeviceContext> m_ctx_ = nullptr;
+        GpGrid m_gps_;
         typename Api::Range3d *m_handle_ = nullptr;
         bool m_trained_ = false;
         std::vector<std::tuple<long, long, Dtype, Dtype>> m_row_partitions_, m_col_partitions_;
@@ -128,6 +224,7 @@ namespace erl::gaussian_process {
             m_ctx_->Check(Api::range3d_create(m_ctx_->Get(), &s, m_sensor_frame_->GetFrameCoordsData(), m_sensor_frame_->Rows(), m_sensor_frame_->Cols(), &m_handle_), "erl_gp_range3d_create");
             long nr = 0, nc = 0;
             m_ctx_->Check(Api::range3d_grid(m_handle_, &nr, &nc), "erl_gp_range3d_grid");
+            m_gps_.Resize(this, nr, nc);
             for (int axis = 0; axis < 2; ++axis) {
                 const long num = axis == 0 ? nr : nc;
                 std::vector<long> il(num), ir(num);
@@ -154,6 +251,11 @@ namespace erl::gaussian_process {
             return m_setting_;
         }
 
+        [[nodiscard]] const GpGrid &
+        GetGps() const {  // include/erl_gaussian_process/range_sensor_gp_3d.hpp:136
+            return m_gps_;
+        }
+
         [[nodiscard]] const std::vector<std::tuple<long, long, Dtype, Dtype>> &
         GetRowPartitions() const {
             return m_row_partitions_;
@@ -172,6 +274,7 @@ namespace erl::gaussian_process {
         void
         Reset() {
             m_trained_ = false;
+            for (long i = 0; i < m_gps_.size(); ++i) { m_gps_.data()[i]->Invalidate(); }
         }
 
         [[nodiscard]] bool

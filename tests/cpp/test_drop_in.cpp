@@ -175,6 +175,24 @@ TestLidar(const char *name, const double tol) {
         }
     }
     CHECK(occ_checked > 10, "too few valid ComputeOcc samples");
+    // GetGps(): the per-partition views a caller of the reference walks (trained flag, n, L, alpha) against the oracle's partition GPs
+    const auto &gps = gp.GetGps();
+    CHECK(gps.size() == ref.gps.size() && gps.size() == gp.GetAnglePartitions().size(), "GetGps size");
+    const double gtol = sizeof(Dtype) == 4 ? 5e-3 : 1e-8;  // alpha carries cond(K)
+    for (std::size_t pi = 0; pi < gps.size(); ++pi) {
+        const auto &rg = ref.gps[pi];
+        CHECK(gps[pi]->IsTrained() == rg.trained, "GetGps()[%zu]->IsTrained", pi);
+        if (!rg.trained) { continue; }
+        const long np = rg.num_samples;
+        CHECK(gps[pi]->GetNumTrainSamples() == np, "GetGps()[%zu] samples %ld vs %ld", pi, gps[pi]->GetNumTrainSamples(), np);
+        double el = 0, ea = 0, sa = 0;
+        for (long c = 0; c < np; ++c) {
+            for (long r = c; r < np; ++r) { el = std::max(el, std::abs(double(gps[pi]->GetCholeskyDecomposition()(r, c)) - double(rg.mat_l[r + c * rg.ld]))); }
+            sa = std::max(sa, std::abs(double(rg.mat_alpha[c])));
+            ea = std::max(ea, std::abs(double(gps[pi]->GetAlpha()[c]) - double(rg.mat_alpha[c])));
+        }
+        CHECK(el < (sizeof(Dtype) == 4 ? 2e-5 : 1e-11) && ea / sa < gtol, "GetGps()[%zu]: L err %.3e alpha err %.3e", pi, el, ea / sa);
+    }
     std::printf("%s %s: mean err %.2e, var err %.2e, %ld invalid rays\n", g_failures ? "----" : "PASS", name, em / scale, ev, invalid);
 }
 
@@ -237,6 +255,26 @@ TestRangeSensor(const char *name, const double tol) {
     }
     CHECK(valid > 1000, "too few valid rays: %ld", valid);
     CHECK(em / scale < tol && ev < tol, "mean err %.3e var err %.3e", em / scale, ev);
+    // GetGps(): the grid of per-partition views (include/erl_gaussian_process/range_sensor_gp_3d.hpp:136)
+    const auto &grid = gp.GetGps();
+    CHECK(grid.rows() == long(ref.row_partitions.size()) && grid.cols() == long(ref.col_partitions.size()), "GetGps grid");
+    long trained_parts = 0;
+    for (long c = 0; c < grid.cols(); c += 3) {
+        for (long r = 0; r < grid.rows(); r += 2) {
+            const auto &rg = ref.gps[r + c * grid.rows()];
+            CHECK(grid(r, c)->IsTrained() == rg.trained, "GetGps()(%ld,%ld)->IsTrained", r, c);
+            if (!rg.trained) { continue; }
+            ++trained_parts;
+            const long np = rg.num_samples;
+            CHECK(grid(r, c)->GetNumTrainSamples() == np, "GetGps()(%ld,%ld) samples", r, c);
+            double el = 0;
+            for (long cc = 0; cc < np; ++cc) {
+                for (long rr = cc; rr < np; ++rr) { el = std::max(el, std::abs(double(grid(r, c)->GetCholeskyDecomposition()(rr, cc)) - double(rg.mat_l[rr + cc * rg.ld]))); }
+            }
+            CHECK(el < (sizeof(Dtype) == 4 ? 5e-5 : 1e-10), "GetGps()(%ld,%ld): L err %.3e", r, c, el);
+        }
+    }
+    CHECK(trained_parts > 3, "too few trained partitions checked");
     std::printf("%s %s: mean err %.2e, var err %.2e, %ld valid rays\n", g_failures ? "----" : "PASS", name, em / scale, ev, valid);
 }
 

@@ -170,7 +170,6 @@ namespace erl::gaussian_process {
               m_ctx_(ctx ? std::move(ctx) : b200::DeviceContext::Default()),
               m_sensor_frame_(sensor_frame ? std::move(sensor_frame) : std::make_shared<LidarFrame2D>(m_setting_->sensor_frame)),
               m_mapping_(MappingDtype::Create(m_setting_->mapping)) {
-            b200::AssertM(!m_setting_->partition_on_hit_rays, "partition_on_hit_rays is not supported (latent out-of-bounds in the reference, src/lidar_gp_2d.cpp:345-347)");
             const VectorX &angles = m_sensor_frame_->GetAnglesInFrame();
             if (angles.size() <= m_setting_->overlap_size) { return; }  // "no enough samples to perform partition", :177-180
             m_setting_->gp->max_num_samples = m_setting_->group_size;  // :249
@@ -187,17 +186,28 @@ namespace erl::gaussian_process {
             s.kernel_scale = m_setting_->gp->kernel->scale;
             s.mapping = static_cast<int>(m_setting_->mapping->type);
             s.mapping_scale = m_setting_->mapping->scale;
+            // PartitionOnHitRays (src/lidar_gp_2d.cpp:302-348): the table is empty until the first Train() and follows the hit rays of
+            // every frame; the reference's out-of-range indices (:329-347) are clamped by the library
+            s.partition_on_hit_rays = m_setting_->partition_on_hit_rays;
             m_ctx_->Check(Api::lidar2d_create(m_ctx_->Get(), &s, angles.data(), angles.size(), &m_handle_), "erl_gp_lidar2d_create");
+            FetchPartitions();
+        }
+
+    protected:
+        void
+        FetchPartitions() {  // m_angle_partitions_ / m_gps_ as the library holds them (m_gps_.resize(num_groups), :317)
             long num = 0;
             m_ctx_->Check(Api::lidar2d_num_partitions(m_handle_, &num), "erl_gp_lidar2d_num_partitions");
             std::vector<long> il(num), ir(num);
             std::vector<Dtype> cl(num), cr(num);
-            m_ctx_->Check(Api::lidar2d_partitions(m_handle_, il.data(), ir.data(), cl.data(), cr.data()), "erl_gp_lidar2d_partitions");
-            for (long i = 0; i < num; ++i) {
-                m_angle_partitions_.emplace_back(il[i], ir[i], cl[i], cr[i]);
-                m_gps_.push_back(std::make_shared<PartitionGp>(this, i));
-            }
+            if (num > 0) { m_ctx_->Check(Api::lidar2d_partitions(m_handle_, il.data(), ir.data(), cl.data(), cr.data()), "erl_gp_lidar2d_partitions"); }
+            m_angle_partitions_.clear();
+            for (long i = 0; i < num; ++i) { m_angle_partitions_.emplace_back(il[i], ir[i], cl[i], cr[i]); }
+            while (static_cast<long>(m_gps_.size()) > num) { m_gps_.pop_back(); }
+            while (static_cast<long>(m_gps_.size()) < num) { m_gps_.push_back(std::make_shared<PartitionGp>(this, static_cast<long>(m_gps_.size()))); }
         }
+
+    public:
 
         LidarGaussianProcess2D(const LidarGaussianProcess2D &) = delete;
         LidarGaussianProcess2D &
@@ -260,6 +270,7 @@ namespace erl::gaussian_process {
             m_ctx_->Check(
                 Api::lidar2d_train(m_handle_, rotation.data(), m_sensor_frame_->GetRanges().data(), b200::MaskData(m_sensor_frame_->GetHitMask()), b200::MaskData(m_sensor_frame_->GetContinuityMask())),
                 "erl_gp_lidar2d_train");
+            if (m_setting_->partition_on_hit_rays) { FetchPartitions(); }  // :364
             m_trained_ = true;
             return true;
         }

@@ -27,6 +27,9 @@ namespace erl_gp {
     int
     LaunchBatch(Context *ctx, const BatchParams<T> &params, const int x_dim, const int mode, const int tiles_per_gp) {
         if (params.num_gps <= 0) { return ERL_GP_STATUS_OK; }
+        if (x_dim < 1 || x_dim > 3) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "batch: x_dim=%d (supported: 1, 2, 3)", x_dim); }
+        // beyond the shared-memory kernels: L stays in HBM / L2 (erl_gp_largegp.cu); src/range_sensor_gp_3d.cpp:213 puts no cap on n
+        if (params.max_n > BatchMaxN<T>()) { return LaunchLargeGp<T>(ctx, params, x_dim, mode, tiles_per_gp); }
         switch (x_dim) {
             case 1: return LaunchBatchXdim<T, 1>(ctx, params, mode, tiles_per_gp);
             case 2: return LaunchBatchXdim<T, 2>(ctx, params, mode, tiles_per_gp);

@@ -26,7 +26,7 @@ namespace erl_gp {
         *out = nullptr;
         if (num_gps <= 0 || max_n <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: num_gps=%ld max_n=%ld", num_gps, max_n); }
         if (x_dim < 1 || x_dim > 3) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "batch: x_dim=%ld (supported: 1, 2, 3)", x_dim); }
-        if (max_n > BatchMaxN<T>()) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "batch: max_n=%ld exceeds %ld", max_n, BatchMaxN<T>()); }
+        if (max_n > LargeGpMaxN()) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "batch: max_n=%ld exceeds %ld", max_n, LargeGpMaxN()); }
         if (kernel < ERL_GP_KERNEL_OU || kernel > ERL_GP_KERNEL_RBF) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: unknown kernel %d", kernel); }
         auto *b = new (std::nothrow) Batch<T>();
         if (b == nullptr) { return ERL_GP_STATUS_ALLOC_FAILED; }

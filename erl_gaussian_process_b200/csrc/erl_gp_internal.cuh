@@ -136,10 +136,18 @@ namespace erl_gp {
     int
     LaunchBatch(Context *ctx, const BatchParams<T> &params, int x_dim, int mode, int tiles_per_gp);
 
-    // maximum capacity (max_n) the one-CTA-per-GP kernel supports for this Dtype
+    // maximum capacity (max_n) the one-CTA-per-GP shared-memory kernels support for this Dtype
     template<typename T>
     long
     BatchMaxN();
+
+    // larger partition GPs (L resident in HBM / L2, erl_gp_largegp.cu): capacity limit and launcher
+    long
+    LargeGpMaxN();
+
+    template<typename T>
+    int
+    LaunchLargeGp(Context *ctx, const BatchParams<T> &params, int x_dim, int mode, int tiles_per_gp);
 
     template<typename T>
     struct Batch {

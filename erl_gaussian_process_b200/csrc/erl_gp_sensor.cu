@@ -10,6 +10,7 @@
 #include "erl_gp_internal.cuh"
 
 #include <algorithm>
+#include <limits>
 
 namespace erl_gp {
 
@@ -75,6 +76,44 @@ namespace erl_gp {
         return t;
     }
 
+    // LidarGaussianProcess2D::PartitionOnHitRays, src/lidar_gp_2d.cpp:302-348: the partitions follow the HIT rays of the current
+    // frame (n = number of hit rays; the symmetric rule is not implemented there either, :322-324).  The reference indexes
+    // hit_ray_indices with group_size-strided positions that reach n (and, for the last group, with an index that is already an
+    // ORIGINAL ray index, :341-343) and reads angles[hit_ray_indices[n - 1] + 1] (:344-347), i.e. past the end whenever the last
+    // ray is a hit.  Here every index into hit_ray_indices is clamped to [0, n - 1] and every index into angles to [0, N - 1];
+    // wherever the reference stays in bounds the table is the reference's.
+    template<typename T>
+    static PartitionTable<T>
+    MakeHitRayPartitionTable(const T *angles, long num_rays, const uint8_t *hit, long group_size, long overlap_size) {
+        PartitionTable<T> t;
+        std::vector<long> hit_idx;
+        hit_idx.reserve(static_cast<std::size_t>(num_rays));
+        for (long i = 0; i < num_rays; ++i) {
+            if (hit[i] != 0) { hit_idx.push_back(i); }
+        }
+        const long n = static_cast<long>(hit_idx.size());
+        if (n == 0) { return t; }
+        auto h = [&](long i) { return hit_idx[static_cast<std::size_t>(i < 0 ? 0 : (i > n - 1 ? n - 1 : i))]; };
+        auto a = [&](long i) { return angles[i < 0 ? 0 : (i > num_rays - 1 ? num_rays - 1 : i)]; };
+        const long step = group_size - overlap_size;
+        const long num_groups = std::max(1l, n / step) + 1;
+        for (long i = 0; i < num_groups - 2; ++i) {
+            const long il = h(i * step);
+            const long ir = h(i * step + group_size);
+            t.Add(il, ir, a(il), a(ir));
+        }
+        long il = (num_groups - 2) * step;
+        long ir = il + (n - il + overlap_size) / 2;
+        il = h(il);
+        ir = h(ir);
+        t.Add(il, ir, a(il), a(ir));
+        il = il + (n - il - overlap_size) / 2;  // (the reference mixes the two index spaces here, :341)
+        il = h(il);
+        ir = h(n - 1) + 1;
+        t.Add(il, ir, a(il), a(ir));
+        return t;
+    }
+
     template<typename T>
     static bool
     PartitionsFit(const PartitionTable<T> &t, long n, long capacity) {
@@ -92,18 +131,23 @@ namespace erl_gp {
         DeviceBuffer<T> cl, cr;
         int count = 0;
 
+        // capacity > t.Size(): the table is padded with empty partitions no coordinate can match (hit-ray partitioning: the
+        // number of partitions changes from frame to frame, the batch of partition GPs does not)
         cudaError_t
-        Upload(const PartitionTable<T> &t, cudaStream_t stream) {
-            count = static_cast<int>(t.Size());
+        Upload(const PartitionTable<T> &t, cudaStream_t stream, long capacity = 0) {
+            count = static_cast<int>(std::max(capacity, t.Size()));
             std::vector<int> hil(t.index_left.begin(), t.index_left.end()), hir(t.index_right.begin(), t.index_right.end());
+            std::vector<T> hcl(t.coord_left), hcr(t.coord_right);
+            hil.resize(count, 0), hir.resize(count, 0);
+            hcl.resize(count, std::numeric_limits<T>::infinity()), hcr.resize(count, -std::numeric_limits<T>::infinity());
             cudaError_t err = il.Reserve(count);
             if (err == cudaSuccess) { err = ir.Reserve(count); }
             if (err == cudaSuccess) { err = cl.Reserve(count); }
             if (err == cudaSuccess) { err = cr.Reserve(count); }
             if (err == cudaSuccess) { err = cudaMemcpyAsync(il.ptr, hil.data(), sizeof(int) * count, cudaMemcpyHostToDevice, stream); }
             if (err == cudaSuccess) { err = cudaMemcpyAsync(ir.ptr, hir.data(), sizeof(int) * count, cudaMemcpyHostToDevice, stream); }
-            if (err == cudaSuccess) { err = cudaMemcpyAsync(cl.ptr, t.coord_left.data(), sizeof(T) * count, cudaMemcpyHostToDevice, stream); }
-            if (err == cudaSuccess) { err = cudaMemcpyAsync(cr.ptr, t.coord_right.data(), sizeof(T) * count, cudaMemcpyHostToDevice, stream); }
+            if (err == cudaSuccess) { err = cudaMemcpyAsync(cl.ptr, hcl.data(), sizeof(T) * count, cudaMemcpyHostToDevice, stream); }
+            if (err == cudaSuccess) { err = cudaMemcpyAsync(cr.ptr, hcr.data(), sizeof(T) * count, cudaMemcpyHostToDevice, stream); }
             if (err == cudaSuccess) { err = cudaStreamSynchronize(stream); }  // host vectors die here
             return err;
         }
@@ -385,6 +429,9 @@ namespace erl_gp {
         long num_rays = 0;
         PartitionTable<T> parts;
         DevicePartitions<T> d_parts;
+        std::vector<T> h_angles;        // partition_on_hit_rays: the table is rebuilt from every frame's hit mask
+        std::vector<uint8_t> h_hit;
+        long capacity = 0;              // partition GPs in the batch (= parts.Size() unless partition_on_hit_rays)
         DeviceBuffer<T> d_angles, d_ranges;
         DeviceBuffer<uint8_t> d_hit, d_con;
         Batch<T> *batch = nullptr;
@@ -428,17 +475,25 @@ namespace erl_gp {
         gp->ctx = ctx;
         gp->setting = *s;
         gp->num_rays = num_rays;
-        gp->parts = MakePartitionTable<T>(angles, 1, num_rays, s->group_size, s->overlap_size, s->margin, s->symmetric_partitions != 0);
-        if (!PartitionsFit(gp->parts, num_rays, s->group_size)) {
-            delete gp;
-            return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "lidar2d: partition table does not fit group_size (margin / overlap out of range)");
+        if (s->partition_on_hit_rays) {
+            // the constructor leaves the table empty (src/lidar_gp_2d.cpp:182); Train() builds it.  At most
+            // max(1, num_rays / step) + 1 partitions (:311 with n <= num_rays)
+            gp->h_angles.assign(angles, angles + num_rays);
+            gp->capacity = std::max(1l, num_rays / (s->group_size - s->overlap_size)) + 1;
+        } else {
+            gp->parts = MakePartitionTable<T>(angles, 1, num_rays, s->group_size, s->overlap_size, s->margin, s->symmetric_partitions != 0);
+            if (!PartitionsFit(gp->parts, num_rays, s->group_size)) {
+                delete gp;
+                return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "lidar2d: partition table does not fit group_size (margin / overlap out of range)");
+            }
+            gp->capacity = gp->parts.Size();
         }
-        int rc = BatchCreate<T>(c, gp->parts.Size(), s->group_size, 1, s->kernel, static_cast<T>(s->kernel_scale), &gp->batch);
+        int rc = BatchCreate<T>(c, gp->capacity, s->group_size, 1, s->kernel, static_cast<T>(s->kernel_scale), &gp->batch);
         if (rc != ERL_GP_STATUS_OK) {
             delete gp;
             return rc;
         }
-        cudaError_t err = gp->d_parts.Upload(gp->parts, ctx->stream);
+        cudaError_t err = gp->d_parts.Upload(gp->parts, ctx->stream, gp->capacity);
         if (err == cudaSuccess) { err = gp->d_angles.Reserve(num_rays); }
         if (err == cudaSuccess) { err = gp->d_ranges.Reserve(num_rays); }
         if (err == cudaSuccess) { err = gp->d_hit.Reserve(num_rays); }
@@ -470,8 +525,18 @@ namespace erl_gp {
         } else {
             ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->d_con.ptr, 1, n, ctx->stream));
         }
+        if (s.partition_on_hit_rays) {  // src/lidar_gp_2d.cpp:364
+            gp->h_hit.resize(static_cast<std::size_t>(n));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->h_hit.data(), hit, n, cudaMemcpyDefault, ctx->stream));  // host or device pointer
+            ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            PartitionTable<T> t = MakeHitRayPartitionTable<T>(gp->h_angles.data(), n, gp->h_hit.data(), s.group_size, s.overlap_size);
+            if (t.Size() > 0) {  // "No hit rays are stored": the previous table stays (:306-309)
+                gp->parts = std::move(t);
+                ERL_GP_CUDA_OK(ctx, gp->d_parts.Upload(gp->parts, ctx->stream, gp->capacity));
+            }
+        }
         Batch<T> *b = gp->batch;
-        const int num_parts = static_cast<int>(gp->parts.Size());
+        const int num_parts = static_cast<int>(gp->capacity);  // padding partitions are empty: their GPs come out untrained
         const int warps_per_block = 4;
         LidarGatherKernel<T><<<static_cast<unsigned>(CeilDiv(num_parts, warps_per_block)), warps_per_block * 32, 0, ctx->stream>>>(
             num_parts, static_cast<int>(b->max_n), gp->d_parts.il.ptr, gp->d_parts.ir.ptr, gp->d_angles.ptr, gp->d_ranges.ptr, gp->d_hit.ptr, gp->d_con.ptr, s.discontinuity_detection,

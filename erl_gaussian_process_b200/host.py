@@ -442,7 +442,7 @@ class LidarGaussianProcess2D:
     class _CSetting(C.Structure):
         _fields_ = [("symmetric_partitions", C.c_int), ("group_size", C.c_long), ("overlap_size", C.c_long), ("margin", C.c_long), ("sensor_range_var", C.c_double),
                     ("discontinuity_var", C.c_double), ("discontinuity_detection", C.c_int), ("kernel", C.c_int), ("kernel_scale", C.c_double), ("mapping", C.c_int),
-                    ("mapping_scale", C.c_double)]
+                    ("mapping_scale", C.c_double), ("partition_on_hit_rays", C.c_int)]
 
     class TestResult:
         def __init__(self, gp, angles, angles_are_local, un_map):
@@ -464,14 +464,13 @@ class LidarGaussianProcess2D:
             return self._var.copy(), self._valid.copy()
 
     def __init__(self, setting: "LidarGaussianProcess2D.Setting", dtype=np.float64, ctx: Context | None = None):
-        if setting.partition_on_hit_rays:
-            raise NotImplementedError("partition_on_hit_rays (latent OOB in the reference, SURVEY.md App. C.8) is out of scope")
         self.setting = setting
         self.dtype = np.dtype(dtype)
         self.ctx = ctx or default_context()
         self.sensor_frame = LidarFrame2D(setting.sensor_frame, dtype)
         cs = self._CSetting(int(setting.symmetric_partitions), setting.group_size, setting.overlap_size, setting.margin, setting.sensor_range_var, setting.discontinuity_var,
-                            int(setting.sensor_frame.discontinuity_detection), _kernel_id(setting.gp.kernel_type), setting.gp.scale, setting.mapping_type, setting.mapping_scale)
+                            int(setting.sensor_frame.discontinuity_detection), _kernel_id(setting.gp.kernel_type), setting.gp.scale, setting.mapping_type, setting.mapping_scale,
+                            int(setting.partition_on_hit_rays))  # src/lidar_gp_2d.cpp:302-348 with the out-of-range indices clamped
         self.handle = C.c_void_p()
         angles = self.sensor_frame.angles
         check(self.ctx.fn("erl_gp_lidar2d_create", dtype)(self.ctx.handle, C.byref(cs), _p(angles), C.c_long(len(angles)), C.byref(self.handle)), "lidar2d_create", self.ctx.handle)

@@ -259,6 +259,8 @@ typedef struct erl_gp_lidar2d_setting {
     double kernel_scale;      /* gp->kernel->scale */
     int mapping;              /* mapping->type, default kInverseSqrt (:57-62) */
     double mapping_scale;     /* mapping->scale */
+    int partition_on_hit_rays; /* Setting::partition_on_hit_rays (:31): the table is rebuilt from the hit rays of every
+                                  Train() (src/lidar_gp_2d.cpp:302-348, 364); out-of-range indices of the reference clamped */
 } erl_gp_lidar2d_setting;
 
 typedef struct erl_gp_lidar2d_f32 erl_gp_lidar2d_f32;

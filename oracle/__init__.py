@@ -154,7 +154,7 @@ class LidarGp2D:
 
     def __init__(self, angles, kernel=OU, scale=1.0, group_size=26, overlap_size=6, margin=1, symmetric=True,
                  sensor_range_var=0.01, discontinuity_var=10.0, discontinuity_detection=False, mapping_type=2,
-                 mapping_scale=1.0, max_valid_range_var=0.1, occ_test_temperature=30.0, dtype=np.float64):
+                 mapping_scale=1.0, max_valid_range_var=0.1, occ_test_temperature=30.0, dtype=np.float64, partition_on_hit_rays=False):
         self.dtype = np.dtype(dtype)
         _, ct = _sfx(dtype)
         self.ct = ct
@@ -164,6 +164,16 @@ class LidarGp2D:
             C.c_int(kernel), ct(scale), C.c_long(group_size), C.c_long(overlap_size), C.c_long(margin), C.c_int(int(symmetric)),
             ct(sensor_range_var), ct(discontinuity_var), C.c_int(int(discontinuity_detection)), C.c_int(mapping_type), ct(mapping_scale),
             ct(max_valid_range_var), ct(occ_test_temperature), _p(self.angles), C.c_long(len(self.angles))))
+        if partition_on_hit_rays:  # src/lidar_gp_2d.cpp:182, 302-348, 364
+            _fn("oracle_lidar_set_partition_on_hit_rays", dtype, None)(self.h, C.c_int(1))
+
+    @property
+    def angle_partitions(self):
+        n = self.num_partitions
+        il, ir = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        cl, cr = np.zeros(n, dtype=self.dtype), np.zeros(n, dtype=self.dtype)
+        _fn("oracle_lidar_partitions", self.dtype, C.c_long)(self.h, _p(il), _p(ir), _p(cl), _p(cr))
+        return [(int(il[i]), int(ir[i]), cl[i], cr[i]) for i in range(n)]
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -509,6 +509,7 @@ namespace erl_gp_oracle {
     template<typename T>
     struct LidarGp2D {
         // Setting (include/erl_gaussian_process/lidar_gp_2d.hpp:28-71)
+        bool partition_on_hit_rays = false;
         bool symmetric_partitions = true;
         long group_size = 26, overlap_size = 6, margin = 1;
         // float literals, as the reference's defaults (lidar_gp_2d.hpp:42-53): 0.01f widened to double is not 0.01
@@ -534,13 +535,54 @@ namespace erl_gp_oracle {
             partitions.clear();
             gps.clear();
             if (n <= overlap_size) { return; }
+            if (partition_on_hit_rays) { return; }  // :182
             partitions = MakePartitions(angles.data(), 1, n, group_size, overlap_size, margin, symmetric_partitions);
+            ResizeGps();
+        }
+
+        void
+        ResizeGps() {
             gps.resize(partitions.size());
             for (auto &gp: gps) {
                 gp.kernel_type = kernel_type;
                 gp.scale = kernel_scale;
                 gp.max_num_samples_setting = group_size;  // :249
             }
+        }
+
+        // PartitionOnHitRays — :302-348 (always the asymmetric rule, :322-324).  The reference reads hit_ray_indices[] at positions
+        // up to n and beyond (:329-330, :337-338, :342) and angles[hit_ray_indices[n - 1] + 1] (:344-347): out of bounds whenever the
+        // last ray is a hit.  This restatement clamps every index into hit_ray_indices to [0, n - 1] and every index into angles
+        // to [0, N - 1] (the C ABI does the same); inside the reference's defined behaviour the two agree.
+        void
+        PartitionOnHitRays(const uint8_t *mask_hit) {
+            const long num_rays = static_cast<long>(angles.size());
+            std::vector<long> hit_ray_indices;
+            for (long i = 0; i < num_rays; ++i) {
+                if (mask_hit[i]) { hit_ray_indices.push_back(i); }
+            }
+            const long n = static_cast<long>(hit_ray_indices.size());
+            if (n == 0) { return; }  // :306-309
+            auto h = [&](const long i) { return hit_ray_indices[static_cast<std::size_t>(std::min(std::max(i, 0l), n - 1))]; };
+            auto a = [&](const long i) { return angles[static_cast<std::size_t>(std::min(std::max(i, 0l), num_rays - 1))]; };
+            const long step = group_size - overlap_size;
+            const long num_groups = std::max(1l, n / step) + 1;
+            partitions.clear();
+            for (long i = 0; i < num_groups - 2; ++i) {
+                const long index_left = h(i * step);
+                const long index_right = h(i * step + group_size);
+                partitions.push_back({index_left, index_right, a(index_left), a(index_right)});
+            }
+            long index_left = (num_groups - 2) * step;
+            long index_right = index_left + (n - index_left + overlap_size) / 2;
+            index_left = h(index_left);
+            index_right = h(index_right);
+            partitions.push_back({index_left, index_right, a(index_left), a(index_right)});
+            index_left = index_left + (n - index_left - overlap_size) / 2;  // :341 (an original ray index used as a hit-ray position)
+            index_left = h(index_left);
+            index_right = h(n - 1) + 1;
+            partitions.push_back({index_left, index_right, a(index_left), a(index_right)});
+            ResizeGps();
         }
 
         // Train — :350-396.  ranges: valid ranges after LidarFrame2D::UpdateRanges;
@@ -553,6 +595,7 @@ namespace erl_gp_oracle {
             mapped.resize(static_cast<std::size_t>(n));
             for (long i = 0; i < n; ++i) { mapped[i] = MappingMap(mapping_type, mapping_scale, ranges[i]); }
             if (!frame_valid) { return false; }
+            if (partition_on_hit_rays) { PartitionOnHitRays(mask_hit); }  // :364
 #pragma omp parallel for schedule(dynamic, 1)
             for (long p = 0; p < static_cast<long>(partitions.size()); ++p) {
                 const auto &part = partitions[p];
@@ -561,6 +604,7 @@ namespace erl_gp_oracle {
                 long cnt = 0;
                 for (long j = part.index_left; j < part.index_right; ++j) {
                     if (!mask_hit[j]) { continue; }
+                    if (cnt >= gp.max_num_samples_setting) { break; }  // (hit-ray tables with clamped indices only: the train set is full)
                     gp.x[cnt] = angles[j];
                     gp.y[cnt] = mapped[j];
                     gp.var[cnt] = (discontinuity_detection && !mask_con[j]) ? discontinuity_var : sensor_range_var;

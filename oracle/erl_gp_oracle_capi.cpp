@@ -166,6 +166,23 @@ namespace {
         return gp;                                                                                                    \
     }                                                                                                                 \
     extern "C" void oracle_lidar_destroy_##SFX(void *h) { delete static_cast<LidarGp2D<T> *>(h); }                    \
+    /* Setting::partition_on_hit_rays; call right after create (the table is then built by every Train) */           \
+    extern "C" void oracle_lidar_set_partition_on_hit_rays_##SFX(void *h, int flag) {                                 \
+        auto *lg = static_cast<LidarGp2D<T> *>(h);                                                                    \
+        lg->partition_on_hit_rays = flag != 0;                                                                        \
+        if (flag != 0) {                                                                                              \
+            lg->partitions.clear();                                                                                   \
+            lg->gps.clear();                                                                                          \
+        }                                                                                                             \
+    }                                                                                                                 \
+    extern "C" long oracle_lidar_partitions_##SFX(void *h, long *il, long *ir, T *cl, T *cr) {                        \
+        auto *lg = static_cast<LidarGp2D<T> *>(h);                                                                    \
+        for (std::size_t i = 0; i < lg->partitions.size(); ++i) {                                                     \
+            il[i] = lg->partitions[i].index_left, ir[i] = lg->partitions[i].index_right;                              \
+            cl[i] = lg->partitions[i].coord_left, cr[i] = lg->partitions[i].coord_right;                              \
+        }                                                                                                             \
+        return static_cast<long>(lg->partitions.size());                                                              \
+    }                                                                                                                 \
     extern "C" long oracle_lidar_num_partitions_##SFX(void *h) {                                                      \
         return static_cast<long>(static_cast<LidarGp2D<T> *>(h)->partitions.size());                                  \
     }                                                                                                                 \

@@ -89,6 +89,57 @@ def make_partitions(coords, group_size, overlap_size, margin, symmetric=True):
     return parts
 
 
+def make_hit_ray_partitions(angles, mask_hit, group_size, overlap_size):
+    """src/lidar_gp_2d.cpp:302-348, written literally (Python raises IndexError where the reference reads out of
+    bounds) when clamp=False semantics are wanted use `strict_hit_ray_partitions`; this one clamps like the C++ oracle."""
+    return _hit_ray_partitions(angles, mask_hit, group_size, overlap_size, clamp=True)
+
+
+def strict_hit_ray_partitions(angles, mask_hit, group_size, overlap_size):
+    """The same formulas without any clamp: raises IndexError exactly where the reference's reads are undefined."""
+    return _hit_ray_partitions(angles, mask_hit, group_size, overlap_size, clamp=False)
+
+
+def _hit_ray_partitions(angles, mask_hit, group_size, overlap_size, clamp):
+    hit = np.flatnonzero(np.asarray(mask_hit))
+    n, num_rays = len(hit), len(angles)
+    if n == 0:
+        return None  # "No hit rays are stored": the table is left as it was (:306-309)
+
+    def h(i):
+        if clamp:
+            i = min(max(i, 0), n - 1)
+        elif not 0 <= i < n:
+            raise IndexError(f"hit_ray_indices[{i}] with {n} hit rays")
+        return int(hit[i])
+
+    def a(i):
+        if clamp:
+            i = min(max(i, 0), num_rays - 1)
+        elif not 0 <= i < num_rays:
+            raise IndexError(f"angles[{i}] with {num_rays} rays")
+        return angles[i]
+
+    def tdiv(p, q):  # C++ integer division truncates toward zero
+        return int(p / q) if p < 0 else p // q
+
+    step = group_size - overlap_size
+    g = max(1, n // step) + 1
+    parts = []
+    for i in range(g - 2):
+        il, ir = h(i * step), h(i * step + group_size)
+        parts.append((il, ir, a(il), a(ir)))
+    il = (g - 2) * step
+    ir = il + tdiv(n - il + overlap_size, 2)
+    il, ir = h(il), h(ir)
+    parts.append((il, ir, a(il), a(ir)))
+    il = il + tdiv(n - il - overlap_size, 2)  # :341 — an original ray index used as a hit-ray position
+    il = h(il)
+    ir = h(n - 1) + 1
+    parts.append((il, ir, a(il), a(ir)))
+    return parts
+
+
 def spgp_fit_predict(kernel, scale, z, x, y, var, xt):
     """Dense SPGP, one update then predict.  src/sparse_pseudo_input_gp.cpp:313-356, 751-791, 43-113, 280-310."""
     one = z.dtype.type(1)

@@ -85,6 +85,81 @@ TestVanillaSiso(const char *name, const double tol) {
     std::printf("%s %s: mean err %.2e, var err %.2e, mae %.6e\n", g_failures ? "----" : "PASS", name, em, ev, mae);
 }
 
+// Setting::partition_on_hit_rays (src/lidar_gp_2d.cpp:302-348, 364): the table is empty after construction and follows the hit rays
+// of every Train(); GetAnglePartitions() / GetGps() are refreshed.  Two frames through one object, against the oracle.
+template<typename Dtype>
+static void
+TestLidarHitRays(const char *name, const double tol) {
+    using Lidar = LidarGaussianProcess2D<Dtype>;
+    constexpr long n = 540, n_test = 5000;
+    auto setting = std::make_shared<typename Lidar::Setting>();
+    setting->partition_on_hit_rays = true;
+    setting->group_size = 40;
+    setting->overlap_size = 10;
+    setting->sensor_frame->angle_min = Dtype(-2.0);
+    setting->sensor_frame->angle_max = Dtype(2.0);
+    setting->sensor_frame->num_rays = n;
+    setting->sensor_frame->valid_range_min = Dtype(0.1);
+    setting->sensor_frame->valid_range_max = Dtype(30);
+    setting->gp->kernel_type = "erl::covariance::OrnsteinUhlenbeck1d";
+    setting->gp->kernel->scale = Dtype(0.05);
+    Lidar gp(setting);
+    CHECK(gp.GetAnglePartitions().empty() && gp.GetGps().empty(), "hit-ray partitions must be empty before Train");
+    const auto &angles = gp.GetSensorFrame()->GetAnglesInFrame();
+    erl_gp_oracle::LidarGp2D<Dtype> ref;
+    ref.partition_on_hit_rays = true;
+    ref.group_size = 40, ref.overlap_size = 10;
+    ref.kernel_type = erl_gp_oracle::kOrnsteinUhlenbeck, ref.kernel_scale = Dtype(0.05);
+    ref.sensor_range_var = setting->sensor_range_var;
+    ref.Init(angles.data(), n);
+    std::mt19937 rng(5);
+    std::uniform_real_distribution<double> uni(0, 1);
+    Eigen::MatrixX<Dtype> rot(2, 2);
+    rot.setZero();
+    rot(0, 0) = rot(1, 1) = 1;
+    Eigen::VectorX<Dtype> trans(2);
+    trans.setZero();
+    double em = 0, ev = 0, scale = 0;
+    for (const double miss: {0.05, 0.35}) {
+        Eigen::VectorX<Dtype> ranges(n);
+        for (long i = 0; i < n; ++i) {
+            ranges[i] = Dtype(5 + 2 * std::sin(3 * double(angles[i])));
+            if (uni(rng) < miss || i >= n - 3) { ranges[i] = Dtype(1000); }
+        }
+        CHECK(gp.Train(rot, trans, ranges), "Train (hit rays)");
+        const auto frame = gp.GetSensorFrame();
+        ref.Train(rot.data(), frame->GetRanges().data(), erl::gaussian_process::b200::MaskData(frame->GetHitMask()), erl::gaussian_process::b200::MaskData(frame->GetContinuityMask()), true);
+        const auto &parts = gp.GetAnglePartitions();
+        CHECK(parts.size() == ref.partitions.size() && gp.GetGps().size() == parts.size(), "hit-ray partitions: %zu vs %zu", parts.size(), ref.partitions.size());
+        for (std::size_t i = 0; i < parts.size() && i < ref.partitions.size(); ++i) {
+            CHECK(std::get<0>(parts[i]) == ref.partitions[i].index_left && std::get<1>(parts[i]) == ref.partitions[i].index_right, "partition %zu indices", i);
+            CHECK(std::get<2>(parts[i]) == ref.partitions[i].coord_left && std::get<3>(parts[i]) == ref.partitions[i].coord_right, "partition %zu coords", i);
+            CHECK(gp.GetGps()[i]->IsTrained() == ref.gps[i].trained, "partition GP %zu trained flag", i);
+        }
+        Eigen::VectorX<Dtype> q(n_test), mean(n_test), var(n_test);
+        for (long i = 0; i < n_test; ++i) {
+            q[i] = Dtype(-2.05 + uni(rng) * 4.1);
+            mean[i] = var[i] = Dtype(-777);
+        }
+        auto result = gp.Test(q, true, true);
+        CHECK(result != nullptr, "Test (hit rays)");
+        const auto ok_mean = result->GetMean(mean, true);
+        (void) result->GetVariance(var, true);
+        std::vector<Dtype> m_ref(n_test, Dtype(-777)), v_ref(n_test, Dtype(-777));
+        std::vector<uint8_t> ok_ref(n_test);
+        ref.Test(q.data(), n_test, true, true, m_ref.data(), v_ref.data(), ok_ref.data());
+        for (long i = 0; i < n_test; ++i) {
+            CHECK(bool(ok_mean[i]) == bool(ok_ref[i]), "valid mask differs at %ld (hit rays)", i);
+            if (!ok_ref[i]) { continue; }
+            scale = std::max(scale, std::abs(double(m_ref[i])));
+            em = std::max(em, std::abs(double(mean[i]) - double(m_ref[i])));
+            ev = std::max(ev, std::abs(double(var[i]) - double(v_ref[i])));
+        }
+    }
+    CHECK(em / scale < tol && ev < tol, "mean err %.3e var err %.3e", em / scale, ev);
+    std::printf("%s %s: mean err %.2e, var err %.2e\n", g_failures ? "----" : "PASS", name, em / scale, ev);
+}
+
 template<typename Dtype>
 static void
 TestLidar(const char *name, const double tol) {
@@ -285,6 +360,8 @@ main() {
         TestVanillaSiso<float>("VanillaGaussianProcess<float> SISO", 1e-4);
         TestLidar<double>("LidarGaussianProcess2D<double>", 1e-10);
         TestLidar<float>("LidarGaussianProcess2D<float>", 1e-4);
+        TestLidarHitRays<double>("LidarGaussianProcess2D<double> partition_on_hit_rays", 1e-10);
+        TestLidarHitRays<float>("LidarGaussianProcess2D<float> partition_on_hit_rays", 1e-4);
         TestRangeSensor<float>("RangeSensorGaussianProcess3D<float>", 1e-4);
         TestRangeSensor<double>("RangeSensorGaussianProcess3D<double>", 1e-10);
         // misuse: hard assertion as ERL_ASSERTM (src/vanilla_gp.cpp:389-392)

@@ -95,11 +95,31 @@ def test_batch_min_num_samples_gate(gp, oracle):
     assert (out["info"] == -1).any() and (out["info"] == 0).any()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("max_n,x_dim,kernel,scale,num_gps", [(300, 2, "matern32", 0.3, 10), (257, 1, "ou", 0.05, 7), (484, 2, "matern32", 0.2, 6), (700, 3, "matern32", 0.4, 3)])
+def test_batch_large_n(gp, oracle, dtype, max_n, x_dim, kernel, scale, num_gps):
+    """Partition GPs beyond the shared-memory kernels (n > 256 float / 192 double; src/range_sensor_gp_3d.cpp:213 puts no cap on
+    row_group_size * col_group_size): L resident in HBM / L2, blocked Cholesky per CTA (erl_gp_largegp.cu).  Ragged sizes incl. 0."""
+    _check_batch(gp, oracle, dtype, kernel, scale, num_gps, max_n, x_dim, seed=max_n, n_lo=0, n_hi=max_n, q_lo=0, q_hi=200)
+    _check_batch(gp, oracle, dtype, kernel, scale, 3, max_n, x_dim, seed=max_n + 1, n_lo=max_n, n_hi=max_n, q_lo=65, q_hi=130)
+
+
+def test_batch_large_n_gate_and_not_spd(gp, oracle):
+    out = _check_batch(gp, oracle, np.float64, "matern32", 0.3, 12, 320, 2, seed=77, min_num_samples=200, n_lo=150, n_hi=320, q_lo=1, q_hi=40)
+    assert (out["info"] == -1).any() and (out["info"] == 0).any()
+    rng = np.random.default_rng(0)
+    n_train, x, y, var, q_offsets, q_x = make_batch(rng, 3, 300, 2, np.float32, fixed_q=8)
+    var[1, 40] = -5.0  # K[40][40] = 1 + var < 0: LLT fails at column 41
+    res = gp.BatchGp(3, 300, 2, "rbf", 0.5, np.float32).train_predict(n_train, x, y, var, q_offsets, q_x)
+    assert res["info"][1] > 0 and (res["info"][[0, 2]] == 0).all()
+    assert not res["valid"][8:16].any() and res["valid"][:8].all() and res["valid"][16:].all()
+
+
 def test_batch_limits(gp):
     with pytest.raises(gp.ErlGpError):
-        gp.BatchGp(4, 257, 2, "ou", 1.0, np.float32)
+        gp.BatchGp(4, 2049, 2, "ou", 1.0, np.float32)
     with pytest.raises(gp.ErlGpError):
-        gp.BatchGp(4, 193, 2, "ou", 1.0, np.float64)
+        gp.BatchGp(4, 2049, 2, "ou", 1.0, np.float64)
     with pytest.raises(gp.ErlGpError):
         gp.BatchGp(4, 64, 4, "ou", 1.0, np.float32)
 

@@ -93,11 +93,13 @@ def _image(rng, rows, cols, dtype):
     return img.astype(dtype)
 
 
-@pytest.mark.parametrize("rg,ro,cg,co,grid,nmax", [(24, 6, 8, 2, (27, 107), 192), (16, 2, 16, 2, (35, 46), 256)])
+@pytest.mark.parametrize("rg,ro,cg,co,grid,nmax", [(24, 6, 8, 2, (27, 107), 192), (16, 2, 16, 2, (35, 46), 256), (22, 2, 22, 2, (25, 33), 484)])
 def test_range_sensor_3d_c3_full_size(gp, oracle, rg, ro, cg, co, grid, nmax):
     """BASELINE config 3: RangeSensorGp3D<float> on a 480 x 640 range image, Matern32 l = 0.05, predict at every pixel
     direction (T = 307 200).  Both groupings SURVEY.md 8(d) recommends: the reference defaults (24,6) x (8,2) -> 27 x 107 =
-    2889 GPs with n <= 192, and (16,2)^2 -> 35 x 46 = 1610 GPs with n = 256 (src/range_sensor_gp_3d.cpp:199-259, 321-407)."""
+    2889 GPs with n <= 192, and (16,2)^2 -> 35 x 46 = 1610 GPs with n = 256 (src/range_sensor_gp_3d.cpp:199-259, 321-407); and
+    the nearest reachable grid to BASELINE's literal "32 x 24": step 20 -> 33 x 25 = 825 GPs of n = 22 x 22 = 484 samples, beyond
+    the shared-memory kernels (large-GP path, erl_gp_largegp.cu)."""
     dtype = np.float32
     rows, cols = 480, 640
     s = gp.RangeSensorGaussianProcess3D.Setting()

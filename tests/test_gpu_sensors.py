@@ -26,8 +26,9 @@ def _c2_scan(rng, n=1080, dtype=np.float32):
     return ang.astype(dtype), rng_.astype(dtype)
 
 
-def _make_lidar(gp, oracle, dtype, angles, group_size, overlap_size, symmetric, kernel, scale, mapping, discon=False, range_max=30.0):
+def _make_lidar(gp, oracle, dtype, angles, group_size, overlap_size, symmetric, kernel, scale, mapping, discon=False, range_max=30.0, on_hit_rays=False):
     s = gp.LidarGaussianProcess2D.Setting()
+    s.partition_on_hit_rays = on_hit_rays
     s.group_size, s.overlap_size, s.margin, s.symmetric_partitions = group_size, overlap_size, 1, symmetric
     s.sensor_range_var, s.discontinuity_var = 0.01, 100.0
     s.sensor_frame.angle_min, s.sensor_frame.angle_max, s.sensor_frame.num_rays = float(angles[0]), float(angles[-1]), len(angles)
@@ -38,7 +39,8 @@ def _make_lidar(gp, oracle, dtype, angles, group_size, overlap_size, symmetric, 
     lg = gp.LidarGaussianProcess2D(s, dtype)
     lg.sensor_frame.angles = np.asarray(angles, dtype=dtype)  # use the log's own angles
     # re-create with exact angles (the stand-in frame would otherwise linspace them)
-    og = oracle.LidarGp2D(lg.sensor_frame.angles, oracle.KERNELS[kernel], scale, group_size, overlap_size, 1, symmetric, 0.01, 100.0, discon, mapping, 1.0, 0.1, 30.0, dtype)
+    og = oracle.LidarGp2D(lg.sensor_frame.angles, oracle.KERNELS[kernel], scale, group_size, overlap_size, 1, symmetric, 0.01, 100.0, discon, mapping, 1.0, 0.1, 30.0, dtype,
+                          partition_on_hit_rays=on_hit_rays)
     return lg, og
 
 
@@ -101,6 +103,56 @@ def test_lidar_reference_log_frames(gp, oracle, dtype):
         assert err_var(var[valid], v_ref[valid]) < tol
         mae = np.abs(mean[valid] - ranges[valid]).mean()
         assert mae < 0.08  # the reference's own threshold, test_lidar_gp_2d.cpp:261
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lidar_partition_on_hit_rays(gp, oracle, dtype):
+    """Setting::partition_on_hit_rays (src/lidar_gp_2d.cpp:302-348, 364): the table follows the hit rays of every frame.  Three
+    frames through ONE object (few misses / 30 % misses / last rays missing - the regime where the reference's own index
+    arithmetic stays in bounds), tables and partition GPs against the oracle, then the reference log's frames."""
+    rng = np.random.default_rng(21)
+    ang, ranges0 = _c2_scan(rng, n=540, dtype=dtype)
+    lg, og = _make_lidar(gp, oracle, dtype, ang, 40, 10, True, "ou", 0.05, 2, on_hit_rays=True)
+    assert lg.num_partitions == 0 == og.num_partitions
+    tol = TOL[np.dtype(dtype)]
+    for frame_id, miss in enumerate([0.02, 0.3, 0.1]):
+        ranges = ranges0.copy()
+        ranges[rng.random(len(ang)) < miss] = 1e3
+        if frame_id == 2:
+            ranges[-4:] = 1e3
+        assert lg.train(np.eye(2), np.zeros(2), ranges)
+        frame = lg.sensor_frame
+        assert og.train(frame.ranges, frame.mask_hit, frame.mask_continuous)
+        parts, parts_ref = lg.angle_partitions, og.angle_partitions
+        assert len(parts) == len(parts_ref) > 3
+        assert [(a, b) for a, b, _, _ in parts] == [(a, b) for a, b, _, _ in parts_ref]
+        # (the library holds the frame's own linspace angles, the oracle the test's: equal up to the rounding of the dtype)
+        assert all(abs(c1 - c2) < 1e-6 and abs(d1 - d2) < 1e-6 for (_, _, c1, d1), (_, _, c2, d2) in zip(parts, parts_ref))
+        for p in range(len(parts)):
+            info, n, l, a = lg.get_gp(p)
+            tr, n_ref, l_ref, a_ref = og.get_gp(p)
+            assert (info == 0) == tr and n == n_ref
+            if tr:
+                assert np.abs(l - l_ref).max() / np.abs(l_ref).max() < (2e-5 if dtype == np.float32 else 1e-11)
+        q = rng.uniform(ang[0] - 0.05, ang[-1] + 0.05, 20000).astype(dtype)
+        res = lg.test(q, True, True)
+        mean, valid = res.get_mean()
+        var, _ = res.get_variance()
+        m_ref, v_ref, ok_ref = og.test(q, True, True)
+        assert np.array_equal(valid, ok_ref) and valid.sum() > 10000
+        assert err_mean(mean[valid], m_ref[valid]) < tol
+        assert err_var(var[valid], v_ref[valid]) < tol
+    data = np.load(GOLDEN)
+    for k in range(min(4, len(data["frame_ids"]))):
+        a, r = data["angles"][k].astype(dtype), data["ranges"][k].astype(dtype)
+        lg, og = _make_lidar(gp, oracle, dtype, a, 26, 6, False, "ou", 0.05, 0, on_hit_rays=True)
+        assert lg.train(np.eye(2), np.zeros(2), r)
+        assert og.train(lg.sensor_frame.ranges, lg.sensor_frame.mask_hit, lg.sensor_frame.mask_continuous)
+        assert [(x, y) for x, y, _, _ in lg.angle_partitions] == [(x, y) for x, y, _, _ in og.angle_partitions]
+        mean, valid = lg.test(a, True, True).get_mean()
+        m_ref, _, ok_ref = og.test(a, True, True)
+        assert valid.any() and np.array_equal(valid, ok_ref)
+        assert err_mean(mean[valid], m_ref[valid]) < tol
 
 
 def test_lidar_world_frame_angles_and_discontinuity(gp, oracle):
@@ -227,7 +279,7 @@ def test_range_sensor_3d_limits(gp):
     with pytest.raises(ValueError):
         gp.RangeSensorGaussianProcess3D(s, np.float32)
     s = gp.RangeSensorGaussianProcess3D.Setting()
-    s.row_group_size, s.col_group_size = 24, 12  # 288 samples per GP > one-CTA limit
+    s.row_group_size, s.col_group_size = 48, 44  # 2112 samples per GP: beyond the large-GP path (2048)
     with pytest.raises(gp.ErlGpError):
         gp.RangeSensorGaussianProcess3D(s, np.float32)
 

@@ -122,3 +122,31 @@ def test_partitions_match_survey_c2(oracle):
     pa = oracle.make_partitions(ang[:270], 26, 6, 1, False)
     ra = onp.make_partitions(ang[:270], 26, 6, 1, False)
     assert [(a, b) for a, b, _, _ in pa] == [(a, b) for a, b, _, _ in ra]
+
+
+def test_hit_ray_partitions(oracle):
+    """PartitionOnHitRays (src/lidar_gp_2d.cpp:302-348): the C++ oracle against the literal numpy restatement.  Where the
+    reference's own reads stay in bounds (last ray a miss, few misses) the clamped table IS the reference's; the clamps only
+    act where the reference is undefined (IndexError in the strict twin)."""
+    rng = np.random.default_rng(11)
+    ang = np.linspace(-2.3, 2.3, 270)
+    strict_ok = 0
+    for trial in range(40):
+        hit = rng.random(270) > rng.choice([0.0, 0.02, 0.3])
+        if trial % 2 == 0:
+            hit[-3:] = False  # the reference reads angles[last hit + 1]: in bounds only if the last ray is a miss
+        lg = oracle.LidarGp2D(ang, oracle.OU, 0.05, 26, 6, 1, False, dtype=np.float64, partition_on_hit_rays=True)
+        assert lg.num_partitions == 0  # the constructor does not partition (:182)
+        ranges = np.where(hit, 5.0 + np.sin(3 * ang), 1e3)
+        assert lg.train(ranges, hit)
+        ref = onp.make_hit_ray_partitions(ang, hit, 26, 6)
+        got = lg.angle_partitions
+        assert [(a, b) for a, b, _, _ in got] == [(a, b) for a, b, _, _ in ref]
+        assert all(c1 == c2 and d1 == d2 for (_, _, c1, d1), (_, _, c2, d2) in zip(got, ref))
+        try:
+            strict = onp.strict_hit_ray_partitions(ang, hit, 26, 6)
+        except IndexError:
+            continue
+        strict_ok += 1
+        assert [(a, b) for a, b, _, _ in strict] == [(a, b) for a, b, _, _ in ref]
+    assert strict_ok >= 5  # the in-bounds regime is exercised

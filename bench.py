@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — GP train+predict test-points/sec on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c1|c2|c3|c3n256|c5|spgp|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c1|c2|c3|c3n256|c3n484|c5|spgp|...]
 
 Default workload = BASELINE.json configs[3] ("c4"): the batched small-GP stream, 50 000 independent
 GPs per GPU (n = 128, 3-D inputs, Matern32, 128 test points each, float32) — the configuration
@@ -14,7 +14,7 @@ only for the barrier and the max-over-ranks of the device time).
 `e2e`    : the same metric through the C-ABI host-buffer call erl_gp_batch_train_predict_f32
            (pinned host buffers; H2D of the training sets and queries and D2H of mean /
            variance / valid / info inside the timed region).
-`--workload c1|c2|c3|c3n256|c5|spgp`: the other BASELINE.json configurations (bench_workloads.py), same line schema: `value` with
+`--workload c1|c2|c3|c3n256|c3n484|c5|spgp`: the other BASELINE.json configurations (bench_workloads.py), same line schema: `value` with
            device-resident inputs, `e2e` through the C-ABI calls with pinned host buffers, `roofline` of the dominant kernel
            (HBM for the partitioned sensor GPs, FP64 tensor peak for the dense / SPGP paths), `cpu_baseline`, `clocks`.
 `--impl reference`: the reference's CPU path (the OpenMP oracle restatement — the reference

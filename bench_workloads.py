@@ -382,7 +382,8 @@ class Range3d(Base):
         ach = by / (ms_dom * 1e-3) / 1e9
         peak = float(peaks["hbm_gbs"])
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "ms_dominant": ms_dom, "algorithmic_bytes_per_launch": by,
-                "kernel": f"erl_gp_range3d_test: Range3dAssign + counting sort + rowgp::RowGpKernel<x_dim=2, NBLK={(self.group[0] * self.group[2] + 15) // 16}, predict>",
+                "kernel": ("erl_gp_range3d_test: Range3dAssign + counting sort + " + (f"rowgp::RowGpKernel<x_dim=2, NBLK={(self.group[0] * self.group[2] + 15) // 16}, predict>"
+                                                                                       if self.group[0] * self.group[2] <= 256 else "largegp::PredictKernel<float> (L resident in HBM / L2)")),
                 "note": "the L write-back of Train() belongs to the other launch of the step; bytes here are the whole step's algorithmic bytes over the predict launch only when "
                         "'ms_dominant' is the predict; see 'step_bytes_over_step_ms' for the whole step", "grid": list(self.grid)}
 
@@ -501,9 +502,11 @@ def make(name):
         return Range3d("c3", 24, 6, 8, 2)
     if name == "c3n256":
         return Range3d("c3n256", 16, 2, 16, 2)
+    if name == "c3n484":  # the nearest reachable grid to BASELINE's literal "32 x 24": 33 x 25 partitions of 22 x 22 samples (large-GP path)
+        return Range3d("c3n484", 22, 2, 22, 2)
     if name == "spgp":
         return Spgp()
     raise KeyError(name)
 
 
-NAMES = ("c1", "c2", "c3", "c3n256", "c5", "spgp")
+NAMES = ("c1", "c2", "c3", "c3n256", "c3n484", "c5", "spgp")

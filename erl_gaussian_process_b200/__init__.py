@@ -11,6 +11,7 @@ from .host import (
     MultiDeviceBatchGp,
     Context,
     LidarGaussianProcess2D,
+    NoisyInputGaussianProcess,
     RangeSensorGaussianProcess3D,
     SparsePseudoInputGaussianProcess,
     VanillaGaussianProcess,
@@ -25,6 +26,7 @@ __all__ = [
     "ErlGpError",
     "KERNELS",
     "LidarGaussianProcess2D",
+    "NoisyInputGaussianProcess",
     "RangeSensorGaussianProcess3D",
     "SparsePseudoInputGaussianProcess",
     "VanillaGaussianProcess",

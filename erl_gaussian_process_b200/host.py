@@ -383,11 +383,15 @@ class LidarFrame2D:
             self.discontinuity_detection = discontinuity_detection
             self.discontinuity_factor = discontinuity_factor
             self.rolling_diff_discount = rolling_diff_discount
+            self.angles = None  # explicit ray angles (e.g. a sensor log's own) instead of linspace(angle_min, angle_max, num_rays)
 
     def __init__(self, setting, dtype=np.float64):
         self.setting = setting
         self.dtype = np.dtype(dtype)
-        self.angles = np.linspace(setting.angle_min, setting.angle_max, setting.num_rays).astype(self.dtype)
+        if setting.angles is not None:
+            self.angles = np.ascontiguousarray(setting.angles, dtype=self.dtype)
+        else:
+            self.angles = np.linspace(setting.angle_min, setting.angle_max, setting.num_rays).astype(self.dtype)
         self.rotation = np.eye(2, dtype=self.dtype)
         self.translation = np.zeros(2, dtype=self.dtype)
         self.ranges = None
@@ -774,3 +778,127 @@ class SparsePseudoInputGaussianProcess:
         lq = np.empty((m, m), dtype=self.dtype)
         check(self.ctx.fn("erl_gp_spgp_get", self.dtype)(self.handle, _p(q), _p(a), _p(lk), _p(lq)), "spgp_get", self.ctx.handle)
         return q.T, a, lk.T, lq.T
+
+
+class NoisyInputGaussianProcess:
+    """Mirror of erl::gaussian_process::NoisyInputGaussianProcess<Dtype> (include/.../noisy_input_gp.hpp): GP with noisy
+    inputs and gradient observations.  ``train(x, y, grad, var_x, var_y, var_grad, grad_flag)`` = Reset + TrainSet fill +
+    Train (src/noisy_input_gp.cpp:700-724, 807-899); ``test(x_test, predict_gradient)`` returns a TestResult with
+    ``get_mean`` / ``get_gradient`` / ``get_mean_variance`` / ``get_gradient_variance`` / ``get_covariance`` (:125-333)."""
+
+    class Setting:
+        def __init__(self, kernel_type="rbf", scale=1.0, max_num_samples=-1, no_gradient_observation=False):
+            self.kernel_type = kernel_type
+            self.scale = scale
+            self.max_num_samples = max_num_samples  # noisy_input_gp.hpp:24: -1 = no limit
+            self.no_gradient_observation = no_gradient_observation
+
+    class TestResult:
+        def __init__(self, gp, x_test, predict_gradient):
+            self._gp = gp
+            self._x_test = np.ascontiguousarray(x_test, dtype=gp.dtype)
+            self.num_test, self.x_dim = self._x_test.shape
+            self.support_gradient = bool(predict_gradient)
+            self._mean = self._grad = self._var = self._gvar = self._cov = None
+
+        def _run(self, mean=False, var=False):
+            gp, t, d = self._gp, self.num_test, self.x_dim
+            sg = self.support_gradient
+            m = np.empty((gp.y_dim, t), dtype=gp.dtype) if mean else None
+            g = np.empty((gp.y_dim, t, d), dtype=gp.dtype) if mean and sg else None
+            v = np.empty(t, dtype=gp.dtype) if var else None
+            gv = np.empty((t, d), dtype=gp.dtype) if var and sg else None
+            cv = np.empty((t, d * (d + 1) // 2), dtype=gp.dtype) if var and sg else None
+            check(gp.ctx.fn("erl_gp_noisy_test", gp.dtype)(gp.handle, C.c_long(t), _p(self._x_test), C.c_long(d), C.c_int(int(sg)), _p(m), _p(g), _p(v), _p(gv), _p(cv)), "noisy_test",
+                  gp.ctx.handle)
+            if mean:
+                self._mean, self._grad = m, g
+            if var:
+                self._var, self._gvar, self._cov = v, gv, cv
+
+        def get_mean(self, y_index=0, parallel=True):
+            if self._mean is None:
+                self._run(mean=True)
+            return self._mean[y_index].copy()
+
+        def get_gradient(self, y_index=0, parallel=True):
+            """-> (gradient (T, x_dim), valid (T,)): a gradient with a non-finite component is invalid (:193-197)"""
+            assert self.support_gradient, "m_support_gradient_ = false"
+            if self._mean is None:
+                self._run(mean=True)
+            g = self._grad[y_index].copy()
+            return g, np.isfinite(g).all(axis=1)
+
+        def get_mean_variance(self, parallel=True):
+            if self._var is None:
+                self._run(var=True)
+            return self._var.copy()
+
+        def get_gradient_variance(self, parallel=True):
+            assert self.support_gradient, "m_support_gradient_ = false"
+            if self._var is None:
+                self._run(var=True)
+            return self._gvar.copy()
+
+        def get_covariance(self, parallel=True):
+            assert self.support_gradient, "m_support_gradient_ = false"
+            if self._var is None:
+                self._run(var=True)
+            return self._cov.copy()
+
+    def __init__(self, setting: "NoisyInputGaussianProcess.Setting", dtype=np.float64, ctx: Context | None = None):
+        self.setting = setting
+        self.dtype = np.dtype(dtype)
+        self.ctx = ctx or default_context()
+        self.handle = C.c_void_p()
+        check(self.ctx.fn("erl_gp_noisy_create", dtype)(self.ctx.handle, C.byref(self.handle)), "noisy_create", self.ctx.handle)
+        self.is_trained = False
+        self.n = self.m = 0
+        self.y_dim = 1
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.fn("erl_gp_noisy_destroy", self.dtype)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def train(self, x, y, grad, var_x, var_y, var_grad, grad_flag) -> bool:
+        """x (n, x_dim); y (n,) or (n, y_dim); grad (n, y_dim, x_dim) or None; var_*: scalars or (n,); grad_flag: scalar or (n,)"""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        n, d = x.shape
+        s = self.setting
+        if n <= 0:
+            return False  # :811-814
+        if not (s.max_num_samples < 0 or n <= s.max_num_samples):
+            raise ValueError(f"max_num_samples should be <= {s.max_num_samples}")  # :711-714
+        y = np.asarray(y, dtype=self.dtype).reshape(n, -1)
+        y_dim = y.shape[1]
+        yf = np.asfortranarray(y)
+        g = None if grad is None else np.ascontiguousarray(np.asarray(grad, dtype=self.dtype).reshape(n, y_dim * d))
+        vx, vy = (np.ascontiguousarray(np.broadcast_to(v, (n,)), dtype=self.dtype) for v in (var_x, var_y))
+        vg = None if var_grad is None else np.ascontiguousarray(np.broadcast_to(var_grad, (n,)), dtype=self.dtype)
+        flag = np.ascontiguousarray(np.broadcast_to(grad_flag, (n,)), dtype=np.int64)
+        _, ct = _sfx(self.dtype)
+        check(self.ctx.fn("erl_gp_noisy_train", self.dtype)(self.handle, C.c_int(_kernel_id(s.kernel_type)), ct(s.scale), C.c_long(d), C.c_long(y_dim), C.c_long(n), _p(x), C.c_long(d), _p(yf),
+                                                            C.c_long(n), _p(g), C.c_long(y_dim * d), _p(vx), _p(vy), _p(vg), _p(flag), C.c_int(int(s.no_gradient_observation))), "noisy_train",
+              self.ctx.handle)
+        self.n, self.y_dim = n, y_dim
+        self.is_trained = True
+        return True
+
+    def test(self, x_test, predict_gradient=True):
+        if not self.is_trained:
+            return None  # :905
+        return NoisyInputGaussianProcess.TestResult(self, x_test, predict_gradient)
+
+    def get(self):
+        """-> info, K (m, m), L (m, m), alpha (m, y_dim): GetKtrainSized / GetCholeskyDecomposition / GetAlphaSized"""
+        rows, info = C.c_long(0), C.c_int(0)
+        check(self.ctx.fn("erl_gp_noisy_get", self.dtype)(self.handle, C.byref(rows), C.byref(info), None, C.c_long(0), None, C.c_long(0), None, C.c_long(0)), "noisy_get", self.ctx.handle)
+        m = self.m = rows.value
+        k, l = np.zeros((m, m), dtype=self.dtype), np.zeros((m, m), dtype=self.dtype)
+        a = np.zeros((self.y_dim, m), dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_noisy_get", self.dtype)(self.handle, C.byref(rows), C.byref(info), _p(k), C.c_long(m), _p(l), C.c_long(m), _p(a), C.c_long(m)), "noisy_get", self.ctx.handle)
+        return info.value, k.T.copy(), l.T.copy(), a.T.copy()

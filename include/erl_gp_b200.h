@@ -388,6 +388,44 @@ int erl_gp_spgp_get_f32(erl_gp_spgp_f32 *gp, float *q_m, float *alpha, float *l_
 int erl_gp_spgp_get_f64(erl_gp_spgp_f64 *gp, double *q_m, double *alpha, double *l_km, double *l_qm);
 
 #if defined(__GNUC__)
+/* ---------------------------------------------------------------------------------------------
+ * NoisyInputGaussianProcess<Dtype> (include/erl_gaussian_process/noisy_input_gp.hpp, src/noisy_input_gp.cpp): a GP with
+ * noisy inputs and gradient observations.  Row layout of K / L / alpha (m = n + x_dim * ng rows, ng = samples with
+ * grad_flag != 0): rows [0, n) the values, row n + j + a * ng the derivative d/dx_a at the j-th flagged sample
+ * (src/noisy_input_gp.cpp:835-846).  Kernels: RadialBiasFunction and Matern32 (OrnsteinUhlenbeck only with
+ * no_gradient_observation and without gradient prediction: it is not differentiable at r = 0).
+ *   train  = Reset + TrainSet fill + UpdateKtrain + Train (:807-899).  x: x_dim x n (ld_x); y: n x y_dim (ld_y);
+ *            grad: (x_dim * y_dim) x n (ld_grad), column i = [dh_1/dx_1 .. dh_1/dx_m, dh_2/dx_1 ..] at sample i
+ *            (noisy_input_gp.hpp:175-177); var_x / var_y / var_grad: n; grad_flag: n (Eigen::VectorXl).
+ *   get    = GetKtrainSized / GetCholeskyDecomposition / GetAlphaSized (:766-800); info = 0 or the failing LLT column.
+ *   test   = Test + TestResult::{GetMean :125-145, GetGradient :168-207, GetMeanVariance :233-246,
+ *            GetGradientVariance :258-277, GetCovariance :300-333}.  Host pointers, any output may be null:
+ *            mean T x y_dim; grad x_dim x T x y_dim; var T; grad_var x_dim x T; cov x_dim (x_dim + 1) / 2 x T.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct erl_gp_noisy_f32 erl_gp_noisy_f32;
+typedef struct erl_gp_noisy_f64 erl_gp_noisy_f64;
+
+int erl_gp_noisy_create_f32(erl_gp_context *ctx, erl_gp_noisy_f32 **gp);
+int erl_gp_noisy_create_f64(erl_gp_context *ctx, erl_gp_noisy_f64 **gp);
+int erl_gp_noisy_destroy_f32(erl_gp_noisy_f32 *gp);
+int erl_gp_noisy_destroy_f64(erl_gp_noisy_f64 *gp);
+int erl_gp_noisy_train_f32(erl_gp_noisy_f32 *gp, int kernel, float scale, long x_dim, long y_dim, long n, const float *x,
+                           long ld_x, const float *y, long ld_y, const float *grad, long ld_grad, const float *var_x,
+                           const float *var_y, const float *var_grad, const long *grad_flag,
+                           int no_gradient_observation);
+int erl_gp_noisy_train_f64(erl_gp_noisy_f64 *gp, int kernel, double scale, long x_dim, long y_dim, long n,
+                           const double *x, long ld_x, const double *y, long ld_y, const double *grad, long ld_grad,
+                           const double *var_x, const double *var_y, const double *var_grad, const long *grad_flag,
+                           int no_gradient_observation);
+int erl_gp_noisy_get_f32(erl_gp_noisy_f32 *gp, long *rows, int *info, float *k, long ld_k, float *l, long ld_l,
+                         float *alpha, long ld_a);
+int erl_gp_noisy_get_f64(erl_gp_noisy_f64 *gp, long *rows, int *info, double *k, long ld_k, double *l, long ld_l,
+                         double *alpha, long ld_a);
+int erl_gp_noisy_test_f32(erl_gp_noisy_f32 *gp, long num_test, const float *x_test, long ld_xt, int predict_gradient,
+                          float *mean, float *grad, float *var, float *grad_var, float *cov);
+int erl_gp_noisy_test_f64(erl_gp_noisy_f64 *gp, long num_test, const double *x_test, long ld_xt, int predict_gradient,
+                          double *mean, double *grad, double *var, double *grad_var, double *cov);
+
 #pragma GCC visibility pop
 #endif
 

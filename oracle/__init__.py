@@ -340,3 +340,52 @@ class Spgp:
         lq = np.zeros((m, m), dtype=self.dtype)
         _fn("oracle_spgp_get", self.dtype)(self.h, _p(q), _p(a), _p(lk), _p(lq))
         return q.T.copy(), a, lk.T.copy(), lq.T.copy()
+
+
+class NoisyInputGp:
+    """oracle NoisyInputGaussianProcess (src/noisy_input_gp.cpp): GP with noisy inputs and gradient observations.
+    x: (n, x_dim); y: (n, y_dim); grad: (n, y_dim, x_dim) = d y_d / d x_k; grad_flag: (n,) ints."""
+
+    def __init__(self, kernel, scale, no_gradient_observation=False, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        _, ct = _sfx(dtype)
+        self.h = C.c_void_p(_fn("oracle_noisy_create", dtype, C.c_void_p)(C.c_int(kernel), ct(scale), C.c_int(int(no_gradient_observation))))
+        self.m = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _fn("oracle_noisy_destroy", self.dtype, None)(self.h)
+            self.h = None
+
+    def train(self, x, y, grad, var_x, var_y, var_grad, grad_flag):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        n, self.x_dim = x.shape
+        y = np.asarray(y, dtype=self.dtype).reshape(n, -1)
+        self.y_dim = y.shape[1]
+        yf = np.asfortranarray(y)  # n x y_dim col-major
+        g = None if grad is None else np.ascontiguousarray(np.asarray(grad, dtype=self.dtype).reshape(n, self.y_dim * self.x_dim))  # column i of the reference's grad matrix
+        vx, vy = (np.ascontiguousarray(np.broadcast_to(v, (n,)), dtype=self.dtype) for v in (var_x, var_y))
+        vg = None if var_grad is None else np.ascontiguousarray(np.broadcast_to(var_grad, (n,)), dtype=self.dtype)
+        flag = np.ascontiguousarray(np.broadcast_to(grad_flag, (n,)), dtype=np.int64)
+        self.m = _fn("oracle_noisy_train", self.dtype, C.c_long)(self.h, C.c_long(n), C.c_long(self.x_dim), C.c_long(self.y_dim), _p(x), _p(yf), _p(g), _p(vx), _p(vy), _p(vg), _p(flag))
+        return self.m > 0
+
+    def get(self):
+        m = self.m
+        k, l = np.zeros((m, m), dtype=self.dtype), np.zeros((m, m), dtype=self.dtype)
+        a = np.zeros((self.y_dim, m), dtype=self.dtype)
+        info = _fn("oracle_noisy_get", self.dtype)(self.h, _p(k), _p(l), _p(a))
+        return info, k.T.copy(), l.T.copy(), a.T.copy()
+
+    def test(self, xt, predict_gradient=True, variance=True):
+        """-> mean (T, y_dim), gradient (T, y_dim, x_dim), var (T), grad_var (T, x_dim), cov (T, x_dim (x_dim + 1) / 2)"""
+        xt = np.ascontiguousarray(xt, dtype=self.dtype)
+        t, d = xt.shape
+        mean = np.zeros((self.y_dim, t), dtype=self.dtype)
+        grad = np.zeros((self.y_dim, t, d), dtype=self.dtype) if predict_gradient else None
+        var = np.zeros(t, dtype=self.dtype) if variance else None
+        gvar = np.zeros((t, d), dtype=self.dtype) if variance and predict_gradient else None
+        cov = np.zeros((t, d * (d + 1) // 2), dtype=self.dtype) if variance and predict_gradient else None
+        rc = _fn("oracle_noisy_test", self.dtype)(self.h, _p(xt), C.c_long(t), C.c_int(int(predict_gradient)), _p(mean), _p(grad), _p(var), _p(gvar), _p(cov))
+        assert rc == 0
+        return mean.T.copy(), (None if grad is None else grad.transpose(1, 0, 2).copy()), var, gvar, cov

@@ -921,4 +921,224 @@ namespace erl_gp_oracle {
         }
     };
 
+    // ---------------------------------------------------------------------------------------
+    // NoisyInputGaussianProcess — src/noisy_input_gp.cpp.
+    //
+    // The derivative-augmented Gram matrix is Covariance::ComputeKtrainWithGradient /
+    // ComputeKtestWithGradient of erl_covariance v0.2.0 (source absent).  Restated from the
+    // definition of a GP with derivative observations,
+    //     cov(f(x), f(x'))               = k(x, x')
+    //     cov(f(x), df(x')/dx'_b)        = dk/dx'_b
+    //     cov(df(x)/dx_a, f(x'))         = dk/dx_a
+    //     cov(df(x)/dx_a, df(x')/dx'_b)  = d2k/dx_a dx'_b
+    // with the index layout the reference's own code fixes (src/noisy_input_gp.cpp:835-846: row n + j + a * ng holds
+    // dh/dx_a of the j-th sample that has a gradient, ng = num_samples_with_grad; TestResult reads column i + (a + 1) * T
+    // for dh/dx_a at test point i, :190-200) and the noise diagonal K[i][i] = 1 + var_x[i] + var_y[i] (the
+    // no_gradient_observation branch passes var_x + var_y, :812-818), K[g][g] += var_grad[i].
+    //   RBF      k = exp(-r^2 / 2l^2):  dk/dx_a = -(x - x')_a k / l^2,  d2k = (delta_ab / l^2 - (x-x')_a (x-x')_b / l^4) k
+    //   Matern32 k = (1 + c r) exp(-c r), c = sqrt(3) / l:  dk/dx_a = -c^2 exp(-c r) (x - x')_a,
+    //            d2k = c^2 exp(-c r) (delta_ab - c (x-x')_a (x-x')_b / r)   (-> c^2 delta_ab = 3 / l^2 at r = 0, the constant the
+    //            reference hard-codes as the gradient's prior variance, :724)
+    // PINNED (RBF): tests/test_oracle_kat.py reproduces the MAE values printed in the reference's own gtest
+    // (test/gtest/test_noisy_input_gp.cpp:174-178, 348-349, 552-554) to 6+ digits, which fixes the signs, the layout and the
+    // noise model.  Matern32 with gradients: unpinned (no reference test uses it).  OrnsteinUhlenbeck is not differentiable
+    // at r = 0: rejected.
+    // ---------------------------------------------------------------------------------------
+    // dk[0] = k, dk[1 + a] = dk/dx_a (first argument), d2k[a * x_dim + b] = d2k/dx_a dx'_b; diff = x - x'
+    template<typename T>
+    inline void
+    KernelWithDerivatives(const int type, const T scale, const long x_dim, const T *x, const T *xp, T *k, T *dk, T *d2k) {
+        T diff[3] = {0, 0, 0};
+        T r2 = 0;
+        for (long a = 0; a < x_dim; ++a) {
+            diff[a] = x[a] - xp[a];
+            r2 += diff[a] * diff[a];
+        }
+        if (type == kRadialBiasFunction) {
+            const T l2 = scale * scale;
+            const T kv = std::exp(-r2 / (T(2) * l2));
+            *k = kv;
+            for (long a = 0; a < x_dim; ++a) {
+                dk[a] = -diff[a] / l2 * kv;
+                for (long b = 0; b < x_dim; ++b) { d2k[a * x_dim + b] = ((a == b ? T(1) / l2 : T(0)) - diff[a] * diff[b] / (l2 * l2)) * kv; }
+            }
+        } else {  // Matern32
+            const T c = std::sqrt(T(3)) / scale;
+            const T r = std::sqrt(r2);
+            const T e = std::exp(-c * r);
+            *k = (T(1) + c * r) * e;
+            for (long a = 0; a < x_dim; ++a) {
+                dk[a] = -c * c * e * diff[a];
+                for (long b = 0; b < x_dim; ++b) {
+                    const T cross = r > T(0) ? c * diff[a] * diff[b] / r : T(0);
+                    d2k[a * x_dim + b] = c * c * e * ((a == b ? T(1) : T(0)) - cross);
+                }
+            }
+        }
+    }
+
+    template<typename T>
+    struct NoisyInputGp {
+        int kernel_type = kRadialBiasFunction;
+        T scale = T(1);
+        bool no_gradient_observation = false;
+        // TrainSet (noisy_input_gp.hpp:166-199)
+        long x_dim = 0, y_dim = 0, num_samples = 0, num_samples_with_grad = 0;
+        std::vector<T> x, y, grad, var_x, var_y, var_grad;  // x: x_dim x n; y: n x y_dim; grad: (x_dim * y_dim) x n
+        std::vector<long> grad_flag;
+        // model
+        long m = 0;  // k_train_rows = n + x_dim * ng
+        std::vector<long> gsample;  // sample index of the j-th gradient observation
+        std::vector<T> mat_k, mat_l, mat_alpha;  // m x m, m x m, m x y_dim
+        T three_over_scale_square = 0;
+        bool trained = false;
+        int info = 0;
+
+        // UpdateKtrain + Train — :807-899
+        bool
+        Train() {
+            trained = false;
+            const long n = num_samples;
+            if (n <= 0) { return false; }  // :811-814
+            if (kernel_type == kOrnsteinUhlenbeck && !no_gradient_observation) { return false; }
+            three_over_scale_square = T(3.0f) / (scale * scale);  // :724 (a float literal in the reference)
+            gsample.clear();
+            if (no_gradient_observation) {
+                std::fill(grad_flag.begin(), grad_flag.begin() + n, 0l);  // :817
+            } else {
+                for (long i = 0; i < n; ++i) {
+                    if (grad_flag[i]) { gsample.push_back(i); }
+                }
+            }
+            const long ng = static_cast<long>(gsample.size());
+            m = n + x_dim * ng;
+            mat_alpha.assign(static_cast<std::size_t>(m * y_dim), T(0));
+            for (long d = 0; d < y_dim; ++d) {  // :835-846
+                T *alpha = mat_alpha.data() + d * m;
+                std::memcpy(alpha, y.data() + d * n, sizeof(T) * n);
+                for (long j = 0; j < ng; ++j) {
+                    const T *grad_i = grad.data() + gsample[j] * (x_dim * y_dim) + d * x_dim;
+                    for (long k = 0; k < x_dim; ++k) { alpha[n + j + k * ng] = grad_i[k]; }
+                }
+            }
+            mat_k.assign(static_cast<std::size_t>(m * m), T(0));
+#pragma omp parallel for schedule(dynamic, 8)
+            for (long c = 0; c < n; ++c) {
+                for (long r = 0; r < n; ++r) {  // (value r, value c) and the gradient rows / columns hanging off them
+                    T k, dk[3], d2k[9];
+                    KernelWithDerivatives(kernel_type, scale, x_dim, x.data() + r * x_dim, x.data() + c * x_dim, &k, dk, d2k);
+                    mat_k[r + c * m] = r == c ? T(1) + var_x[r] + var_y[r] : k;
+                    (void) d2k;
+                }
+            }
+#pragma omp parallel for schedule(dynamic, 8)
+            for (long jc = 0; jc < ng; ++jc) {
+                const long c = gsample[jc];
+                for (long r = 0; r < n; ++r) {
+                    T k, dk[3], d2k[9];
+                    KernelWithDerivatives(kernel_type, scale, x_dim, x.data() + r * x_dim, x.data() + c * x_dim, &k, dk, d2k);
+                    for (long b = 0; b < x_dim; ++b) {
+                        // cov(f(x_r), df(x_c)/dx_c,b) = dk/dx'_b = -dk/dx_b
+                        mat_k[r + (n + jc + b * ng) * m] = -dk[b];
+                        mat_k[(n + jc + b * ng) + r * m] = -dk[b];
+                    }
+                }
+                for (long jr = 0; jr < ng; ++jr) {
+                    const long r = gsample[jr];
+                    T k, dk[3], d2k[9];
+                    KernelWithDerivatives(kernel_type, scale, x_dim, x.data() + r * x_dim, x.data() + c * x_dim, &k, dk, d2k);
+                    for (long a = 0; a < x_dim; ++a) {
+                        for (long b = 0; b < x_dim; ++b) {
+                            T v = d2k[a * x_dim + b];
+                            if (jr == jc && a == b) { v += var_grad[r]; }
+                            mat_k[(n + jr + a * ng) + (n + jc + b * ng) * m] = v;
+                        }
+                    }
+                }
+            }
+            mat_l.assign(static_cast<std::size_t>(m * m), T(0));
+            info = Llt(mat_k.data(), m, m, mat_l.data(), m);  // :891
+            for (long d = 0; d < y_dim; ++d) {
+                SolveLowerInPlace(mat_l.data(), m, m, mat_alpha.data() + d * m);           // :892
+                SolveLowerTransposeInPlace(mat_l.data(), m, m, mat_alpha.data() + d * m);  // :893
+            }
+            trained = true;
+            return true;
+        }
+
+        // column i of Ktest (value at test point xt) and, with gradient, columns i + (a + 1) * T (dh/dx_a at xt) — TestResult ctor :38-71
+        void
+        KtestColumns(const T *xt, const bool with_gradient, T *cols /* m x (1 + x_dim), ld = m */) const {
+            const long n = num_samples, ng = static_cast<long>(gsample.size());
+            for (long r = 0; r < n; ++r) {
+                T k, dk[3], d2k[9];
+                KernelWithDerivatives(kernel_type, scale, x_dim, x.data() + r * x_dim, xt, &k, dk, d2k);
+                cols[r] = k;
+                if (with_gradient) {
+                    for (long b = 0; b < x_dim; ++b) { cols[r + (b + 1) * m] = -dk[b]; }  // cov(f(x_r), df(xt)/dxt_b)
+                }
+            }
+            for (long j = 0; j < ng; ++j) {
+                const long r = gsample[j];
+                T k, dk[3], d2k[9];
+                KernelWithDerivatives(kernel_type, scale, x_dim, x.data() + r * x_dim, xt, &k, dk, d2k);
+                for (long a = 0; a < x_dim; ++a) {
+                    cols[n + j + a * ng] = dk[a];  // cov(df(x_r)/dx_a, f(xt))
+                    if (with_gradient) {
+                        for (long b = 0; b < x_dim; ++b) { cols[(n + j + a * ng) + (b + 1) * m] = d2k[a * x_dim + b]; }
+                    }
+                }
+            }
+        }
+
+        // Test + TestResult::{GetMean :125-145, GetGradient :168-207, GetMeanVariance :233-246, GetGradientVariance :258-277,
+        // GetCovariance :300-333, PrepareAlphaTest :362-376}.  Outputs (any may be null):
+        //   mean: T x y_dim; gradient: x_dim x T x y_dim; var: T; grad_var: x_dim x T; cov: x_dim (x_dim + 1) / 2 x T
+        bool
+        Test(const T *x_test, const long num_test, const bool predict_gradient, T *mean, T *gradient, T *var, T *grad_var, T *cov) const {
+            if (!trained) { return false; }
+            const long nc = predict_gradient ? x_dim + 1 : 1;
+            const long ncov = x_dim * (x_dim + 1) / 2;
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long i = 0; i < num_test; ++i) {
+                std::vector<T> cols(static_cast<std::size_t>(m * nc));
+                KtestColumns(x_test + i * x_dim, predict_gradient, cols.data());
+                for (long d = 0; d < y_dim; ++d) {
+                    const T *alpha = mat_alpha.data() + d * m;
+                    if (mean != nullptr) {
+                        T f = 0;
+                        for (long p = 0; p < m; ++p) { f += cols[p] * alpha[p]; }
+                        mean[i + d * num_test] = f;
+                    }
+                    if (gradient != nullptr && predict_gradient) {
+                        for (long a = 0; a < x_dim; ++a) {
+                            T g = 0;
+                            for (long p = 0; p < m; ++p) { g += cols[p + (a + 1) * m] * alpha[p]; }
+                            gradient[a + i * x_dim + d * x_dim * num_test] = g;
+                        }
+                    }
+                }
+                if (var == nullptr && grad_var == nullptr && cov == nullptr) { continue; }
+                for (long c = 0; c < nc; ++c) { SolveLowerInPlace(mat_l.data(), m, m, cols.data() + c * m); }
+                auto dot = [&](const long ca, const long cb) {
+                    T s = 0;
+                    for (long p = 0; p < m; ++p) { s += cols[p + ca * m] * cols[p + cb * m]; }
+                    return s;
+                };
+                if (var != nullptr) { var[i] = T(1.0f) - dot(0, 0); }
+                if (predict_gradient && grad_var != nullptr) {
+                    for (long a = 0; a < x_dim; ++a) { grad_var[a + i * x_dim] = three_over_scale_square - dot(a + 1, a + 1); }
+                }
+                if (predict_gradient && cov != nullptr) {
+                    T *out = cov + i * ncov;
+                    for (long j = 0; j < x_dim; ++j) {
+                        *out++ = -dot(j + 1, 0);                                  // cov(dh/dx_j, h)
+                        for (long k = 0; k < j; ++k) { *out++ = -dot(j + 1, k + 1); }  // cov(dh/dx_j, dh/dx_k)
+                    }
+                }
+            }
+            return true;
+        }
+    };
+
 }  // namespace erl_gp_oracle

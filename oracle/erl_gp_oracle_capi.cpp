@@ -278,6 +278,47 @@ namespace {
         return BatchedTrainPredict<T>(kernel, scale, x_dim, num_gps, max_n, n_train, x, y, var, q_offsets, q_x,       \
                                       mat_l, alpha, info, mean, variance);                                            \
     }                                                                                                                 \
+    /* ---- NoisyInputGaussianProcess ---- */                                                                         \
+    extern "C" void *oracle_noisy_create_##SFX(int kernel, T scale, int no_gradient_observation) {                    \
+        auto *gp = new NoisyInputGp<T>();                                                                             \
+        gp->kernel_type = kernel;                                                                                     \
+        gp->scale = scale;                                                                                            \
+        gp->no_gradient_observation = no_gradient_observation != 0;                                                   \
+        return gp;                                                                                                    \
+    }                                                                                                                 \
+    extern "C" void oracle_noisy_destroy_##SFX(void *h) { delete static_cast<NoisyInputGp<T> *>(h); }                 \
+    extern "C" long oracle_noisy_train_##SFX(void *h, long n, long x_dim, long y_dim, const T *x, const T *y,         \
+                                             const T *grad, const T *var_x, const T *var_y, const T *var_grad,        \
+                                             const long *grad_flag) {                                                 \
+        auto *gp = static_cast<NoisyInputGp<T> *>(h);                                                                 \
+        gp->x_dim = x_dim, gp->y_dim = y_dim, gp->num_samples = n;                                                    \
+        gp->x.assign(x, x + n * x_dim);                                                                               \
+        gp->y.assign(y, y + n * y_dim);                                                                               \
+        gp->grad.assign(static_cast<std::size_t>(n * x_dim * y_dim), T(0));                                           \
+        if (grad != nullptr) { gp->grad.assign(grad, grad + n * x_dim * y_dim); }                                     \
+        gp->var_x.assign(var_x, var_x + n);                                                                           \
+        gp->var_y.assign(var_y, var_y + n);                                                                           \
+        gp->var_grad.assign(static_cast<std::size_t>(n), T(0));                                                       \
+        if (var_grad != nullptr) { gp->var_grad.assign(var_grad, var_grad + n); }                                     \
+        gp->grad_flag.assign(grad_flag, grad_flag + n);                                                               \
+        if (!gp->Train()) { return -1; }                                                                              \
+        return gp->m;                                                                                                 \
+    }                                                                                                                 \
+    extern "C" int oracle_noisy_get_##SFX(void *h, T *k, T *l, T *alpha) {                                            \
+        auto *gp = static_cast<NoisyInputGp<T> *>(h);                                                                 \
+        const std::size_t mm = static_cast<std::size_t>(gp->m * gp->m);                                               \
+        if (k != nullptr) { std::memcpy(k, gp->mat_k.data(), mm * sizeof(T)); }                                       \
+        if (l != nullptr) { std::memcpy(l, gp->mat_l.data(), mm * sizeof(T)); }                                       \
+        if (alpha != nullptr) { std::memcpy(alpha, gp->mat_alpha.data(), gp->m * gp->y_dim * sizeof(T)); }            \
+        return gp->info;                                                                                              \
+    }                                                                                                                 \
+    extern "C" int oracle_noisy_test_##SFX(void *h, const T *x_test, long num_test, int predict_gradient, T *mean,    \
+                                           T *gradient, T *var, T *grad_var, T *cov) {                                \
+        return static_cast<NoisyInputGp<T> *>(h)->Test(x_test, num_test, predict_gradient != 0, mean, gradient, var,  \
+                                                       grad_var, cov)                                                 \
+                   ? 0                                                                                                \
+                   : -1;                                                                                              \
+    }                                                                                                                 \
     /* ---- SPGP (dense) ---- */                                                                                      \
     extern "C" void *oracle_spgp_create_##SFX(int kernel, T scale, long x_dim, long m, const T *pseudo) {             \
         auto *gp = new Spgp<T>();                                                                                     \

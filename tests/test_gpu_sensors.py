@@ -36,9 +36,8 @@ def _make_lidar(gp, oracle, dtype, angles, group_size, overlap_size, symmetric, 
     s.sensor_frame.discontinuity_detection = discon
     s.gp.kernel_type, s.gp.scale = kernel, scale
     s.mapping_type = mapping
+    s.sensor_frame.angles = np.asarray(angles, dtype=dtype)  # the test's / the log's own angles, not the stand-in frame's linspace
     lg = gp.LidarGaussianProcess2D(s, dtype)
-    lg.sensor_frame.angles = np.asarray(angles, dtype=dtype)  # use the log's own angles
-    # re-create with exact angles (the stand-in frame would otherwise linspace them)
     og = oracle.LidarGp2D(lg.sensor_frame.angles, oracle.KERNELS[kernel], scale, group_size, overlap_size, 1, symmetric, 0.01, 100.0, discon, mapping, 1.0, 0.1, 30.0, dtype,
                           partition_on_hit_rays=on_hit_rays)
     return lg, og
@@ -126,8 +125,7 @@ def test_lidar_partition_on_hit_rays(gp, oracle, dtype):
         parts, parts_ref = lg.angle_partitions, og.angle_partitions
         assert len(parts) == len(parts_ref) > 3
         assert [(a, b) for a, b, _, _ in parts] == [(a, b) for a, b, _, _ in parts_ref]
-        # (the library holds the frame's own linspace angles, the oracle the test's: equal up to the rounding of the dtype)
-        assert all(abs(c1 - c2) < 1e-6 and abs(d1 - d2) < 1e-6 for (_, _, c1, d1), (_, _, c2, d2) in zip(parts, parts_ref))
+        assert all(c1 == c2 and d1 == d2 for (_, _, c1, d1), (_, _, c2, d2) in zip(parts, parts_ref))
         for p in range(len(parts)):
             info, n, l, a = lg.get_gp(p)
             tr, n_ref, l_ref, a_ref = og.get_gp(p)

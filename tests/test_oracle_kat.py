@@ -150,3 +150,57 @@ def test_hit_ray_partitions(oracle):
         strict_ok += 1
         assert [(a, b) for a, b, _, _ in strict] == [(a, b) for a, b, _, _ in ref]
     assert strict_ok >= 5  # the in-bounds regime is exercised
+
+
+def test_noisy_input_gp_reference_mae_values(oracle):
+    """NoisyInputGaussianProcess: the oracle's derivative-augmented Gram (erl_covariance's ComputeKtrainWithGradient is absent)
+    reproduces the mean-absolute errors the reference's own gtest printed into its source
+    (test/gtest/test_noisy_input_gp.cpp:174-178, 348-349): RBF 1-D, 100 samples of sin(2x) on [0, 2 pi], noise 1e-4 on x, y and
+    the gradient, 200 test points.  Agreement to 6+ digits fixes the signs, the row / column layout and the noise model
+    K[i][i] = 1 + var_x + var_y, K[g][g] = 1 / l^2 + var_grad."""
+    n, t = 100, 200
+    x = np.linspace(0, 2 * np.pi, n)[:, None]
+    xt = np.linspace(0, 2 * np.pi, t)[:, None]
+    y, g = np.sin(2 * x[:, 0]), 2 * np.cos(2 * x[:, 0])
+    yt, gt = np.sin(2 * xt[:, 0]), 2 * np.cos(2 * xt[:, 0])
+    # with gradient observations (:174-178)
+    for scale, mae_ref, mae_grad_ref in [(0.5, 8.523327884661321e-06, 0.0001228380577847092), (0.4, 6.453961399301211e-06, 0.0001125665082426853),
+                                         (0.3, 4.4761251597013675e-06, 8.851481085195954e-05), (0.2, 4.1624286843223515e-06, 7.139121709502966e-05),
+                                         (0.1, 1.756325489369356e-05, 0.00034785637964318994)]:
+        gp = oracle.NoisyInputGp(oracle.RBF, scale, False, np.float64)
+        assert gp.train(x, y, g[:, None, None], 1e-4, 1e-4, 1e-4, 1) and gp.m == 2 * n
+        mean, grad, _, _, _ = gp.test(xt, True, False)
+        mae, mae_grad = np.abs(mean[:, 0] - yt).mean(), np.abs(grad[:, 0, 0] - gt).mean()
+        # cond(K) grows with the scale (1e8 at 0.2, 1e11 at 0.5): the printed digits are only reproducible to that accuracy
+        rtol = 1e-6 if scale <= 0.2 else 2e-2
+        assert abs(mae - mae_ref) / mae_ref < rtol and abs(mae_grad - mae_grad_ref) / mae_grad_ref < rtol, (scale, mae, mae_grad)
+    # without gradient observations (:348-349): the gradient is still predicted
+    for scale, mae_ref, mae_grad_ref in [(0.5, 0.00019489369361661352, 0.003074427178772044), (0.2, 7.377464439757659e-05, 0.0024347632450979033)]:
+        gp = oracle.NoisyInputGp(oracle.RBF, scale, True, np.float64)
+        assert gp.train(x, y, None, 1e-4, 1e-4, None, 0) and gp.m == n
+        mean, grad, _, _, _ = gp.test(xt, True, False)
+        mae, mae_grad = np.abs(mean[:, 0] - yt).mean(), np.abs(grad[:, 0, 0] - gt).mean()
+        rtol = 1e-6 if scale <= 0.2 else 2e-2
+        assert abs(mae - mae_ref) / mae_ref < rtol and abs(mae_grad - mae_grad_ref) / mae_grad_ref < rtol, (scale, mae, mae_grad)
+
+
+def test_noisy_input_gp_reference_mae_values_2d(oracle):
+    """The 2-D case of the same gtest (:366-410, 552-554): 50 x 50 samples of 2 sin(10 x) cos(5 y) with both partial derivatives
+    (7500 x 7500 system), RBF l = 0.1, 100 x 100 test points."""
+    def values(n):
+        xs, ys = np.linspace(-2, 2, n), np.linspace(-1, 1, n)
+        px, py = np.meshgrid(xs, ys, indexing="ij")  # xi outer, yi inner (:361-362)
+        pts = np.stack([px.ravel(), py.ravel()], axis=1)
+        z = 2 * np.sin(10 * pts[:, 0]) * np.cos(5 * pts[:, 1])
+        gx = 20 * np.cos(10 * pts[:, 0]) * np.cos(5 * pts[:, 1])
+        gy = -10 * np.sin(10 * pts[:, 0]) * np.sin(5 * pts[:, 1])
+        return pts, z, gx, gy
+
+    pts, z, gx, gy = values(50)
+    gp = oracle.NoisyInputGp(oracle.RBF, 0.1, False, np.float64)
+    assert gp.train(pts, z, np.stack([gx, gy], axis=1)[:, None, :], 1e-4, 1e-4, 1e-4, 1) and gp.m == 7500
+    pt, zt, gxt, gyt = values(100)
+    mean, grad, _, _, _ = gp.test(pt, True, False)
+    mae, mae_x, mae_y = np.abs(mean[:, 0] - zt).mean(), np.abs(grad[:, 0, 0] - gxt).mean(), np.abs(grad[:, 0, 1] - gyt).mean()
+    for got, ref in ((mae, 9.516671456234042e-06), (mae_x, 0.00010712550862064423), (mae_y, 0.0002508214688791491)):
+        assert abs(got - ref) / ref < 1e-4, (mae, mae_x, mae_y)

@@ -59,6 +59,12 @@ namespace erl::gaussian_process::b200 {
         using Batch = erl_gp_batch_##SFX;                                                \
         using Lidar2d = erl_gp_lidar2d_##SFX;                                            \
         using Range3d = erl_gp_range3d_##SFX;                                            \
+        using Noisy = erl_gp_noisy_##SFX;                                                \
+        static constexpr auto noisy_create = erl_gp_noisy_create_##SFX;                  \
+        static constexpr auto noisy_destroy = erl_gp_noisy_destroy_##SFX;                \
+        static constexpr auto noisy_train = erl_gp_noisy_train_##SFX;                    \
+        static constexpr auto noisy_get = erl_gp_noisy_get_##SFX;                        \
+        static constexpr auto noisy_test = erl_gp_noisy_test_##SFX;                      \
         static constexpr auto compute_ktrain = erl_gp_compute_ktrain_##SFX;              \
         static constexpr auto compute_ktest = erl_gp_compute_ktest_##SFX;                \
         static constexpr auto vanilla_create = erl_gp_vanilla_create_##SFX;              \

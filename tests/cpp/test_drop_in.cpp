@@ -3,6 +3,7 @@
 // checked against the CPU oracle.  TEST INFRASTRUCTURE: this is the only C++ translation unit that includes the
 // oracle.  Needs a CUDA device; run by tests/test_gpu_cpp_dropin.py.
 #include "erl_gaussian_process_b200/lidar_gp_2d.hpp"
+#include "erl_gaussian_process_b200/noisy_input_gp.hpp"
 #include "erl_gaussian_process_b200/range_sensor_gp_3d.hpp"
 #include "erl_gaussian_process_b200/vanilla_gp.hpp"
 
@@ -83,6 +84,90 @@ TestVanillaSiso(const char *name, const double tol) {
     CHECK(el < tol * 10, "L err %.3e", el);
     CHECK(gp.GetLltInfo() == 0, "llt info");
     std::printf("%s %s: mean err %.2e, var err %.2e, mae %.6e\n", g_failures ? "----" : "PASS", name, em, ev, mae);
+}
+
+// NoisyInputGaussianProcess driven the way the reference's gtest drives it (test/gtest/test_noisy_input_gp.cpp:13-60, 366-430):
+// Reset, fill the TrainSet (x, y, grad, var_x, var_y, var_grad, grad_flag, num_samples, num_samples_with_grad), Train, Test with
+// gradient prediction; 2-D inputs, every second sample with a gradient observation; every TestResult output against the oracle.
+template<typename Dtype>
+static void
+TestNoisyInput(const char *name, const double tol) {
+    using Gp = NoisyInputGaussianProcess<Dtype>;
+    constexpr long n = 160, n_test = 900, d = 2;
+    auto setting = std::make_shared<typename Gp::Setting>();
+    setting->kernel_type = "erl::covariance::RadialBiasFunction2d";
+    setting->kernel->scale = Dtype(0.5);
+    setting->kernel->x_dim = d;
+    setting->max_num_samples = n;
+    Gp gp(setting);
+    std::mt19937 rng(17);
+    std::uniform_real_distribution<double> uni(-1, 1);
+    Eigen::MatrixX<Dtype> xt(d, n_test);
+    for (long i = 0; i < n_test; ++i) { xt(0, i) = Dtype(uni(rng)), xt(1, i) = Dtype(uni(rng)); }
+    CHECK(gp.Test(xt, true) == nullptr, "Test before Train must return nullptr");
+    gp.Reset(n, d, 1);
+    auto &ts = gp.GetTrainSet();
+    erl_gp_oracle::NoisyInputGp<Dtype> ref;
+    ref.kernel_type = erl_gp_oracle::kRadialBiasFunction, ref.scale = Dtype(0.5);
+    ref.x_dim = d, ref.y_dim = 1, ref.num_samples = n;
+    long ng = 0;
+    for (long i = 0; i < n; ++i) {
+        const double a = uni(rng), b = uni(rng);
+        ts.x(0, i) = Dtype(a), ts.x(1, i) = Dtype(b);
+        ts.y(i, 0) = Dtype(std::sin(2 * a) * std::cos(b));
+        ts.grad(0, i) = Dtype(2 * std::cos(2 * a) * std::cos(b));
+        ts.grad(1, i) = Dtype(-std::sin(2 * a) * std::sin(b));
+        ts.var_x[i] = Dtype(0.01), ts.var_y[i] = Dtype(0.01), ts.var_grad[i] = Dtype(0.02);
+        ts.grad_flag[i] = i % 2 == 0;
+        ng += i % 2 == 0;
+        ref.x.push_back(ts.x(0, i)), ref.x.push_back(ts.x(1, i));
+        ref.y.push_back(ts.y(i, 0));
+        ref.grad.push_back(ts.grad(0, i)), ref.grad.push_back(ts.grad(1, i));
+        ref.var_x.push_back(ts.var_x[i]), ref.var_y.push_back(ts.var_y[i]), ref.var_grad.push_back(ts.var_grad[i]);
+        ref.grad_flag.push_back(ts.grad_flag[i]);
+    }
+    ts.num_samples = n;
+    ts.num_samples_with_grad = ng;
+    CHECK(gp.Train(), "Train");
+    CHECK(!gp.Train(), "second Train() without Reset must fail");
+    CHECK(ref.Train(), "oracle Train");
+    const long m = n + d * ng;
+    CHECK(gp.GetKtrainSized().rows() == m && gp.GetCholeskyDecomposition().cols() == m && gp.GetAlphaSized().rows() == m, "K / L / alpha are m x m, m = n + d ng");
+    double el = 0;
+    for (long c = 0; c < m; ++c) {
+        for (long r = c; r < m; ++r) { el = std::max(el, std::abs(double(gp.GetCholeskyDecomposition()(r, c)) - double(ref.mat_l[r + c * m]))); }
+    }
+    CHECK(el < (sizeof(Dtype) == 4 ? 5e-4 : 1e-10), "L err %.3e", el);
+    auto result = gp.Test(xt, true);
+    CHECK(result != nullptr, "Test");
+    Eigen::VectorX<Dtype> mean(n_test), var(n_test);
+    Eigen::MatrixX<Dtype> grad(d, n_test), gvar(d, n_test), cov(d * (d + 1) / 2, n_test);
+    result->GetMean(0, mean, true);
+    const auto valid = result->GetGradient(0, grad, true);
+    result->GetMeanVariance(var, true);
+    result->GetGradientVariance(gvar, true);
+    result->GetCovariance(cov, true);
+    std::vector<Dtype> m_r(n_test), g_r(d * n_test), v_r(n_test), gv_r(d * n_test), c_r(3 * n_test);
+    ref.Test(xt.data(), n_test, true, m_r.data(), g_r.data(), v_r.data(), gv_r.data(), c_r.data());
+    const double prior = 3.0 / 0.25;
+    double em = 0, eg = 0, ev = 0, egv = 0, ec = 0, sm = 0, sg = 0;
+    for (long i = 0; i < n_test; ++i) {
+        CHECK(bool(valid[i]), "gradient %ld must be valid", i);
+        sm = std::max(sm, std::abs(double(m_r[i])));
+        em = std::max(em, std::abs(double(mean[i]) - double(m_r[i])));
+        ev = std::max(ev, std::abs(double(var[i]) - double(v_r[i])));
+        for (long j = 0; j < d; ++j) {
+            sg = std::max(sg, std::abs(double(g_r[j + i * d])));
+            eg = std::max(eg, std::abs(double(grad(j, i)) - double(g_r[j + i * d])));
+            egv = std::max(egv, std::abs(double(gvar(j, i)) - double(gv_r[j + i * d])) / prior);
+        }
+        for (long j = 0; j < 3; ++j) { ec = std::max(ec, std::abs(double(cov(j, i)) - double(c_r[j + i * 3])) / prior); }
+    }
+    CHECK(em / sm < tol && eg / sg < tol && ev < tol && egv < tol && ec < tol, "mean %.2e grad %.2e var %.2e grad var %.2e cov %.2e", em / sm, eg / sg, ev, egv, ec);
+    Dtype f1 = 0, g1[2] = {0, 0};
+    result->GetMean(5, 0, f1);
+    CHECK(result->GetGradient(5, 0, g1) && f1 == mean[5] && g1[0] == grad(0, 5) && g1[1] == grad(1, 5), "single-index accessors");
+    std::printf("%s %s: mean %.2e grad %.2e var %.2e grad var %.2e cov %.2e\n", g_failures ? "----" : "PASS", name, em / sm, eg / sg, ev, egv, ec);
 }
 
 // Setting::partition_on_hit_rays (src/lidar_gp_2d.cpp:302-348, 364): the table is empty after construction and follows the hit rays
@@ -360,6 +445,8 @@ main() {
         TestVanillaSiso<float>("VanillaGaussianProcess<float> SISO", 1e-4);
         TestLidar<double>("LidarGaussianProcess2D<double>", 1e-10);
         TestLidar<float>("LidarGaussianProcess2D<float>", 1e-4);
+        TestNoisyInput<double>("NoisyInputGaussianProcess<double>", 1e-10);
+        TestNoisyInput<float>("NoisyInputGaussianProcess<float>", 1e-4);
         TestLidarHitRays<double>("LidarGaussianProcess2D<double> partition_on_hit_rays", 1e-10);
         TestLidarHitRays<float>("LidarGaussianProcess2D<float> partition_on_hit_rays", 1e-4);
         TestRangeSensor<float>("RangeSensorGaussianProcess3D<float>", 1e-4);

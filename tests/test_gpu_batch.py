@@ -3,6 +3,7 @@ Everything goes through the C ABI (ctypes)."""
 import numpy as np
 import pytest
 
+from oracle import oracle_np as onp
 from tests.util import TOL, err_mean, err_var, make_batch
 
 pytestmark = pytest.mark.gpu
@@ -65,8 +66,18 @@ def _check_batch(gp, oracle, dtype, kernel, scale, num_gps, max_n, x_dim, seed, 
         lg, lr = out["L"][g][:n, :n], ref64["L"][g][:n, :n]
         assert np.abs(np.triu(lg, 1)).max() == 0, "strict upper triangle of L must be zero"
         assert np.abs(lg - lr).max() / np.abs(lr).max() < ltol
+        # alpha = K^-1 y carries cond(K): the bar is the measured distance between two correct implementations at
+        # this precision (float: the FP32 port vs the FP64 port; double: the port vs LAPACK potrf / potrs), times 10
         ag, ar = out["alpha"][g][:n], ref64["alpha"][g][:n]
-        assert np.abs(ag - ar).max() / np.abs(ar).max() < (5e-3 if dtype == np.float32 else 1e-8)
+        if dtype == np.float32:
+            other = ref["alpha"][g][:n]
+        else:
+            xg, yg, vg = (np.asarray(v[g][:n], dtype=np.float64) for v in (x, y, var))
+            other = onp.vanilla_train(kid, scale, xg, yg, vg)[1]
+        floor = np.abs(other - ar).max() / np.abs(ar).max()
+        # (float: the 3xTF32 products of the row-GP kernel carry a unit round-off of ~2^-20 against 2^-24 for the FP32 port's FMAs, so up
+        # to 16x the port's own distance from the FP64 answer is expected - measured 13x on the 1-D OU case; the bar is 32x)
+        assert np.abs(ag - ar).max() / np.abs(ar).max() < max((32 if dtype == np.float32 else 10) * floor, 1e-5 if dtype == np.float32 else 1e-13)
     return out
 
 

@@ -46,6 +46,10 @@ namespace erl_gp {
         if (err == cudaSuccess) { err = b->alpha.Reserve(bn); }
         if (err == cudaSuccess) { err = b->l.Reserve(bn * max_n); }
         if (err == cudaSuccess) { err = cudaMemsetAsync(b->info.ptr, 0xff, sizeof(int) * num_gps, ctx->stream); }  // -1 = untrained
+        // the kernels write rows / columns [0, n) of a GP's alpha / L slice only: start from zeros so that the padding a caller downloads
+        // does not depend on what the allocator handed out
+        if (err == cudaSuccess) { err = cudaMemsetAsync(b->alpha.ptr, 0, sizeof(T) * bn, ctx->stream); }
+        if (err == cudaSuccess) { err = cudaMemsetAsync(b->l.ptr, 0, sizeof(T) * bn * max_n, ctx->stream); }
         if (err != cudaSuccess) {
             delete b;
             return SetError(ctx, ERL_GP_STATUS_ALLOC_FAILED, "batch: %s", cudaGetErrorString(err));

@@ -11,6 +11,8 @@
 #include "erl_gp_dense.cuh"
 
 #include <algorithm>
+#include <thread>
+#include <vector>
 
 namespace erl_gp {
 
@@ -84,8 +86,9 @@ namespace erl_gp {
     // mean: num_test x y_dim (ld = num_test) or null; var: num_test or null.  kind selects host / device pointers.
     template<typename T>
     static int
-    VanillaTest(Vanilla<T> *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
+    VanillaTest(Vanilla<T> *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind, long ld_mean = 0) {
         if (gp == nullptr || x_test == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        if (ld_mean < num_test) { ld_mean = num_test; }  // rows between two output columns of `mean` (a slice of a longer test set: the whole set's length)
         Context *ctx = gp->ctx;
         if (!gp->trained) { return SetError(ctx, ERL_GP_STATUS_NOT_TRAINED, "vanilla: Test() before Train()"); }  // src/vanilla_gp.cpp:556-558
         if (num_test <= 0) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "vanilla: num_test = %ld, it should be > 0", num_test); }  // :529-532
@@ -108,7 +111,7 @@ namespace erl_gp {
                 if (mean != nullptr) {
                     const int rc = PredictMean<T>(ctx, gp->kernel, gp->scale, d, n, tt, gp->x.ptr, gp->xt.ptr, gp->alpha.ptr, n, gp->y_dim, gp->mean.ptr, tt);
                     if (rc != ERL_GP_STATUS_OK) { return rc; }
-                    ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(mean + t0, sizeof(T) * num_test, gp->mean.ptr, sizeof(T) * tt, sizeof(T) * tt, gp->y_dim, out_kind, ctx->stream));
+                    ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(mean + t0, sizeof(T) * ld_mean, gp->mean.ptr, sizeof(T) * tt, sizeof(T) * tt, gp->y_dim, out_kind, ctx->stream));
                 }
                 if (var != nullptr) {
                     int rc = PredictVariance<T>(ctx, gp->kernel, gp->scale, d, n, tt, gp->x.ptr, gp->xt.ptr, gp->l.ptr, n, gp->linv.ptr, gp->w.ptr, gp->sumsq.ptr);
@@ -136,7 +139,7 @@ namespace erl_gp {
             if (mean != nullptr) {
                 rc = GemvT<T>(ctx, n, tt, gp->w.ptr, n, gp->alpha.ptr, n, gp->y_dim, gp->mean.ptr, tt);
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
-                ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(mean + t0, sizeof(T) * num_test, gp->mean.ptr, sizeof(T) * tt, sizeof(T) * tt, gp->y_dim, out_kind, ctx->stream));
+                ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(mean + t0, sizeof(T) * ld_mean, gp->mean.ptr, sizeof(T) * tt, sizeof(T) * tt, gp->y_dim, out_kind, ctx->stream));
             }
             if (var != nullptr) {
                 ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->sumsq.ptr, 0, sizeof(T) * tt, ctx->stream));
@@ -146,6 +149,79 @@ namespace erl_gp {
                 if (rc != ERL_GP_STATUS_OK) { return rc; }
                 ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(var + t0, gp->variance.ptr, sizeof(T) * tt, out_kind, ctx->stream));
             }
+        }
+        return ERL_GP_STATUS_OK;
+    }
+
+    // ---- one process, several GPUs (C1 / C5 predict shards over test points, the factorisation is "replicas only") ----
+    // Copy the trained state of `src` (training points, L, the inverses of its diagonal blocks, alpha) to `dst`, a VanillaGaussianProcess
+    // on another context / device: cudaMemcpyPeerAsync, i.e. NVLink when peer access is available (2 GiB of L at n = 16384 instead of a
+    // redundant 62 ms factorisation per device).  K is not copied (predict does not read it): GetKtrain() stays with `src`.
+    template<typename T>
+    static int
+    VanillaReplicate(Vanilla<T> *src, Vanilla<T> *dst) {
+        if (src == nullptr || dst == nullptr || src == dst) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *sc = src->ctx, *dc = dst->ctx;
+        if (!src->trained) { return SetError(sc, ERL_GP_STATUS_NOT_TRAINED, "vanilla: replicate before Train()"); }
+        dst->trained = false;
+        const long n = src->n, num_panels = CeilDiv(n, kPanel);
+        ERL_GP_CUDA_OK(dc, cudaSetDevice(dc->device));
+        if (dc->device != sc->device) {
+            int can = 0;
+            ERL_GP_CUDA_OK(dc, cudaDeviceCanAccessPeer(&can, dc->device, sc->device));
+            if (can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(sc->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ERL_GP_CUDA_OK(dc, e); }
+                (void) cudaGetLastError();
+            }
+        }
+        ERL_GP_CUDA_OK(dc, dst->x.Reserve(static_cast<size_t>(n) * src->x_dim));
+        ERL_GP_CUDA_OK(dc, dst->alpha.Reserve(static_cast<size_t>(n) * src->y_dim));
+        ERL_GP_CUDA_OK(dc, dst->l.Reserve(static_cast<size_t>(n) * n));
+        ERL_GP_CUDA_OK(dc, dst->linv.Reserve(static_cast<size_t>(num_panels) * kPanel * kPanel));
+        ERL_GP_CUDA_OK(dc, dst->s_buf.Reserve(static_cast<size_t>(kPanel) * (src->y_dim > 8192 ? src->y_dim : 8192)));
+        ERL_GP_CUDA_OK(dc, dst->info.Reserve(1));
+        ERL_GP_CUDA_OK(sc, cudaSetDevice(sc->device));
+        ERL_GP_CUDA_OK(sc, cudaStreamSynchronize(sc->stream));  // the training of `src` is complete
+        ERL_GP_CUDA_OK(dc, cudaSetDevice(dc->device));
+        auto copy = [&](void *d, const void *s_, size_t bytes) { return cudaMemcpyPeerAsync(d, dc->device, s_, sc->device, bytes, dc->stream); };
+        ERL_GP_CUDA_OK(dc, copy(dst->x.ptr, src->x.ptr, sizeof(T) * n * src->x_dim));
+        ERL_GP_CUDA_OK(dc, copy(dst->alpha.ptr, src->alpha.ptr, sizeof(T) * n * src->y_dim));
+        ERL_GP_CUDA_OK(dc, copy(dst->l.ptr, src->l.ptr, sizeof(T) * n * n));
+        ERL_GP_CUDA_OK(dc, copy(dst->linv.ptr, src->linv.ptr, sizeof(T) * num_panels * kPanel * kPanel));
+        ERL_GP_CUDA_OK(dc, copy(dst->info.ptr, src->info.ptr, sizeof(int)));
+        ERL_GP_CUDA_OK(dc, cudaStreamSynchronize(dc->stream));
+        dst->n = n, dst->x_dim = src->x_dim, dst->y_dim = src->y_dim, dst->kernel = src->kernel, dst->scale = src->scale;
+        dst->trained = true;
+        return ERL_GP_STATUS_OK;
+    }
+
+    // Test() of one trained GP replicated on several devices: contiguous ranges of the test points, one host thread per replica, every
+    // replica writes its range straight into the caller's arrays (the host gather).
+    template<typename T>
+    static int
+    VanillaTestMulti(Vanilla<T> *const *gps, long num_gps, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {
+        if (gps == nullptr || num_gps <= 0 || x_test == nullptr || num_test <= 0) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        for (long i = 0; i < num_gps; ++i) {
+            if (gps[i] == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        }
+        std::vector<int> status(static_cast<size_t>(num_gps), ERL_GP_STATUS_OK);
+        auto run = [&](const long i) {
+            const long t0 = num_test * i / num_gps, t1 = num_test * (i + 1) / num_gps;
+            if (t1 <= t0) { return; }
+            status[i] = VanillaTest<T>(gps[i], t1 - t0, x_test + t0 * ld_xt, ld_xt, mean != nullptr ? mean + t0 : nullptr, var != nullptr ? var + t0 : nullptr, cudaMemcpyHostToDevice,
+                                       cudaMemcpyDeviceToHost, num_test);
+            if (status[i] == ERL_GP_STATUS_OK) {
+                const cudaError_t e = cudaStreamSynchronize(gps[i]->ctx->stream);
+                if (e != cudaSuccess) { status[i] = SetError(gps[i]->ctx, ERL_GP_STATUS_CUDA_ERROR, "vanilla multi: %s", cudaGetErrorString(e)); }
+            }
+        };
+        std::vector<std::thread> workers;
+        for (long i = 1; i < num_gps; ++i) { workers.emplace_back(run, i); }
+        run(0);
+        for (std::thread &w : workers) { w.join(); }
+        for (long i = 0; i < num_gps; ++i) {
+            if (status[i] != ERL_GP_STATUS_OK) { return status[i]; }
         }
         return ERL_GP_STATUS_OK;
     }
@@ -424,6 +500,10 @@ extern "C" {
         const int rc = VanillaTest<T>(gp, num_test, x_test, ld_xt, mean, var, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost);                                               \
         if (rc != ERL_GP_STATUS_OK) { return rc; }                                                                                                                           \
         return erl_gp_context_synchronize(gp->ctx);                                                                                                                          \
+    }                                                                                                                                                                        \
+    int erl_gp_vanilla_replicate_##SFX(erl_gp_vanilla_##SFX *src, erl_gp_vanilla_##SFX *dst) { return VanillaReplicate<T>(src, dst); }                                      \
+    int erl_gp_vanilla_test_multi_##SFX(erl_gp_vanilla_##SFX *const *gps, long num_gps, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                        \
+        return VanillaTestMulti<T>(reinterpret_cast<Vanilla<T> *const *>(gps), num_gps, num_test, x_test, ld_xt, mean, var);                                                 \
     }                                                                                                                                                                        \
     int erl_gp_vanilla_test_dev_##SFX(erl_gp_vanilla_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                                               \
         return VanillaTest<T>(gp, num_test, x_test, ld_xt, mean, var, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);                                                   \

@@ -205,6 +205,24 @@ class VanillaGaussianProcess:
         self.is_trained = True
         return True
 
+    def replicate_to(self, other: "VanillaGaussianProcess"):
+        """erl_gp_vanilla_replicate: copy the trained state (x_train, L, alpha) to `other`, a GP on another context / device."""
+        check(self.ctx.fn("erl_gp_vanilla_replicate", self.dtype)(self.handle, other.handle), "vanilla_replicate", self.ctx.handle)
+        other.n, other.y_dim, other.info, other.is_trained = self.n, self.y_dim, self.info, True
+
+    @staticmethod
+    def test_multi(gps, x_test):
+        """erl_gp_vanilla_test_multi: one trained GP replicated on several devices, test points split into contiguous ranges, one
+        host thread per replica.  Returns (mean (y_dim, T), variance (T))."""
+        g0 = gps[0]
+        x_test = np.ascontiguousarray(x_test, dtype=g0.dtype)
+        t, d = x_test.shape
+        mean = np.empty((g0.y_dim, t), dtype=g0.dtype)
+        var = np.empty(t, dtype=g0.dtype)
+        handles = (C.c_void_p * len(gps))(*[g.handle for g in gps])
+        check(g0.ctx.fn("erl_gp_vanilla_test_multi", g0.dtype)(handles, C.c_long(len(gps)), C.c_long(t), _p(x_test), C.c_long(d), _p(mean), _p(var)), "vanilla_test_multi", g0.ctx.handle)
+        return mean, var
+
     # ---- device-resident entry points (x, y, var, x_test, mean, var are device pointers, e.g. torch tensors) ----
     def train_dev(self, x, y, var, n, x_dim, y_dim=1):
         """erl_gp_vanilla_train_dev: asynchronous on the context's stream; `info` is read by vanilla_info()."""

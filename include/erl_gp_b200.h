@@ -143,6 +143,17 @@ int erl_gp_vanilla_test_f32(erl_gp_vanilla_f32 *gp, long num_test, const float *
                             float *var);
 int erl_gp_vanilla_test_f64(erl_gp_vanilla_f64 *gp, long num_test, const double *x_test, long ld_xt, double *mean,
                             double *var);
+/* One process, several GPUs (north_star: "sharded across the 8 GPUs of one box with only a host gather"; the factorisation is
+ * single-GPU, the predict of src/vanilla_gp.cpp:521-559, 61-150 shards over test points).  replicate: copy the trained state of
+ * `src` (x_train, L, alpha) to `dst`, a GP created on another context / device (cudaMemcpyPeerAsync: NVLink with peer access)
+ * instead of one redundant factorisation per device.  test_multi: Test() + GetMean + GetVariance over contiguous ranges of the
+ * test points, one host thread per replica, results written straight into the caller's arrays. */
+int erl_gp_vanilla_replicate_f32(erl_gp_vanilla_f32 *src, erl_gp_vanilla_f32 *dst);
+int erl_gp_vanilla_replicate_f64(erl_gp_vanilla_f64 *src, erl_gp_vanilla_f64 *dst);
+int erl_gp_vanilla_test_multi_f32(erl_gp_vanilla_f32 *const *gps, long num_gps, long num_test, const float *x_test,
+                                  long ld_xt, float *mean, float *var);
+int erl_gp_vanilla_test_multi_f64(erl_gp_vanilla_f64 *const *gps, long num_gps, long num_test, const double *x_test,
+                                  long ld_xt, double *mean, double *var);
 int erl_gp_vanilla_test_dev_f32(erl_gp_vanilla_f32 *gp, long num_test, const float *x_test, long ld_xt, float *mean,
                                 float *var);
 int erl_gp_vanilla_test_dev_f64(erl_gp_vanilla_f64 *gp, long num_test, const double *x_test, long ld_xt,

@@ -103,6 +103,46 @@ def test_vanilla_shapes(gp, oracle, dtype, n, t, d, kernel, scale, ydim):
     assert err_var(res.get_variance(), v_ref) < tol
 
 
+@pytest.mark.parametrize("dtype,ydim", [(np.float64, 1), (np.float64, 2), (np.float32, 1)])
+def test_vanilla_replicate_and_test_multi(gp, oracle, dtype, ydim):
+    """erl_gp_vanilla_replicate / erl_gp_vanilla_test_multi (the dense predict shards over test points): train once,
+    copy (x_train, L, alpha) to replicas on other contexts - other GPUs where the box has several (cudaMemcpyPeerAsync), further
+    contexts of device 0 everywhere - and predict contiguous ranges of the test points with one host thread per replica.  The
+    result must agree with the single-device call (mean bit for bit) and be within tolerance of the oracle."""
+    rng = np.random.default_rng(17)
+    n, t, d = 700, 3001, 2
+    x = rng.uniform(-1, 1, (n, d)).astype(dtype)
+    y = np.stack([np.sin(3 * x).sum(axis=1) * (c + 1) for c in range(ydim)], axis=1).astype(dtype)
+    var = rng.uniform(0.005, 0.02, n).astype(dtype)
+    xt = rng.uniform(-1, 1, (t, d)).astype(dtype)
+    g, o = _vanilla_pair(gp, oracle, dtype, "matern32", 0.3, x, y if ydim > 1 else y[:, 0], var)
+    res = g.test(xt)
+    single_mean = np.stack([res.get_mean(c) for c in range(ydim)])
+    single_var = res.get_variance()
+    devices = [0, 0] + list(range(1, gp._capi.device_count()))
+    replicas = [g]
+    for dev in devices:
+        r = gp.VanillaGaussianProcess(g.setting, dtype, gp.Context(dev))
+        g.replicate_to(r)
+        replicas.append(r)
+    mean, variance = gp.VanillaGaussianProcess.test_multi(replicas, xt)
+    # the mean is a per-point dot product: bit-identical; the variance kernel sums ||v||^2 in an order that depends on a point's place
+    # in its 128-point tile, and a shard's first point starts a new tile: identical up to the rounding of that sum
+    eps = 1e-6 if dtype == np.float32 else 1e-13
+    assert np.array_equal(mean, single_mean) and np.abs(variance - single_var).max() < eps
+    # a replica alone answers like the original
+    alone = replicas[-1].test(xt[:100])
+    assert np.array_equal(alone.get_mean(0), single_mean[0][:100]) and np.abs(alone.get_variance() - single_var[:100]).max() < eps
+    m_ref, v_ref = o.test(xt)
+    tol = TOL[np.dtype(dtype)]
+    for c in range(ydim):
+        assert err_mean(mean[c], m_ref[:, c] if ydim > 1 else m_ref) < tol
+    assert err_var(variance, v_ref) < tol
+    fresh = gp.VanillaGaussianProcess(g.setting, dtype)
+    with pytest.raises(gp.ErlGpError):
+        fresh.replicate_to(replicas[1])  # not trained
+
+
 def test_vanilla_misuse(gp):
     s = gp.VanillaGaussianProcess.Setting("rbf", 0.5, max_num_samples=10)
     g = gp.VanillaGaussianProcess(s, np.float64)

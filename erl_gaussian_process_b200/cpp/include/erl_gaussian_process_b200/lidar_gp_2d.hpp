@@ -8,6 +8,9 @@
 #include "sensor_frames.hpp"
 #include "vanilla_gp.hpp"
 
+#include <cmath>
+#include <sstream>
+#include <string>
 #include <tuple>
 
 namespace erl::gaussian_process {
@@ -291,6 +294,123 @@ namespace erl::gaussian_process {
             return ok != 0;
         }
 
+        // ---- operator== / Write / Read (src/lidar_gp_2d.cpp:461-635): tokens setting, trained, gps, angle_partitions, sensor_frame,
+        // mapped_distances in the reference's order; framing in serialization.hpp.  Read() needs an object constructed with the same
+        // Setting (the stream's copy is checked against it), restores the frame and replays Train() on the device; the stored partition
+        // table and partition GPs are the check.
+        [[nodiscard]] bool
+        operator==(const LidarGaussianProcess2D &other) const {
+            namespace ser = b200::serialization;
+            if (SettingText() != other.SettingText() || m_trained_ != other.m_trained_) { return false; }
+            if (m_angle_partitions_ != other.m_angle_partitions_ || m_gps_.size() != other.m_gps_.size()) { return false; }
+            if (!m_trained_) { return true; }
+            for (std::size_t i = 0; i < m_gps_.size(); ++i) {
+                if (!ser::SamePartitionGp(*m_gps_[i], *other.m_gps_[i])) { return false; }
+            }
+            const auto &r0 = m_sensor_frame_->GetRanges(), &r1 = other.m_sensor_frame_->GetRanges();
+            if (r0.size() != r1.size()) { return false; }
+            for (long i = 0; i < r0.size(); ++i) {
+                if (!(r0[i] == r1[i]) && !(std::isnan(r0[i]) && std::isnan(r1[i]))) { return false; }
+            }
+            return true;
+        }
+
+        [[nodiscard]] bool
+        operator!=(const LidarGaussianProcess2D &other) const {
+            return !(*this == other);
+        }
+
+        [[nodiscard]] bool
+        Write(std::ostream &s) const {
+            namespace ser = b200::serialization;
+            return ser::WriteTokens(
+                s,
+                {{"setting", [this](std::ostream &o) { o << SettingText() << '\n'; return o.good(); }},  // (a whole line: the kernel type name may hold blanks)
+                 {"trained", ser::ScalarWriter(m_trained_)},
+                 {"gps",
+                  [this](std::ostream &o) {
+                      o << m_gps_.size() << '\n';
+                      for (const auto &g: m_gps_) {
+                          const char has_gp = 1;
+                          o.write(&has_gp, 1);
+                          if (!ser::WritePartitionGp(o, *g)) { return false; }
+                      }
+                      return o.good();
+                  }},
+                 {"angle_partitions", [this](std::ostream &o) { return ser::WritePartitions(o, m_angle_partitions_); }},
+                 {"sensor_frame",
+                  [this](std::ostream &o) {
+                      return ser::SaveMatrix(o, m_sensor_frame_->GetRotationMatrix()) && ser::SaveMatrix(o, m_sensor_frame_->GetTranslationVector()) &&
+                             ser::SaveMatrix(o, m_sensor_frame_->GetRanges());
+                  }},
+                 {"mapped_distances",
+                  [this](std::ostream &o) {
+                      VectorX mapped(m_sensor_frame_->GetRanges().size());
+                      for (long i = 0; i < mapped.size(); ++i) { mapped[i] = m_mapping_->map(m_sensor_frame_->GetRanges()[i]); }  // m_mapped_distances_, :234
+                      return ser::SaveMatrix(o, mapped);
+                  }}});
+        }
+
+        [[nodiscard]] bool
+        Read(std::istream &s) {
+            namespace ser = b200::serialization;
+            bool trained = false;
+            std::string setting_text;
+            std::vector<std::tuple<long, long, Dtype, Dtype>> parts;
+            std::string gps_bytes;
+            std::size_t num_gps = 0;
+            MatrixX rotation;
+            VectorX translation, ranges, mapped;
+            std::streampos gps_pos;
+            const bool ok = ser::ReadTokens(
+                s,
+                {{"setting", [&setting_text](std::istream &i) { return static_cast<bool>(std::getline(i, setting_text)); }},
+                 {"trained", ser::ScalarReader(trained)},
+                 {"gps",
+                  [&](std::istream &i) {  // parsed now (to find the end of the token), compared after the training has been replayed
+                      i >> num_gps;
+                      ser::SkipLine(i);
+                      gps_pos = i.tellg();
+                      if (i.fail() || num_gps > (1u << 24)) { return false; }
+                      for (std::size_t g = 0; g < num_gps; ++g) {
+                          char has_gp = 0;
+                          i.read(&has_gp, 1);
+                          if (has_gp && !ser::ReadAndComparePartitionGp(i, PartitionGp(this, 0), false)) { return false; }
+                      }
+                      return i.good();
+                  }},
+                 {"angle_partitions", [&parts](std::istream &i) { return ser::ReadPartitions(i, parts); }},
+                 {"sensor_frame", [&](std::istream &i) { return ser::LoadMatrix(i, rotation) && ser::LoadVector(i, translation) && ser::LoadVector(i, ranges); }},
+                 {"mapped_distances", [&mapped](std::istream &i) { return ser::LoadVector(i, mapped); }}});
+            if (!ok || setting_text != SettingText()) { return false; }
+            Reset();
+            if (!trained) { return m_setting_->partition_on_hit_rays || parts == m_angle_partitions_; }
+            if (!Train(rotation, translation, ranges) || parts != m_angle_partitions_ || num_gps != m_gps_.size()) { return false; }
+            const std::streampos after = s.tellg();
+            s.seekg(gps_pos);
+            for (std::size_t g = 0; g < num_gps; ++g) {
+                char has_gp = 0;
+                s.read(&has_gp, 1);
+                if (has_gp && !ser::ReadAndComparePartitionGp(s, *m_gps_[g], true)) { return false; }
+            }
+            s.seekg(after);
+            return s.good();
+        }
+
+    protected:
+        [[nodiscard]] std::string
+        SettingText() const {  // one line: every Setting field that shapes the model (the reference writes its Setting as YAML)
+            std::ostringstream o;
+            o.precision(17);
+            const auto &t = *m_setting_;
+            o << t.partition_on_hit_rays << ' ' << t.symmetric_partitions << ' ' << t.group_size << ' ' << t.overlap_size << ' ' << t.margin << ' ' << t.init_variance << ' ' << t.sensor_range_var << ' '
+              << t.discontinuity_var << ' ' << t.max_valid_range_var << ' ' << t.occ_test_temperature << ' ' << t.sensor_frame->num_rays << ' ' << t.sensor_frame->angle_min << ' '
+              << t.sensor_frame->angle_max << ' ' << t.sensor_frame->valid_range_min << ' ' << t.sensor_frame->valid_range_max << ' ' << t.sensor_frame->discontinuity_detection << ' '
+              << static_cast<int>(t.mapping->type) << ' ' << t.mapping->scale << ' ' << t.gp->kernel->scale << ' ' << t.gp->kernel_type;
+            return o.str();
+        }
+
+    public:
         // batched form of ComputeOcc for the per-voxel caller pattern: pos_local is 2 x T
         [[nodiscard]] Eigen::VectorXb
         ComputeOcc(const MatrixX &pos_local, VectorX &dist_pos, VectorX &range_pred, VectorX &occ) const {

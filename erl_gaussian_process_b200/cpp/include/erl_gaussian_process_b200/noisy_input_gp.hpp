@@ -9,6 +9,7 @@
 #include "c_api.hpp"
 #include "covariance.hpp"
 #include "eigen_shim.hpp"
+#include "serialization.hpp"
 
 #include <cmath>
 #include <memory>
@@ -62,6 +63,61 @@ namespace erl::gaussian_process {
                 }
                 num_samples = 0;
                 num_samples_with_grad = 0;
+            }
+
+            [[nodiscard]] bool
+            operator==(const TrainSet &other) const {  // src/noisy_input_gp.cpp:404-434
+                namespace ser = b200::serialization;
+                if (x_dim != other.x_dim || y_dim != other.y_dim || num_samples != other.num_samples || num_samples_with_grad != other.num_samples_with_grad) { return false; }
+                if (num_samples == 0) { return true; }
+                if (!ser::SameTopLeft(x, other.x, x_dim, num_samples) || !ser::SameTopLeft(y, other.y, num_samples, y_dim)) { return false; }
+                if (grad_flag.size() < num_samples || other.grad_flag.size() < num_samples) { return false; }
+                for (long i = 0; i < num_samples; ++i) {
+                    if (grad_flag[i] != other.grad_flag[i] || !(var_x[i] == other.var_x[i]) || !(var_y[i] == other.var_y[i])) { return false; }
+                }
+                if (num_samples_with_grad == 0) { return true; }
+                if (!ser::SameTopLeft(grad, other.grad, x_dim * y_dim, num_samples)) { return false; }
+                for (long i = 0; i < num_samples; ++i) {
+                    if (!(var_grad[i] == other.var_grad[i])) { return false; }
+                }
+                return true;
+            }
+
+            [[nodiscard]] bool
+            operator!=(const TrainSet &other) const {
+                return !(*this == other);
+            }
+
+            [[nodiscard]] bool
+            Write(std::ostream &s) const {  // src/noisy_input_gp.cpp:436-517
+                namespace ser = b200::serialization;
+                return ser::WriteTokens(s, {{"x_dim", ser::ScalarWriter(x_dim)},
+                                            {"y_dim", ser::ScalarWriter(y_dim)},
+                                            {"num_samples", ser::ScalarWriter(num_samples)},
+                                            {"num_samples_with_grad", ser::ScalarWriter(num_samples_with_grad)},
+                                            {"x", [this](std::ostream &o) { return ser::SaveMatrix(o, x); }},
+                                            {"y", [this](std::ostream &o) { return ser::SaveMatrix(o, y); }},
+                                            {"grad", [this](std::ostream &o) { return ser::SaveMatrix(o, grad); }},
+                                            {"var_x", [this](std::ostream &o) { return ser::SaveMatrix(o, var_x); }},
+                                            {"var_y", [this](std::ostream &o) { return ser::SaveMatrix(o, var_y); }},
+                                            {"var_grad", [this](std::ostream &o) { return ser::SaveMatrix(o, var_grad); }},
+                                            {"grad_flag", [this](std::ostream &o) { return ser::SaveMatrix(o, grad_flag); }}});
+            }
+
+            [[nodiscard]] bool
+            Read(std::istream &s) {  // src/noisy_input_gp.cpp:519-606
+                namespace ser = b200::serialization;
+                return ser::ReadTokens(s, {{"x_dim", ser::ScalarReader(x_dim)},
+                                           {"y_dim", ser::ScalarReader(y_dim)},
+                                           {"num_samples", ser::ScalarReader(num_samples)},
+                                           {"num_samples_with_grad", ser::ScalarReader(num_samples_with_grad)},
+                                           {"x", [this](std::istream &i) { return ser::LoadMatrix(i, x); }},
+                                           {"y", [this](std::istream &i) { return ser::LoadMatrix(i, y); }},
+                                           {"grad", [this](std::istream &i) { return ser::LoadMatrix(i, grad); }},
+                                           {"var_x", [this](std::istream &i) { return ser::LoadVector(i, var_x); }},
+                                           {"var_y", [this](std::istream &i) { return ser::LoadVector(i, var_y); }},
+                                           {"var_grad", [this](std::istream &i) { return ser::LoadVector(i, var_grad); }},
+                                           {"grad_flag", [this](std::istream &i) { return ser::LoadVector(i, grad_flag); }}});
             }
         };
 
@@ -367,6 +423,82 @@ namespace erl::gaussian_process {
         Test(const Eigen::Ref<const MatrixX> &mat_x_test, const bool predict_gradient) const {  // :901-907
             if (!m_trained_) { return nullptr; }
             return std::make_shared<TestResult>(this, mat_x_test, predict_gradient);
+        }
+
+        // ---- operator== / Write / Read (src/noisy_input_gp.cpp:909-1160): same tokens in the same order; see serialization.hpp ----
+        [[nodiscard]] bool
+        operator==(const NoisyInputGaussianProcess &other) const {
+            namespace ser = b200::serialization;
+            if (!ser::SameGpSetting(*m_setting_, *other.m_setting_) || m_setting_->no_gradient_observation != other.m_setting_->no_gradient_observation) { return false; }
+            if (m_trained_ != other.m_trained_ || m_trained_once_ != other.m_trained_once_ || m_k_train_updated_ != other.m_k_train_updated_) { return false; }
+            if (m_k_train_rows_ != other.m_k_train_rows_ || m_k_train_cols_ != other.m_k_train_cols_) { return false; }
+            if (!(m_three_over_scale_square_ == other.m_three_over_scale_square_)) { return false; }
+            if (m_train_set_ != other.m_train_set_) { return false; }
+            if (!m_k_train_updated_) { return true; }
+            Materialise();
+            other.Materialise();
+            return ser::SameTopLeft(m_mat_k_train_, other.m_mat_k_train_, m_k_train_rows_, m_k_train_cols_) &&
+                   ser::SameTopLeft(m_mat_l_, other.m_mat_l_, m_k_train_rows_, m_k_train_cols_) && m_mat_alpha_.cols() == other.m_mat_alpha_.cols() &&
+                   ser::SameTopLeft(m_mat_alpha_, other.m_mat_alpha_, m_k_train_cols_, m_mat_alpha_.cols());
+        }
+
+        [[nodiscard]] bool
+        operator!=(const NoisyInputGaussianProcess &other) const {
+            return !(*this == other);
+        }
+
+        [[nodiscard]] virtual bool
+        Write(std::ostream &s) const {
+            namespace ser = b200::serialization;
+            Materialise();
+            return ser::WriteTokens(s, {{"setting", [this](std::ostream &o) { return ser::WriteGpSetting(o, *m_setting_) && (o << ' ' << m_setting_->no_gradient_observation).good(); }},
+                                        {"trained", ser::ScalarWriter(m_trained_)},
+                                        {"trained_once", ser::ScalarWriter(m_trained_once_)},
+                                        {"k_train_updated", ser::ScalarWriter(m_k_train_updated_)},
+                                        {"k_train_rows", ser::ScalarWriter(m_k_train_rows_)},
+                                        {"k_train_cols", ser::ScalarWriter(m_k_train_cols_)},
+                                        {"three_over_scale_square", [this](std::ostream &o) { o.write(reinterpret_cast<const char *>(&m_three_over_scale_square_), sizeof(Dtype)); return o.good(); }},
+                                        {"kernel", [](std::ostream &o) { o << true << '\n'; return o.good(); }},
+                                        {"mat_k_train", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_k_train_); }},
+                                        {"mat_l", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_l_); }},
+                                        {"mat_alpha", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_alpha_); }},
+                                        {"train_set", [this](std::ostream &o) { return m_train_set_.Write(o); }}});
+        }
+
+        [[nodiscard]] virtual bool
+        Read(std::istream &s) {
+            namespace ser = b200::serialization;
+            bool trained = false, trained_once = false, updated = false, has_kernel = false;
+            long rows = 0, cols = 0;
+            MatrixX k, l, alpha;
+            const bool ok = ser::ReadTokens(
+                s,
+                {{"setting", [this](std::istream &i) { return ser::ReadGpSetting(i, *m_setting_) && !(i >> m_setting_->no_gradient_observation).fail(); }},
+                 {"trained", ser::ScalarReader(trained)},
+                 {"trained_once", ser::ScalarReader(trained_once)},
+                 {"k_train_updated", ser::ScalarReader(updated)},
+                 {"k_train_rows", ser::ScalarReader(rows)},
+                 {"k_train_cols", ser::ScalarReader(cols)},
+                 {"three_over_scale_square", [this](std::istream &i) { i.read(reinterpret_cast<char *>(&m_three_over_scale_square_), sizeof(Dtype)); return i.good(); }},
+                 {"kernel", [&has_kernel](std::istream &i) { i >> has_kernel; ser::SkipLine(i); return !i.fail(); }},
+                 {"mat_k_train", [&k](std::istream &i) { return ser::LoadMatrix(i, k); }},
+                 {"mat_l", [&l](std::istream &i) { return ser::LoadMatrix(i, l); }},
+                 {"mat_alpha", [&alpha](std::istream &i) { return ser::LoadMatrix(i, alpha); }},
+                 {"train_set", [this](std::istream &i) { return m_train_set_.Read(i); }}});
+            if (!ok) { return false; }
+            m_trained_ = false;
+            m_k_train_updated_ = false;
+            m_host_copy_valid_ = false;
+            if (updated) {  // rebuild the device state: the training is bit-reproducible, the stored L is the check
+                m_trained_once_ = false;
+                if (!Train()) { return false; }
+                Materialise();
+                if (m_k_train_rows_ != rows || m_k_train_cols_ != cols || !ser::SameTopLeft(m_mat_l_, l, rows, cols) || !ser::SameTopLeft(m_mat_alpha_, alpha, cols, alpha.cols())) { return false; }
+            }
+            m_trained_ = trained;
+            m_trained_once_ = trained_once;
+            m_k_train_updated_ = updated;
+            return true;
         }
 
     protected:

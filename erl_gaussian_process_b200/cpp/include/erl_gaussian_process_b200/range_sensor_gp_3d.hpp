@@ -6,6 +6,8 @@
 #include "sensor_frames.hpp"
 #include "vanilla_gp.hpp"
 
+#include <sstream>
+#include <string>
 #include <tuple>
 
 namespace erl::gaussian_process {
@@ -314,6 +316,115 @@ namespace erl::gaussian_process {
             return ok != 0;
         }
 
+        // ---- operator== / Write / Read (src/range_sensor_gp_3d.cpp:441-655): tokens setting, trained, gps, row_partitions, col_partitions,
+        // sensor_frame, mapped_distances in the reference's order; framing in serialization.hpp.  Read() needs an object constructed
+        // with the same Setting, restores the frame and replays Train() on the device; the stored tables and partition GPs are the check.
+        [[nodiscard]] bool
+        operator==(const RangeSensorGaussianProcess3D &other) const {
+            namespace ser = b200::serialization;
+            if (SettingText() != other.SettingText() || m_trained_ != other.m_trained_) { return false; }
+            if (m_row_partitions_ != other.m_row_partitions_ || m_col_partitions_ != other.m_col_partitions_ || m_gps_.size() != other.m_gps_.size()) { return false; }
+            if (!m_trained_) { return true; }
+            for (long i = 0; i < m_gps_.size(); ++i) {
+                if (!ser::SamePartitionGp(*m_gps_.data()[i], *other.m_gps_.data()[i])) { return false; }
+            }
+            return true;
+        }
+
+        [[nodiscard]] bool
+        operator!=(const RangeSensorGaussianProcess3D &other) const {
+            return !(*this == other);
+        }
+
+        [[nodiscard]] bool
+        Write(std::ostream &s) const {
+            namespace ser = b200::serialization;
+            return ser::WriteTokens(
+                s,
+                {{"setting", [this](std::ostream &o) { o << SettingText() << '\n'; return o.good(); }},  // (a whole line: the kernel type name may hold blanks)
+                 {"trained", ser::ScalarWriter(m_trained_)},
+                 {"gps",
+                  [this](std::ostream &o) {
+                      o << m_gps_.rows() << ' ' << m_gps_.cols() << '\n';
+                      for (long i = 0; i < m_gps_.size(); ++i) {
+                          const char has_gp = 1;
+                          o.write(&has_gp, 1);
+                          if (!ser::WritePartitionGp(o, *m_gps_.data()[i])) { return false; }
+                      }
+                      return o.good();
+                  }},
+                 {"row_partitions", [this](std::ostream &o) { return ser::WritePartitions(o, m_row_partitions_); }},
+                 {"col_partitions", [this](std::ostream &o) { return ser::WritePartitions(o, m_col_partitions_); }},
+                 {"sensor_frame", [this](std::ostream &o) { return ser::SaveMatrix(o, m_sensor_frame_->GetRotationMatrix()) && ser::SaveMatrix(o, m_sensor_frame_->GetRanges()); }},
+                 {"mapped_distances",
+                  [this](std::ostream &o) {
+                      MatrixX mapped(m_sensor_frame_->GetRanges().rows(), m_sensor_frame_->GetRanges().cols());
+                      for (long i = 0; i < mapped.size(); ++i) { mapped.data()[i] = m_mapping_->map(m_sensor_frame_->GetRanges().data()[i]); }
+                      return ser::SaveMatrix(o, mapped);
+                  }}});
+        }
+
+        [[nodiscard]] bool
+        Read(std::istream &s) {
+            namespace ser = b200::serialization;
+            bool trained = false;
+            std::string setting_text;
+            std::vector<std::tuple<long, long, Dtype, Dtype>> row_parts, col_parts;
+            long gp_rows = 0, gp_cols = 0;
+            MatrixX rotation, ranges, mapped;
+            std::streampos gps_pos;
+            const bool ok = ser::ReadTokens(
+                s,
+                {{"setting", [&setting_text](std::istream &i) { return static_cast<bool>(std::getline(i, setting_text)); }},
+                 {"trained", ser::ScalarReader(trained)},
+                 {"gps",
+                  [&](std::istream &i) {
+                      i >> gp_rows >> gp_cols;
+                      ser::SkipLine(i);
+                      gps_pos = i.tellg();
+                      if (i.fail() || gp_rows < 0 || gp_cols < 0 || gp_rows * gp_cols > (1 << 24)) { return false; }
+                      for (long g = 0; g < gp_rows * gp_cols; ++g) {
+                          char has_gp = 0;
+                          i.read(&has_gp, 1);
+                          if (has_gp && !ser::ReadAndComparePartitionGp(i, PartitionGp(this, 0, 0), false)) { return false; }
+                      }
+                      return i.good();
+                  }},
+                 {"row_partitions", [&row_parts](std::istream &i) { return ser::ReadPartitions(i, row_parts); }},
+                 {"col_partitions", [&col_parts](std::istream &i) { return ser::ReadPartitions(i, col_parts); }},
+                 {"sensor_frame", [&](std::istream &i) { return ser::LoadMatrix(i, rotation) && ser::LoadMatrix(i, ranges); }},
+                 {"mapped_distances", [&mapped](std::istream &i) { return ser::LoadMatrix(i, mapped); }}});
+            if (!ok || setting_text != SettingText() || row_parts != m_row_partitions_ || col_parts != m_col_partitions_ || gp_rows != m_gps_.rows() || gp_cols != m_gps_.cols()) { return false; }
+            Reset();
+            if (!trained) { return true; }
+            Eigen::VectorX<Dtype> translation(3);
+            translation[0] = translation[1] = translation[2] = 0;
+            if (!Train(rotation, translation, ranges)) { return false; }
+            const std::streampos after = s.tellg();
+            s.seekg(gps_pos);
+            for (long g = 0; g < m_gps_.size(); ++g) {
+                char has_gp = 0;
+                s.read(&has_gp, 1);
+                if (has_gp && !ser::ReadAndComparePartitionGp(s, *m_gps_.data()[g], true)) { return false; }
+            }
+            s.seekg(after);
+            return s.good();
+        }
+
+    protected:
+        [[nodiscard]] std::string
+        SettingText() const {  // one line: every Setting field that shapes the model (the reference writes its Setting as YAML)
+            std::ostringstream o;
+            o.precision(17);
+            const auto &t = *m_setting_;
+            o << t.row_group_size << ' ' << t.row_overlap_size << ' ' << t.row_margin << ' ' << t.col_group_size << ' ' << t.col_overlap_size << ' ' << t.col_margin << ' '
+              << t.min_num_samples_per_group << ' ' << t.init_variance << ' ' << t.sensor_range_var << ' ' << t.max_valid_range_var << ' ' << t.occ_test_temperature << ' '
+              << m_sensor_frame_->Rows() << ' ' << m_sensor_frame_->Cols() << ' ' << t.sensor_frame->valid_range_min << ' ' << t.sensor_frame->valid_range_max << ' '
+              << static_cast<int>(t.mapping->type) << ' ' << t.mapping->scale << ' ' << t.gp->kernel->scale << ' ' << t.gp->kernel_type;
+            return o.str();
+        }
+
+    public:
         // batched form for the per-voxel caller pattern: pos_local is 3 x T
         [[nodiscard]] Eigen::VectorXb
         ComputeOcc(const Matrix3X &pos_local, VectorX &dist_pos, VectorX &range_pred, VectorX &occ) const {

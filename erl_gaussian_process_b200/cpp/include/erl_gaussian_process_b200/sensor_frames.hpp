@@ -105,6 +105,11 @@ namespace erl::geometry {
             return m_rotation_;
         }
 
+        [[nodiscard]] const VectorX &
+        GetTranslationVector() const {
+            return m_translation_;
+        }
+
         [[nodiscard]] bool
         IsValid() const {
             return m_num_hit_ > 0;
@@ -188,6 +193,11 @@ namespace erl::geometry {
         [[nodiscard]] const Eigen::MatrixXb &
         GetHitMask() const {
             return m_mask_hit_;
+        }
+
+        [[nodiscard]] const MatrixX &
+        GetRotationMatrix() const {
+            return m_rotation_;
         }
 
         [[nodiscard]] bool

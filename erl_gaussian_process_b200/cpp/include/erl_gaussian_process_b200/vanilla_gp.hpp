@@ -10,6 +10,7 @@
 #include "c_api.hpp"
 #include "covariance.hpp"
 #include "eigen_shim.hpp"
+#include "serialization.hpp"
 
 #include <memory>
 #include <string>
@@ -48,6 +49,46 @@ namespace erl::gaussian_process {
                 if (y.rows() < max_num_samples || y.cols() < y_dim) { y.resize(max_num_samples, y_dim); }
                 if (var.size() < max_num_samples) { var.resize(max_num_samples); }
                 num_samples = 0;
+            }
+
+            [[nodiscard]] bool
+            operator==(const TrainSet &other) const {  // src/vanilla_gp.cpp:163-183
+                namespace ser = b200::serialization;
+                if (x_dim != other.x_dim || y_dim != other.y_dim || num_samples != other.num_samples) { return false; }
+                if (num_samples == 0) { return true; }
+                if (!ser::SameTopLeft(x, other.x, x_dim, num_samples) || !ser::SameTopLeft(y, other.y, num_samples, y_dim)) { return false; }
+                if (var.size() < num_samples || other.var.size() < num_samples) { return false; }
+                for (long i = 0; i < num_samples; ++i) {
+                    if (!(var[i] == other.var[i])) { return false; }
+                }
+                return true;
+            }
+
+            [[nodiscard]] bool
+            operator!=(const TrainSet &other) const {
+                return !(*this == other);
+            }
+
+            [[nodiscard]] bool
+            Write(std::ostream &s) const {  // src/vanilla_gp.cpp:191-235
+                namespace ser = b200::serialization;
+                return ser::WriteTokens(s, {{"x_dim", ser::ScalarWriter(x_dim)},
+                                            {"y_dim", ser::ScalarWriter(y_dim)},
+                                            {"num_samples", ser::ScalarWriter(num_samples)},
+                                            {"x", [this](std::ostream &o) { return ser::SaveMatrix(o, x); }},
+                                            {"y", [this](std::ostream &o) { return ser::SaveMatrix(o, y); }},
+                                            {"var", [this](std::ostream &o) { return ser::SaveMatrix(o, var); }}});
+            }
+
+            [[nodiscard]] bool
+            Read(std::istream &s) {  // src/vanilla_gp.cpp:237-285
+                namespace ser = b200::serialization;
+                return ser::ReadTokens(s, {{"x_dim", ser::ScalarReader(x_dim)},
+                                           {"y_dim", ser::ScalarReader(y_dim)},
+                                           {"num_samples", ser::ScalarReader(num_samples)},
+                                           {"x", [this](std::istream &i) { return ser::LoadMatrix(i, x); }},
+                                           {"y", [this](std::istream &i) { return ser::LoadMatrix(i, y); }},
+                                           {"var", [this](std::istream &i) { return ser::LoadVector(i, var); }}});
             }
         };
 
@@ -232,6 +273,77 @@ namespace erl::gaussian_process {
             if (!m_trained_) { return nullptr; }          // src/vanilla_gp.cpp:556-558
             if (mat_x_test.cols() == 0) { return nullptr; }  // ComputeKtest warns and fails on num_test == 0 (:529-532)
             return std::make_shared<TestResult>(this, mat_x_test);
+        }
+
+        // ---- operator== / Write / Read (src/vanilla_gp.cpp:561-790): same tokens in the same order; see serialization.hpp ----
+        [[nodiscard]] bool
+        operator==(const VanillaGaussianProcess &other) const {
+            namespace ser = b200::serialization;
+            if (!ser::SameGpSetting(*m_setting_, *other.m_setting_)) { return false; }
+            if (m_trained_ != other.m_trained_ || m_trained_once_ != other.m_trained_once_ || m_k_train_updated_ != other.m_k_train_updated_) { return false; }
+            if (m_k_train_rows_ != other.m_k_train_rows_ || m_k_train_cols_ != other.m_k_train_cols_) { return false; }
+            if (m_train_set_ != other.m_train_set_) { return false; }
+            if (!m_k_train_updated_) { return true; }
+            Materialise();
+            other.Materialise();
+            return ser::SameTopLeft(m_mat_k_train_, other.m_mat_k_train_, m_k_train_rows_, m_k_train_cols_) &&
+                   ser::SameTopLeft(m_mat_l_, other.m_mat_l_, m_k_train_rows_, m_k_train_cols_) && m_mat_alpha_.cols() == other.m_mat_alpha_.cols() &&
+                   ser::SameTopLeft(m_mat_alpha_, other.m_mat_alpha_, m_k_train_cols_, m_mat_alpha_.cols());
+        }
+
+        [[nodiscard]] bool
+        operator!=(const VanillaGaussianProcess &other) const {
+            return !(*this == other);
+        }
+
+        [[nodiscard]] bool
+        Write(std::ostream &s) const {
+            namespace ser = b200::serialization;
+            Materialise();
+            return ser::WriteTokens(s, {{"setting", [this](std::ostream &o) { return ser::WriteGpSetting(o, *m_setting_); }},
+                                        {"trained", ser::ScalarWriter(m_trained_)},
+                                        {"trained_once", ser::ScalarWriter(m_trained_once_)},
+                                        {"k_train_updated", ser::ScalarWriter(m_k_train_updated_)},
+                                        {"k_train_rows", ser::ScalarWriter(m_k_train_rows_)},
+                                        {"k_train_cols", ser::ScalarWriter(m_k_train_cols_)},
+                                        {"kernel", [](std::ostream &o) { o << true << '\n'; return o.good(); }},  // the kernel's own state is its Setting, written above
+                                        {"mat_k_train", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_k_train_); }},
+                                        {"mat_l", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_l_); }},
+                                        {"mat_alpha", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_alpha_); }},
+                                        {"train_set", [this](std::ostream &o) { return m_train_set_.Write(o); }}});
+        }
+
+        [[nodiscard]] bool
+        Read(std::istream &s) {
+            namespace ser = b200::serialization;
+            bool trained = false, trained_once = false, updated = false, has_kernel = false;
+            long rows = 0, cols = 0;
+            MatrixX k, l, alpha;
+            const bool ok = ser::ReadTokens(s, {{"setting", [this](std::istream &i) { return ser::ReadGpSetting(i, *m_setting_); }},
+                                                {"trained", ser::ScalarReader(trained)},
+                                                {"trained_once", ser::ScalarReader(trained_once)},
+                                                {"k_train_updated", ser::ScalarReader(updated)},
+                                                {"k_train_rows", ser::ScalarReader(rows)},
+                                                {"k_train_cols", ser::ScalarReader(cols)},
+                                                {"kernel", [&has_kernel](std::istream &i) { i >> has_kernel; ser::SkipLine(i); return !i.fail(); }},
+                                                {"mat_k_train", [&k](std::istream &i) { return ser::LoadMatrix(i, k); }},
+                                                {"mat_l", [&l](std::istream &i) { return ser::LoadMatrix(i, l); }},
+                                                {"mat_alpha", [&alpha](std::istream &i) { return ser::LoadMatrix(i, alpha); }},
+                                                {"train_set", [this](std::istream &i) { return m_train_set_.Read(i); }}});
+            if (!ok) { return false; }
+            m_trained_ = false;
+            m_k_train_updated_ = false;
+            m_host_copy_valid_ = false;
+            if (updated) {  // rebuild the device state: the training is bit-reproducible, the stored L is the check
+                m_trained_once_ = false;
+                if (!Train()) { return false; }
+                Materialise();
+                if (m_k_train_rows_ != rows || m_k_train_cols_ != cols || !ser::SameTopLeft(m_mat_l_, l, rows, cols) || !ser::SameTopLeft(m_mat_alpha_, alpha, cols, alpha.cols())) { return false; }
+            }
+            m_trained_ = trained;
+            m_trained_once_ = trained_once;
+            m_k_train_updated_ = updated;
+            return true;
         }
 
     protected:

@@ -10,6 +10,7 @@
 #include "../../oracle/erl_gp_oracle.hpp"
 
 #include <cstdio>
+#include <sstream>
 #include <random>
 
 using namespace erl::gaussian_process;
@@ -168,6 +169,170 @@ TestNoisyInput(const char *name, const double tol) {
     result->GetMean(5, 0, f1);
     CHECK(result->GetGradient(5, 0, g1) && f1 == mean[5] && g1[0] == grad(0, 5) && g1[1] == grad(1, 5), "single-index accessors");
     std::printf("%s %s: mean %.2e grad %.2e var %.2e grad var %.2e cov %.2e\n", g_failures ? "----" : "PASS", name, em / sm, eg / sg, ev, egv, ec);
+}
+
+// Write / Read / operator== (src/vanilla_gp.cpp:561-790, src/noisy_input_gp.cpp:909-1160; the reference's gtests round-trip every GP
+// through Serialization<>::Write / Read and assert gp == gp_read, e.g. test_noisy_input_gp.cpp:182-185): a trained GP goes through a
+// stream into a fresh object whose device state is rebuilt; equal objects, identical predictions, a damaged stream is rejected.
+template<typename Dtype>
+static void
+TestSerialization(const char *name) {
+    using Gp = VanillaGaussianProcess<Dtype>;
+    using Ngp = NoisyInputGaussianProcess<Dtype>;
+    constexpr long n = 300, n_test = 500, d = 2;
+    std::mt19937 rng(23);
+    std::uniform_real_distribution<double> uni(-1, 1);
+    Eigen::MatrixX<Dtype> xt(d, n_test);
+    for (long i = 0; i < n_test; ++i) { xt(0, i) = Dtype(uni(rng)), xt(1, i) = Dtype(uni(rng)); }
+    {
+        auto setting = std::make_shared<typename Gp::Setting>();
+        setting->kernel_type = "erl::covariance::Matern32<double, 2>";
+        setting->kernel->scale = Dtype(0.4);
+        setting->max_num_samples = n;
+        Gp gp(setting);
+        gp.Reset(n, d, 2);
+        auto &ts = gp.GetTrainSet();
+        for (long i = 0; i < n; ++i) {
+            ts.x(0, i) = Dtype(uni(rng)), ts.x(1, i) = Dtype(uni(rng));
+            ts.y(i, 0) = Dtype(std::sin(3 * double(ts.x(0, i)))), ts.y(i, 1) = Dtype(std::cos(2 * double(ts.x(1, i))));
+            ts.var[i] = Dtype(0.01);
+        }
+        ts.num_samples = n;
+        std::stringstream untrained;
+        CHECK(gp.Write(untrained), "Write (untrained)");
+        CHECK(gp.Train(), "Train");
+        std::stringstream stream;
+        CHECK(gp.Write(stream), "Write");
+        auto setting2 = std::make_shared<typename Gp::Setting>();
+        Gp gp2(setting2);
+        CHECK(gp != gp2, "a fresh GP differs from a trained one");
+        CHECK(gp2.Read(stream), "Read");
+        CHECK(gp == gp2 && gp2.IsTrained() && !gp2.Train(), "gp == gp_read, trained, second Train() refused");
+        Eigen::VectorX<Dtype> m1(n_test), m2(n_test), v1(n_test), v2(n_test);
+        gp.Test(xt)->GetMean(1, m1, true), gp2.Test(xt)->GetMean(1, m2, true);
+        gp.Test(xt)->GetVariance(v1, true), gp2.Test(xt)->GetVariance(v2, true);
+        // the mean is bit-identical; the variance kernel combines its split reductions with atomics (few test tiles): equal up to rounding
+        bool same = true;
+        for (long i = 0; i < n_test; ++i) { same = same && m1[i] == m2[i] && std::abs(double(v1[i]) - double(v2[i])) < (sizeof(Dtype) == 4 ? 1e-5 : 1e-12); }
+        CHECK(same, "predictions of the restored GP must match (mean bit for bit)");
+        Gp gp3(std::make_shared<typename Gp::Setting>());
+        CHECK(gp3.Read(untrained) && !gp3.IsTrained() && gp3.GetTrainSet() == gp.GetTrainSet() && gp3.Train() && gp3 == gp, "untrained round trip, then Train()");
+        std::string bytes = stream.str();
+        bytes[bytes.size() * 5 / 8] ^= 0x55;  // inside the stored L
+        std::stringstream damaged(bytes);
+        Gp gp4(std::make_shared<typename Gp::Setting>());
+        CHECK(!gp4.Read(damaged) || gp4 != gp, "a damaged stream must not yield an equal GP");
+    }
+    {
+        auto setting = std::make_shared<typename Ngp::Setting>();
+        setting->kernel_type = "erl::covariance::RadialBiasFunction2d";
+        setting->kernel->scale = Dtype(0.5);
+        Ngp gp(setting);
+        gp.Reset(n, d, 1);
+        auto &ts = gp.GetTrainSet();
+        long ng = 0;
+        for (long i = 0; i < n; ++i) {
+            const double a = uni(rng), b = uni(rng);
+            ts.x(0, i) = Dtype(a), ts.x(1, i) = Dtype(b);
+            ts.y(i, 0) = Dtype(std::sin(2 * a) * std::cos(b));
+            ts.grad(0, i) = Dtype(2 * std::cos(2 * a) * std::cos(b)), ts.grad(1, i) = Dtype(-std::sin(2 * a) * std::sin(b));
+            ts.var_x[i] = ts.var_y[i] = Dtype(0.01), ts.var_grad[i] = Dtype(0.02);
+            ts.grad_flag[i] = i % 3 == 0;
+            ng += i % 3 == 0;
+        }
+        ts.num_samples = n, ts.num_samples_with_grad = ng;
+        CHECK(gp.Train(), "Train (noisy input)");
+        std::stringstream stream;
+        CHECK(gp.Write(stream), "Write (noisy input)");
+        Ngp gp2(std::make_shared<typename Ngp::Setting>());
+        CHECK(gp2.Read(stream) && gp == gp2, "NoisyInputGaussianProcess: gp == gp_read");  // test_noisy_input_gp.cpp:182-185
+        Eigen::VectorX<Dtype> m1(n_test), m2(n_test);
+        Eigen::MatrixX<Dtype> g1(d, n_test), g2(d, n_test);
+        gp.Test(xt, true)->GetMean(0, m1, true), gp2.Test(xt, true)->GetMean(0, m2, true);
+        (void) gp.Test(xt, true)->GetGradient(0, g1, true), (void) gp2.Test(xt, true)->GetGradient(0, g2, true);
+        bool same = true;
+        for (long i = 0; i < n_test; ++i) { same = same && m1[i] == m2[i] && g1(0, i) == g2(0, i) && g1(1, i) == g2(1, i); }
+        CHECK(same, "predictions of the restored noisy-input GP must be bit-identical");
+    }
+    std::printf("%s %s\n", g_failures ? "----" : "PASS", name);
+}
+
+// Write / Read / operator== of the two sensor GPs (src/lidar_gp_2d.cpp:461-635, src/range_sensor_gp_3d.cpp:441-655)
+template<typename Dtype>
+static void
+TestSensorSerialization(const char *name) {
+    std::mt19937 rng(29);
+    std::uniform_real_distribution<double> uni(0, 1);
+    {
+        using Lidar = LidarGaussianProcess2D<Dtype>;
+        auto make_setting = [] {
+            auto s = std::make_shared<typename Lidar::Setting>();
+            s->group_size = 32, s->overlap_size = 8;
+            s->sensor_frame->angle_min = Dtype(-2), s->sensor_frame->angle_max = Dtype(2), s->sensor_frame->num_rays = 360;
+            s->sensor_frame->valid_range_min = Dtype(0.1), s->sensor_frame->valid_range_max = Dtype(30);
+            s->gp->kernel_type = "erl::covariance::OrnsteinUhlenbeck1d";
+            s->gp->kernel->scale = Dtype(0.05);
+            return s;
+        };
+        Lidar gp(make_setting());
+        Eigen::VectorX<Dtype> ranges(360);
+        const auto &angles = gp.GetSensorFrame()->GetAnglesInFrame();
+        for (long i = 0; i < 360; ++i) { ranges[i] = uni(rng) < 0.05 ? Dtype(1000) : Dtype(4 + std::sin(3 * double(angles[i]))); }
+        Eigen::MatrixX<Dtype> rot(2, 2);
+        rot.setZero();
+        rot(0, 0) = rot(1, 1) = 1;
+        Eigen::VectorX<Dtype> trans(2);
+        trans.setZero();
+        CHECK(gp.Train(rot, trans, ranges), "Train");
+        std::stringstream stream;
+        CHECK(gp.Write(stream), "LidarGaussianProcess2D::Write");
+        Lidar gp2(make_setting());
+        CHECK(gp != gp2, "untrained != trained");
+        CHECK(gp2.Read(stream), "LidarGaussianProcess2D::Read");
+        CHECK(gp == gp2 && gp2.IsTrained(), "LidarGaussianProcess2D: gp == gp_read");
+        Eigen::VectorX<Dtype> q(500), m1(500), m2(500);
+        for (long i = 0; i < 500; ++i) { q[i] = Dtype(-1.9 + 3.8 * uni(rng)), m1[i] = m2[i] = 0; }
+        const auto ok1 = gp.Test(q, true, true)->GetMean(m1, true);
+        const auto ok2 = gp2.Test(q, true, true)->GetMean(m2, true);
+        bool same = true;
+        for (long i = 0; i < 500; ++i) { same = same && bool(ok1[i]) == bool(ok2[i]) && m1[i] == m2[i]; }
+        CHECK(same, "restored lidar GP predicts bit-identically");
+        auto other = make_setting();
+        other->overlap_size = 6;
+        Lidar gp3(other);
+        std::stringstream again(stream.str());
+        CHECK(!gp3.Read(again), "a stream written under another Setting is rejected");
+    }
+    {
+        using Rg = RangeSensorGaussianProcess3D<Dtype>;
+        constexpr long rows = 40, cols = 48;
+        auto make_setting = [] {
+            auto s = std::make_shared<typename Rg::Setting>();
+            s->row_group_size = 12, s->row_overlap_size = 2, s->col_group_size = 10, s->col_overlap_size = 4;
+            s->sensor_frame->azimuth_min = Dtype(-0.4), s->sensor_frame->azimuth_max = Dtype(0.4), s->sensor_frame->num_azimuth_lines = rows;
+            s->sensor_frame->elevation_min = Dtype(-0.3), s->sensor_frame->elevation_max = Dtype(0.3), s->sensor_frame->num_elevation_lines = cols;
+            s->sensor_frame->valid_range_min = Dtype(0.1), s->sensor_frame->valid_range_max = Dtype(30);
+            s->gp->kernel_type = "erl::covariance::Matern32<float, 2>";
+            s->gp->kernel->scale = Dtype(0.05);
+            return s;
+        };
+        Rg gp(make_setting());
+        Eigen::MatrixX<Dtype> ranges(rows, cols), rot(3, 3);
+        for (long c = 0; c < cols; ++c) {
+            for (long r = 0; r < rows; ++r) { ranges(r, c) = uni(rng) < 0.05 ? Dtype(1000) : Dtype(4 + 0.5 * std::sin(r / 5.0) * std::cos(c / 7.0)); }
+        }
+        rot.setZero();
+        rot(0, 0) = rot(1, 1) = rot(2, 2) = 1;
+        Eigen::VectorX<Dtype> trans(3);
+        trans.setZero();
+        CHECK(gp.Train(rot, trans, ranges), "Train");
+        std::stringstream stream;
+        CHECK(gp.Write(stream), "RangeSensorGaussianProcess3D::Write");
+        Rg gp2(make_setting());
+        CHECK(gp2.Read(stream), "RangeSensorGaussianProcess3D::Read");
+        CHECK(gp == gp2 && gp2.IsTrained(), "RangeSensorGaussianProcess3D: gp == gp_read");
+    }
+    std::printf("%s %s\n", g_failures ? "----" : "PASS", name);
 }
 
 // Setting::partition_on_hit_rays (src/lidar_gp_2d.cpp:302-348, 364): the table is empty after construction and follows the hit rays
@@ -440,6 +605,7 @@ TestRangeSensor(const char *name, const double tol) {
 
 int
 main() {
+    std::setvbuf(stdout, nullptr, _IOLBF, 0);  // progress survives a crash
     try {
         TestVanillaSiso<double>("VanillaGaussianProcess<double> SISO", 1e-10);
         TestVanillaSiso<float>("VanillaGaussianProcess<float> SISO", 1e-4);
@@ -447,6 +613,10 @@ main() {
         TestLidar<float>("LidarGaussianProcess2D<float>", 1e-4);
         TestNoisyInput<double>("NoisyInputGaussianProcess<double>", 1e-10);
         TestNoisyInput<float>("NoisyInputGaussianProcess<float>", 1e-4);
+        TestSerialization<double>("Write / Read / operator== <double>");
+        TestSerialization<float>("Write / Read / operator== <float>");
+        TestSensorSerialization<double>("sensor GPs Write / Read / operator== <double>");
+        TestSensorSerialization<float>("sensor GPs Write / Read / operator== <float>");
         TestLidarHitRays<double>("LidarGaussianProcess2D<double> partition_on_hit_rays", 1e-10);
         TestLidarHitRays<float>("LidarGaussianProcess2D<float> partition_on_hit_rays", 1e-4);
         TestRangeSensor<float>("RangeSensorGaussianProcess3D<float>", 1e-4);

@@ -30,6 +30,16 @@
 #include "erl_gp_rowgp.cuh"
 
 namespace erl_gp {
+    namespace rowgp64 {
+        // FP64 row-GP kernel on DMMA m8n8k4, n <= 128 (erl_gp_rowgp64.cuh, instantiated in erl_gp_rowgp64_x<dim>.cu)
+        template<int XDIM>
+        int
+        Launch(Context *ctx, const BatchParams<double> &params, int mode, int tiles_per_gp);
+        extern template int Launch<1>(Context *, const BatchParams<double> &, int, int);
+        extern template int Launch<2>(Context *, const BatchParams<double> &, int, int);
+        extern template int Launch<3>(Context *, const BatchParams<double> &, int, int);
+    }  // namespace rowgp64
+
     namespace rowgp_tc {
         // tcgen05 / TMEM fused train + predict kernel, n <= 128 (erl_gp_rowgp_tc.cuh, instantiated in erl_gp_rowgp_tc_x<dim>.cu)
         template<int XDIM>
@@ -695,6 +705,11 @@ namespace erl_gp {
             }
             if (max_n <= 128 && !legacy) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
             if (max_n <= 256 && !legacy && !legacy_large) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
+        }
+        if constexpr (sizeof(T) == 8) {
+            // FP64, n <= 128: the DMMA row-GP kernel (erl_gp_rowgp64.cuh); ERL_GP_BATCH_LEGACY=1 keeps the generic kernel below
+            static const bool legacy64 = std::getenv("ERL_GP_BATCH_LEGACY") != nullptr;
+            if (max_n <= 128 && !legacy64) { return rowgp64::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
         }
         if (max_n <= 64) { return LaunchBatchMode<T, XDIM, 4>(ctx, params, mode, tiles_per_gp); }
         if (max_n <= 128) { return LaunchBatchMode<T, XDIM, 8>(ctx, params, mode, tiles_per_gp); }

@@ -1,0 +1,539 @@
+// FP64 twin of the row-GP kernel (erl_gp_rowgp.cuh) on the FP64 tensor path: mma.sync.m8n8k4.f64 (SASS DMMA), n <= 128.
+//
+// One CTA (256 threads, 8 warps, 2 CTAs per SM) per GP runs, for LidarGaussianProcess2D<double> / RangeSensorGaussianProcess3D<double>
+// partitions and the double variant of the batched stream, what the reference runs per partition:
+//   VanillaGaussianProcess::UpdateKtrain + Solve        src/vanilla_gp.cpp:476-505
+//   ComputeKtest + TestResult::GetMean / GetVariance    src/vanilla_gp.cpp:521-552, 61-150
+// The design is the FP32 kernel's, without the 3xTF32 split (double needs none):
+//   * L lives in shared memory, column-major, packed by 16-column blocks (block b keeps rows >= 16 b) with a column stride == 2 (mod
+//     16) doubles: "one row per lane", "one column per lane" and both MMA fragment patterns are bank-conflict free for 64-bit loads;
+//   * train = left-looking blocked Cholesky with 16-column panels, one 16 x 16 tile per warp: (A) P = K - L[tile] L[pivot rows]^T
+//     as 8 x 8 x 4 DMMAs whose reduction index is permuted (k-slot t of group e <-> column 2 t + e) so that A and B fragments are
+//     single conflict-free LDS.64; the Gram entries are generated in the accumulator layout; (B) warp 0 factorises the 16 x 16
+//     pivot tile with shuffles, lanes 16 .. 31 run the same elimination on the unit vectors and end up with the columns of its
+//     inverse Dinv, z = L^-1 y rides along; (C) L_i = P_i Dinv^T straight from the accumulators: an 8 x 8 accumulator tile (row g,
+//     columns 2 t, 2 t + 1) IS the A operand of two DMMAs under the same k permutation;
+//   * alpha = L^-T z blocked through Dinv; L goes to HBM one column per warp and step (coalesced);
+//   * predict = transposed substitution V^T = Kt^T L^-T, one warp per 8 queries with its 8 x 128 accumulators resident (64 registers):
+//     V_j = X_j Dinv_j^T, X_i -= V_j L_ij^T, accumulator -> A operand without data movement, Ktest entries generated in the accumulator
+//     layout, mean = k*^T alpha on the way, ||v||^2 from the finished blocks.
+// Work per GP at n = 128 with 128 queries: ~6000 DMMAs (512 flop each); the DMMA pipe (37 TFLOP/s measured) bounds the C4 stream
+// in double at 3.8 ms per 50 000 GPs.
+#pragma once
+
+#include "erl_gp_dense_mma.cuh"
+#include "erl_gp_internal.cuh"
+
+#include <cstdlib>
+
+namespace erl_gp {
+    namespace rowgp64 {
+
+        constexpr unsigned kFull = 0xffffffffu;
+        constexpr int kThreads = 256;
+        constexpr int kWarps = kThreads / 32;
+        constexpr int kQTile = 8 * kWarps;  // queries per pass: 8 per warp
+
+        template<int NBLK>
+        struct Layout {
+            static constexpr int kNp = 16 * NBLK;
+
+            __host__ __device__ static constexpr int
+            Stride(const int cb) {  // doubles between consecutive columns of column block cb (== 2 mod 16)
+                return kNp - 16 * cb + 2;
+            }
+
+            __host__ __device__ static constexpr int
+            Base(const int cb) {  // first double of column block cb: sum_{b < cb} 16 * Stride(b)
+                return 16 * cb * (kNp + 2) - 128 * cb * (cb - 1);
+            }
+
+            static constexpr int kDinvLd = 18;  // column stride of a 16 x 16 inverse block (== 2 mod 16)
+            static constexpr int kL = 0;
+            static constexpr int kPts = kL + Base(NBLK);          // [kNp][4]: x, y, z, -
+            static constexpr int kAl = kPts + 4 * kNp;            // y -> z -> alpha
+            static constexpr int kVar = kAl + kNp;                // noise variances
+            static constexpr int kDinv = kVar + kNp;              // inverses of the 16 x 16 diagonal blocks, column-major
+            static constexpr int kMisc = kDinv + NBLK * 16 * kDinvLd;
+            static constexpr int kEnd = kMisc + 2;
+            static constexpr size_t kBytes = static_cast<size_t>(kEnd) * sizeof(double);
+        };
+
+        template<int XDIM>
+        __device__ __forceinline__ double
+        Dist2(const double *__restrict__ a, const double (&b)[XDIM]) {
+            double r2 = 0;
+#pragma unroll
+            for (int d = 0; d < XDIM; ++d) {
+                const double diff = a[d] - b[d];
+                r2 += diff * diff;
+            }
+            return r2;
+        }
+
+        // 16 x 16 pivot tile: lanes 0 .. 15 own its rows, lanes 16 + j start from the unit vector e_j and run the very same elimination
+        // (with sc = a[c] / d the update a[cc] -= sc A[cc][c] is the forward substitution of L x = e_j: the scaled entries l[c] that
+        // lanes 0 .. 15 read as row r of L are, in lane 16 + j, column j of L^-1).  z = L^-1 y rides along in zacc.
+        __device__ __forceinline__ void
+        PivotBlock(double (&a)[16], double &zacc, double (&l)[16], const int c0, const int lane, int &fail, double *__restrict__ al) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const double d = __shfl_sync(kFull, a[c], c);
+                const double zc = __shfl_sync(kFull, zacc, c);
+                double t[16];
+#pragma unroll
+                for (int cc = c + 1; cc < 16; ++cc) { t[cc] = __shfl_sync(kFull, a[c], cc); }  // A[cc][c] = A[c][cc] from lane cc
+                if (!(d > 0.0) && fail == 0) { fail = c0 + c + 1; }
+                const double rsv = rsqrt(d);
+                const double sc = a[c] * (rsv * rsv);
+#pragma unroll
+                for (int cc = c + 1; cc < 16; ++cc) { a[cc] = fma(-sc, t[cc], a[cc]); }
+                zacc = fma(-sc, zc, zacc);
+                l[c] = a[c] * rsv;
+                if (lane == 0) { al[c0 + c] = zc * rsv; }
+            }
+        }
+
+        // blocked left-looking Cholesky of the Gram matrix (never stored: its entries are generated when a panel is updated)
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ int
+        Factorize(const Covariance<double> &cov, double *__restrict__ smem, const int n, const int nblk) {
+            using Lay = Layout<NBLK>;
+            double *lp = smem + Lay::kL;
+            const double *pts = smem + Lay::kPts;
+            double *al = smem + Lay::kAl;
+            const double *sv = smem + Lay::kVar;
+            double *dinv = smem + Lay::kDinv;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction
+            const int lane = tid & 31;
+            const int g = lane >> 2, t = lane & 3;
+            int fail = 0;
+            for (int kb = 0; kb < nblk; ++kb) {
+                const int c0 = 16 * kb;
+                const int mt = nblk - kb;  // 16-row tiles of this panel: tile w -> warp w (mt <= 8)
+                const int stride_k = Lay::Stride(kb);
+                double *panel = lp + Lay::Base(kb);  // element (row c0, column c0)
+                const int rel = 16 * warp;           // my tile's first row, relative to c0
+                double acc[2][2][2];
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) { acc[rh][ch][0] = acc[rh][ch][1] = 0.0; }
+                }
+                if (warp < mt) {
+                    // ---- A: P = K[tile, panel] - L[tile, 0:c0] L[pivot rows, 0:c0]^T ----
+                    for (int jb = 0; jb < kb; ++jb) {
+                        const int stride = Lay::Stride(jb);
+                        const double *blk = lp + Lay::Base(jb) + (c0 - 16 * jb) + g;  // (row c0 + g, column 16 jb)
+#pragma unroll
+                        for (int ck = 0; ck < 2; ++ck) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const double *col = blk + (8 * ck + 2 * t + e) * stride;
+                                const double b0 = col[0], b1 = col[8];
+                                const double a0 = col[rel], a1 = col[rel + 8];
+                                Dmma884(acc[0][0], a0, b0);
+                                Dmma884(acc[0][1], a0, b1);
+                                Dmma884(acc[1][0], a1, b0);
+                                Dmma884(acc[1][1], a1, b1);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const int row = c0 + rel + 8 * rh + g;
+                        double xr[XDIM];
+#pragma unroll
+                        for (int d = 0; d < XDIM; ++d) { xr[d] = pts[4 * row + d]; }
+                        const double diag = row < n ? 1.0 + sv[row] : 1.0;  // K[i][i] = 1 + var[i]; identity padding
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = c0 + 8 * ch + 2 * t + e;
+                                double kv = 0.0;
+                                if (row == col) {
+                                    kv = diag;
+                                } else if (row < n && col < n) {
+                                    kv = cov(Dist2<XDIM>(pts + 4 * col, xr));
+                                }
+                                acc[rh][ch][e] = kv - acc[rh][ch][e];
+                            }
+                        }
+                    }
+                }
+                // ---- B: pivot tile (warp 0 holds it) ----
+                if (warp == 0) {
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { panel[(8 * ch + 2 * t + e) * stride_k + 8 * rh + g] = acc[rh][ch][e]; }
+                        }
+                    }
+                    const int r = lane & 15, hh = lane >> 4;
+                    // z: sum_{j < c0} L[c0 + r][j] z_j (two lanes per row: even / odd column blocks)
+                    double zp0 = 0.0, zp1 = 0.0;
+                    for (int jb = hh; jb < kb; jb += 2) {
+                        const int stride = Lay::Stride(jb);
+                        const double *rowp = lp + Lay::Base(jb) + (c0 + r - 16 * jb);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            zp0 = fma(rowp[j * stride], al[16 * jb + j], zp0);
+                            zp1 = fma(rowp[(j + 1) * stride], al[16 * jb + j + 1], zp1);
+                        }
+                    }
+                    double zs = zp0 + zp1;
+                    zs += __shfl_xor_sync(kFull, zs, 16);
+                    __syncwarp();
+                    double zacc = lane < 16 ? al[c0 + r] - zs : 0.0;  // al[c0 + r] still holds y
+                    double prow[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const double pv = panel[c * stride_k + r];
+                        prow[c] = lane < 16 ? pv : (c == r ? 1.0 : 0.0);
+                    }
+                    __syncwarp();  // everybody has read y and the raw tile
+                    PivotBlock(prow, zacc, l, c0, lane, fail, al);
+                    if (lane < 16) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { panel[c * stride_k + r] = c > r ? 0.0 : l[c]; }
+                    } else {
+                        double *dst = dinv + kb * 16 * Lay::kDinvLd + r * Lay::kDinvLd;  // column r of Dinv (zero above the diagonal)
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { dst[c] = l[c]; }
+                    }
+                }
+                __syncthreads();  // #1: pivot tile, Dinv, z of this panel are published
+                if (mt > 1) {
+                    if (warp > 0 && warp < mt) {
+                        // ---- C: L_i = P_i Dinv^T; Dinv is lower triangular: the (ck = 1, ch = 0) block is zero ----
+                        const double *dv = dinv + kb * 16 * Lay::kDinvLd + g;
+                        double out[2][2][2];
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+                            for (int ch = 0; ch < 2; ++ch) { out[rh][ch][0] = out[rh][ch][1] = 0.0; }
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                            for (int ck = 0; ck <= ch; ++ck) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const double b = dv[(8 * ck + 2 * t + e) * Lay::kDinvLd + 8 * ch];  // Dinv[8 ch + g][8 ck + 2 t + e]
+                                    Dmma884(out[0][ch], acc[0][ck][e], b);
+                                    Dmma884(out[1][ch], acc[1][ck][e], b);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+                            for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) { panel[(8 * ch + 2 * t + e) * stride_k + rel + 8 * rh + g] = out[rh][ch][e]; }
+                            }
+                        }
+                    }
+                    __syncthreads();  // #2: the whole panel is published
+                }
+            }
+            return fail;
+        }
+
+        // alpha = L^-T z (al holds z on entry, alpha on exit); thread = column, blocked from the bottom through Dinv
+        template<int NBLK>
+        __device__ __forceinline__ void
+        BackSolve(double *__restrict__ smem, const int nblk) {
+            using Lay = Layout<NBLK>;
+            const double *lp = smem + Lay::kL;
+            double *al = smem + Lay::kAl;
+            const double *dinv = smem + Lay::kDinv;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            double s = 0.0;  // sum_{r > my block} L[r][tid] alpha[r]
+            for (int kb = nblk - 1; kb >= 0; --kb) {
+                const int c0 = 16 * kb;
+                if (warp == (c0 >> 5)) {
+                    const int lb = c0 & 31;
+                    const bool mine = lane >= lb && lane < lb + 16;
+                    const int jj = mine ? lane - lb : 0;
+                    const double vj = al[c0 + jj] - s;
+                    const double *dcol = dinv + kb * 16 * Lay::kDinvLd + jj * Lay::kDinvLd;  // column jj of Dinv
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 16; r += 2) {  // alpha_blk = Dinv^T (z_blk - s_blk); rows r < jj of the column are zero
+                        a0 = fma(dcol[r], __shfl_sync(kFull, vj, lb + r), a0);
+                        a1 = fma(dcol[r + 1], __shfl_sync(kFull, vj, lb + r + 1), a1);
+                    }
+                    if (mine) { al[c0 + jj] = a0 + a1; }
+                }
+                __syncthreads();
+                if (tid < c0) {
+                    const int cb = tid >> 4;
+                    const double *colp = lp + Lay::Base(cb) + (tid & 15) * Lay::Stride(cb) + (c0 - 16 * cb);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) { s = fma(colp[k], al[c0 + k], s); }
+                }
+            }
+        }
+
+        // inverses of the 16 x 16 diagonal blocks (predict-only mode: L was reloaded from HBM): lane c < 16 solves L x = e_c
+        template<int NBLK>
+        __device__ __forceinline__ void
+        ComputeDinv(double *__restrict__ smem, const int nblk) {
+            using Lay = Layout<NBLK>;
+            const double *lp = smem + Lay::kL;
+            double *dinv = smem + Lay::kDinv;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (lane >= 16) { return; }
+            for (int kb = warp; kb < nblk; kb += kWarps) {
+                const double *blk = lp + Lay::Base(kb);
+                const int stride = Lay::Stride(kb);
+                double x[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    double sum = r == lane ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < r; ++k) { sum = fma(-blk[k * stride + r], x[k], sum); }  // L[r][k] x[k]
+                    x[r] = r < lane ? 0.0 : sum / blk[r * stride + r];
+                }
+                double *dst = dinv + kb * 16 * Lay::kDinvLd + lane * Lay::kDinvLd;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { dst[r] = x[r]; }
+            }
+        }
+
+        // one pass: 8 queries per warp, V^T = Kt^T L^-T with the 8 x (16 NBLK) accumulators resident
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ void
+        PredictTile(const BatchParams<double> &p, const double *__restrict__ smem, const int n, const int nblk, const long q_begin, const int nq) {
+            using Lay = Layout<NBLK>;
+            const double *lp = smem + Lay::kL;
+            const double *pts = smem + Lay::kPts;
+            const double *al = smem + Lay::kAl;
+            const double *dinv = smem + Lay::kDinv;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            const int g = lane >> 2, t = lane & 3;
+            if (8 * warp >= nq) { return; }  // (no barrier below)
+            const int qi = 8 * warp + g;
+            const bool active = qi < nq;
+            double xq[XDIM];
+#pragma unroll
+            for (int d = 0; d < XDIM; ++d) { xq[d] = active ? p.q_x[(q_begin + qi) * XDIM + d] : 0.0; }
+            // Ktest entries in the accumulator layout: tile ct holds (query g, training points 8 ct + 2 t, 8 ct + 2 t + 1)
+            double x[2 * NBLK][2];
+            double mean = 0.0;
+#pragma unroll
+            for (int ct = 0; ct < 2 * NBLK; ++ct) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * ct + 2 * t + e;
+                    double kv = 0.0;
+                    if (ct < 2 * nblk && col < n) {
+                        kv = p.cov(Dist2<XDIM>(pts + 4 * col, xq));
+                        mean = fma(kv, al[col], mean);
+                    }
+                    x[ct][e] = kv;
+                }
+            }
+            double ss = 0.0;
+#pragma unroll
+            for (int j = 0; j < NBLK; ++j) {
+                if (j < nblk) {
+                    // V_j = X_j Dinv_j^T
+                    const double *dv = dinv + j * 16 * Lay::kDinvLd + g;
+                    double v[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                        for (int ck = 0; ck <= ch; ++ck) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { Dmma884(v[ch], x[2 * j + ck][e], dv[(8 * ck + 2 * t + e) * Lay::kDinvLd + 8 * ch]); }
+                        }
+                    }
+                    ss = fma(v[0][0], v[0][0], ss);
+                    ss = fma(v[0][1], v[0][1], ss);
+                    ss = fma(v[1][0], v[1][0], ss);
+                    ss = fma(v[1][1], v[1][1], ss);
+                    const double nv[2][2] = {{-v[0][0], -v[0][1]}, {-v[1][0], -v[1][1]}};
+                    // X_i -= V_j L_ij^T for the block rows below
+                    const int stride = Lay::Stride(j);
+                    const double *base = lp + Lay::Base(j) + g;
+#pragma unroll
+                    for (int i = j + 1; i < NBLK; ++i) {
+                        if (i < nblk) {
+#pragma unroll
+                            for (int ck = 0; ck < 2; ++ck) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const double *col = base + (8 * ck + 2 * t + e) * stride + 16 * (i - j);  // L[16 i + g (+ 8)][16 j + 8 ck + 2 t + e]
+                                    Dmma884(x[2 * i], nv[ck][e], col[0]);
+                                    Dmma884(x[2 * i + 1], nv[ck][e], col[8]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            mean += __shfl_xor_sync(kFull, mean, 1);
+            mean += __shfl_xor_sync(kFull, mean, 2);
+            ss += __shfl_xor_sync(kFull, ss, 1);
+            ss += __shfl_xor_sync(kFull, ss, 2);
+            if (t == 0 && active) {
+                const long src = q_begin + qi;
+                const long dst = p.q_out_index != nullptr ? p.q_out_index[src] : src;
+                if (p.mean != nullptr) {
+                    double f = mean;
+                    if (p.mapping != ERL_GP_MAPPING_NONE) { f = MappingInv<double>(p.mapping, p.mapping_scale, f); }
+                    p.mean[dst] = f;
+                }
+                if (p.variance != nullptr) { p.variance[dst] = 1.0 - ss; }  // literal prior 1.0f, src/vanilla_gp.cpp:121
+                if (p.valid != nullptr) { p.valid[dst] = 1; }
+            }
+        }
+
+        template<int XDIM, int NBLK, int MODE>
+        __global__ void __launch_bounds__(kThreads, 2)
+        RowGp64Kernel(const BatchParams<double> p) {
+            using Lay = Layout<NBLK>;
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            double *smem = reinterpret_cast<double *>(smem_raw);
+            double *lp = smem + Lay::kL;
+            double *pts = smem + Lay::kPts;
+            double *al = smem + Lay::kAl;
+            double *sv = smem + Lay::kVar;
+            int *s_fail = reinterpret_cast<int *>(smem + Lay::kMisc);
+            const int g = blockIdx.x;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            const int n = p.n_train[g];
+            const long q0 = (MODE & kBatchPredict) ? p.q_offsets[g] : 0;
+            const long q1 = (MODE & kBatchPredict) ? p.q_offsets[g + 1] : 0;
+            auto invalidate = [&]() {
+                if ((MODE & kBatchPredict) && p.valid != nullptr) {
+                    for (long q = q0 + tid; q < q1; q += kThreads) { p.valid[p.q_out_index != nullptr ? p.q_out_index[q] : q] = 0; }
+                }
+            };
+            if constexpr ((MODE & kBatchTrain) != 0) {
+                if (n <= p.min_train || n <= 0) {  // the reference's `cnt > min_num_samples_per_group` / `cnt > 0` gate
+                    if (tid == 0) { p.info[g] = -1; }
+                    invalidate();
+                    return;
+                }
+            } else {
+                if (p.info[g] != 0 || q1 <= q0) { return; }  // untrained / failed GP: outputs stay untouched
+            }
+            const int nblk = (n + 15) >> 4;
+            const int npr = 16 * nblk;
+            const double *gx = p.x + static_cast<long>(g) * p.max_n * XDIM;
+            for (int e = tid; e < Lay::kNp; e += kThreads) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { pts[4 * e + d] = (d < XDIM && e < n) ? gx[e * XDIM + (d < XDIM ? d : 0)] : 0.0; }
+            }
+            if constexpr ((MODE & kBatchTrain) != 0) {
+                const double *gy = p.y + static_cast<long>(g) * p.max_n;
+                const double *gv = p.var + static_cast<long>(g) * p.max_n;
+                for (int e = tid; e < Lay::kNp; e += kThreads) {
+                    al[e] = e < n ? gy[e] : 0.0;
+                    sv[e] = e < n ? gv[e] : 0.0;
+                }
+                __syncthreads();
+                const int fail = Factorize<XDIM, NBLK>(p.cov, smem, n, nblk);
+                if (tid == 0) { *s_fail = fail; }  // warp 0 tracked every pivot
+                __syncthreads();
+                const int failed = *s_fail;
+                if (failed != 0) {
+                    if (tid == 0) { p.info[g] = failed; }
+                    invalidate();
+                    return;
+                }
+                if (p.write_l) {  // L write-back: one column per warp and step, rows along the lanes
+                    double *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
+                    for (int c = warp; c < n; c += kWarps) {
+                        const int cb = c >> 4;
+                        const double *col = lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) - 16 * cb;
+                        double *gcol = gl + static_cast<long>(c) * p.max_n;
+                        for (int r = lane; r < n; r += 32) { gcol[r] = r >= 16 * cb ? col[r] : 0.0; }
+                    }
+                }
+                BackSolve<NBLK>(smem, nblk);
+                __syncthreads();
+                double *ga = p.alpha + static_cast<long>(g) * p.max_n;
+                for (int e = tid; e < n; e += kThreads) { ga[e] = al[e]; }
+                if (tid == 0) { p.info[g] = 0; }
+            } else {
+                // ---- predict-only: reload L and alpha, rebuild the inverses of the diagonal blocks ----
+                const double *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
+                const double *ga = p.alpha + static_cast<long>(g) * p.max_n;
+                for (int e = tid; e < Lay::kNp; e += kThreads) { al[e] = e < n ? ga[e] : 0.0; }
+                for (int c = warp; c < npr; c += kWarps) {
+                    const int cb = c >> 4;
+                    double *col = lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) - 16 * cb;
+                    const double *gcol = gl + static_cast<long>(c) * p.max_n;
+                    for (int r = 16 * cb + lane; r < npr; r += 32) {
+                        double v = 0.0;
+                        if (r < n && c < n) {
+                            v = r >= c ? gcol[r] : 0.0;
+                        } else if (r == c) {
+                            v = 1.0;  // identity padding
+                        }
+                        col[r] = v;
+                    }
+                }
+                __syncthreads();
+                ComputeDinv<NBLK>(smem, nblk);
+            }
+            if constexpr ((MODE & kBatchPredict) != 0) {
+                __syncthreads();
+                for (long qb = q0 + static_cast<long>(blockIdx.y) * kQTile; qb < q1; qb += static_cast<long>(gridDim.y) * kQTile) {
+                    const int nq = static_cast<int>(q1 - qb < kQTile ? q1 - qb : kQTile);
+                    PredictTile<XDIM, NBLK>(p, smem, n, nblk, qb, nq);
+                }
+            }
+        }
+
+        template<int XDIM, int NBLK, int MODE>
+        static int
+        LaunchInstance(Context *ctx, const BatchParams<double> &params, const int tiles_per_gp) {
+            using Lay = Layout<NBLK>;
+            auto kernel = RowGp64Kernel<XDIM, NBLK, MODE>;
+            if (static_cast<int>(Lay::kBytes) > ctx->max_smem_optin) {
+                return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "FP64 row-GP kernel needs %zu B of shared memory, device allows %d", Lay::kBytes, ctx->max_smem_optin);
+            }
+            ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Lay::kBytes)));
+            const dim3 grid(static_cast<unsigned>(params.num_gps), static_cast<unsigned>(tiles_per_gp < 1 ? 1 : tiles_per_gp));
+            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(params);
+            ctx->launches += 1;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            return ERL_GP_STATUS_OK;
+        }
+
+        template<int XDIM, int NBLK>
+        static int
+        LaunchMode(Context *ctx, const BatchParams<double> &params, const int mode, const int tiles_per_gp) {
+            switch (mode) {
+                case kBatchTrain: return LaunchInstance<XDIM, NBLK, kBatchTrain>(ctx, params, 1);
+                case kBatchPredict: return LaunchInstance<XDIM, NBLK, kBatchPredict>(ctx, params, tiles_per_gp);
+                case kBatchTrainPredict: return LaunchInstance<XDIM, NBLK, kBatchTrainPredict>(ctx, params, 1);
+                default: return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "batch: bad mode %d", mode);
+            }
+        }
+
+        // max_n <= 128
+        template<int XDIM>
+        int
+        Launch(Context *ctx, const BatchParams<double> &params, const int mode, const int tiles_per_gp) {
+            if (params.max_n <= 64) { return LaunchMode<XDIM, 4>(ctx, params, mode, tiles_per_gp); }
+            return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp);
+        }
+
+    }  // namespace rowgp64
+}  // namespace erl_gp

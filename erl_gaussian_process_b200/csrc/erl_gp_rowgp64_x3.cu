@@ -1,0 +1,8 @@
+// Instantiates the FP64 row-GP kernels (erl_gp_rowgp64.cuh) for x_dim = 3 (own translation unit: build time).
+#include "erl_gp_rowgp64.cuh"
+
+namespace erl_gp {
+    namespace rowgp64 {
+        template int Launch<3>(Context *, const BatchParams<double> &, int, int);
+    }  // namespace rowgp64
+}  // namespace erl_gp

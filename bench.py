@@ -634,7 +634,10 @@ def main():
                        "l2": f"per-step inputs+outputs {alg_bytes / 1e9:.2f} GB >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                         "kernel": (f"rowgp::RowGpKernel<x_dim={d}, NBLK={(n + 15) // 16}, train+predict>" if w["dtype"] == "f32" else f"BatchedGpKernel<double, x_dim={d}, n<={n}, train+predict>") + " (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": (f"rowgp::RowGpKernel<x_dim={d}, NBLK={(n + 15) // 16}, train+predict>" if w["dtype"] == "f32" else (f"rowgp64::RowGp64Kernel<x_dim={d}, NBLK={(n + 15) // 16}, train+predict> (mma.sync.m8n8k4.f64)" if n <= 128 and not os.environ.get("ERL_GP_BATCH_LEGACY")
+                                          else f"BatchedGpKernel<double, x_dim={d}, n<={n}, train+predict>")) + " (one launch per step)", "algorithmic_bytes_per_launch": alg_bytes,
+                         # FP64: the DMMA pipe (37.03 TFLOP/s measured, tools/mma_rate.cu) bounds the double-precision stream
+                         "fp64_tensor_pipe": {"useful_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_tflops": 37.03, "frac": fl / (ms_step * 1e-3) / 1e12 / 37.03} if w["dtype"] == "f64" else None,
                          # the kernel's real bound: 3xTF32 mma.sync work (3 HMMA products per FP32 product; 276 TFLOP/s TF32 measured
                          # => 92 TFLOP/s FP32-equivalent); 590 HMMA.1688 per 16 queries and GP at n = t = 128
                          "tensor_pipe": {"useful_tflops_fp32_equiv": fl / (ms_step * 1e-3) / 1e12, "peak_tflops_fp32_equiv": 276.46 / 3,

@@ -66,6 +66,11 @@ namespace erl_gp {
 #else
         constexpr bool kBackSolveDinv = true;
 #endif
+#ifdef ERL_GP_PIVOT_RSQRT_CHAIN  // A/B: the round-1 pivot chain (refined MUFU.RSQ per column)
+        constexpr bool kPivotRcpChain = false;
+#else
+        constexpr bool kPivotRcpChain = true;
+#endif
 #ifndef ERL_GP_ROWGP_FFMA_TRAIN
         constexpr bool kMmaTrain = true;
 #else
@@ -184,6 +189,38 @@ namespace erl_gp {
         template<int SRC>
         __device__ __forceinline__ void
         PivotBlock(float (&acc)[16], float &zacc, float (&l)[16], const int half, const int c0, const int lane, int &fail, float *__restrict__ rs, float *__restrict__ al) {
+            if constexpr (SRC == 2 && kPivotRcpChain) {
+                // Tensor-path factorisation, round 2: only MUFU.RCP (1 ulp) sits on the serial chain d_c -> 1 / d_c -> sc -> acc[c + 1] -> d_{c+1};
+                // the square roots that turn the eliminated entries into L (l = acc / sqrt(d), z = zc / sqrt(d)) are taken after the
+                // loop, one per lane in parallel (lane c keeps d_c) instead of sixteen refined MUFU.RSQ in sequence on every lane:
+                // four dependent FP32 instructions less per pivot column on the critical path of every factorisation.
+                float dmine = 1.0f, zraw = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float d = __shfl_sync(kFull, acc[c], c);
+                    const float zc = __shfl_sync(kFull, zacc, c);
+                    float t[16];
+#pragma unroll
+                    for (int cc = c + 1; cc < 16; ++cc) { t[cc] = __shfl_sync(kFull, acc[c], cc); }
+                    if (!(d > 0.f) && fail == 0) { fail = c0 + c + 1; }
+                    float invd;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invd) : "f"(d));
+                    const float sc = acc[c] * invd;
+#pragma unroll
+                    for (int cc = c + 1; cc < 16; ++cc) { acc[cc] = fmaf(-sc, t[cc], acc[cc]); }
+                    zacc = fmaf(-sc, zc, zacc);
+                    l[c] = acc[c];  // unscaled: acc[c] is final here
+                    if ((lane & 15) == c) { dmine = d, zraw = zc; }
+                }
+                const float rsv = RsqrtRefined(dmine);  // lane c (and c + 16): 1 / sqrt(d_c)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { l[c] *= __shfl_sync(kFull, rsv, c); }
+                if (lane < 16) {
+                    rs[c0 + lane] = rsv;
+                    al[c0 + lane] = zraw * rsv;
+                }
+                return;
+            }
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const int src = SRC == 2 ? c : SRC == 1 ? 2 * c : (c < half ? 2 * c : 2 * (c - half) + 1);

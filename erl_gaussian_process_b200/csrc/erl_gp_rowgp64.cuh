@@ -7,9 +7,10 @@
 // The design is the FP32 kernel's, without the 3xTF32 split (double needs none):
 //   * L lives in shared memory, column-major, packed by 16-column blocks (block b keeps rows >= 16 b) with a column stride == 2 (mod
 //     16) doubles: "one row per lane", "one column per lane" and both MMA fragment patterns are bank-conflict free for 64-bit loads;
-//   * train = left-looking blocked Cholesky with 16-column panels, one 16 x 16 tile per warp: (A) P = K - L[tile] L[pivot rows]^T
+//   * the Gram entries are generated up front by all threads into L's own storage (no dependency, ~60 instructions each in double);
+//   * train = left-looking blocked Cholesky in place, 16-column panels, one 16 x 16 tile per warp: (A) P = K - L[tile] L[pivot rows]^T
 //     as 8 x 8 x 4 DMMAs whose reduction index is permuted (k-slot t of group e <-> column 2 t + e) so that A and B fragments are
-//     single conflict-free LDS.64; the Gram entries are generated in the accumulator layout; (B) warp 0 factorises the 16 x 16
+//     single conflict-free LDS.64; (B) warp 0 factorises the 16 x 16
 //     pivot tile with shuffles, lanes 16 .. 31 run the same elimination on the unit vectors and end up with the columns of its
 //     inverse Dinv, z = L^-1 y rides along; (C) L_i = P_i Dinv^T straight from the accumulators: an 8 x 8 accumulator tile (row g,
 //     columns 2 t, 2 t + 1) IS the A operand of two DMMAs under the same k permutation;
@@ -25,6 +26,12 @@
 #include "erl_gp_internal.cuh"
 
 #include <cstdlib>
+
+#ifdef ERL_GP_ROWGP64_TIMING  // per-phase cycle counters, printed by one CTA (kernel experiments only)
+#define ERL_GP64_TICK(acc_) { const long long now_ = clock64(); acc_ += now_ - tm_t; tm_t = now_; }
+#else
+#define ERL_GP64_TICK(acc_)
+#endif
 
 namespace erl_gp {
     namespace rowgp64 {
@@ -71,11 +78,73 @@ namespace erl_gp {
             return r2;
         }
 
+        // The three erl_covariance kernels in double with hand-rolled exp / sqrt.  In double a library covariance entry costs ~100 FP64
+        // instructions (IEEE sqrt + exp with their special cases) and the entries (n^2 / 2 Gram + n t Ktest per GP) were half of the run
+        // time of the first version of this kernel; these take ~40, accurate to a few ulp on the arguments that occur (r2 >= 0, exponent
+        // argument in [-745, 0]):
+        //   sqrt(r2) = r2 * rsqrt(r2) with one Newton correction (0 at r2 = 0);
+        //   exp(x)   = 2^k p(r), k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite), p = Taylor polynomial of degree 12 on |r| <= 0.347
+        //              (truncation error 1.7e-16), 2^k assembled in the exponent field.
+        struct Cov64 {
+            int type;
+            double a;  // Matern32: sqrt(3) / l    OU: 1 / l    RBF: 1 / (2 l^2)
+
+            __device__ __forceinline__ explicit Cov64(const Covariance<double> &cov) {
+                type = cov.type;
+                a = cov.type == ERL_GP_KERNEL_MATERN32 ? cov.c0 : 1.0 / cov.c0;
+            }
+
+            __device__ __forceinline__ static double
+            Sqrt(const double r2) {
+                const double y = rsqrt(r2);
+                double r = r2 * y;
+                r = fma(0.5 * y, fma(-r, r, r2), r);
+                return r2 > 0.0 ? r : 0.0;
+            }
+
+            __device__ __forceinline__ static double
+            Exp(const double x) {  // x <= 0
+                constexpr double kLog2e = 1.4426950408889634074, kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10, kMagic = 6755399441055744.0;
+                const double kd = fma(x, kLog2e, kMagic) - kMagic;  // rint(x log2 e)
+                double r = fma(kd, -kLn2Hi, x);
+                r = fma(kd, -kLn2Lo, r);
+                double p = 1.0 / 479001600.0;
+                p = fma(p, r, 1.0 / 39916800.0);
+                p = fma(p, r, 1.0 / 3628800.0);
+                p = fma(p, r, 1.0 / 362880.0);
+                p = fma(p, r, 1.0 / 40320.0);
+                p = fma(p, r, 1.0 / 5040.0);
+                p = fma(p, r, 1.0 / 720.0);
+                p = fma(p, r, 1.0 / 120.0);
+                p = fma(p, r, 1.0 / 24.0);
+                p = fma(p, r, 1.0 / 6.0);
+                p = fma(p, r, 0.5);
+                p = fma(p, r, 1.0);
+                p = fma(p, r, 1.0);
+                const int k = static_cast<int>(kd);
+                const double scale = __hiloint2double((k + 1023) << 20, 0);  // 2^k, k >= -1022
+                return x > -708.0 ? p * scale : 0.0;
+            }
+
+            // (a __noinline__ call instead of 32 inlined copies per predict pass was measured: no gain, 16.04 vs 16.08 ms)
+            __device__ __forceinline__ double
+            operator()(const double r2) const {
+                if (type == ERL_GP_KERNEL_RBF) { return Exp(-r2 * a); }
+                const double ar = a * Sqrt(r2);
+                const double e = Exp(-ar);
+                return type == ERL_GP_KERNEL_MATERN32 ? fma(ar, e, e) : e;
+            }
+        };
+
         // 16 x 16 pivot tile: lanes 0 .. 15 own its rows, lanes 16 + j start from the unit vector e_j and run the very same elimination
         // (with sc = a[c] / d the update a[cc] -= sc A[cc][c] is the forward substitution of L x = e_j: the scaled entries l[c] that
         // lanes 0 .. 15 read as row r of L are, in lane 16 + j, column j of L^-1).  z = L^-1 y rides along in zacc.
         __device__ __forceinline__ void
         PivotBlock(double (&a)[16], double &zacc, double (&l)[16], const int c0, const int lane, int &fail, double *__restrict__ al) {
+            // Only the reciprocal of the pivot sits on the serial chain (MUFU.RCP64H seed + two Newton steps); the square roots that turn
+            // the eliminated entries into L (l = a / sqrt(d), z = zc / sqrt(d)) are taken after the loop: lane c keeps d_c, ONE rsqrt per
+            // lane in parallel instead of sixteen in sequence on every lane.
+            double dmine = 1.0, zraw = 0.0;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const double d = __shfl_sync(kFull, a[c], c);
@@ -84,31 +153,73 @@ namespace erl_gp {
 #pragma unroll
                 for (int cc = c + 1; cc < 16; ++cc) { t[cc] = __shfl_sync(kFull, a[c], cc); }  // A[cc][c] = A[c][cc] from lane cc
                 if (!(d > 0.0) && fail == 0) { fail = c0 + c + 1; }
-                const double rsv = rsqrt(d);
-                const double sc = a[c] * (rsv * rsv);
+                double inv;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
+                inv = fma(inv, fma(-d, inv, 1.0), inv);
+                inv = fma(inv, fma(-d, inv, 1.0), inv);
+                const double sc = a[c] * inv;
 #pragma unroll
                 for (int cc = c + 1; cc < 16; ++cc) { a[cc] = fma(-sc, t[cc], a[cc]); }
                 zacc = fma(-sc, zc, zacc);
-                l[c] = a[c] * rsv;
-                if (lane == 0) { al[c0 + c] = zc * rsv; }
+                l[c] = a[c];  // unscaled: a[c] is final here
+                if ((lane & 15) == c) { dmine = d, zraw = zc; }
             }
+            const double rsv = rsqrt(dmine);  // lane c (and c + 16): 1 / sqrt(d_c)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { l[c] *= __shfl_sync(kFull, rsv, c); }
+            if (lane < 16) { al[c0 + lane] = zraw * rsv; }
         }
 
-        // blocked left-looking Cholesky of the Gram matrix (never stored: its entries are generated when a panel is updated)
+        // Gram matrix straight into L's own packed storage (block b: rows >= 16 b of its 16 columns, the diagonal tile in full): in double
+        // a covariance entry costs ~60 instructions (exp + sqrt), far more than its share of the factorisation, and has no dependency
+        // on anything - all 256 threads generate them up front instead of the panel's warps on the critical path of the factorisation.
+        // K[i][i] = 1 + var[i]; rows / columns >= n are identity padding.
         template<int XDIM, int NBLK>
-        __device__ __forceinline__ int
-        Factorize(const Covariance<double> &cov, double *__restrict__ smem, const int n, const int nblk) {
+        __device__ __forceinline__ void
+        FillGram(const Cov64 &cov, double *__restrict__ smem, const int n, const int nblk) {
             using Lay = Layout<NBLK>;
             double *lp = smem + Lay::kL;
             const double *pts = smem + Lay::kPts;
-            double *al = smem + Lay::kAl;
             const double *sv = smem + Lay::kVar;
+            const int npr = 16 * nblk;
+            for (int cb = 0; cb < nblk; ++cb) {
+                const int rows = npr - 16 * cb;  // rows of this column block (multiple of 16)
+                double *blk = lp + Lay::Base(cb);
+                const int stride = Lay::Stride(cb);
+                for (int e = threadIdx.x; e < rows * 16; e += kThreads) {
+                    const int c = e / rows, r = e - c * rows;  // consecutive threads -> consecutive rows of one column
+                    const int row = 16 * cb + r, col = 16 * cb + c;
+                    double kv = 0.0;
+                    if (row == col) {
+                        kv = row < n ? 1.0 + sv[row] : 1.0;
+                    } else if (row < n && col < n) {
+                        double xr[XDIM];
+#pragma unroll
+                        for (int d = 0; d < XDIM; ++d) { xr[d] = pts[4 * row + d]; }
+                        kv = cov(Dist2<XDIM>(pts + 4 * col, xr));
+                    }
+                    blk[c * stride + r] = kv;
+                }
+            }
+        }
+
+        // blocked left-looking Cholesky, in place: the panels hold the Gram entries on entry (FillGram)
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ int
+        Factorize(double *__restrict__ smem, const int n, const int nblk) {
+            using Lay = Layout<NBLK>;
+            double *lp = smem + Lay::kL;
+            double *al = smem + Lay::kAl;
             double *dinv = smem + Lay::kDinv;
+            (void) n;
             const int tid = threadIdx.x;
             const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction
             const int lane = tid & 31;
             const int g = lane >> 2, t = lane & 3;
             int fail = 0;
+#ifdef ERL_GP_ROWGP64_TIMING
+            long long tm_a = 0, tm_b = 0, tm_w1 = 0, tm_c = 0, tm_w2 = 0, tm_t = clock64();
+#endif
             for (int kb = 0; kb < nblk; ++kb) {
                 const int c0 = 16 * kb;
                 const int mt = nblk - kb;  // 16-row tiles of this panel: tile w -> warp w (mt <= 8)
@@ -141,28 +252,15 @@ namespace erl_gp {
                         }
                     }
 #pragma unroll
-                    for (int rh = 0; rh < 2; ++rh) {
-                        const int row = c0 + rel + 8 * rh + g;
-                        double xr[XDIM];
-#pragma unroll
-                        for (int d = 0; d < XDIM; ++d) { xr[d] = pts[4 * row + d]; }
-                        const double diag = row < n ? 1.0 + sv[row] : 1.0;  // K[i][i] = 1 + var[i]; identity padding
+                    for (int rh = 0; rh < 2; ++rh) {  // P = K - update: the Gram entries wait in the panel's own storage (FillGram)
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int col = c0 + 8 * ch + 2 * t + e;
-                                double kv = 0.0;
-                                if (row == col) {
-                                    kv = diag;
-                                } else if (row < n && col < n) {
-                                    kv = cov(Dist2<XDIM>(pts + 4 * col, xr));
-                                }
-                                acc[rh][ch][e] = kv - acc[rh][ch][e];
-                            }
+                            for (int e = 0; e < 2; ++e) { acc[rh][ch][e] = panel[(8 * ch + 2 * t + e) * stride_k + rel + 8 * rh + g] - acc[rh][ch][e]; }
                         }
                     }
                 }
+                ERL_GP64_TICK(tm_a)
                 // ---- B: pivot tile (warp 0 holds it) ----
                 if (warp == 0) {
 #pragma unroll
@@ -206,7 +304,9 @@ namespace erl_gp {
                         for (int c = 0; c < 16; ++c) { dst[c] = l[c]; }
                     }
                 }
+                ERL_GP64_TICK(tm_b)
                 __syncthreads();  // #1: pivot tile, Dinv, z of this panel are published
+                ERL_GP64_TICK(tm_w1)
                 if (mt > 1) {
                     if (warp > 0 && warp < mt) {
                         // ---- C: L_i = P_i Dinv^T; Dinv is lower triangular: the (ck = 1, ch = 0) block is zero ----
@@ -238,9 +338,14 @@ namespace erl_gp {
                             }
                         }
                     }
+                    ERL_GP64_TICK(tm_c)
                     __syncthreads();  // #2: the whole panel is published
+                    ERL_GP64_TICK(tm_w2)
                 }
             }
+#ifdef ERL_GP_ROWGP64_TIMING
+            if (blockIdx.x == 20000 && lane == 0 && warp < 3) { printf("rowgp64 cta %d warp %d: A %lld  B %lld  wait1 %lld  C %lld  wait2 %lld\n", blockIdx.x, warp, tm_a, tm_b, tm_w1, tm_c, tm_w2); }
+#endif
             return fail;
         }
 
@@ -328,6 +433,7 @@ namespace erl_gp {
 #pragma unroll
             for (int d = 0; d < XDIM; ++d) { xq[d] = active ? p.q_x[(q_begin + qi) * XDIM + d] : 0.0; }
             // Ktest entries in the accumulator layout: tile ct holds (query g, training points 8 ct + 2 t, 8 ct + 2 t + 1)
+            const Cov64 cov(p.cov);
             double x[2 * NBLK][2];
             double mean = 0.0;
 #pragma unroll
@@ -337,7 +443,7 @@ namespace erl_gp {
                     const int col = 8 * ct + 2 * t + e;
                     double kv = 0.0;
                     if (ct < 2 * nblk && col < n) {
-                        kv = p.cov(Dist2<XDIM>(pts + 4 * col, xq));
+                        kv = cov(Dist2<XDIM>(pts + 4 * col, xq));
                         mean = fma(kv, al[col], mean);
                     }
                     x[ct][e] = kv;
@@ -446,7 +552,14 @@ namespace erl_gp {
                     sv[e] = e < n ? gv[e] : 0.0;
                 }
                 __syncthreads();
-                const int fail = Factorize<XDIM, NBLK>(p.cov, smem, n, nblk);
+#ifdef ERL_GP_ROWGP64_TIMING
+                long long tm_fill = 0, tm_fact = 0, tm_wb = 0, tm_bs = 0, tm_t = clock64();
+#endif
+                FillGram<XDIM, NBLK>(Cov64(p.cov), smem, n, nblk);
+                __syncthreads();
+                ERL_GP64_TICK(tm_fill)
+                const int fail = Factorize<XDIM, NBLK>(smem, n, nblk);
+                ERL_GP64_TICK(tm_fact)
                 if (tid == 0) { *s_fail = fail; }  // warp 0 tracked every pivot
                 __syncthreads();
                 const int failed = *s_fail;
@@ -464,8 +577,13 @@ namespace erl_gp {
                         for (int r = lane; r < n; r += 32) { gcol[r] = r >= 16 * cb ? col[r] : 0.0; }
                     }
                 }
+                ERL_GP64_TICK(tm_wb)
                 BackSolve<NBLK>(smem, nblk);
                 __syncthreads();
+                ERL_GP64_TICK(tm_bs)
+#ifdef ERL_GP_ROWGP64_TIMING
+                if (blockIdx.x == 20000 && tid == 0) { printf("rowgp64 cta %d: fill %lld  factorize %lld  write-back %lld  back-solve %lld\n", blockIdx.x, tm_fill, tm_fact, tm_wb, tm_bs); }
+#endif
                 double *ga = p.alpha + static_cast<long>(g) * p.max_n;
                 for (int e = tid; e < n; e += kThreads) { ga[e] = al[e]; }
                 if (tid == 0) { p.info[g] = 0; }
@@ -493,10 +611,16 @@ namespace erl_gp {
             }
             if constexpr ((MODE & kBatchPredict) != 0) {
                 __syncthreads();
+#ifdef ERL_GP_ROWGP64_TIMING
+                const long long tp0 = clock64();
+#endif
                 for (long qb = q0 + static_cast<long>(blockIdx.y) * kQTile; qb < q1; qb += static_cast<long>(gridDim.y) * kQTile) {
                     const int nq = static_cast<int>(q1 - qb < kQTile ? q1 - qb : kQTile);
                     PredictTile<XDIM, NBLK>(p, smem, n, nblk, qb, nq);
                 }
+#ifdef ERL_GP_ROWGP64_TIMING
+                if (blockIdx.x == 20000 && (tid & 31) == 0 && tid < 96) { printf("rowgp64 cta %d warp %d: predict %lld\n", blockIdx.x, tid >> 5, clock64() - tp0); }
+#endif
             }
         }
 

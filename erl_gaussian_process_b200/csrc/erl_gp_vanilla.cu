@@ -435,6 +435,69 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // Gradient of the SPGP predictive mean, TestResult::GetGradient (src/sparse_pseudo_input_gp.cpp:187-278): the reference builds the
+    // gradient columns of Ktest (ComputeKtestWithGradient with no gradient observation among the pseudo-points, :82-91) and dots them
+    // with alpha.  Fused here: one thread per test point accumulates sum_j alpha_j dk(z_j, x*) / dx*_a over the pseudo-points staged in
+    // shared memory - no M x T(d + 1) Ktest.   RBF: dk/dx*_a = (z - x*)_a k / l^2;   Matern32: 3 / l^2 exp(-sqrt(3) r / l) (z - x*)_a.
+    template<typename T>
+    __global__ void
+    SpgpGradientKernel(const int type, const T scale, const int x_dim, const long m, const T *__restrict__ z, const T *__restrict__ alpha, const long t, const T *__restrict__ xt,
+                       T *__restrict__ grad) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        T *zs = reinterpret_cast<T *>(smem_raw);  // [256][4]: point + alpha
+        const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+        T x[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
+        if (i < t) {
+            for (int a = 0; a < x_dim; ++a) { x[a] = xt[i * x_dim + a]; }
+        }
+        const T l2 = scale * scale;
+        const T c = sqrt(T(3)) / scale;
+        for (long j0 = 0; j0 < m; j0 += blockDim.x) {
+            const long j = j0 + threadIdx.x;
+            __syncthreads();
+            for (int a = 0; a < 3; ++a) { zs[4 * threadIdx.x + a] = (j < m && a < x_dim) ? z[j * x_dim + a] : T(0); }
+            zs[4 * threadIdx.x + 3] = j < m ? alpha[j] : T(0);
+            __syncthreads();
+            const int cnt = static_cast<int>(m - j0 < blockDim.x ? m - j0 : blockDim.x);
+            for (int k = 0; k < cnt; ++k) {
+                T diff[3], r2 = 0;
+                for (int a = 0; a < 3; ++a) {
+                    diff[a] = zs[4 * k + a] - x[a];
+                    r2 += diff[a] * diff[a];
+                }
+                const T w = zs[4 * k + 3] * (type == ERL_GP_KERNEL_RBF ? exp(-r2 / (T(2) * l2)) / l2 : c * c * exp(-c * sqrt(r2)));
+                for (int a = 0; a < 3; ++a) { acc[a] += w * diff[a]; }
+            }
+        }
+        if (i < t) {
+            for (int a = 0; a < x_dim; ++a) { grad[a + i * x_dim] = acc[a]; }
+        }
+    }
+
+    // grad: x_dim x num_test (host).  raw_alpha != 0 reproduces the reference's batched accessor, which dots with the UNSOLVED alpha
+    // (m_gp_->m_mat_alpha_, :212) while its per-index accessor (:252) and GetMean use Q_M^-1 alpha; the default is the consistent one.
+    template<typename T>
+    static int
+    SpgpTestGradient(Spgp<T> *gp, long num_test, const T *x_test, long ld_xt, T *grad, int raw_alpha) {
+        if (gp == nullptr || x_test == nullptr || grad == nullptr || num_test <= 0) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        if (gp->kernel == ERL_GP_KERNEL_OU) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "spgp: OrnsteinUhlenbeck has no gradient"); }
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        int rc = SpgpPrepareLqm(gp);
+        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        const long m = gp->m, d = gp->x_dim;
+        ERL_GP_CUDA_OK(ctx, gp->xt.Reserve(static_cast<size_t>(num_test) * d));
+        ERL_GP_CUDA_OK(ctx, gp->w.Reserve(static_cast<size_t>(num_test) * d));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(gp->xt.ptr, sizeof(T) * d, x_test, sizeof(T) * ld_xt, sizeof(T) * d, num_test, cudaMemcpyDefault, ctx->stream));
+        SpgpGradientKernel<T><<<static_cast<unsigned>(CeilDiv(num_test, 256)), 256, 256 * 4 * sizeof(T), ctx->stream>>>(gp->kernel, gp->scale, static_cast<int>(d), m, gp->z.ptr,
+                                                                                                                     raw_alpha ? gp->alpha.ptr : gp->alpha_solved.ptr, num_test, gp->xt.ptr, gp->w.ptr);
+        ctx->launches += 1;
+        ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(grad, gp->w.ptr, sizeof(T) * num_test * d, cudaMemcpyDefault, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
     template<typename T>
     static int
     SpgpGet(Spgp<T> *gp, T *q_m, T *alpha, T *l_km, T *l_qm) {
@@ -522,6 +585,9 @@ extern "C" {
     int erl_gp_spgp_update_##SFX(erl_gp_spgp_##SFX *gp, long n, const T *x, long ld_x, const T *y, const T *var) { return SpgpUpdate<T>(gp, n, x, ld_x, y, var); }           \
     int erl_gp_spgp_test_##SFX(erl_gp_spgp_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                                                         \
         return SpgpTest<T>(gp, num_test, x_test, ld_xt, mean, var);                                                                                                          \
+    }                                                                                                                                                                        \
+    int erl_gp_spgp_test_gradient_##SFX(erl_gp_spgp_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *grad, int raw_alpha) {                                         \
+        return SpgpTestGradient<T>(gp, num_test, x_test, ld_xt, grad, raw_alpha);                                                                                            \
     }                                                                                                                                                                        \
     int erl_gp_spgp_get_##SFX(erl_gp_spgp_##SFX *gp, T *q_m, T *alpha, T *l_km, T *l_qm) { return SpgpGet<T>(gp, q_m, alpha, l_km, l_qm); }
 

@@ -788,6 +788,16 @@ class SparsePseudoInputGaussianProcess:
         check(self.ctx.fn("erl_gp_spgp_test", self.dtype)(self.handle, C.c_long(t), _p(xt), C.c_long(self.x_dim), _p(mean), _p(var)), "spgp_test", self.ctx.handle)
         return mean, var
 
+    def test_gradient(self, x_test, raw_alpha=False):
+        """TestResult::GetGradient (src/sparse_pseudo_input_gp.cpp:187-278): gradient of the predictive mean, (T, x_dim).
+        raw_alpha=True dots with the unsolved alpha, as the reference's batched accessor does (:212)."""
+        xt = np.ascontiguousarray(x_test, dtype=self.dtype)
+        t = xt.shape[0]
+        grad = np.empty((t, self.x_dim), dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_spgp_test_gradient", self.dtype)(self.handle, C.c_long(t), _p(xt), C.c_long(self.x_dim), _p(grad), C.c_int(int(raw_alpha))), "spgp_test_gradient",
+              self.ctx.handle)
+        return grad
+
     def get(self):
         m = self.m
         q = np.empty((m, m), dtype=self.dtype)

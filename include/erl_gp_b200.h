@@ -394,6 +394,13 @@ int erl_gp_spgp_test_f32(erl_gp_spgp_f32 *gp, long num_test, const float *x_test
                          float *var);
 int erl_gp_spgp_test_f64(erl_gp_spgp_f64 *gp, long num_test, const double *x_test, long ld_xt, double *mean,
                          double *var);
+/* TestResult::GetGradient (src/sparse_pseudo_input_gp.cpp:187-278): gradient of the predictive mean, x_dim x num_test col-major.
+ * raw_alpha = 0: dotted with Q_M^-1 alpha like GetMean and the per-index accessor (:252); raw_alpha = 1: with the unsolved alpha,
+ * as the reference's batched accessor does (:212).  RBF and Matern32 only. */
+int erl_gp_spgp_test_gradient_f32(erl_gp_spgp_f32 *gp, long num_test, const float *x_test, long ld_xt, float *grad,
+                                  int raw_alpha);
+int erl_gp_spgp_test_gradient_f64(erl_gp_spgp_f64 *gp, long num_test, const double *x_test, long ld_xt, double *grad,
+                                  int raw_alpha);
 /* Q_M, L_KM, L_QM: M x M col-major (ld = M); alpha: M.  Any may be NULL. */
 int erl_gp_spgp_get_f32(erl_gp_spgp_f32 *gp, float *q_m, float *alpha, float *l_km, float *l_qm);
 int erl_gp_spgp_get_f64(erl_gp_spgp_f64 *gp, double *q_m, double *alpha, double *l_km, double *l_qm);

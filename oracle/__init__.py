@@ -332,6 +332,13 @@ class Spgp:
         _fn("oracle_spgp_test", self.dtype)(self.h, _p(xt), C.c_long(t), _p(mean), _p(var))
         return mean, var
 
+    def test_gradient(self, xt, raw_alpha=False):
+        xt = np.ascontiguousarray(xt, dtype=self.dtype)
+        t = xt.shape[0]
+        grad = np.zeros((t, self.d), dtype=self.dtype)
+        _fn("oracle_spgp_test_gradient", self.dtype)(self.h, _p(xt), C.c_long(t), _p(grad), C.c_int(int(raw_alpha)))
+        return grad
+
     def get(self):
         m = self.m
         q = np.zeros((m, m), dtype=self.dtype)

@@ -919,6 +919,42 @@ namespace erl_gp_oracle {
                 }
             }
         }
+        // TestResult::GetGradient — src/sparse_pseudo_input_gp.cpp:187-278 with the gradient columns of ComputeKtestWithGradient for
+        // pseudo-points without gradient observations (:82-91): grad_a(x*) = sum_j alpha_j dk(z_j, x*) / dx*_a.  raw_alpha: the unsolved
+        // alpha of the batched accessor (:212) instead of Q_M^-1 alpha (:252).  (KernelWithDerivatives is defined further down.)
+        void
+        TestGradient(const T *x_test, const long num_test, T *grad, const bool raw_alpha) {
+            if (!l_qm_updated) {  // PrepareLqm :835-842
+                l_qm.assign(static_cast<std::size_t>(m * m), T(0));
+                Llt(q_m.data(), m, m, l_qm.data(), m);
+                l_qm_updated = true;
+            }
+            std::vector<T> a = alpha;
+            if (!raw_alpha) {
+                SolveLowerInPlace(l_qm.data(), m, m, a.data());
+                SolveLowerTransposeInPlace(l_qm.data(), m, m, a.data());
+            }
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < num_test; ++i) {
+                T g[3] = {0, 0, 0};
+                for (long j = 0; j < m; ++j) {
+                    T diff[3] = {0, 0, 0}, r2 = 0;
+                    for (long d = 0; d < x_dim; ++d) {
+                        diff[d] = z[j * x_dim + d] - x_test[i * x_dim + d];
+                        r2 += diff[d] * diff[d];
+                    }
+                    T w;
+                    if (kernel_type == kRadialBiasFunction) {
+                        w = std::exp(-r2 / (T(2) * scale * scale)) / (scale * scale);
+                    } else {
+                        const T c = std::sqrt(T(3)) / scale;
+                        w = c * c * std::exp(-c * std::sqrt(r2));
+                    }
+                    for (long d = 0; d < x_dim; ++d) { g[d] += a[j] * w * diff[d]; }
+                }
+                for (long d = 0; d < x_dim; ++d) { grad[d + i * x_dim] = g[d]; }
+            }
+        }
     };
 
     // ---------------------------------------------------------------------------------------

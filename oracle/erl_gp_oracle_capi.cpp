@@ -335,6 +335,10 @@ namespace {
         static_cast<Spgp<T> *>(h)->Test(x_test, num_test, mean, variance);                                            \
         return 0;                                                                                                     \
     }                                                                                                                 \
+    extern "C" int oracle_spgp_test_gradient_##SFX(void *h, const T *x_test, long num_test, T *grad, int raw_alpha) {  \
+        static_cast<Spgp<T> *>(h)->TestGradient(x_test, num_test, grad, raw_alpha != 0);                              \
+        return 0;                                                                                                     \
+    }                                                                                                                 \
     extern "C" int oracle_spgp_get_##SFX(void *h, T *q_m, T *alpha, T *l_km, T *l_qm) {                               \
         auto *gp = static_cast<Spgp<T> *>(h);                                                                         \
         const std::size_t mm = static_cast<std::size_t>(gp->m * gp->m);                                               \

@@ -215,6 +215,52 @@ def test_spgp_2d_incremental(gp, oracle, dtype):
     assert np.abs(lk - lk_ref).max() / np.abs(lk_ref).max() < (1e-3 if dtype == np.float32 else 1e-10)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kernel,scale", [("rbf", 0.25), ("matern32", 0.8)])
+def test_spgp_gradient(gp, oracle, dtype, kernel, scale):
+    """TestResult::GetGradient of the SPGP (src/sparse_pseudo_input_gp.cpp:187-278): against the oracle, and - independently of any
+    restated formula - against central differences of the library's own predictive mean."""
+    if kernel == "rbf" and dtype == np.float32:
+        pytest.skip("K_M of an RBF grid (no noise term, src/sparse_pseudo_input_gp.cpp:340) is not positive definite in FP32 at this spacing")
+    if dtype == np.float32:
+        scale = 0.35  # cond(K_M) grows quickly with l / spacing and K_M carries no noise term: keep FP32 in a regime it can resolve
+    rng = np.random.default_rng(12)
+    gx = np.linspace(-2, 2, 12)
+    z = np.array([[a, b] for a in gx for b in gx])
+    g = gp.SparsePseudoInputGaussianProcess(kernel, scale, z, dtype)
+    o = oracle.Spgp(oracle.KERNELS[kernel], scale, z, dtype)
+    x = rng.uniform(-2, 2, (800, 2))
+    y = np.sin(1.5 * x[:, 0]) * np.cos(x[:, 1])
+    var = np.full(len(x), 1e-2)
+    assert g.update(x, y, var) and o.update(x, y, var)
+    xt = rng.uniform(-1.8, 1.8, (600, 2))
+    grad = g.test_gradient(xt)
+    ref = o.test_gradient(xt)
+    # the solved alpha carries cond(Q_M) (as in test_spgp_2d_incremental): the bar in float is 4 x the measured distance between two
+    # correct implementations at that precision (the port in float vs the port in double)
+    o64 = oracle.Spgp(oracle.KERNELS[kernel], scale, z, np.float64)
+    assert o64.update(x, y, var)
+    ref64 = o64.test_gradient(xt)
+    floor = np.abs(ref - ref64).max() / np.abs(ref64).max()
+    tol = max(1e-4, 10 * floor) if dtype == np.float32 else 1e-8
+    err = np.abs(grad - ref64).max() / np.abs(ref64).max()
+    print(f"spgp gradient {kernel} {np.dtype(dtype).name}: CUDA vs double port {err:.2e}, float port vs double port {floor:.2e}")
+    assert err < tol, (err, floor)
+    raw = g.test_gradient(xt, raw_alpha=True)
+    assert np.abs(raw - o64.test_gradient(xt, raw_alpha=True)).max() / np.abs(raw).max() < (1e-4 if dtype == np.float32 else 1e-10)  # no solve: the budget itself
+    if dtype == np.float64:
+        h = 1e-5
+        for a in range(2):
+            e = np.zeros(2)
+            e[a] = h
+            fd = (g.test(xt + e)[0] - g.test(xt - e)[0]) / (2 * h)
+            assert np.abs(fd - grad[:, a]).max() / np.abs(grad).max() < 1e-6
+    ou = gp.SparsePseudoInputGaussianProcess("ou", 0.5, z, dtype)
+    ou.update(x, y, var)
+    with pytest.raises(gp.ErlGpError):
+        ou.test_gradient(xt)
+
+
 def test_vanilla_train_is_deterministic(gp):
     """The factorisation runs on three streams (block-column / panel look-ahead) and the alpha solve spins on flags: two
     trainings of the same data must give bit-identical L and alpha (a missing dependency shows up as a difference)."""

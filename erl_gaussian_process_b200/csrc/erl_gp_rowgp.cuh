@@ -66,6 +66,11 @@ namespace erl_gp {
 #else
         constexpr bool kBackSolveDinv = true;
 #endif
+#ifdef ERL_GP_ROWGP_LOOKAHEAD  // A/B: FactorizeMmaLa (pivot tile looked ahead, tiles dealt to the three warps that do not factorise).  Measured on
+        constexpr bool kLookAhead = true;   // C4: train alone 2.74 -> 2.62 ms, but fused 4.80 -> 5.38 ms (= train + predict: the idle warps
+#else                                       // of the default version are what lets the co-resident CTAs' predicts overlap) - off by default
+        constexpr bool kLookAhead = false;
+#endif
 #ifdef ERL_GP_PIVOT_RSQRT_CHAIN  // A/B: the round-1 pivot chain (refined MUFU.RSQ per column)
         constexpr bool kPivotRcpChain = false;
 #else
@@ -737,6 +742,259 @@ namespace erl_gp {
             return fail;
         }
 
+        // --------------------------------------------------------------------------------------
+        // FactorizeMma with the pivot tile LOOKED AHEAD (round 2; 128-thread instances, n <= 128).
+        //
+        // In FactorizeMma the serial chain of a panel is  update of the pivot tile (all earlier blocks, warp 0) -> pivot tile (warp 0, the
+        // other warps wait) -> L_i = P_i Dinv^T: 62 k cycles per factorisation, all of it on warp 0 (27 k of updates + 32 k of pivot
+        // tiles).  Here the pivot tile of panel kb + 1 is finished by the warp that will factorise it while panel kb is still in
+        // flight, and the other tiles are dealt to the three warps that are NOT factorising:
+        //   * panel kb is factorised by warp p = kb % 4; the tiles below (kb + 1 ...) are dealt to the helper warps p + 1, p + 2, p + 3,
+        //     tile kb + 1 always to p + 1 = the warp that factorises panel kb + 1;
+        //   * while p runs the pivot tile (shuffles, one warp), the helpers run the left-looking update of their tiles; the owner of
+        //     tile kb + 1 also accumulates that tile's product with ITSELF over the earlier blocks (its A fragments are, re-ordered,
+        //     the B fragments: no extra loads);
+        //   * after the barrier (Dinv of panel kb published) the helpers form L_i = P_i Dinv^T; the owner of tile kb + 1 adds the
+        //     product of the rows it has just computed with themselves (both operands are its own accumulator registers), subtracts
+        //     from the Gram tile and holds P_{kb+1,kb+1}: after the second barrier it factorises it at once.
+        // Serial chain per panel: pivot tile || update of <= 3 tiles, then 9 + 12 HMMA products.  Same instruction count as FactorizeMma.
+        // --------------------------------------------------------------------------------------
+        template<int XDIM, int NBLK>
+        __device__ __forceinline__ int
+        FactorizeMmaLa(const CovCoef cov, float *__restrict__ smem, const int n, const int nblk) {
+            using Lay = Layout<NBLK>;
+            static_assert(ThreadsFor<NBLK>::value == 128 && NBLK <= 8, "four warps, at most 7 tiles below a pivot tile");
+            float *lp = smem + Lay::kL;
+            const float4 *pts = reinterpret_cast<const float4 *>(smem + Lay::kPts);
+            float *rs = smem + Lay::kRs;
+            float *al = smem + Lay::kAl;
+            const float *sv = smem + Lay::kVar;
+            float *dinv = smem + Lay::kDinv;
+            const float2 *soa = reinterpret_cast<const float2 *>(smem + Lay::kSoa);
+            int *s_fail4 = reinterpret_cast<int *>(smem + Lay::kMisc);  // one slot per warp
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            const int g = lane >> 2, t = lane & 3;
+            int fail = 0;
+            float pt[2][4];  // the pivot tile this warp factorises next (accumulator layout)
+
+            // Gram tile K[row0 + (g, g + 8)][col0 + 8 nt + 2 t + (0, 1)] in the accumulator layout (fused noise diagonal, identity padding)
+            auto gram = [&](const int row0, const int col0, float (&kt)[2][4]) {
+                float2 pcx[2][XDIM];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                    for (int d = 0; d < XDIM; ++d) { pcx[nt][d] = soa[d * (Lay::kNp / 2) + (col0 + 8 * nt) / 2 + t]; }
+                }
+                const bool ragged = col0 + 16 > n;
+#pragma unroll
+                for (int hr = 0; hr < 2; ++hr) {
+                    const int row = row0 + g + 8 * hr;
+                    const float4 pr = pts[row];
+                    float negr[XDIM];
+                    negr[0] = -pr.x;
+                    if (XDIM > 1) { negr[XDIM > 1 ? 1 : 0] = -pr.y; }
+                    if (XDIM > 2) { negr[XDIM > 2 ? 2 : 0] = -pr.z; }
+                    const float diag = row < n ? 1.0f + sv[row] : 1.0f;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int col = col0 + 8 * nt + 2 * t;
+                        float2 kv = CovPair(cov, Dist2Pair<XDIM>(pcx[nt], negr));
+                        if (row >= n) { kv = make_float2(0.f, 0.f); }
+                        if (ragged) {
+                            if (col >= n) { kv.x = 0.f; }
+                            if (col + 1 >= n) { kv.y = 0.f; }
+                        }
+                        if (row == col) { kv.x = diag; }
+                        if (row == col + 1) { kv.y = diag; }
+                        kt[nt][2 * hr] = kv.x;
+                        kt[nt][2 * hr + 1] = kv.y;
+                    }
+                }
+            };
+
+            if (warp == 0) { gram(0, 0, pt); }
+            for (int kb = 0; kb < nblk; ++kb) {
+                const int c0 = 16 * kb;
+                const int p = kb & 3;         // the warp that factorises this panel's pivot tile
+                const int ntl = nblk - kb - 1;  // tiles below the pivot tile
+                const int stride_k = Lay::kNp - 16 * kb + 4;
+                float *panel = lp + (16 * kb * (Lay::kNp + 4) - 128 * kb * (kb - 1));  // element (row c0, column c0)
+                const int h = (warp - p - 1) & 3;  // helper index 0 .. 2 (3: the pivot warp)
+                // tile u (rows c0 + 16 (1 + u)) of helper h in slot s: h = 0: {0, 5}, h = 1: {1, 3, 6}, h = 2: {2, 4}
+                const int u1 = h == 0 ? 5 : (h == 1 ? 3 : 4);
+                const int tile_u[3] = {h, u1, h == 1 ? 6 : 99};
+                float acc[3][2][4], pn[2][4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { acc[0][nt][e] = acc[1][nt][e] = acc[2][nt][e] = pn[nt][e] = 0.f; }
+                }
+                if (warp != p) {
+                    // ---- helpers: left-looking update of my tiles (+ the self product of tile kb + 1 on helper 0) ----
+                    for (int jb = 0; jb < kb; ++jb) {
+                        const int stride = Lay::kNp - 16 * jb + 4;
+                        const float *cb = lp + (16 * jb * (Lay::kNp + 4) - 128 * jb * (jb - 1)) + 2 * t * stride + g;
+                        const float *brow = cb + (c0 - 16 * jb);
+#pragma unroll
+                        for (int kt = 0; kt < 2; ++kt) {
+                            float b[2][2];
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+                                b[nt][0] = brow[8 * kt * stride + 8 * nt];
+                                b[nt][1] = brow[(8 * kt + 1) * stride + 8 * nt];
+                            }
+                            uint32_t bl[2][2];
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) { Tf32LoPair(b[nt][0], b[nt][1], bl[nt][0], bl[nt][1]); }
+#pragma unroll
+                            for (int sl = 0; sl < 3; ++sl) {
+                                if (tile_u[sl] < ntl) {
+                                    const float *arow = brow + 16 * (1 + tile_u[sl]) + 8 * kt * stride;
+                                    const float a[4] = {arow[0], arow[8], arow[stride], arow[stride + 8]};
+                                    uint32_t ahi[4], alo[4];
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) { ahi[k] = __float_as_uint(a[k]); }
+                                    Tf32LoPair(a[0], a[1], alo[0], alo[1]);
+                                    Tf32LoPair(a[2], a[3], alo[2], alo[3]);
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], alo, __float_as_uint(b[nt][0]), __float_as_uint(b[nt][1])); }
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], ahi, bl[nt][0], bl[nt][1]); }
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) { MmaTf32(acc[sl][nt], ahi, __float_as_uint(b[nt][0]), __float_as_uint(b[nt][1])); }
+                                    if (sl == 0 && h == 0) {
+                                        // tile kb + 1 times itself: B[k][n] = L[row n][col k] are my own A entries (rows g -> n-tile 0, g + 8 -> n-tile 1)
+                                        MmaTf32(pn[0], alo, ahi[0], ahi[2]);
+                                        MmaTf32(pn[1], alo, ahi[1], ahi[3]);
+                                        MmaTf32(pn[0], ahi, alo[0], alo[2]);
+                                        MmaTf32(pn[1], ahi, alo[1], alo[3]);
+                                        MmaTf32(pn[0], ahi, ahi[0], ahi[2]);
+                                        MmaTf32(pn[1], ahi, ahi[1], ahi[3]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < 3; ++sl) {
+                        if (tile_u[sl] < ntl) {
+                            float kt[2][4];
+                            gram(c0 + 16 * (1 + tile_u[sl]), c0, kt);
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { acc[sl][nt][e] = kt[nt][e] - acc[sl][nt][e]; }
+                            }
+                        }
+                    }
+                } else {
+                    // ---- the pivot warp: P_kb,kb is in pt ----
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            panel[(8 * nt + 2 * t + e) * stride_k + g] = pt[nt][e];
+                            panel[(8 * nt + 2 * t + e) * stride_k + g + 8] = pt[nt][2 + e];
+                        }
+                    }
+                    const int r = lane & 15, hh = lane >> 4;
+                    float zp[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int jb = hh; jb < kb; jb += 2) {
+                        const int stride = Lay::kNp - 16 * jb + 4;
+                        const float *rowp = lp + (16 * jb * (Lay::kNp + 4) - 128 * jb * (jb - 1)) + (c0 + r - 16 * jb);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 z4 = *reinterpret_cast<const float4 *>(al + 16 * jb + 4 * j4);
+                            zp[0] = fmaf(rowp[(4 * j4) * stride], z4.x, zp[0]);
+                            zp[1] = fmaf(rowp[(4 * j4 + 1) * stride], z4.y, zp[1]);
+                            zp[2] = fmaf(rowp[(4 * j4 + 2) * stride], z4.z, zp[2]);
+                            zp[3] = fmaf(rowp[(4 * j4 + 3) * stride], z4.w, zp[3]);
+                        }
+                    }
+                    float zs = (zp[0] + zp[1]) + (zp[2] + zp[3]);
+                    zs += __shfl_xor_sync(kFull, zs, 16);
+                    float zacc = al[c0 + r] - zs;  // al[c0 + r] still holds y
+                    __syncwarp();
+                    float prow[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float pv = panel[c * stride_k + r];
+                        prow[c] = lane < 16 ? pv : (c == r ? 1.0f : 0.f);
+                    }
+                    PivotBlock<2>(prow, zacc, l, 0, c0, lane, fail, rs, al);
+                    __syncwarp();  // everybody has read the raw tile
+                    if (lane < 16) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { panel[c * stride_k + r] = c > r ? 0.f : l[c]; }
+                    } else {
+                        float *dst = dinv + kb * 16 * Lay::kDinvLd + r * Lay::kDinvLd;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) { *reinterpret_cast<float4 *>(dst + 4 * k4) = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]); }
+                    }
+                }
+                __syncthreads();  // #1: pivot tile, Dinv, rs, z of this panel are published
+                if (ntl > 0) {
+                    if (warp != p) {
+                        const float *dv = dinv + kb * 16 * Lay::kDinvLd + 2 * t * Lay::kDinvLd + g;
+#pragma unroll
+                        for (int sl = 0; sl < 3; ++sl) {
+                            if (tile_u[sl] < ntl) {
+                                float v[2][4];
+                                MulDinvT<Lay::kDinvLd>(acc[sl][0], acc[sl][1], dv, v);
+                                float *dst = panel + 16 * (1 + tile_u[sl]) + g;
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        dst[(8 * nt + 2 * t + e) * stride_k] = v[nt][e];
+                                        dst[(8 * nt + 2 * t + e) * stride_k + 8] = v[nt][2 + e];
+                                    }
+                                }
+                                if (sl == 0 && h == 0) {
+                                    // look-ahead: P_{kb+1,kb+1} = K - (earlier blocks) - L_{kb+1,kb} L_{kb+1,kb}^T, both operands from v
+#pragma unroll
+                                    for (int kt = 0; kt < 2; ++kt) {
+                                        uint32_t ahi[4], alo[4];
+                                        AccToA(v[kt], 1.0f, ahi, alo);
+                                        uint32_t bl0[2], bl1[2];
+                                        Tf32LoPair(v[kt][0], v[kt][1], bl0[0], bl0[1]);
+                                        Tf32LoPair(v[kt][2], v[kt][3], bl1[0], bl1[1]);
+                                        MmaTf32(pn[0], alo, __float_as_uint(v[kt][0]), __float_as_uint(v[kt][1]));
+                                        MmaTf32(pn[1], alo, __float_as_uint(v[kt][2]), __float_as_uint(v[kt][3]));
+                                        MmaTf32(pn[0], ahi, bl0[0], bl0[1]);
+                                        MmaTf32(pn[1], ahi, bl1[0], bl1[1]);
+                                        MmaTf32(pn[0], ahi, __float_as_uint(v[kt][0]), __float_as_uint(v[kt][1]));
+                                        MmaTf32(pn[1], ahi, __float_as_uint(v[kt][2]), __float_as_uint(v[kt][3]));
+                                    }
+                                    float kt2[2][4];
+                                    gram(c0 + 16, c0 + 16, kt2);
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) { pt[nt][e] = kt2[nt][e] - pn[nt][e]; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();  // #2: the whole panel is published
+                }
+            }
+            // every warp factorised some of the pivot tiles: the first failing column over the four of them
+            if (lane == 0) { s_fail4[warp] = fail; }
+            __syncthreads();
+            int first = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int f = s_fail4[w];
+                if (f != 0 && (first == 0 || f < first)) { first = f; }
+            }
+            __syncthreads();  // (slot 0 is rewritten by the caller)
+            return first;
+        }
+
         // alpha = L^-T z (al holds z on entry, alpha on exit); thread = column, blocked from the bottom
         // USE_DINV: the inverses of the diagonal blocks are in shared memory (FactorizeMma)
         template<int NBLK, bool USE_DINV>
@@ -1288,7 +1546,9 @@ namespace erl_gp {
                 }
                 __syncthreads();
                 int fail;
-                if constexpr (kMmaTrain || NBLK > 8) {  // the FFMA version is thread-per-row: n <= 128 only
+                if constexpr (kMmaTrain && kLookAhead && NBLK <= 8) {
+                    fail = FactorizeMmaLa<XDIM, NBLK>(cov, smem, n, nblk);
+                } else if constexpr (kMmaTrain || NBLK > 8) {  // the FFMA version is thread-per-row: n <= 128 only
                     fail = FactorizeMma<XDIM, NBLK>(cov, smem, n, nblk);
                 } else {
                     fail = Factorize<XDIM, NBLK>(cov, smem, n, nblk);

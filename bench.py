@@ -355,6 +355,8 @@ def main():
     ap.add_argument("--rowgp-tc", type=int, default=-1, choices=[-1, 0, 1],
                     help="fused FP32 kernel for n <= 128: 1 = tcgen05 / TMEM kernel, 0 = mma.sync kernel, -1 = library default (mma.sync)")
     ap.add_argument("--no-tc-variant", action="store_true", help="N=1: do not time the tcgen05 kernel in a child process beside the default kernel")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="default workload, N=1: do not append the short child runs of the other BASELINE.json configurations (`other_workloads` in the JSON line)")
     ap.add_argument("--phase", default="fused", choices=["fused", "train", "predict", "split"],
                     help="diagnostics only: time the train kernel, the predict kernel or both as separate launches (the reported metric is always the fused step)")
     args = ap.parse_args()
@@ -667,6 +669,26 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_baseline(w, args.ref_sample)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and args.workload == "c4" and args.phase == "fused" and not args.no_other_workloads and not tc_now and not args.num_gps:
+            # The other BASELINE.json configurations, each as a short child run of this same script (same timing rules, clocks
+            # sampled inside the child): the headline stays C4, these put a number next to every configuration in the same record.
+            import subprocess
+
+            others = {}
+            for name, extra in (("c4f64", ["--steps", "5"]), ("c1", ["--steps", "10"]), ("c2", ["--steps", "10"]), ("c3", ["--steps", "10"]), ("c3n256", ["--steps", "10"]),
+                                ("spgp", ["--steps", "5"]), ("c5", ["--steps", "1", "--no-e2e"])):
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--warmup", "3" if name != "c5" else "1", "--no-cpu-baseline", "--no-other-workloads"] + extra
+                try:
+                    res = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+                    child = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+                    others[name] = {"workload": child["config"]["workload"], "ms_per_step": child["ms_per_step"], "value": child["value"], "unit": child["unit"], "dtype": child["dtype"],
+                                    "steps": child["steps"], "warmup": child["warmup"], "e2e_ms_per_step": (child.get("e2e") or {}).get("ms_per_step"),
+                                    "roofline": {k: child["roofline"].get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel")}, "clocks": child.get("clocks")}
+                    if "phases" in child:
+                        others[name]["phases"] = child["phases"]
+                except Exception as exc:
+                    others[name] = {"unavailable": repr(exc)[:200]}
+            line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -233,7 +233,11 @@ namespace erl_gp {
         Context *ctx = gp->ctx;
         if (!gp->trained) { return SetError(ctx, ERL_GP_STATUS_NOT_TRAINED, "vanilla: not trained"); }
         const long n = gp->n;
-        if (k != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(k, sizeof(T) * ld_k, gp->k.ptr, sizeof(T) * n, sizeof(T) * n, n, cudaMemcpyDeviceToHost, ctx->stream)); }
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        if (k != nullptr) {
+            if (gp->k.capacity < static_cast<size_t>(n) * n) { return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "vanilla: this GP is a replica (erl_gp_vanilla_replicate): Ktrain stays with the GP it was trained on"); }
+            ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(k, sizeof(T) * ld_k, gp->k.ptr, sizeof(T) * n, sizeof(T) * n, n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         if (l != nullptr) { ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(l, sizeof(T) * ld_l, gp->l.ptr, sizeof(T) * n, sizeof(T) * n, n, cudaMemcpyDeviceToHost, ctx->stream)); }
         if (alpha != nullptr) {
             ERL_GP_CUDA_OK(ctx, cudaMemcpy2DAsync(alpha, sizeof(T) * ld_a, gp->alpha.ptr, sizeof(T) * n, sizeof(T) * n, gp->y_dim, cudaMemcpyDeviceToHost, ctx->stream));

@@ -225,6 +225,69 @@ namespace erl_gp {
         DiagInverse(d, dinv, lane, invs);
     }
 
+    // ---- 16x16 diagonal block AND its inverse in one elimination (round 2) ------------------
+    // Lanes 0 .. 15 own the rows of the block, lanes 16 + j start from the unit vector e_j and run the very same instructions: with
+    // sc = a[c] / d the update a[cc] -= sc A[cc][c] is, on e_j, the forward substitution of L x = e_j, so lane 16 + j ends with column j
+    // of L^-1 - the inverse costs no instruction of its own (DiagInverse was a second 136-step dependent chain).  The shuffles read
+    // the RAW entries A[cc][c] (symmetric tile), so only the reciprocal of the pivot (MUFU seed + Newton) sits on the serial chain; the
+    // square roots that scale the eliminated entries into L are taken after the loop, one per lane.  d: col-major 16 x 16, full
+    // symmetric tile on entry; dinv: row-major, stride DinvLd.  Returns 0 or the 1-based failing column (warp-uniform).
+    __device__ __forceinline__ float
+    RcpChain(const float d) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+        return r * fmaf(-d, r, 2.0f);
+    }
+
+    __device__ __forceinline__ double
+    RcpChain(const double d) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+        r = fma(r, fma(-d, r, 1.0), r);
+        return fma(r, fma(-d, r, 1.0), r);
+    }
+
+    template<typename T>
+    __device__ __forceinline__ int
+    DiagCholeskyInverse(T *d, T *dinv, const int lane) {
+        constexpr unsigned kFull = 0xffffffffu;
+        constexpr int kLd = DinvLd<T>::value;
+        const int r = lane & (kNB - 1);
+        T a[kNB], l[kNB];
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+            const T v = r >= c ? d[r + kNB * c] : d[c + kNB * r];  // the block holds its lower triangle: read the mirror entry above the diagonal
+            a[c] = lane < kNB ? v : (c == r ? T(1) : T(0));
+        }
+        int fail = 0;
+        T dmine = T(1);
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+            const T dc = __shfl_sync(kFull, a[c], c);
+            T t[kNB];
+#pragma unroll
+            for (int cc = c + 1; cc < kNB; ++cc) { t[cc] = __shfl_sync(kFull, a[c], cc); }
+            if (!(dc > T(0)) && fail == 0) { fail = c + 1; }
+            const T sc = a[c] * RcpChain(dc);
+#pragma unroll
+            for (int cc = c + 1; cc < kNB; ++cc) { a[cc] -= sc * t[cc]; }
+            l[c] = a[c];
+            if (r == c) { dmine = dc; }
+        }
+        const T rsv = InvSqrt(dmine);
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) { l[c] *= __shfl_sync(kFull, rsv, c); }
+        __syncwarp();  // every lane has read the raw block
+        if (lane < kNB) {
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) { d[lane + kNB * c] = c <= lane ? l[c] : T(0); }
+        } else {
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) { dinv[c * kLd + r] = l[c]; }  // column r of the inverse: Dinv[c][r]
+        }
+        return fail;
+    }
+
     // ---- blocked right-looking Cholesky of the block-packed lower triangle in smem ---------
     // On return lp holds L (diagonal blocks with zero strict upper), dinv the inverses of the
     // diagonal blocks.  *s_fail (shared) = 0 or the 1-based failing column.
@@ -239,11 +302,16 @@ namespace erl_gp {
             T *dkk = lp + LowerBlock(kb, kb);
             T *dinv_k = dinv + kb * kNB * kLd;
             if (warp == 0) {
+#ifdef ERL_GP_DIAG_TWO_PASS  // A/B: round-1 version (Cholesky with the scaled entries on the shuffle chain, then a separate inverse)
                 T invs[kNB];
                 const int fail = DiagCholesky(dkk, lane, invs);
                 if (fail != 0 && lane == 0 && *s_fail == 0) { *s_fail = kb * kNB + fail; }
                 __syncwarp();
                 DiagInverse(dkk, dinv_k, lane, invs);
+#else
+                const int fail = DiagCholeskyInverse(dkk, dinv_k, lane);
+                if (fail != 0 && lane == 0 && *s_fail == 0) { *s_fail = kb * kNB + fail; }
+#endif
             }
             __syncthreads();
             const int m = nblk - kb - 1;  // block rows below the diagonal block

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "erl_gp_batched.cuh"
+#include "erl_gp_rowgp64.cuh"
 
 namespace erl_gp {
 
@@ -769,6 +770,27 @@ namespace erl_gp {
         }
     }
 
+    // L11 (in place) and its inverse for one 128 x 128 diagonal block.  FP64: the DMMA kernel of erl_gp_rowgp64.cuh (round 2; the
+    // generic shared-memory kernel above with ERL_GP_DIAG_LEGACY=1); FP32: the generic kernel.
+    template<typename T>
+    static void
+    LaunchDiagFactor(cudaStream_t stream, T *a, const long ld, const int nk, T *linv, int *info, const int col_offset) {
+        using Smem = BatchSmem<T, 1, kDiagBlocks>;
+        if constexpr (sizeof(T) == 8) {
+            static const bool legacy = std::getenv("ERL_GP_DIAG_LEGACY") != nullptr;
+            static const bool attr = [] {
+                cudaFuncSetAttribute(rowgp64::DiagFactor64Kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rowgp64::DiagFactor64SmemBytes()));
+                return true;
+            }();
+            (void) attr;
+            if (!legacy) {
+                rowgp64::DiagFactor64Kernel<8><<<1, rowgp64::kThreads, rowgp64::DiagFactor64SmemBytes(), stream>>>(a, ld, nk, linv, info, col_offset);
+                return;
+            }
+        }
+        DiagFactorKernel<T><<<1, kBatchThreads, Smem::kBytes, stream>>>(a, ld, nk, linv, info, col_offset);
+    }
+
     // Look-ahead of one diagonal block on the stream `la`: once `chain` has produced the k columns at `a` (rows of the
     // block), update the nt x nt diagonal tile `c` with them and factor it; ev_la_done fires when L11 and its inverse exist.
     template<typename T>
@@ -778,7 +800,7 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_la_start, chain));
         ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(la, ctx->ev_la_start, 0));
         SyrkTileKernel<T><<<dim3(4, 4), 256, 0, la>>>(nt, k, a, lda, c, ldc);
-        DiagFactorKernel<T><<<1, kBatchThreads, Smem::kBytes, la>>>(c, ldc, nt, linv_k, info, static_cast<int>(col));
+        LaunchDiagFactor<T>(la, c, ldc, nt, linv_k, info, static_cast<int>(col));
         ctx->launches += 2;
         ERL_GP_CUDA_OK(ctx, cudaGetLastError());
         ERL_GP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_la_done, la));
@@ -808,7 +830,7 @@ namespace erl_gp {
                 ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(chain, ctx->ev_la_done, 0));
                 diag_done = false;
             } else {
-                DiagFactorKernel<T><<<1, kBatchThreads, Smem::kBytes, chain>>>(l + k0 + k0 * ld, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
+                LaunchDiagFactor<T>(chain, l + k0 + k0 * ld, ld, static_cast<int>(nk), linv_k, info, static_cast<int>(k0));
                 ctx->launches += 1;
                 ERL_GP_CUDA_OK(ctx, cudaGetLastError());
             }

@@ -505,6 +505,124 @@ namespace erl_gp {
             }
         }
 
+        // ------------------------------------------------------------------------------------------------------------
+        // The 128 x 128 diagonal block of the dense blocked Cholesky (erl_gp_dense.cu: Potrf keeps the INVERSE of every diagonal block so
+        // that the panel solve and every later triangular solve are GEMMs).  Same machinery as a partition GP: the tile is loaded into the
+        // packed layout, factorised in place by Factorize (DMMA updates, shuffle pivot tiles, Dinv of the 16 x 16 blocks), and the full
+        // inverse is the transposed substitution of the predict applied to the identity: V^T = I L^-T, so the warp that owns the eight
+        // "queries" e_q ... e_{q+7} ends with columns q ... q + 7 of L^-1 (zero above the diagonal: the walk starts at q's own block).
+        // ------------------------------------------------------------------------------------------------------------
+        template<int NBLK>
+        __device__ __forceinline__ void
+        InverseFromIdentity(const double *__restrict__ smem, const int nblk, double *__restrict__ linv, const int ld_inv) {
+            using Lay = Layout<NBLK>;
+            const double *lp = smem + Lay::kL;
+            const double *dinv = smem + Lay::kDinv;
+            const int tid = threadIdx.x;
+            const int warp = __shfl_sync(kFull, tid >> 5, 0);
+            const int lane = tid & 31;
+            const int g = lane >> 2, t = lane & 3;
+            for (int pass = 0; pass < 2 * NBLK / kWarps; ++pass) {
+                const int q0 = 8 * (kWarps * pass + warp);  // my eight columns of the inverse
+                if (q0 >= 16 * nblk) { continue; }
+                const int jq = q0 >> 4;
+                double x[2 * NBLK][2];
+#pragma unroll
+                for (int ct = 0; ct < 2 * NBLK; ++ct) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { x[ct][e] = (8 * ct + 2 * t + e == q0 + g) ? 1.0 : 0.0; }
+                }
+#pragma unroll
+                for (int j = 0; j < NBLK; ++j) {
+                    if (j >= jq && j < nblk) {
+                        const double *dv = dinv + j * 16 * Lay::kDinvLd + g;
+                        double v[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                            for (int ck = 0; ck <= ch; ++ck) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) { Dmma884(v[ch], x[2 * j + ck][e], dv[(8 * ck + 2 * t + e) * Lay::kDinvLd + 8 * ch]); }
+                            }
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) { linv[(16 * j + 8 * ch + 2 * t + e) + (q0 + g) * ld_inv] = v[ch][e]; }  // Linv[row][column q0 + g]
+                        }
+                        const double nv[2][2] = {{-v[0][0], -v[0][1]}, {-v[1][0], -v[1][1]}};
+                        const int stride = Lay::Stride(j);
+                        const double *base = lp + Lay::Base(j) + g;
+#pragma unroll
+                        for (int i = j + 1; i < NBLK; ++i) {
+                            if (i < nblk) {
+#pragma unroll
+                                for (int ck = 0; ck < 2; ++ck) {
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        const double *col = base + (8 * ck + 2 * t + e) * stride + 16 * (i - j);
+                                        Dmma884(x[2 * i], nv[ck][e], col[0]);
+                                        Dmma884(x[2 * i + 1], nv[ck][e], col[8]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // a: nk x nk (ld) lower triangle of the diagonal block, factorised in place; linv: 128 x 128 (ld 128), identity-padded inverse
+        template<int NBLK>
+        __global__ void __launch_bounds__(kThreads, 1)
+        DiagFactor64Kernel(double *__restrict__ a, const long ld, const int nk, double *__restrict__ linv, int *__restrict__ info, const int col_offset) {
+            static_assert(NBLK == 8, "128 x 128 diagonal blocks");
+            using Lay = Layout<NBLK>;
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            double *smem = reinterpret_cast<double *>(smem_raw);
+            double *lp = smem + Lay::kL;
+            double *al = smem + Lay::kAl;
+            int *s_fail = reinterpret_cast<int *>(smem + Lay::kMisc);
+            const int tid = threadIdx.x;
+            const int warp = tid >> 5, lane = tid & 31;
+            const int nblk = (nk + 15) >> 4;
+            const int npr = 16 * nblk;
+            // the tile into the packed layout (column block cb keeps rows >= 16 cb; the diagonal tiles in full: mirror entries)
+            for (int cb = 0; cb < nblk; ++cb) {
+                double *blk = lp + Lay::Base(cb);
+                const int stride = Lay::Stride(cb);
+                const int rows = npr - 16 * cb;
+                for (int c = warp; c < 16; c += kWarps) {
+                    const int col = 16 * cb + c;
+                    for (int r = lane; r < rows; r += 32) {
+                        const int row = 16 * cb + r;
+                        double v = row == col ? 1.0 : 0.0;
+                        if (row < nk && col < nk) { v = row >= col ? a[row + static_cast<long>(col) * ld] : a[col + static_cast<long>(row) * ld]; }
+                        blk[c * stride + r] = v;
+                    }
+                }
+            }
+            for (int e = tid; e < Lay::kNp; e += kThreads) { al[e] = 0.0; }  // (the z that rides along with the pivot tiles is not used here)
+            __syncthreads();
+            const int fail = Factorize<1, NBLK>(smem, nk, nblk);
+            if (tid == 0) { *s_fail = fail; }
+            __syncthreads();
+            if (*s_fail != 0 && tid == 0 && *info == 0) { *info = col_offset + *s_fail; }
+            for (int c = warp; c < nk; c += kWarps) {
+                const int cb = c >> 4;
+                const double *col = lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb) - 16 * cb;
+                for (int r = lane; r < nk; r += 32) { a[r + static_cast<long>(c) * ld] = r >= 16 * cb ? col[r] : 0.0; }
+            }
+            for (int e = tid; e < 128 * 128; e += kThreads) { linv[e] = ((e & 127) == (e >> 7) && (e >> 7) >= npr) ? 1.0 : 0.0; }
+            __syncthreads();
+            InverseFromIdentity<NBLK>(smem, nblk, linv, 128);
+        }
+
+        inline size_t
+        DiagFactor64SmemBytes() {
+            return Layout<8>::kBytes;
+        }
+
         template<int XDIM, int NBLK, int MODE>
         __global__ void __launch_bounds__(kThreads, 2)
         RowGp64Kernel(const BatchParams<double> p) {

@@ -96,34 +96,12 @@ namespace erl_gp {
 
             __device__ __forceinline__ static double
             Sqrt(const double r2) {
-                const double y = rsqrt(r2);
-                double r = r2 * y;
-                r = fma(0.5 * y, fma(-r, r, r2), r);
-                return r2 > 0.0 ? r : 0.0;
+                return FastSqrt(r2);  // erl_gp_common.cuh
             }
 
             __device__ __forceinline__ static double
-            Exp(const double x) {  // x <= 0
-                constexpr double kLog2e = 1.4426950408889634074, kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10, kMagic = 6755399441055744.0;
-                const double kd = fma(x, kLog2e, kMagic) - kMagic;  // rint(x log2 e)
-                double r = fma(kd, -kLn2Hi, x);
-                r = fma(kd, -kLn2Lo, r);
-                double p = 1.0 / 479001600.0;
-                p = fma(p, r, 1.0 / 39916800.0);
-                p = fma(p, r, 1.0 / 3628800.0);
-                p = fma(p, r, 1.0 / 362880.0);
-                p = fma(p, r, 1.0 / 40320.0);
-                p = fma(p, r, 1.0 / 5040.0);
-                p = fma(p, r, 1.0 / 720.0);
-                p = fma(p, r, 1.0 / 120.0);
-                p = fma(p, r, 1.0 / 24.0);
-                p = fma(p, r, 1.0 / 6.0);
-                p = fma(p, r, 0.5);
-                p = fma(p, r, 1.0);
-                p = fma(p, r, 1.0);
-                const int k = static_cast<int>(kd);
-                const double scale = __hiloint2double((k + 1023) << 20, 0);  // 2^k, k >= -1022
-                return x > -708.0 ? p * scale : 0.0;
+            Exp(const double x) {
+                return FastExpNeg(x);
             }
 
             // (a __noinline__ call instead of 32 inlined copies per predict pass was measured: no gain, 16.04 vs 16.08 ms)

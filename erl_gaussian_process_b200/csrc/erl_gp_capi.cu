@@ -199,6 +199,7 @@ namespace erl_gp {
         if (b->copy_in == nullptr) {
             ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
             ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
+            ERL_GP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&b->compute2, cudaStreamNonBlocking));
         }
         while (static_cast<long>(b->ev_in.size()) < num_chunks) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -211,6 +212,11 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, cudaEventRecord(b->ev_kernel[0], ctx->stream));
         ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(b->copy_in, b->ev_kernel[0], 0));
         ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(b->copy_out, b->ev_kernel[0], 0));
+        ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(b->compute2, b->ev_kernel[0], 0));
+        // Chunks alternate between two compute streams: kernels of one stream run back to back, so the last, partly filled wave of chunk
+        // c would leave SMs idle until chunk c + 1 may start; on two streams the head of c + 1 fills them (the chunks are independent).
+        static const bool one_stream = std::getenv("ERL_GP_BATCH_ONE_COMPUTE_STREAM") != nullptr;  // A/B
+        cudaStream_t const main_stream = ctx->stream;
         ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->q_offsets.ptr, q_offsets, sizeof(long) * (num_gps + 1), cudaMemcpyHostToDevice, b->copy_in));
         // Uneven cut: a short first chunk (the first kernel starts after 1/4 of a nominal chunk's upload instead of a whole one)
         // and a short last chunk (a short download after the last kernel); the interior is cut evenly.
@@ -232,8 +238,9 @@ namespace erl_gp {
             ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->var.ptr + g0 * max_n, var + g0 * max_n, sizeof(T) * gn, cudaMemcpyHostToDevice, b->copy_in));
             if (t1 > t0) { ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->q_x.ptr + t0 * d, q_x + t0 * d, sizeof(T) * (t1 - t0) * d, cudaMemcpyHostToDevice, b->copy_in)); }
             ERL_GP_CUDA_OK(ctx, cudaEventRecord(b->ev_in[c], b->copy_in));
-            ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_in[c], 0));
-            if (t1 > t0) { ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(b->valid.ptr + t0, 0, t1 - t0, ctx->stream)); }
+            cudaStream_t const cs = (!one_stream && (c & 1)) ? b->compute2 : main_stream;
+            ERL_GP_CUDA_OK(ctx, cudaStreamWaitEvent(cs, b->ev_in[c], 0));
+            if (t1 > t0) { ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(b->valid.ptr + t0, 0, t1 - t0, cs)); }
             // L is always materialised in HBM (downloaded only on demand)
             BatchParams<T> p = b->Params(min_num_samples, 1);
             p.num_gps = static_cast<int>(g1 - g0);
@@ -249,10 +256,12 @@ namespace erl_gp {
             p.mean = mean != nullptr ? b->mean.ptr : nullptr;
             p.variance = variance != nullptr ? b->variance.ptr : nullptr;
             p.valid = b->valid.ptr;
+            ctx->stream = cs;  // LaunchBatch launches on the context's stream
             const int rc = LaunchBatch<T>(ctx, p, static_cast<int>(d), kBatchTrainPredict, 1);
+            ctx->stream = main_stream;
             if (rc != ERL_GP_STATUS_OK) { return rc; }
-            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->info_host.ptr + g0, b->info.ptr + g0, sizeof(int) * (g1 - g0), cudaMemcpyDeviceToHost, ctx->stream));
-            ERL_GP_CUDA_OK(ctx, cudaEventRecord(b->ev_kernel[c], ctx->stream));
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(b->info_host.ptr + g0, b->info.ptr + g0, sizeof(int) * (g1 - g0), cudaMemcpyDeviceToHost, cs));
+            ERL_GP_CUDA_OK(ctx, cudaEventRecord(b->ev_kernel[c], cs));
         }
         // ---- downloads, chunk by chunk as the kernels finish ----
         std::vector<T> tmp;
@@ -295,6 +304,7 @@ namespace erl_gp {
             }
         }
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(b->copy_out));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(b->compute2));
         ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         return ERL_GP_STATUS_OK;
     }

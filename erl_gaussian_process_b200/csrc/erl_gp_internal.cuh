@@ -162,13 +162,14 @@ namespace erl_gp {
         DeviceBuffer<T> q_x, mean, variance;
         DeviceBuffer<uint8_t> valid;
         // host-buffer pipeline (BatchTrainPredictHost): copy streams and per-chunk events, created on first use
-        cudaStream_t copy_in = nullptr, copy_out = nullptr;
+        cudaStream_t copy_in = nullptr, copy_out = nullptr, compute2 = nullptr;  // compute2: odd chunks of the host-buffer pipeline
         std::vector<cudaEvent_t> ev_in, ev_kernel;
         PinnedBuffer<int> info_host;
 
         ~Batch() {
             if (copy_in != nullptr) { cudaStreamDestroy(copy_in); }
             if (copy_out != nullptr) { cudaStreamDestroy(copy_out); }
+            if (compute2 != nullptr) { cudaStreamDestroy(compute2); }
             for (cudaEvent_t e: ev_in) { cudaEventDestroy(e); }
             for (cudaEvent_t e: ev_kernel) { cudaEventDestroy(e); }
         }

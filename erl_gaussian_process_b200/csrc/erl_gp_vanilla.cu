@@ -271,6 +271,25 @@ namespace erl_gp {
         }
     }
 
+    // diagonal-Q_M mode (src/sparse_pseudo_input_gp.cpp:775-776): q[r] += sum_i Ks[r][i] K_MN[r][i]
+    template<typename T>
+    __global__ void
+    SpgpDiagUpdateKernel(const long m, const long n, const T *__restrict__ k_s, const T *__restrict__ k_mn, T *__restrict__ q) {
+        const long r = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (r >= m) { return; }
+        T s = 0;
+        for (long i = 0; i < n; ++i) { s += k_s[r + i * m] * k_mn[r + i * m]; }
+        q[r] += s;
+    }
+
+    // out[r] = fill (a == nullptr) or a[r] / q[r] (TestResult ctor in diagonal mode, :100-101)
+    template<typename T>
+    __global__ void
+    SpgpDiagSolveKernel(const long m, const T *__restrict__ a, const T *__restrict__ q, const T fill, T *__restrict__ out) {
+        const long r = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (r < m) { out[r] = a != nullptr ? a[r] / q[r] : fill; }
+    }
+
     template<typename T>
     struct Spgp {
         Context *ctx = nullptr;
@@ -278,6 +297,8 @@ namespace erl_gp {
         int kernel = 0;
         T scale = T(1);
         bool l_qm_updated = false;
+        bool diagonal_qm = false;  // Setting::diagonal_qm (sparse_pseudo_input_gp.hpp:57): Q_M kept as its diagonal only
+        DeviceBuffer<T> q_diag;
         DeviceBuffer<T> z, k_m, l_km, linv_km, q_m, l_qm, linv_qm, alpha, alpha_solved, panel;
         DeviceBuffer<int> info;
         DeviceBuffer<T> x, y, var, k_mn, k_s, w, s_buf, sumsq, sumsq2, xt, mean, variance;
@@ -364,9 +385,15 @@ namespace erl_gp {
         SpgpScaleKernel<T><<<grid, 256, 0, ctx->stream>>>(m, n, gp->k_mn.ptr, gp->sumsq.ptr, gp->var.ptr, gp->k_s.ptr);
         ctx->launches += 1;
         ERL_GP_CUDA_OK(ctx, cudaGetLastError());
-        // Q_M += Ks K_MN^T (:778) ; alpha += Ks y (:780)
-        rc = Gemm<T>(ctx, kOpN, kOpT, m, m, n, T(1), gp->k_s.ptr, m, gp->k_mn.ptr, m, T(1), gp->q_m.ptr, m, false);
-        if (rc != ERL_GP_STATUS_OK) { return rc; }
+        // Q_M += Ks K_MN^T (:778), or its diagonal only (:775-776); alpha += Ks y (:780)
+        if (gp->diagonal_qm) {
+            SpgpDiagUpdateKernel<T><<<static_cast<unsigned>(CeilDiv(m, 128)), 128, 0, ctx->stream>>>(m, n, gp->k_s.ptr, gp->k_mn.ptr, gp->q_diag.ptr);
+            ctx->launches += 1;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        } else {
+            rc = Gemm<T>(ctx, kOpN, kOpT, m, m, n, T(1), gp->k_s.ptr, m, gp->k_mn.ptr, m, T(1), gp->q_m.ptr, m, false);
+            if (rc != ERL_GP_STATUS_OK) { return rc; }
+        }
         rc = Gemm<T>(ctx, kOpN, kOpN, m, 1, n, T(1), gp->k_s.ptr, m, gp->y.ptr, n, T(1), gp->alpha.ptr, m, false);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         gp->l_qm_updated = false;
@@ -380,6 +407,13 @@ namespace erl_gp {
         if (gp->l_qm_updated) { return ERL_GP_STATUS_OK; }
         Context *ctx = gp->ctx;
         const long m = gp->m;
+        if (gp->diagonal_qm) {  // no L_QM (:839); alpha / diag(Q_M) (:100-101)
+            SpgpDiagSolveKernel<T><<<static_cast<unsigned>(CeilDiv(m, 128)), 128, 0, ctx->stream>>>(m, gp->alpha.ptr, gp->q_diag.ptr, T(0), gp->alpha_solved.ptr);
+            ctx->launches += 1;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+            gp->l_qm_updated = true;
+            return ERL_GP_STATUS_OK;
+        }
         int rc = CopyLower<T>(ctx, m, gp->q_m.ptr, m, gp->l_qm.ptr, m);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         rc = Potrf<T>(ctx, m, gp->l_qm.ptr, m, gp->linv_qm.ptr, gp->panel.ptr, gp->info.ptr + 1);
@@ -400,6 +434,9 @@ namespace erl_gp {
         if (gp == nullptr || x_test == nullptr || num_test <= 0) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
         Context *ctx = gp->ctx;
         ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        if (gp->diagonal_qm && var != nullptr) {
+            return SetError(ctx, ERL_GP_STATUS_UNSUPPORTED, "spgp: no variance in diagonal_qm mode (the reference never builds the L_QM its variance solves with, src/sparse_pseudo_input_gp.cpp:304-310, 839)");
+        }
         int rc = SpgpPrepareLqm(gp);
         if (rc != ERL_GP_STATUS_OK) { return rc; }
         const long m = gp->m, d = gp->x_dim;
@@ -502,6 +539,41 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // Setting::diagonal_qm (ctor :346-347: Q_M = ones(M)); call before the first update: Q_M and alpha are reset
+    template<typename T>
+    static int
+    SpgpSetDiagonalQm(Spgp<T> *gp, int on) {
+        if (gp == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        const long m = gp->m;
+        gp->diagonal_qm = on != 0;
+        gp->l_qm_updated = false;
+        ERL_GP_CUDA_OK(ctx, cudaMemsetAsync(gp->alpha.ptr, 0, sizeof(T) * m, ctx->stream));
+        if (on) {
+            ERL_GP_CUDA_OK(ctx, gp->q_diag.Reserve(m));
+            SpgpDiagSolveKernel<T><<<static_cast<unsigned>(CeilDiv(m, 128)), 128, 0, ctx->stream>>>(m, nullptr, nullptr, T(1), gp->q_diag.ptr);
+            ctx->launches += 1;
+            ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+        } else {
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->q_m.ptr, gp->k_m.ptr, sizeof(T) * m * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
+    template<typename T>
+    static int
+    SpgpGetQmDiagonal(Spgp<T> *gp, T *q) {
+        if (gp == nullptr || q == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        if (!gp->diagonal_qm) { return SetError(ctx, ERL_GP_STATUS_INVALID_ARGUMENT, "spgp: not in diagonal_qm mode"); }
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(q, gp->q_diag.ptr, sizeof(T) * gp->m, cudaMemcpyDeviceToHost, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return ERL_GP_STATUS_OK;
+    }
+
     template<typename T>
     static int
     SpgpGet(Spgp<T> *gp, T *q_m, T *alpha, T *l_km, T *l_qm) {
@@ -590,6 +662,8 @@ extern "C" {
     int erl_gp_spgp_test_##SFX(erl_gp_spgp_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *mean, T *var) {                                                         \
         return SpgpTest<T>(gp, num_test, x_test, ld_xt, mean, var);                                                                                                          \
     }                                                                                                                                                                        \
+    int erl_gp_spgp_set_diagonal_qm_##SFX(erl_gp_spgp_##SFX *gp, int on) { return SpgpSetDiagonalQm<T>(gp, on); }                                                            \
+    int erl_gp_spgp_get_qm_diagonal_##SFX(erl_gp_spgp_##SFX *gp, T *q) { return SpgpGetQmDiagonal<T>(gp, q); }                                                               \
     int erl_gp_spgp_test_gradient_##SFX(erl_gp_spgp_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *grad, int raw_alpha) {                                         \
         return SpgpTestGradient<T>(gp, num_test, x_test, ld_xt, grad, raw_alpha);                                                                                            \
     }                                                                                                                                                                        \

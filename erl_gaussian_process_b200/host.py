@@ -788,6 +788,22 @@ class SparsePseudoInputGaussianProcess:
         check(self.ctx.fn("erl_gp_spgp_test", self.dtype)(self.handle, C.c_long(t), _p(xt), C.c_long(self.x_dim), _p(mean), _p(var)), "spgp_test", self.ctx.handle)
         return mean, var
 
+    def set_diagonal_qm(self, on=True):
+        """Setting::diagonal_qm: Q_M kept as its diagonal (call before the first update); mean and gradient only."""
+        check(self.ctx.fn("erl_gp_spgp_set_diagonal_qm", self.dtype)(self.handle, C.c_int(int(on))), "spgp_set_diagonal_qm", self.ctx.handle)
+
+    def get_qm_diagonal(self):
+        q = np.empty(self.m, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_spgp_get_qm_diagonal", self.dtype)(self.handle, _p(q)), "spgp_get_qm_diagonal", self.ctx.handle)
+        return q
+
+    def test_mean(self, x_test):
+        xt = np.ascontiguousarray(x_test, dtype=self.dtype)
+        t = xt.shape[0]
+        mean = np.empty(t, dtype=self.dtype)
+        check(self.ctx.fn("erl_gp_spgp_test", self.dtype)(self.handle, C.c_long(t), _p(xt), C.c_long(self.x_dim), _p(mean), None), "spgp_test", self.ctx.handle)
+        return mean
+
     def test_gradient(self, x_test, raw_alpha=False):
         """TestResult::GetGradient (src/sparse_pseudo_input_gp.cpp:187-278): gradient of the predictive mean, (T, x_dim).
         raw_alpha=True dots with the unsolved alpha, as the reference's batched accessor does (:212)."""

@@ -394,6 +394,13 @@ int erl_gp_spgp_test_f32(erl_gp_spgp_f32 *gp, long num_test, const float *x_test
                          float *var);
 int erl_gp_spgp_test_f64(erl_gp_spgp_f64 *gp, long num_test, const double *x_test, long ld_xt, double *mean,
                          double *var);
+/* Setting::diagonal_qm (sparse_pseudo_input_gp.hpp:57): Q_M is kept as its diagonal (ctor :346-347 ones(M), update :775-776,
+ * alpha / diag(Q_M) at test time :100-101).  Call before the first update (Q_M and alpha are reset).  Mean and gradient only: the
+ * reference's variance solves with an L_QM this mode never builds (:304-310, :839), erl_gp_spgp_test_* rejects var != NULL. */
+int erl_gp_spgp_set_diagonal_qm_f32(erl_gp_spgp_f32 *gp, int on);
+int erl_gp_spgp_set_diagonal_qm_f64(erl_gp_spgp_f64 *gp, int on);
+int erl_gp_spgp_get_qm_diagonal_f32(erl_gp_spgp_f32 *gp, float *q);
+int erl_gp_spgp_get_qm_diagonal_f64(erl_gp_spgp_f64 *gp, double *q);
 /* TestResult::GetGradient (src/sparse_pseudo_input_gp.cpp:187-278): gradient of the predictive mean, x_dim x num_test col-major.
  * raw_alpha = 0: dotted with Q_M^-1 alpha like GetMean and the per-index accessor (:252); raw_alpha = 1: with the unsolved alpha,
  * as the reference's batched accessor does (:212).  RBF and Matern32 only. */

@@ -332,6 +332,14 @@ class Spgp:
         _fn("oracle_spgp_test", self.dtype)(self.h, _p(xt), C.c_long(t), _p(mean), _p(var))
         return mean, var
 
+    def set_diagonal_qm(self, on=True):
+        _fn("oracle_spgp_set_diagonal_qm", self.dtype, None)(self.h, C.c_int(int(on)))
+
+    def get_qm_diagonal(self):
+        q = np.zeros(self.m, dtype=self.dtype)
+        _fn("oracle_spgp_get_qm_diagonal", self.dtype)(self.h, _p(q))
+        return q
+
     def test_gradient(self, xt, raw_alpha=False):
         xt = np.ascontiguousarray(xt, dtype=self.dtype)
         t = xt.shape[0]

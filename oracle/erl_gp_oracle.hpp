@@ -836,6 +836,8 @@ namespace erl_gp_oracle {
         std::vector<T> z;  // x_dim x m pseudo points
         std::vector<T> k_m, l_km, q_m, l_qm, alpha;
         bool l_qm_updated = false;
+        bool diagonal_qm = false;  // Setting::diagonal_qm: Q_M kept as its diagonal (ctor :346-347, update :775-776, test :100-101)
+        std::vector<T> q_diag;
 
         void
         Init(const T *pseudo, const long xd, const long num_pseudo) {
@@ -847,6 +849,7 @@ namespace erl_gp_oracle {
             l_km.assign(static_cast<std::size_t>(m * m), T(0));
             Llt(k_m.data(), m, m, l_km.data(), m);  // :341
             q_m = k_m;                              // :349
+            q_diag.assign(static_cast<std::size_t>(m), T(1));  // :346-347 (diagonal_qm)
             alpha.assign(static_cast<std::size_t>(m), T(0));
             l_qm_updated = false;
         }
@@ -868,7 +871,12 @@ namespace erl_gp_oracle {
                 const T w = T(1) / (lambda + var[i]);
                 for (long p = 0; p < m; ++p) { k_s[p + i * m] *= w; }
             }
-            // Q_M += Ks * K_MN^T ; alpha += Ks * y
+            // Q_M += Ks * K_MN^T (or its diagonal only, :775-776) ; alpha += Ks * y
+            if (diagonal_qm) {
+                for (long i = 0; i < n; ++i) {
+                    for (long r = 0; r < m; ++r) { q_diag[r] += k_s[r + i * m] * k_mn[r + i * m]; }
+                }
+            } else
 #pragma omp parallel for schedule(static)
             for (long c = 0; c < m; ++c) {
                 T *qc = q_m.data() + c * m;
@@ -888,14 +896,19 @@ namespace erl_gp_oracle {
 
         void
         Test(const T *x_test, const long num_test, T *mean, T *variance) {
-            if (!l_qm_updated) {  // PrepareLqm :835-842
-                l_qm.assign(static_cast<std::size_t>(m * m), T(0));
-                Llt(q_m.data(), m, m, l_qm.data(), m);
-                l_qm_updated = true;
-            }
             std::vector<T> a = alpha;  // :100-106
-            SolveLowerInPlace(l_qm.data(), m, m, a.data());
-            SolveLowerTransposeInPlace(l_qm.data(), m, m, a.data());
+            if (diagonal_qm) {
+                for (long r = 0; r < m; ++r) { a[r] /= q_diag[r]; }
+                variance = nullptr;  // (the reference's variance solves with an L_QM this mode never builds, :304-310, :839)
+            } else {
+                if (!l_qm_updated) {  // PrepareLqm :835-842
+                    l_qm.assign(static_cast<std::size_t>(m * m), T(0));
+                    Llt(q_m.data(), m, m, l_qm.data(), m);
+                    l_qm_updated = true;
+                }
+                SolveLowerInPlace(l_qm.data(), m, m, a.data());
+                SolveLowerTransposeInPlace(l_qm.data(), m, m, a.data());
+            }
             std::vector<T> k_t(static_cast<std::size_t>(m * num_test));
             ComputeKtest(kernel_type, scale, x_dim, z.data(), x_dim, m, x_test, x_dim, num_test, k_t.data(), m);
 #pragma omp parallel for schedule(static)
@@ -924,13 +937,15 @@ namespace erl_gp_oracle {
         // alpha of the batched accessor (:212) instead of Q_M^-1 alpha (:252).  (KernelWithDerivatives is defined further down.)
         void
         TestGradient(const T *x_test, const long num_test, T *grad, const bool raw_alpha) {
-            if (!l_qm_updated) {  // PrepareLqm :835-842
+            if (!l_qm_updated && !diagonal_qm) {  // PrepareLqm :835-842
                 l_qm.assign(static_cast<std::size_t>(m * m), T(0));
                 Llt(q_m.data(), m, m, l_qm.data(), m);
                 l_qm_updated = true;
             }
             std::vector<T> a = alpha;
-            if (!raw_alpha) {
+            if (!raw_alpha && diagonal_qm) {
+                for (long r = 0; r < m; ++r) { a[r] /= q_diag[r]; }
+            } else if (!raw_alpha) {
                 SolveLowerInPlace(l_qm.data(), m, m, a.data());
                 SolveLowerTransposeInPlace(l_qm.data(), m, m, a.data());
             }

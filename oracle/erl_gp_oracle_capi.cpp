@@ -335,6 +335,19 @@ namespace {
         static_cast<Spgp<T> *>(h)->Test(x_test, num_test, mean, variance);                                            \
         return 0;                                                                                                     \
     }                                                                                                                 \
+    extern "C" void oracle_spgp_set_diagonal_qm_##SFX(void *h, int on) {                                             \
+        auto *gp = static_cast<Spgp<T> *>(h);                                                                         \
+        gp->diagonal_qm = on != 0;                                                                                    \
+        std::fill(gp->q_diag.begin(), gp->q_diag.end(), T(1));                                                        \
+        std::fill(gp->alpha.begin(), gp->alpha.end(), T(0));                                                          \
+        gp->q_m = gp->k_m;                                                                                            \
+        gp->l_qm_updated = false;                                                                                     \
+    }                                                                                                                 \
+    extern "C" int oracle_spgp_get_qm_diagonal_##SFX(void *h, T *q) {                                                 \
+        auto *gp = static_cast<Spgp<T> *>(h);                                                                         \
+        std::memcpy(q, gp->q_diag.data(), gp->m * sizeof(T));                                                         \
+        return 0;                                                                                                     \
+    }                                                                                                                 \
     extern "C" int oracle_spgp_test_gradient_##SFX(void *h, const T *x_test, long num_test, T *grad, int raw_alpha) {  \
         static_cast<Spgp<T> *>(h)->TestGradient(x_test, num_test, grad, raw_alpha != 0);                              \
         return 0;                                                                                                     \

@@ -261,6 +261,35 @@ def test_spgp_gradient(gp, oracle, dtype, kernel, scale):
         ou.test_gradient(xt)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_spgp_diagonal_qm(gp, oracle, dtype):
+    """Setting::diagonal_qm (src/sparse_pseudo_input_gp.cpp:346-347, 775-776, 100-101): Q_M kept as its diagonal; mean and gradient
+    against the oracle over two incremental updates; the variance is rejected (the reference never builds the L_QM it would need)."""
+    rng = np.random.default_rng(31)
+    gx = np.linspace(-2, 2, 10)
+    z = np.array([[a, b] for a in gx for b in gx])
+    g = gp.SparsePseudoInputGaussianProcess("matern32", 0.5, z, dtype)
+    o = oracle.Spgp(oracle.MATERN32, 0.5, z, dtype)
+    g.set_diagonal_qm(True)
+    o.set_diagonal_qm(True)
+    for it in range(2):
+        x = rng.uniform(-2, 2, (600 + 50 * it, 2))
+        y = np.sin(1.5 * x[:, 0]) * np.cos(x[:, 1])
+        var = np.full(len(x), 1e-2)
+        assert g.update(x, y, var) and o.update(x, y, var)
+    q, q_ref = g.get_qm_diagonal(), o.get_qm_diagonal()
+    rel = 2e-4 if dtype == np.float32 else 1e-10
+    assert np.abs(q - q_ref).max() / np.abs(q_ref).max() < rel
+    xt = rng.uniform(-1.8, 1.8, (500, 2))
+    mean = g.test_mean(xt)
+    m_ref, _ = o.test(xt)
+    assert err_mean(mean, m_ref) < rel
+    grad, g_ref = g.test_gradient(xt), o.test_gradient(xt)
+    assert np.abs(grad - g_ref).max() / np.abs(g_ref).max() < rel
+    with pytest.raises(gp.ErlGpError):
+        g.test(xt)  # asks for the variance
+
+
 def test_vanilla_train_is_deterministic(gp):
     """The factorisation runs on three streams (block-column / panel look-ahead) and the alpha solve spins on flags: two
     trainings of the same data must give bit-identical L and alpha (a missing dependency shows up as a difference)."""

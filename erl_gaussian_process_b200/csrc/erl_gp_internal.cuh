@@ -127,6 +127,9 @@ namespace erl_gp {
         // row-GP kernel, fused train + predict: CTA slot k of an SM (first wave only) starts k * stagger_cycles late
         int stagger_cycles = 0;
         int sm_count = 148;
+        // row-GP kernel: L goes to HBM with one bulk asynchronous copy (TMA, cp.async.bulk shared -> global) per column instead of
+        // LDS + STG by the warps; needs the L slices zero above the diagonal blocks (erl_gp_batch_create zeroes them once)
+        int tma_writeback = 0;
     };
 
     enum BatchMode : int { kBatchTrain = 1, kBatchPredict = 2, kBatchTrainPredict = 3 };

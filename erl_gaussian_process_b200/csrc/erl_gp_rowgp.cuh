@@ -54,6 +54,7 @@ namespace erl_gp {
         };
         constexpr unsigned kFull = 0xffffffffu;
         constexpr int kDefaultStaggerCycles = 0;  // per CTA slot, see RowGpKernel
+        constexpr int kDefaultTmaWriteback = 1;   // ERL_GP_ROWGP_TMA_WB: L to HBM by bulk asynchronous copies (TMA), see RowGpKernel
         // A/B switches (measured on the B200, C4, fused / train-only ms): z-dot hoisted before the update 5.80 / 2.76, in phase B
         // 5.56 / 2.74; back-substitution through Dinv 5.56 / 2.74, as a 16-step shuffle chain 5.47 / 2.98.
 #ifdef ERL_GP_V_ZDOT_EARLY
@@ -1565,7 +1566,22 @@ namespace erl_gp {
                     return;
                 }
                 // ---- L write-back (coalesced, one column per warp and step), issued before the back-substitution ----
-                if (p.write_l) {
+                if (p.write_l && p.tma_writeback && (p.max_n & 3) == 0 && (n & 3) == 0) {
+                    // One bulk asynchronous copy (TMA engine) per column: the stored part of column c (rows 16 cb .. n, 16-byte aligned in
+                    // the packed layout and in the caller's column-major slice) goes to HBM without passing through registers, and
+                    // the copies run under the back-substitution and the predict.  Rows above the column's diagonal block are never
+                    // written: the slice starts from zeros (erl_gp_batch_create) and only lower-triangular entries are ever stored.
+                    float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy stores of L, ordered before the async-proxy reads
+                    for (int c = tid; c < n; c += kThr) {
+                        const int cb = c >> 4;
+                        const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb)));
+                        float *dst = gl + static_cast<long>(c) * p.max_n + 16 * cb;
+                        const uint32_t bytes = static_cast<uint32_t>(n - 16 * cb) * 4u;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                } else if (p.write_l) {
                     float *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                     if ((p.max_n & 3) == 0) {
                         constexpr int kRowChunks = (Lay::kNp + 127) / 128;  // 128 rows per warp and step
@@ -1701,6 +1717,10 @@ namespace erl_gp {
                     }
                 }
             }
+            if constexpr ((MODE & kBatchTrain) != 0) {
+                // the bulk copies of L read this CTA's shared memory: they must have completed before it is released
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
         }
 
         template<int XDIM, int NBLK, int MODE>
@@ -1718,6 +1738,10 @@ namespace erl_gp {
                 static const char *env = std::getenv("ERL_GP_ROWGP_STAGGER");
                 launch_params.stagger_cycles = env != nullptr ? std::atoi(env) : kDefaultStaggerCycles;
                 launch_params.sm_count = ctx->sm_count;
+            }
+            {
+                static const char *env = std::getenv("ERL_GP_ROWGP_TMA_WB");
+                launch_params.tma_writeback = env != nullptr ? std::atoi(env) : kDefaultTmaWriteback;
             }
             kernel<<<grid, ThreadsFor<NBLK>::value, Lay::kBytes, ctx->stream>>>(launch_params);
             ctx->launches += 1;

@@ -664,7 +664,20 @@ namespace erl_gp {
                     invalidate();
                     return;
                 }
-                if (p.write_l) {  // L write-back: one column per warp and step, rows along the lanes
+                if (p.write_l && p.tma_writeback && ((p.max_n | n) & 1) == 0) {
+                    // one bulk asynchronous copy (TMA engine) per column, rows 16 cb .. n: see the FP32 kernel (erl_gp_rowgp.cuh); the
+                    // slice is zero above the diagonal blocks from erl_gp_batch_create on
+                    double *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    for (int c = tid; c < n; c += kThreads) {
+                        const int cb = c >> 4;
+                        const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(lp + Lay::Base(cb) + (c & 15) * Lay::Stride(cb)));
+                        double *dst = gl + static_cast<long>(c) * p.max_n + 16 * cb;
+                        const uint32_t bytes = static_cast<uint32_t>(n - 16 * cb) * 8u;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                } else if (p.write_l) {  // L write-back: one column per warp and step, rows along the lanes
                     double *gl = p.l + static_cast<long>(g) * p.max_n * p.max_n;
                     for (int c = warp; c < n; c += kWarps) {
                         const int cb = c >> 4;
@@ -718,6 +731,9 @@ namespace erl_gp {
                 if (blockIdx.x == 20000 && (tid & 31) == 0 && tid < 96) { printf("rowgp64 cta %d warp %d: predict %lld\n", blockIdx.x, tid >> 5, clock64() - tp0); }
 #endif
             }
+            if constexpr ((MODE & kBatchTrain) != 0) {
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the bulk copies of L read this CTA's shared memory
+            }
         }
 
         template<int XDIM, int NBLK, int MODE>
@@ -730,7 +746,12 @@ namespace erl_gp {
             }
             ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Lay::kBytes)));
             const dim3 grid(static_cast<unsigned>(params.num_gps), static_cast<unsigned>(tiles_per_gp < 1 ? 1 : tiles_per_gp));
-            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(params);
+            BatchParams<double> launch_params = params;
+            {
+                static const char *env = std::getenv("ERL_GP_ROWGP_TMA_WB");
+                launch_params.tma_writeback = env != nullptr ? std::atoi(env) : 1;
+            }
+            kernel<<<grid, kThreads, Lay::kBytes, ctx->stream>>>(launch_params);
             ctx->launches += 1;
             ERL_GP_CUDA_OK(ctx, cudaGetLastError());
             return ERL_GP_STATUS_OK;

@@ -481,6 +481,124 @@ namespace erl_gp {
         }
     }
 
+    // ---- the 16-warp GEMM fed by the TMA engine ----------------------------------------------------------------------------
+    // C = alpha A B^T + beta C with both operands outer-contiguous (the SYRK / GEMM trailing updates of the blocked Cholesky and the
+    // panel updates of the triangular solves): column kk of a 128 x 16 operand slab is 1 KB of contiguous, 16-byte aligned HBM, so a
+    // slab is 16 one-dimensional bulk copies (cp.async.bulk.shared::cluster.global, no tensor map needed) that land in the padded
+    // [k][132] layout SlabMma-style fragment loads want, and complete on the stage's mbarrier (expect_tx = the bytes of both slabs).
+    // Warp 0 issues the 32 copies of a stage, one per lane; nobody spends LDG / STS issue slots or staging registers on operands, and
+    // kGemmTmaStages slabs are in flight instead of one.  A stage is reused after the CTA barrier that ends its k-step (measured:
+    // per-stage `empty` mbarriers instead of that barrier, so that the warps may drift apart, made Potrf n = 16384 slower - 65.1 ms
+    // against 59.8 ms - the 16 warps share one slab and run best in step).
+    // Preconditions (checked by Gemm(), else the register-staged kernel runs): k % 16 == 0, m and n even, lda and ldb even,
+    // 16-byte aligned operands.  Rows past the matrix edge are never copied: they only feed accumulators that are not stored.
+    constexpr int kGemmTmaStages = 4;
+
+    __device__ __forceinline__ void
+    MbarWaitParity(const uint32_t bar, const uint32_t parity) {
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        } while (done == 0);
+    }
+
+    __global__ void __launch_bounds__(kGemmThreads512, 1)
+    GemmKernelDmmaTma(const long m, const long n, const long k, const double alpha, const double *__restrict__ a, const long lda, const double *__restrict__ b, const long ldb, const double beta,
+                      double *__restrict__ c, const long ldc, const int lower_only) {
+        constexpr int kLd = kGemmBM + kGemmPad;
+        constexpr int kSlab = kGemmBK * kLd;
+        extern __shared__ __align__(128) unsigned char smem_raw[];
+        double *as = reinterpret_cast<double *>(smem_raw);  // [stages][BK][kLd]
+        double *bs = as + kGemmTmaStages * kSlab;
+        const uint32_t bars = static_cast<uint32_t>(__cvta_generic_to_shared(bs + kGemmTmaStages * kSlab));  // one 8-byte mbarrier per stage
+        const long row0 = static_cast<long>(blockIdx.x) * kGemmBM;
+        const long col0 = static_cast<long>(blockIdx.y) * kGemmBN;
+        if (lower_only && col0 > row0 + kGemmBM - 1) { return; }
+        if (lower_only == 2 && blockIdx.x == 0 && blockIdx.y == 0) { return; }
+        const int tid = threadIdx.x;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wm = warp & 3, wn = warp >> 2;
+        const int g = lane >> 2, kq = lane & 3;
+        if (tid == 0) {
+#pragma unroll
+            for (int st = 0; st < kGemmTmaStages; ++st) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * st) : "memory"); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const uint32_t a_bytes = static_cast<uint32_t>(m - row0 < kGemmBM ? m - row0 : kGemmBM) * 8u;
+        const uint32_t b_bytes = static_cast<uint32_t>(n - col0 < kGemmBN ? n - col0 : kGemmBN) * 8u;
+        const long num_kt = k / kGemmBK;
+        // lane l < 16: column l of the A slab, lane 16 + l: column l of the B slab
+        const int kk = lane & 15;
+        const double *src = lane < 16 ? a + row0 + kk * lda : b + col0 + kk * ldb;
+        const long src_step = kGemmBK * (lane < 16 ? lda : ldb);
+        const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared((lane < 16 ? as : bs) + kk * kLd));
+        const uint32_t my_bytes = lane < 16 ? a_bytes : b_bytes;
+        auto issue = [&](const long kt) {  // warp 0, all lanes
+            const int st = static_cast<int>(kt % kGemmTmaStages);
+            const uint32_t bar = bars + 8 * st;
+            if (lane == 0) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kGemmBK * (a_bytes + b_bytes)) : "memory"); }
+            __syncwarp();
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst0 + st * kSlab * 8), "l"(src + kt * src_step), "r"(my_bytes), "r"(bar)
+                         : "memory");
+        };
+        if (warp == 0) {
+            for (long kt = 0; kt < kGemmTmaStages && kt < num_kt; ++kt) { issue(kt); }
+        }
+        double acc[4][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = acc[mi][ni][1] = 0.0; }
+        }
+        for (long kt = 0; kt < num_kt; ++kt) {
+            const int st = static_cast<int>(kt % kGemmTmaStages);
+            MbarWaitParity(bars + 8 * st, static_cast<uint32_t>(kt / kGemmTmaStages) & 1u);
+            const double *at = as + st * kSlab;
+            const double *bt = bs + st * kSlab;
+#pragma unroll
+            for (int k4 = 0; k4 < kGemmBK / 4; ++k4) {
+                const double *ap = at + (4 * k4 + kq) * kLd + 32 * wm + g;
+                const double *bp = bt + (4 * k4 + kq) * kLd + 32 * wn + g;
+                double av[4], bv[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) { av[mi] = ap[8 * mi]; }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) { bv[ni] = bp[8 * ni]; }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) { Dmma884(acc[mi][ni], av[mi], bv[ni]); }
+                }
+            }
+            __syncthreads();  // every warp is done with stage st
+            if (warp == 0 && kt + kGemmTmaStages < num_kt) { issue(kt + kGemmTmaStages); }
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long col = col0 + 32 * wn + 8 * ni + 2 * kq + e;
+                if (col >= n) { continue; }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const long row = row0 + 32 * wm + 8 * mi + g;
+                    if (row >= m || (lower_only && row < col)) { continue; }
+                    double *dst = c + row + col * ldc;
+                    const double prev = beta == 0.0 ? 0.0 : beta * (*dst);
+                    *dst = alpha * acc[mi][ni][e] + prev;
+                }
+            }
+        }
+    }
+
+    // ERL_GP_DENSE_TMA=0: the register-staged 16-warp kernel for every shape (A/B)
+    static bool
+    GemmUseTma() {
+        static const char *env = std::getenv("ERL_GP_DENSE_TMA");
+        return env == nullptr || std::atoi(env) != 0;
+    }
+
     static bool
     GemmUse512() {
         static const bool off = std::getenv("ERL_GP_DENSE_256") != nullptr;  // A/B: the 8-warp kernel (Potrf n = 16384: 63.9 ms vs 61.9 ms)
@@ -526,6 +644,18 @@ namespace erl_gp {
         ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
         kern<<<grid, (sizeof(T) == 8 && GemmUse512() && !GemmUseCpAsync() && std::getenv("ERL_GP_DENSE_FMA") == nullptr) ? kGemmThreads512 : kGemmThreads, smem, ctx->stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, lower_only);    \
     }
+        if constexpr (sizeof(T) == 8) {
+            if (op_a == kOpN && op_b == kOpT && GemmUseTma() && GemmUse512() && !GemmUseCpAsync() && std::getenv("ERL_GP_DENSE_FMA") == nullptr && k > 0 && (k % kGemmBK) == 0 &&
+                ((m | n | lda | ldb) & 1) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+                const size_t smem_tma = sizeof(double) * 2 * kGemmTmaStages * kGemmBK * (kGemmBM + kGemmPad) + 8 * kGemmTmaStages;
+                ERL_GP_CUDA_OK(ctx, cudaFuncSetAttribute(GemmKernelDmmaTma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_tma)));
+                GemmKernelDmmaTma<<<grid, kGemmThreads512, smem_tma, ctx->stream>>>(m, n, k, alpha, reinterpret_cast<const double *>(a), lda, reinterpret_cast<const double *>(b), ldb, beta,
+                                                                                   reinterpret_cast<double *>(c), ldc, lower_only);
+                ctx->launches += 1;
+                ERL_GP_CUDA_OK(ctx, cudaGetLastError());
+                return ERL_GP_STATUS_OK;
+            }
+        }
         if (op_a == kOpN && op_b == kOpT) {
             ERL_GP_GEMM_LAUNCH(false, false)
         } else if (op_a == kOpN && op_b == kOpN) {

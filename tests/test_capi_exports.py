@@ -69,3 +69,17 @@ def test_tc_sass_is_tcgen05():
     assert "RowGpTcKernel" in sass
     for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTCBAR"):
         assert mnemonic in sass, mnemonic
+
+
+def test_tma_bulk_copies_in_sass():
+    """The TMA engine moves L to HBM in both row-GP kernels (UBLKCP.G.S: shared -> global) and feeds the operands of the dense
+    FP64 A B^T GEMM (UBLKCP.S.G: global -> shared, completing on an mbarrier: SYNCS)."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    build = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "csrc")
+    objs = {"erl_gp_dense.o": ("GemmKernelDmmaTma", "UBLKCP.S.G", "SYNCS", "DMMA"), "erl_gp_rowgp64_x3.o": ("RowGp64Kernel", "UBLKCP.G.S", "DMMA")}
+    if not os.path.exists(cuobjdump) or not all(os.path.exists(os.path.join(build, o)) for o in objs):
+        pytest.skip("cuobjdump or the object files are not available on this box")
+    for obj, needles in objs.items():
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(build, obj)], capture_output=True, text=True, timeout=300).stdout
+        for needle in needles:
+            assert needle in sass, (obj, needle)

@@ -14,6 +14,7 @@ from .host import (
     NoisyInputGaussianProcess,
     RangeSensorGaussianProcess3D,
     SparsePseudoInputGaussianProcess,
+    SpGpOccupancyMap,
     VanillaGaussianProcess,
     compute_ktest,
     compute_ktrain,
@@ -29,6 +30,7 @@ __all__ = [
     "NoisyInputGaussianProcess",
     "RangeSensorGaussianProcess3D",
     "SparsePseudoInputGaussianProcess",
+    "SpGpOccupancyMap",
     "VanillaGaussianProcess",
     "compute_ktest",
     "compute_ktrain",

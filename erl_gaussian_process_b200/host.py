@@ -824,6 +824,86 @@ class SparsePseudoInputGaussianProcess:
         return q.T, a, lk.T, lq.T
 
 
+class SpGpOccupancyMap:
+    """Mirror of erl::gaussian_process::SpGpOccupancyMap<Dtype, Dim> (include/.../spgp_occupancy_map.hpp, src/spgp_occupancy_map.cpp):
+    a log-odds occupancy field regressed by an SPGP.  ``update_with_dataset`` is Update() after the dataset exists (:106-123: labels ->
+    logodd_occupied / logodd_free, constant logodd_variance, SPGP Reset + Update); ``predict`` is Predict (:126-140).  The dataset
+    generator of the reference lives in erl_geometry (absent dependency): ``generate_dataset`` is a stand-in with the documented
+    meaning of the Setting fields, its random stream is its own."""
+
+    def __init__(self, kernel, scale, pseudo_points, boundary_center, boundary_half_sizes, seed=0, dtype=np.float64, ctx: Context | None = None,
+                 min_distance=0.5, max_distance=30.0, free_points_per_meter=2.0, free_sampling_margin=0.05, logodd_free=-5.0, logodd_occupied=5.0,
+                 logodd_variance=1e-4, max_num_samples=256):
+        self.sp_gp = SparsePseudoInputGaussianProcess(kernel, scale, pseudo_points, dtype, ctx)
+        self.dtype = np.dtype(dtype)
+        self.dim = self.sp_gp.x_dim
+        self.center = np.asarray(boundary_center, dtype=np.float64)
+        self.half_sizes = np.asarray(boundary_half_sizes, dtype=np.float64)
+        self.rng = np.random.default_rng(seed)
+        self.min_distance, self.max_distance = float(min_distance), float(max_distance)
+        self.free_points_per_meter, self.free_sampling_margin = float(free_points_per_meter), float(free_sampling_margin)
+        self.logodd_free, self.logodd_occupied, self.logodd_variance = float(logodd_free), float(logodd_occupied), float(logodd_variance)
+        self.max_num_samples = int(max_num_samples)
+        self.trained = False
+
+    def _inside(self, p):
+        return np.all(np.abs(p - self.center) <= self.half_sizes, axis=-1)
+
+    def generate_dataset(self, sensor_position, points, point_indices=None, max_dataset_size=-1):
+        """-> (dataset_points (n, dim), dataset_labels (n,), hit_indices): hit points (label 1) + free points along the rays (label 0)."""
+        sensor = np.asarray(sensor_position, dtype=np.float64)
+        pts = np.asarray(points, dtype=np.float64)
+        idx = np.arange(len(pts)) if point_indices is None or len(point_indices) == 0 else np.asarray(point_indices, dtype=np.int64)
+        out_p, out_l, hits = [], [], []
+        count = 0
+        for i in idx:
+            if 0 < max_dataset_size <= count:
+                break
+            v = pts[i] - sensor
+            r = float(np.linalg.norm(v))
+            if not np.isfinite(r) or r < self.min_distance or r > self.max_distance:
+                continue
+            if self._inside(pts[i]):
+                out_p.append(pts[i]), out_l.append(1.0), hits.append(int(i))
+                count += 1
+            for _ in range(int(np.floor(r * self.free_points_per_meter))):
+                if 0 < max_dataset_size <= count:
+                    break
+                q = sensor + self.rng.uniform(self.free_sampling_margin, 1.0 - self.free_sampling_margin) * v
+                if self._inside(q):
+                    out_p.append(q), out_l.append(0.0)
+                    count += 1
+        return np.asarray(out_p, dtype=self.dtype).reshape(-1, self.dim), np.asarray(out_l, dtype=self.dtype), hits
+
+    def update_with_dataset(self, dataset_points, dataset_labels) -> bool:
+        x = np.ascontiguousarray(dataset_points, dtype=self.dtype)
+        if len(x) == 0:
+            return False  # "No valid points generated for update. Skipping update."
+        if len(x) > self.max_num_samples:
+            raise ValueError(f"max_num_samples should be <= {self.max_num_samples}")  # SPGP Reset, src/sparse_pseudo_input_gp.cpp:405-408
+        y = np.where(np.asarray(dataset_labels) > 0, self.logodd_occupied, self.logodd_free).astype(self.dtype)
+        ok = self.sp_gp.update(x, y, np.full(len(x), self.logodd_variance, dtype=self.dtype))
+        self.trained = self.trained or ok
+        return ok
+
+    def update(self, sensor_position, points, point_indices=None):
+        """Update (:82-124) -> (ok, dataset_points, dataset_labels, hit_indices)."""
+        p, l, hits = self.generate_dataset(sensor_position, points, point_indices, self.max_num_samples)
+        return self.update_with_dataset(p, l), p, l, hits
+
+    def predict(self, points, compute_gradient=False):
+        """-> logodd (T,) [, gradient (T, dim)]"""
+        if not self.trained:
+            raise RuntimeError("predict() before the first successful update (Test() returns nullptr until trained)")
+        logodd = self.sp_gp.test_mean(points)
+        if not compute_gradient:
+            return logodd
+        return logodd, self.sp_gp.test_gradient(points)
+
+    def predict_gradient(self, points):
+        return self.predict(points, True)[1]
+
+
 class NoisyInputGaussianProcess:
     """Mirror of erl::gaussian_process::NoisyInputGaussianProcess<Dtype> (include/.../noisy_input_gp.hpp): GP with noisy
     inputs and gradient observations.  ``train(x, y, grad, var_x, var_y, var_grad, grad_flag)`` = Reset + TrainSet fill +

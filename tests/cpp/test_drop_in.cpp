@@ -5,6 +5,7 @@
 #include "erl_gaussian_process_b200/lidar_gp_2d.hpp"
 #include "erl_gaussian_process_b200/noisy_input_gp.hpp"
 #include "erl_gaussian_process_b200/range_sensor_gp_3d.hpp"
+#include "erl_gaussian_process_b200/spgp_occupancy_map.hpp"
 #include "erl_gaussian_process_b200/vanilla_gp.hpp"
 
 #include "../../oracle/erl_gp_oracle.hpp"
@@ -603,6 +604,168 @@ TestRangeSensor(const char *name, const double tol) {
     std::printf("%s %s: mean err %.2e, var err %.2e, %ld valid rays\n", g_failures ? "----" : "PASS", name, em / scale, ev, valid);
 }
 
+template<typename Dtype>
+static void
+TestSpGpOccupancyMap(const char *name, const double tol) {
+    // the flow of src/spgp_occupancy_map.cpp:82-152 on a synthetic 2-D scan: a sensor inside a circular room; two scans from
+    // two positions (Q_M and alpha accumulate over Update() calls, src/sparse_pseudo_input_gp.cpp:751-791), then log-odds and
+    // their gradient on a grid, against the oracle SPGP fed with the same dataset
+    using Map = SpGpOccupancyMap<Dtype, 2>;
+    auto setting = std::make_shared<typename Map::Setting>();
+    setting->sp_gp->kernel_type = "erl::covariance::Matern32<Dtype, 2>";
+    setting->sp_gp->kernel->x_dim = 2;
+    setting->sp_gp->kernel->scale = Dtype(1.2);
+    setting->sp_gp->max_num_samples = 900;
+    setting->min_distance = Dtype(0.3);
+    setting->max_distance = Dtype(10);
+    setting->logodd_variance = Dtype(0.01);
+    constexpr long grid = 12, m = grid * grid;
+    Eigen::MatrixX<Dtype> pseudo(2, m);
+    for (long i = 0; i < grid; ++i) {
+        for (long j = 0; j < grid; ++j) {
+            pseudo(0, i * grid + j) = Dtype(-4.4 + 0.8 * i);
+            pseudo(1, i * grid + j) = Dtype(-4.4 + 0.8 * j);
+        }
+    }
+    typename Map::AabbD boundary;
+    boundary.center.resize(2);
+    boundary.half_sizes.resize(2);
+    boundary.center[0] = boundary.center[1] = 0;
+    boundary.half_sizes[0] = boundary.half_sizes[1] = Dtype(4.5);
+    Map map(setting, pseudo, boundary, 7);
+
+    erl_gp_oracle::Spgp<Dtype> ref;
+    ref.kernel_type = erl_gp_oracle::kMatern32;
+    ref.scale = Dtype(1.2);
+    ref.Init(pseudo.data(), 2, m);
+    // the same restatement in double on the same (Dtype-rounded) dataset: its distance to `ref` is the floor two correct
+    // implementations in Dtype are apart by (M = 144 pseudo-points, noise 0.01: cond(Q_M) ~ 1e5)
+    erl_gp_oracle::Spgp<double> ref64;
+    ref64.kernel_type = erl_gp_oracle::kMatern32;
+    ref64.scale = double(Dtype(1.2));
+    {
+        std::vector<double> z(static_cast<std::size_t>(2 * m));
+        for (long i = 0; i < 2 * m; ++i) { z[i] = pseudo.data()[i]; }
+        ref64.Init(z.data(), 2, m);
+    }
+
+    Eigen::MatrixX<Dtype> grad_before;
+    Eigen::VectorX<Dtype> logodd_before;
+    bool threw = false;
+    try {
+        map.Predict(pseudo, false, true, logodd_before, grad_before);
+    } catch (const std::logic_error &) { threw = true; }
+    CHECK(threw, "Predict before Update must fail (Test() returns nullptr until trained)");
+
+    const Dtype sensors[2][2] = {{Dtype(0.5), Dtype(-0.3)}, {Dtype(-1.0), Dtype(1.2)}};
+    long total_hits = 0;
+    for (int scan = 0; scan < 2; ++scan) {
+        constexpr long rays = 90;
+        Eigen::VectorX<Dtype> sensor(2);
+        sensor[0] = sensors[scan][0], sensor[1] = sensors[scan][1];
+        Eigen::MatrixX<Dtype> points(2, rays);
+        for (long i = 0; i < rays; ++i) {  // hits on the circle |p| = 3.5 (ray / circle intersection)
+            const double a = 2 * M_PI * i / rays, dx = std::cos(a), dy = std::sin(a);
+            const double b = sensor[0] * dx + sensor[1] * dy, c = sensor[0] * sensor[0] + sensor[1] * sensor[1] - 3.5 * 3.5;
+            const double t = -b + std::sqrt(b * b - c);
+            points(0, i) = Dtype(sensor[0] + t * dx);
+            points(1, i) = Dtype(sensor[1] + t * dy);
+        }
+        long num_samples = 0;
+        Eigen::MatrixX<Dtype> dataset_points;
+        Eigen::VectorX<Dtype> dataset_labels;
+        std::vector<long> hit_indices;
+        CHECK(map.Update(sensor, points, {}, num_samples, dataset_points, dataset_labels, hit_indices), "Update");
+        CHECK(num_samples > rays && num_samples <= 900, "dataset size %ld", num_samples);
+        CHECK(static_cast<long>(hit_indices.size()) == rays, "%zu hit points", hit_indices.size());
+        total_hits += static_cast<long>(hit_indices.size());
+        long free_points = 0;
+        for (long i = 0; i < num_samples; ++i) {
+            const double r = std::hypot(double(dataset_points(0, i)), double(dataset_points(1, i)));
+            if (dataset_labels[i] > 0) {
+                CHECK(std::abs(r - 3.5) < 1e-3, "hit point off the wall: %f", r);
+            } else {
+                ++free_points;
+                CHECK(r < 3.5, "free point outside the room: %f", r);
+            }
+        }
+        CHECK(free_points > 2 * rays, "%ld free points", free_points);
+        std::vector<Dtype> y(static_cast<std::size_t>(num_samples)), var(static_cast<std::size_t>(num_samples), setting->logodd_variance);
+        std::vector<Dtype> x(static_cast<std::size_t>(2 * num_samples));
+        for (long i = 0; i < num_samples; ++i) {
+            y[i] = dataset_labels[i] > 0 ? setting->logodd_occupied : setting->logodd_free;
+            x[2 * i] = dataset_points(0, i), x[2 * i + 1] = dataset_points(1, i);
+        }
+        CHECK(ref.Update(x.data(), y.data(), var.data(), num_samples), "oracle Update");
+        std::vector<double> x64(x.begin(), x.end()), y64(y.begin(), y.end()), var64(var.begin(), var.end());
+        CHECK(ref64.Update(x64.data(), y64.data(), var64.data(), num_samples), "oracle Update (double)");
+    }
+    CHECK(map.GetSpGp().IsTrained(), "IsTrained");
+
+    constexpr long tg = 40, nt = tg * tg;
+    Eigen::MatrixX<Dtype> xt(2, nt);
+    for (long i = 0; i < tg; ++i) {
+        for (long j = 0; j < tg; ++j) {
+            xt(0, i * tg + j) = Dtype(-4.0 + 8.0 * i / (tg - 1));
+            xt(1, i * tg + j) = Dtype(-4.0 + 8.0 * j / (tg - 1));
+        }
+    }
+    Eigen::VectorX<Dtype> logodd;
+    Eigen::MatrixX<Dtype> gradient;
+    map.Predict(xt, true, true, logodd, gradient);
+    std::vector<Dtype> mean_ref(nt), var_ref(nt), grad_ref(2 * nt);
+    ref.Test(xt.data(), nt, mean_ref.data(), var_ref.data());
+    ref.TestGradient(xt.data(), nt, grad_ref.data(), false);
+    std::vector<double> xt64(static_cast<std::size_t>(2 * nt)), mean64(nt), var64(nt), grad64(2 * nt);
+    for (long i = 0; i < 2 * nt; ++i) { xt64[i] = xt.data()[i]; }
+    ref64.Test(xt64.data(), nt, mean64.data(), var64.data());
+    ref64.TestGradient(xt64.data(), nt, grad64.data(), false);
+    double em = 0, eg = 0, sm = 0, sg = 0, fm = 0, fg = 0;
+    for (long i = 0; i < nt; ++i) {
+        em = std::max(em, std::abs(double(logodd[i]) - double(mean_ref[i])));
+        fm = std::max(fm, std::abs(mean64[i] - double(mean_ref[i])));
+        sm = std::max(sm, std::abs(double(mean_ref[i])));
+        for (int d = 0; d < 2; ++d) {
+            eg = std::max(eg, std::abs(double(gradient(d, i)) - double(grad_ref[2 * i + d])));
+            fg = std::max(fg, std::abs(grad64[2 * i + d] - double(grad_ref[2 * i + d])));
+            sg = std::max(sg, std::abs(double(grad_ref[2 * i + d])));
+        }
+    }
+    // bar: the north-star tolerance relative to the field's scale, or 10x the measured floor of the precision
+    CHECK(em <= std::max(tol * std::max(1.0, sm), 10 * fm), "log-odds err %.3e (scale %.2f, floor %.3e)", em, sm, fm);
+    CHECK(eg <= std::max(tol * std::max(1.0, sg), 10 * fg), "gradient err %.3e (scale %.2f, floor %.3e)", eg, sg, fg);
+    // the field separates the two classes: free space near the sensors, occupied on the wall
+    Dtype lo_free = 0, lo_wall = 0;
+    Eigen::VectorX<Dtype> p(2), g(2);
+    p[0] = Dtype(0.5), p[1] = Dtype(-0.3);
+    map.Predict(p, true, lo_free, g);
+    p[0] = Dtype(3.5), p[1] = Dtype(0);
+    map.Predict(p, true, lo_wall, g);
+    CHECK(lo_free < -2 && lo_wall > 1, "log-odds at the sensor %.2f, on the wall %.2f", double(lo_free), double(lo_wall));
+    CHECK(g[0] > 0, "the log-odds must grow outwards through the wall: d/dx = %.2f", double(g[0]));
+    Eigen::MatrixX<Dtype> gradient_only;
+    map.PredictGradient(xt, true, gradient_only);
+    CHECK(gradient_only == gradient, "PredictGradient must repeat Predict's gradient");
+    // variance of the SPGP behind the map and its host-side state
+    auto result = map.GetSpGp().Test(xt, false);
+    Eigen::VectorX<Dtype> var(nt);
+    result->GetVariance(var, true);
+    double ev = 0;
+    for (long i = 0; i < nt; ++i) { ev = std::max(ev, std::abs(double(var[i]) - double(var_ref[i]))); }
+    double fv = 0;
+    for (long i = 0; i < nt; ++i) { fv = std::max(fv, std::abs(var64[i] - double(var_ref[i]))); }
+    CHECK(ev <= std::max(tol, 10 * fv), "variance err %.3e (floor %.3e)", ev, fv);
+    const auto &alpha = map.GetSpGp().GetMatAlpha();
+    double ea = 0, sa = 0;
+    for (long i = 0; i < m; ++i) {
+        ea = std::max(ea, std::abs(double(alpha(i, 0)) - double(ref.alpha[i])));
+        sa = std::max(sa, std::abs(double(ref.alpha[i])));
+    }
+    CHECK(ea <= tol * std::max(1.0, sa), "alpha err %.3e (scale %.2f)", ea, sa);
+    std::printf("%s %s: log-odds err %.2e (scale %.1f, floor %.1e), gradient err %.2e (scale %.1f, floor %.1e), var err %.2e (floor %.1e), %ld hit points\n", g_failures ? "----" : "PASS", name, em, sm,
+                fm, eg, sg, fg, ev, fv, total_hits);
+}
+
 int
 main() {
     std::setvbuf(stdout, nullptr, _IOLBF, 0);  // progress survives a crash
@@ -621,6 +784,8 @@ main() {
         TestLidarHitRays<float>("LidarGaussianProcess2D<float> partition_on_hit_rays", 1e-4);
         TestRangeSensor<float>("RangeSensorGaussianProcess3D<float>", 1e-4);
         TestRangeSensor<double>("RangeSensorGaussianProcess3D<double>", 1e-10);
+        TestSpGpOccupancyMap<double>("SpGpOccupancyMap<double, 2>", 1e-10);
+        TestSpGpOccupancyMap<float>("SpGpOccupancyMap<float, 2>", 1e-4);
         // misuse: hard assertion as ERL_ASSERTM (src/vanilla_gp.cpp:389-392)
         bool threw = false;
         try {

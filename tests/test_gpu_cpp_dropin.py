@@ -20,4 +20,4 @@ def test_cpp_drop_in_classes(exe):
     print(out.stdout)
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
     assert "ALL PASS" in out.stdout
-    assert out.stdout.count("PASS ") >= 14
+    assert out.stdout.count("PASS ") >= 16

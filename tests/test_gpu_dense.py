@@ -307,3 +307,43 @@ def test_vanilla_train_is_deterministic(gp):
             ref = (l.copy(), a.copy())
         else:
             assert np.array_equal(ref[0], l) and np.array_equal(ref[1], a)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_spgp_occupancy_map(gp, oracle, dtype):
+    """SpGpOccupancyMap (src/spgp_occupancy_map.cpp:82-152): two scans of a circular room, log-odds and gradient on a grid against the
+    oracle SPGP fed with the same dataset."""
+    gx = np.linspace(-4.4, 4.4, 12)
+    z = np.array([[a, b] for a in gx for b in gx])
+    occ = gp.SpGpOccupancyMap("matern32", 1.2, z, [0, 0], [4.5, 4.5], seed=3, dtype=dtype, min_distance=0.3, max_distance=10.0, logodd_variance=1e-2, max_num_samples=900)
+    o = oracle.Spgp(oracle.MATERN32, 1.2, z, dtype)
+    o64 = oracle.Spgp(oracle.MATERN32, float(dtype(1.2)), z.astype(dtype).astype(np.float64), np.float64)
+    with pytest.raises(RuntimeError):
+        occ.predict(z)
+    ang = np.linspace(0, 2 * np.pi, 90, endpoint=False)
+    d = np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    for sensor in (np.array([0.5, -0.3]), np.array([-1.0, 1.2])):
+        b = d @ sensor
+        t = -b + np.sqrt(b * b - (sensor @ sensor - 3.5**2))
+        hits = sensor + t[:, None] * d
+        ok, p, l, hit_idx = occ.update(sensor, hits)
+        assert ok and len(hit_idx) == 90 and 90 < len(p) <= 900
+        r = np.linalg.norm(p.astype(np.float64), axis=1)
+        assert np.all(np.abs(r[l > 0] - 3.5) < 1e-3) and np.all(r[l == 0] < 3.5)
+        y = np.where(l > 0, 5.0, -5.0)
+        assert o.update(p, y, np.full(len(p), 1e-2)) and o64.update(p.astype(np.float64), y, np.full(len(p), float(dtype(1e-2))))
+    g1 = np.linspace(-4, 4, 40)
+    xt = np.array([[a, b] for a in g1 for b in g1]).astype(dtype)
+    logodd, grad = occ.predict(xt, True)
+    m_ref, _ = o.test(xt)
+    g_ref = o.test_gradient(xt)
+    m64, _ = o64.test(xt.astype(np.float64))
+    g64 = o64.test_gradient(xt.astype(np.float64))
+    sm, sg = np.abs(m64).max(), np.abs(g64).max()
+    floor_m, floor_g = np.abs(m_ref - m64).max(), np.abs(g_ref - g64).max()
+    tol = 1e-4 if dtype == np.float32 else 1e-10
+    assert np.abs(logodd - m_ref).max() <= max(tol * sm, 10 * floor_m), (np.abs(logodd - m_ref).max(), floor_m)
+    assert np.abs(grad - g_ref).max() <= max(tol * sg, 10 * floor_g), (np.abs(grad - g_ref).max(), floor_g)
+    assert occ.predict(np.array([[0.5, -0.3]]))[0] < -2 and occ.predict(np.array([[3.5, 0.0]]))[0] > 1
+    np.testing.assert_array_equal(occ.predict_gradient(xt), grad)
+    assert not occ.update_with_dataset(np.zeros((0, 2)), np.zeros(0))

@@ -11,6 +11,7 @@
 #include "c_api.hpp"
 #include "covariance.hpp"
 #include "eigen_shim.hpp"
+#include "serialization.hpp"
 #include "vanilla_gp.hpp"
 
 #include <memory>
@@ -263,7 +264,92 @@ namespace erl::gaussian_process {
             return std::make_shared<TestResult>(this, mat_x_test, predict_gradient);
         }
 
+        [[nodiscard]] bool
+        operator==(const SparsePseudoInputGaussianProcess &other) const {  // :498-532
+            namespace ser = b200::serialization;
+            if (!SameSetting(*m_setting_, *other.m_setting_)) { return false; }
+            if (m_trained_ != other.m_trained_ || m_trained_once_ != other.m_trained_once_) { return false; }
+            if (!(m_pseudo_points_ == other.m_pseudo_points_)) { return false; }
+            Fetch();
+            other.Fetch();
+            if (!(m_mat_qm_ == other.m_mat_qm_) || !(m_mat_alpha_ == other.m_mat_alpha_) || !(m_mat_l_km_ == other.m_mat_l_km_)) { return false; }
+            return m_train_set_ == other.m_train_set_;
+        }
+
+        [[nodiscard]] bool
+        operator!=(const SparsePseudoInputGaussianProcess &other) const {
+            return !(*this == other);
+        }
+
+        // Token stream as src/sparse_pseudo_input_gp.cpp:539-640 (own framing, serialization.hpp).  K_M, L_KM and L_QM are not
+        // stored: they follow from the pseudo-points and Q_M, which Read() hands to a fresh device handle.
+        [[nodiscard]] bool
+        Write(std::ostream &s) const {
+            namespace ser = b200::serialization;
+            Fetch();
+            return ser::WriteTokens(s, {{"setting", [this](std::ostream &o) { return ser::WriteGpSetting(o, *m_setting_); }},
+                                        {"spgp_setting",
+                                         [this](std::ostream &o) {
+                                             o.precision(17);
+                                             o << m_setting_->sparse_zero_threshold << ' ' << m_setting_->use_sparse << ' ' << m_setting_->diagonal_qm;
+                                             return o.good();
+                                         }},
+                                        {"trained", ser::ScalarWriter(m_trained_)},
+                                        {"trained_once", ser::ScalarWriter(m_trained_once_)},
+                                        {"pseudo_points", [this](std::ostream &o) { return ser::SaveMatrix(o, m_pseudo_points_); }},
+                                        {"mat_qm", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_qm_); }},
+                                        {"mat_alpha", [this](std::ostream &o) { return ser::SaveMatrix(o, m_mat_alpha_); }},
+                                        {"train_set", [this](std::ostream &o) { return m_train_set_.Write(o); }}});
+        }
+
+        [[nodiscard]] bool
+        Read(std::istream &s) {  // :642-749
+            namespace ser = b200::serialization;
+            bool trained = false, trained_once = false;
+            MatrixX pseudo, qm, alpha;
+            auto setting = std::make_shared<Setting>();
+            const bool ok = ser::ReadTokens(s, {{"setting", [&setting](std::istream &i) { return ser::ReadGpSetting(i, *setting); }},
+                                                {"spgp_setting",
+                                                 [&setting](std::istream &i) {
+                                                     i >> setting->sparse_zero_threshold >> setting->use_sparse >> setting->diagonal_qm;
+                                                     return !i.fail();
+                                                 }},
+                                                {"trained", ser::ScalarReader(trained)},
+                                                {"trained_once", ser::ScalarReader(trained_once)},
+                                                {"pseudo_points", [&pseudo](std::istream &i) { return ser::LoadMatrix(i, pseudo); }},
+                                                {"mat_qm", [&qm](std::istream &i) { return ser::LoadMatrix(i, qm); }},
+                                                {"mat_alpha", [&alpha](std::istream &i) { return ser::LoadMatrix(i, alpha); }},
+                                                {"train_set", [this](std::istream &i) { return m_train_set_.Read(i); }}});
+            if (!ok || setting->use_sparse) { return false; }
+            const long m = pseudo.cols();
+            if (m <= 0 || pseudo.rows() < 1 || alpha.rows() != m || alpha.cols() != 1 || qm.rows() != m || qm.cols() != (setting->diagonal_qm ? 1 : m)) { return false; }
+            int kernel = 0;
+            try {
+                kernel = covariance::KernelFromTypeName(setting->kernel_type);
+            } catch (const std::logic_error &) { return false; }
+            // a fresh device handle for the stored pseudo-points (K_M, L_KM), then the accumulated state
+            typename Abi::Handle *handle = nullptr;
+            if (Abi::create(m_ctx_->Get(), kernel, setting->kernel->scale, pseudo.rows(), m, pseudo.data(), &handle) != ERL_GP_STATUS_OK) { return false; }
+            if ((setting->diagonal_qm && Abi::set_diagonal_qm(handle, 1) != ERL_GP_STATUS_OK) || Abi::set_state(handle, qm.data(), alpha.data()) != ERL_GP_STATUS_OK) {
+                Abi::destroy(handle);
+                return false;
+            }
+            if (m_handle_ != nullptr) { Abi::destroy(m_handle_); }
+            m_handle_ = handle;
+            *m_setting_ = *setting;  // the caller's shared Setting object follows the stream, like Yamlable::Read in the reference
+            m_pseudo_points_ = pseudo;
+            m_trained_ = trained;
+            m_trained_once_ = trained_once;
+            m_host_valid_ = false;
+            return true;
+        }
+
     private:
+        static bool
+        SameSetting(const Setting &a, const Setting &b) {
+            return b200::serialization::SameGpSetting(a, b) && a.sparse_zero_threshold == b.sparse_zero_threshold && a.use_sparse == b.use_sparse && a.diagonal_qm == b.diagonal_qm;
+        }
+
         struct Abi {
             using Handle = std::conditional_t<std::is_same_v<Dtype, float>, erl_gp_spgp_f32, erl_gp_spgp_f64>;
             template<typename F32, typename F64>
@@ -283,6 +369,7 @@ namespace erl::gaussian_process {
             static constexpr auto set_diagonal_qm = Pick(erl_gp_spgp_set_diagonal_qm_f32, erl_gp_spgp_set_diagonal_qm_f64);
             static constexpr auto get_qm_diagonal = Pick(erl_gp_spgp_get_qm_diagonal_f32, erl_gp_spgp_get_qm_diagonal_f64);
             static constexpr auto get = Pick(erl_gp_spgp_get_f32, erl_gp_spgp_get_f64);
+            static constexpr auto set_state = Pick(erl_gp_spgp_set_state_f32, erl_gp_spgp_set_state_f64);
         };
 
         void

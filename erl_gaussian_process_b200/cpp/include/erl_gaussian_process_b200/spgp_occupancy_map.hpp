@@ -16,7 +16,9 @@
 
 #include <cmath>
 #include <cstdint>
+#include <istream>
 #include <memory>
+#include <ostream>
 #include <random>
 #include <utility>
 #include <vector>
@@ -202,6 +204,54 @@ namespace erl::gaussian_process {
             b200::AssertM(test_result != nullptr, "PredictGradient() before the first successful Update()");
             if (gradient.rows() != Dim || gradient.cols() < points.cols()) { gradient.resize(Dim, points.cols()); }
             (void) test_result->GetGradient(0, gradient, parallel);
+        }
+
+        [[nodiscard]] bool
+        operator==(const SpGpOccupancyMap &other) const {  // :244-254: setting, SPGP, boundary (not the generator)
+            const Setting &a = *m_setting_, &b = *other.m_setting_;
+            if (a.min_distance != b.min_distance || a.max_distance != b.max_distance || a.free_points_per_meter != b.free_points_per_meter ||
+                a.free_sampling_margin != b.free_sampling_margin || a.parallel != b.parallel || a.logodd_free != b.logodd_free || a.logodd_occupied != b.logodd_occupied ||
+                a.logodd_variance != b.logodd_variance) {
+                return false;
+            }
+            if (m_sp_gp_ != other.m_sp_gp_) { return false; }
+            return m_map_boundary_.center == other.m_map_boundary_.center && m_map_boundary_.half_sizes == other.m_map_boundary_.half_sizes;
+        }
+
+        [[nodiscard]] bool
+        operator!=(const SpGpOccupancyMap &other) const {
+            return !(*this == other);
+        }
+
+        [[nodiscard]] bool
+        Write(std::ostream &s) const {  // :164-203
+            namespace ser = b200::serialization;
+            return ser::WriteTokens(s, {{"setting",
+                                         [this](std::ostream &o) {
+                                             const Setting &g = *m_setting_;
+                                             o.precision(17);
+                                             o << g.min_distance << ' ' << g.max_distance << ' ' << g.free_points_per_meter << ' ' << g.free_sampling_margin << ' ' << g.parallel << ' '
+                                               << g.logodd_free << ' ' << g.logodd_occupied << ' ' << g.logodd_variance;
+                                             return o.good();
+                                         }},
+                                        {"sp_gp", [this](std::ostream &o) { return m_sp_gp_.Write(o); }},
+                                        {"map_boundary", [this](std::ostream &o) { return ser::SaveMatrix(o, m_map_boundary_.center) && ser::SaveMatrix(o, m_map_boundary_.half_sizes); }},
+                                        {"generator", [this](std::ostream &o) { o << m_generator_; return o.good(); }}});
+        }
+
+        [[nodiscard]] bool
+        Read(std::istream &s) {  // :205-242
+            namespace ser = b200::serialization;
+            return ser::ReadTokens(s, {{"setting",
+                                        [this](std::istream &i) {
+                                            Setting &g = *m_setting_;
+                                            i >> g.min_distance >> g.max_distance >> g.free_points_per_meter >> g.free_sampling_margin >> g.parallel >> g.logodd_free >> g.logodd_occupied >>
+                                                g.logodd_variance;
+                                            return !i.fail();
+                                        }},
+                                       {"sp_gp", [this](std::istream &i) { return m_sp_gp_.Read(i); }},
+                                       {"map_boundary", [this](std::istream &i) { return ser::LoadVector(i, m_map_boundary_.center) && ser::LoadVector(i, m_map_boundary_.half_sizes); }},
+                                       {"generator", [this](std::istream &i) { i >> m_generator_; return !i.fail(); }}});
         }
 
     private:

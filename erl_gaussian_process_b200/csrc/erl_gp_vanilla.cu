@@ -574,6 +574,25 @@ namespace erl_gp {
         return ERL_GP_STATUS_OK;
     }
 
+    // Read() of the reference restores Q_M and alpha from the stream (src/sparse_pseudo_input_gp.cpp:721-740); K_M and L_KM follow
+    // from the pseudo-points at construction, L_QM is refactored lazily.  q_m: M x M col-major, or M values in diagonal_qm mode.
+    template<typename T>
+    static int
+    SpgpSetState(Spgp<T> *gp, const T *q_m, const T *alpha) {
+        if (gp == nullptr || q_m == nullptr || alpha == nullptr) { return ERL_GP_STATUS_INVALID_ARGUMENT; }
+        Context *ctx = gp->ctx;
+        ERL_GP_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        if (gp->diagonal_qm) {
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->q_diag.ptr, q_m, sizeof(T) * gp->m, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->q_m.ptr, q_m, sizeof(T) * gp->m * gp->m, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        ERL_GP_CUDA_OK(ctx, cudaMemcpyAsync(gp->alpha.ptr, alpha, sizeof(T) * gp->m, cudaMemcpyHostToDevice, ctx->stream));
+        ERL_GP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffers may go away
+        gp->l_qm_updated = false;
+        return ERL_GP_STATUS_OK;
+    }
+
     template<typename T>
     static int
     SpgpGet(Spgp<T> *gp, T *q_m, T *alpha, T *l_km, T *l_qm) {
@@ -667,6 +686,7 @@ extern "C" {
     int erl_gp_spgp_test_gradient_##SFX(erl_gp_spgp_##SFX *gp, long num_test, const T *x_test, long ld_xt, T *grad, int raw_alpha) {                                         \
         return SpgpTestGradient<T>(gp, num_test, x_test, ld_xt, grad, raw_alpha);                                                                                            \
     }                                                                                                                                                                        \
+    int erl_gp_spgp_set_state_##SFX(erl_gp_spgp_##SFX *gp, const T *q_m, const T *alpha) { return SpgpSetState<T>(gp, q_m, alpha); }                                        \
     int erl_gp_spgp_get_##SFX(erl_gp_spgp_##SFX *gp, T *q_m, T *alpha, T *l_km, T *l_qm) { return SpgpGet<T>(gp, q_m, alpha, l_km, l_qm); }
 
 ERL_GP_DEFINE_DENSE(float, f32)

@@ -408,6 +408,10 @@ int erl_gp_spgp_test_gradient_f32(erl_gp_spgp_f32 *gp, long num_test, const floa
                                   int raw_alpha);
 int erl_gp_spgp_test_gradient_f64(erl_gp_spgp_f64 *gp, long num_test, const double *x_test, long ld_xt, double *grad,
                                   int raw_alpha);
+/* Read() (src/sparse_pseudo_input_gp.cpp:721-740): restores the accumulated Q_M (M x M col-major; M values in diagonal_qm mode)
+ * and alpha (M) of a saved SPGP into a handle created with the same pseudo-points; L_QM is refactored at the next test. */
+int erl_gp_spgp_set_state_f32(erl_gp_spgp_f32 *gp, const float *q_m, const float *alpha);
+int erl_gp_spgp_set_state_f64(erl_gp_spgp_f64 *gp, const double *q_m, const double *alpha);
 /* Q_M, L_KM, L_QM: M x M col-major (ld = M); alpha: M.  Any may be NULL. */
 int erl_gp_spgp_get_f32(erl_gp_spgp_f32 *gp, float *q_m, float *alpha, float *l_km, float *l_qm);
 int erl_gp_spgp_get_f64(erl_gp_spgp_f64 *gp, double *q_m, double *alpha, double *l_km, double *l_qm);

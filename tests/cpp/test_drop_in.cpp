@@ -762,6 +762,45 @@ TestSpGpOccupancyMap(const char *name, const double tol) {
         sa = std::max(sa, std::abs(double(ref.alpha[i])));
     }
     CHECK(ea <= tol * std::max(1.0, sa), "alpha err %.3e (scale %.2f)", ea, sa);
+    // Write / Read / operator== (src/spgp_occupancy_map.cpp:164-254, src/sparse_pseudo_input_gp.cpp:498-749): a map built on other
+    // pseudo-points and another seed becomes equal after Read, predicts the same bits, and - the generator travels too - produces the
+    // same dataset and the same state from the next scan
+    {
+        std::stringstream stream;
+        CHECK(map.Write(stream), "Write");
+        auto setting2 = std::make_shared<typename Map::Setting>();
+        setting2->sp_gp->kernel_type = "erl::covariance::RadialBiasFunction<Dtype, 2>";
+        setting2->sp_gp->kernel->x_dim = 2;
+        Eigen::MatrixX<Dtype> pseudo2(2, 4);
+        for (long i = 0; i < 4; ++i) { pseudo2(0, i) = Dtype(i & 1), pseudo2(1, i) = Dtype(i >> 1); }
+        Map map2(setting2, pseudo2, boundary, 99);
+        CHECK(map != map2, "different maps must differ");
+        CHECK(map2.Read(stream), "Read");
+        CHECK(map == map2, "Read must restore an equal map");
+        CHECK(map2.GetSpGp().IsTrained() && map2.GetSpGp().GetPseudoPoints().cols() == m, "restored SPGP state");
+        Eigen::VectorX<Dtype> logodd2;
+        Eigen::MatrixX<Dtype> gradient2;
+        map2.Predict(xt, true, true, logodd2, gradient2);
+        bool same = gradient2 == gradient;
+        for (long i = 0; i < nt; ++i) { same = same && logodd2[i] == logodd[i]; }
+        CHECK(same, "the restored map must predict the same bits");
+        Eigen::VectorX<Dtype> sensor(2);
+        sensor[0] = Dtype(1.5), sensor[1] = Dtype(1.0);
+        Eigen::MatrixX<Dtype> points(2, 40);
+        for (long i = 0; i < 40; ++i) {
+            const double a = 2 * M_PI * i / 40;
+            points(0, i) = Dtype(3.5 * std::cos(a)), points(1, i) = Dtype(3.5 * std::sin(a));
+        }
+        long n1 = 0, n2 = 0;
+        Eigen::MatrixX<Dtype> dp1, dp2;
+        Eigen::VectorX<Dtype> dl1, dl2;
+        std::vector<long> h1, h2;
+        CHECK(map.Update(sensor, points, {}, n1, dp1, dl1, h1) && map2.Update(sensor, points, {}, n2, dp2, dl2, h2), "Update after Read");
+        CHECK(n1 == n2 && h1 == h2 && b200::serialization::SameTopLeft(dp1, dp2, 2, n1), "the restored generator must continue the same stream (%ld vs %ld samples)", n1, n2);
+        CHECK(map == map2, "equal maps stay equal under the same update");
+        std::stringstream damaged(stream.str().substr(0, stream.str().size() / 2));
+        CHECK(!map2.Read(damaged), "a truncated stream must be rejected");
+    }
     std::printf("%s %s: log-odds err %.2e (scale %.1f, floor %.1e), gradient err %.2e (scale %.1f, floor %.1e), var err %.2e (floor %.1e), %ld hit points\n", g_failures ? "----" : "PASS", name, em, sm,
                 fm, eg, sg, fg, ev, fv, total_hits);
 }

@@ -545,6 +545,12 @@ namespace erl_gp {
         if (warp == 0) {
             for (long kt = 0; kt < kGemmTmaStages && kt < num_kt; ++kt) { issue(kt); }
         }
+        // The epilogue reads the C tile once, at the very end, and nothing hides that DRAM latency (ncu: C is 70 % of the DRAM reads
+        // of a rank-512 update).  One bulk L2 prefetch per column now, so that the tile waits in L2 when the k loop is done.
+        if (beta != 0.0 && tid >= 32 && tid < 32 + kGemmBN && (ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+            const long col = col0 + (tid - 32);
+            if (col < n) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c + row0 + col * ldc), "r"(a_bytes) : "memory"); }
+        }
         double acc[4][4][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {

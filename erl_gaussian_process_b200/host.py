@@ -814,6 +814,16 @@ class SparsePseudoInputGaussianProcess:
               self.ctx.handle)
         return grad
 
+    def set_state(self, q_m, alpha):
+        """Read() of the reference (src/sparse_pseudo_input_gp.cpp:721-740): restores the accumulated Q_M ((M, M); (M,) in diagonal_qm
+        mode) and alpha (M,) into an instance created with the same pseudo-points; L_QM is refactored at the next test."""
+        q = np.asarray(q_m, dtype=self.dtype)
+        q = np.ascontiguousarray(q.T if q.ndim == 2 else q)  # the C ABI is column-major (Q_M is symmetric up to rounding: keep the caller's entries)
+        a = np.ascontiguousarray(alpha, dtype=self.dtype)
+        if a.shape != (self.m,) or q.shape not in ((self.m, self.m), (self.m,)):
+            raise ValueError("set_state: q_m must be (M, M) or (M,), alpha (M,)")
+        check(self.ctx.fn("erl_gp_spgp_set_state", self.dtype)(self.handle, _p(q), _p(a)), "spgp_set_state", self.ctx.handle)
+
     def get(self):
         m = self.m
         q = np.empty((m, m), dtype=self.dtype)

@@ -347,3 +347,32 @@ def test_spgp_occupancy_map(gp, oracle, dtype):
     assert occ.predict(np.array([[0.5, -0.3]]))[0] < -2 and occ.predict(np.array([[3.5, 0.0]]))[0] > 1
     np.testing.assert_array_equal(occ.predict_gradient(xt), grad)
     assert not occ.update_with_dataset(np.zeros((0, 2)), np.zeros(0))
+
+
+@pytest.mark.parametrize("diagonal", [False, True])
+def test_spgp_set_state_round_trip(gp, diagonal):
+    """erl_gp_spgp_set_state_* (what Read() restores, src/sparse_pseudo_input_gp.cpp:721-740): a fresh instance on the same pseudo-points
+    that receives Q_M and alpha predicts the same bits and keeps accumulating like the original."""
+    rng = np.random.default_rng(21)
+    gx = np.linspace(-2, 2, 10)
+    z = np.array([[a, b] for a in gx for b in gx])
+    a = gp.SparsePseudoInputGaussianProcess("matern32", 0.7, z, np.float64)
+    b = gp.SparsePseudoInputGaussianProcess("matern32", 0.7, z, np.float64)
+    if diagonal:
+        a.set_diagonal_qm(True), b.set_diagonal_qm(True)
+    x = rng.uniform(-2, 2, (300, 2))
+    assert a.update(x, np.sin(x[:, 0]) * x[:, 1], np.full(300, 1e-2))
+    q, alpha, _, _ = (a.get_qm_diagonal(), a.get()[1], None, None) if diagonal else a.get()
+    b.set_state(q, alpha)
+    xt = rng.uniform(-2, 2, (500, 2))
+    np.testing.assert_array_equal(a.test_mean(xt), b.test_mean(xt))
+    np.testing.assert_array_equal(a.test_gradient(xt), b.test_gradient(xt))
+    if not diagonal:
+        # (the variance kernel combines its warps' partial sums of squares with atomics: reproducible to rounding, not to the bit)
+        np.testing.assert_allclose(a.test(xt)[1], b.test(xt)[1], rtol=0, atol=1e-13)
+    x2 = rng.uniform(-2, 2, (200, 2))
+    for g in (a, b):
+        assert g.update(x2, np.cos(x2[:, 1]), np.full(200, 1e-2))
+    np.testing.assert_array_equal(a.test_mean(xt), b.test_mean(xt))
+    with pytest.raises(ValueError):
+        b.set_state(np.zeros((3, 3)), alpha)

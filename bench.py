@@ -683,7 +683,8 @@ def main():
                     child = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
                     others[name] = {"workload": child["config"]["workload"], "ms_per_step": child["ms_per_step"], "value": child["value"], "unit": child["unit"], "dtype": child["dtype"],
                                     "steps": child["steps"], "warmup": child["warmup"], "e2e_ms_per_step": (child.get("e2e") or {}).get("ms_per_step"),
-                                    "roofline": {k: child["roofline"].get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel")}, "clocks": child.get("clocks")}
+                                    "roofline": {k: child["roofline"].get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "train") if k in child["roofline"]},
+                                    "clocks": child.get("clocks")}
                     if "phases" in child:
                         others[name]["phases"] = child["phases"]
                 except Exception as exc:

@@ -76,7 +76,7 @@ def test_tma_bulk_copies_in_sass():
     FP64 A B^T GEMM (UBLKCP.S.G: global -> shared, completing on an mbarrier: SYNCS)."""
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     build = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "csrc")
-    objs = {"erl_gp_dense.o": ("GemmKernelDmmaTma", "UBLKCP.S.G", "SYNCS", "DMMA"), "erl_gp_rowgp64_x3.o": ("RowGp64Kernel", "UBLKCP.G.S", "DMMA")}
+    objs = {"erl_gp_dense.o": ("GemmKernelDmmaTma", "UBLKCP.S.G", "UBLKPF", "SYNCS", "DMMA"), "erl_gp_rowgp64_x3.o": ("RowGp64Kernel", "UBLKCP.G.S", "DMMA")}
     if not os.path.exists(cuobjdump) or not all(os.path.exists(os.path.join(build, o)) for o in objs):
         pytest.skip("cuobjdump or the object files are not available on this box")
     for obj, needles in objs.items():

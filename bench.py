@@ -48,7 +48,9 @@ WORKLOADS = {
                  num_gps=8_000, n=192, x_dim=2, q_per_gp=192, kernel="matern32", scale=0.3, dtype="f32"),
     "n256": dict(desc="diagnostic: 5k independent GPs per GPU, n=256, x_dim=2, Matern32(0.3), 256 test points per GP, f32",
                  num_gps=5_000, n=256, x_dim=2, q_per_gp=256, kernel="matern32", scale=0.3, dtype="f32"),
-    # diagnostic: the same stream in double (generic one-CTA-per-GP kernel); not the bench line
+    "n192f64": dict(desc="diagnostic: 8k independent GPs per GPU, n=192, x_dim=2, Matern32(0.3), 192 test points per GP, f64",
+                    num_gps=8_000, n=192, x_dim=2, q_per_gp=192, kernel="matern32", scale=0.3, dtype="f64"),
+    # diagnostic: the same stream in double (DMMA row-GP kernel); not the bench line
     "c4f64": dict(desc="batched small-GP stream in double: 50k independent GPs per GPU, n=128, x_dim=3, Matern32(0.3), 128 test points per GP, f64 (diagnostic)",
                   num_gps=50_000, n=128, x_dim=3, q_per_gp=128, kernel="matern32", scale=0.3, dtype="f64"),
 }

@@ -775,9 +775,11 @@ namespace erl_gp {
             if (max_n <= 256 && !legacy && !legacy_large) { return rowgp::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
         }
         if constexpr (sizeof(T) == 8) {
-            // FP64, n <= 128: the DMMA row-GP kernel (erl_gp_rowgp64.cuh); ERL_GP_BATCH_LEGACY=1 keeps the generic kernel below
+            // FP64, n <= 192: the DMMA row-GP kernel (erl_gp_rowgp64.cuh); ERL_GP_BATCH_LEGACY=1 keeps the generic kernel below
             static const bool legacy64 = std::getenv("ERL_GP_BATCH_LEGACY") != nullptr;
+            static const bool legacy64_large = std::getenv("ERL_GP_BATCH_LEGACY_LARGE") != nullptr;  // only 128 < n <= 192 on the generic kernel
             if (max_n <= 128 && !legacy64) { return rowgp64::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
+            if (max_n <= 192 && !legacy64 && !legacy64_large) { return rowgp64::Launch<XDIM>(ctx, params, mode, tiles_per_gp); }
         }
         if (max_n <= 64) { return LaunchBatchMode<T, XDIM, 4>(ctx, params, mode, tiles_per_gp); }
         if (max_n <= 128) { return LaunchBatchMode<T, XDIM, 8>(ctx, params, mode, tiles_per_gp); }

@@ -194,23 +194,27 @@ namespace erl_gp {
             const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform by construction
             const int lane = tid & 31;
             const int g = lane >> 2, t = lane & 3;
+            constexpr int kTpw = (NBLK + kWarps - 1) / kWarps;  // 16-row tiles of a panel per warp
             int fail = 0;
 #ifdef ERL_GP_ROWGP64_TIMING
             long long tm_a = 0, tm_b = 0, tm_w1 = 0, tm_c = 0, tm_w2 = 0, tm_t = clock64();
 #endif
             for (int kb = 0; kb < nblk; ++kb) {
                 const int c0 = 16 * kb;
-                const int mt = nblk - kb;  // 16-row tiles of this panel: tile w -> warp w (mt <= 8)
+                const int mt = nblk - kb;  // 16-row tiles of this panel: tile w + 8 ti -> warp w (one tile per warp up to n = 128, two beyond)
                 const int stride_k = Lay::Stride(kb);
                 double *panel = lp + Lay::Base(kb);  // element (row c0, column c0)
-                const int rel = 16 * warp;           // my tile's first row, relative to c0
-                double acc[2][2][2];
+                double acc_t[kTpw][2][2][2];
+#pragma unroll
+                for (int ti = 0; ti < kTpw; ++ti) {
+                double (&acc)[2][2][2] = acc_t[ti];
+                const int rel = 16 * (warp + kWarps * ti);  // my tile's first row, relative to c0
 #pragma unroll
                 for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) { acc[rh][ch][0] = acc[rh][ch][1] = 0.0; }
                 }
-                if (warp < mt) {
+                if (warp + kWarps * ti < mt) {
                     // ---- A: P = K[tile, panel] - L[tile, 0:c0] L[pivot rows, 0:c0]^T ----
                     for (int jb = 0; jb < kb; ++jb) {
                         const int stride = Lay::Stride(jb);
@@ -238,9 +242,11 @@ namespace erl_gp {
                         }
                     }
                 }
+                }
                 ERL_GP64_TICK(tm_a)
                 // ---- B: pivot tile (warp 0 holds it) ----
                 if (warp == 0) {
+                    double (&acc)[2][2][2] = acc_t[0];
 #pragma unroll
                     for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
@@ -286,7 +292,11 @@ namespace erl_gp {
                 __syncthreads();  // #1: pivot tile, Dinv, z of this panel are published
                 ERL_GP64_TICK(tm_w1)
                 if (mt > 1) {
-                    if (warp > 0 && warp < mt) {
+#pragma unroll
+                    for (int ti = 0; ti < kTpw; ++ti) {
+                    double (&acc)[2][2][2] = acc_t[ti];
+                    const int rel = 16 * (warp + kWarps * ti);
+                    if (warp + kWarps * ti > 0 && warp + kWarps * ti < mt) {
                         // ---- C: L_i = P_i Dinv^T; Dinv is lower triangular: the (ck = 1, ch = 0) block is zero ----
                         const double *dv = dinv + kb * 16 * Lay::kDinvLd + g;
                         double out[2][2][2];
@@ -315,6 +325,7 @@ namespace erl_gp {
                                 for (int e = 0; e < 2; ++e) { panel[(8 * ch + 2 * t + e) * stride_k + rel + 8 * rh + g] = out[rh][ch][e]; }
                             }
                         }
+                    }
                     }
                     ERL_GP64_TICK(tm_c)
                     __syncthreads();  // #2: the whole panel is published
@@ -602,7 +613,7 @@ namespace erl_gp {
         }
 
         template<int XDIM, int NBLK, int MODE>
-        __global__ void __launch_bounds__(kThreads, 2)
+        __global__ void __launch_bounds__(kThreads, NBLK <= 8 ? 2 : 1)
         RowGp64Kernel(const BatchParams<double> p) {
             using Lay = Layout<NBLK>;
             extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -768,12 +779,13 @@ namespace erl_gp {
             }
         }
 
-        // max_n <= 128
+        // max_n <= 192 (n in (128, 192]: one CTA per SM, 200 KB of shared memory, two 16-row tiles per warp in the factorisation)
         template<int XDIM>
         int
         Launch(Context *ctx, const BatchParams<double> &params, const int mode, const int tiles_per_gp) {
             if (params.max_n <= 64) { return LaunchMode<XDIM, 4>(ctx, params, mode, tiles_per_gp); }
-            return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp);
+            if (params.max_n <= 128) { return LaunchMode<XDIM, 8>(ctx, params, mode, tiles_per_gp); }
+            return LaunchMode<XDIM, 12>(ctx, params, mode, tiles_per_gp);
         }
 
     }  // namespace rowgp64

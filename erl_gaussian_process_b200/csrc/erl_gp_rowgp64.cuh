@@ -26,6 +26,7 @@
 #include "erl_gp_internal.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 #ifdef ERL_GP_ROWGP64_TIMING  // per-phase cycle counters, printed by one CTA (kernel experiments only)
 #define ERL_GP64_TICK(acc_) { const long long now_ = clock64(); acc_ += now_ - tm_t; tm_t = now_; }
@@ -402,6 +403,18 @@ namespace erl_gp {
             }
         }
 
+        // compile-time loop: the body sees its index as a constant, so that register arrays indexed by it stay in registers whatever the
+        // unroller's size limits are (with #pragma unroll the 66 block updates of the n <= 192 predict were only partly unrolled and its
+        // accumulators went to local memory)
+        template<int I, int N, typename F>
+        __device__ __forceinline__ void
+        StaticFor(F &&f) {
+            if constexpr (I < N) {
+                f(std::integral_constant<int, I>{});
+                StaticFor<I + 1, N>(f);
+            }
+        }
+
         // one pass: 8 queries per warp, V^T = Kt^T L^-T with the 8 x (16 NBLK) accumulators resident
         template<int XDIM, int NBLK>
         __device__ __forceinline__ void
@@ -439,8 +452,8 @@ namespace erl_gp {
                 }
             }
             double ss = 0.0;
-#pragma unroll
-            for (int j = 0; j < NBLK; ++j) {
+            StaticFor<0, NBLK>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
                 if (j < nblk) {
                     // V_j = X_j Dinv_j^T
                     const double *dv = dinv + j * 16 * Lay::kDinvLd + g;
@@ -461,8 +474,8 @@ namespace erl_gp {
                     // X_i -= V_j L_ij^T for the block rows below
                     const int stride = Lay::Stride(j);
                     const double *base = lp + Lay::Base(j) + g;
-#pragma unroll
-                    for (int i = j + 1; i < NBLK; ++i) {
+                    StaticFor<j + 1, NBLK>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
                         if (i < nblk) {
 #pragma unroll
                             for (int ck = 0; ck < 2; ++ck) {
@@ -474,9 +487,9 @@ namespace erl_gp {
                                 }
                             }
                         }
-                    }
+                    });
                 }
-            }
+            });
             mean += __shfl_xor_sync(kFull, mean, 1);
             mean += __shfl_xor_sync(kFull, mean, 2);
             ss += __shfl_xor_sync(kFull, ss, 1);
